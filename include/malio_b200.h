@@ -1,0 +1,227 @@
+/*
+ * malio_b200.h — C-ABI of the B200-native MA-LIO measurement hot path.
+ *
+ * Drop-in boundary.  The reference's plug-in point is the IKFoM
+ * measurement-model callback
+ *     typedef void measurementModel_dyn_share(state&, dyn_share_datastruct<double>&)
+ *         MA_LIO/include/IKFoM_toolkit/esekfom/esekfom.hpp:130   (installed :152-168, invoked :512)
+ * implemented by
+ *     void h_share_model(state_ikfom&, esekfom::dyn_share_datastruct<double>&)
+ *         MA_LIO/src/laserMapping.cpp:552-760
+ * which in turn calls
+ *     KD_TREE::Nearest_Search(PointType, int k, PointVector&, vector<float>&, float)
+ *         MA_LIO/include/ikd-Tree/ikd_Tree.h:328 / ikd_Tree.cpp:426-461  (call site laserMapping.cpp:586)
+ * and whose N_eff x 24 output is reduced by
+ *     esekf::update_iterated_dyn_share_modified        esekfom.hpp:495-721  (O(N) part :621-637).
+ *
+ * Because the device path fuses the H^T R^-1 H / H^T R^-1 h reduction, this ABI sits one
+ * level above the callback: malio_measure() replaces h_share_model *and* esekfom.hpp:622-635
+ * and returns the reduced c x c system.  malio_ieskf_update() is the host-side iterated
+ * update (replaces esekfom.hpp:495-721 as a whole).
+ *
+ * Conventions: plain C types only; caller owns every host buffer (pinned memory recommended);
+ * the handle owns device memory, streams, events and the NCCL communicator.  Every call returns
+ * a malio_status; calls on one handle must come from one thread at a time; all calls are
+ * synchronous at return unless stated otherwise.
+ */
+#ifndef MALIO_B200_H_
+#define MALIO_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MALIO_MAX_LIDAR 3   /* use-ikfom.hpp:14-27 builds the manifold for 3 LiDARs; L is run-time here (1..3) */
+#define MALIO_K 5           /* NUM_MATCH_POINTS, common_lib.h:22 */
+#define MALIO_MAX_COLS (6 * (MALIO_MAX_LIDAR + 1))            /* c = 6(L+1), laserMapping.cpp:642 */
+#define MALIO_MAX_DOF (17 + 6 * MALIO_MAX_LIDAR)              /* n = 17+6L, esekfom.hpp:158 */
+#define MALIO_MAX_TREE_DEPTH 96                              /* traversal stack bound; deeper snapshots are rejected */
+#define MALIO_NCCL_UNIQUE_ID_BYTES 128
+
+typedef enum malio_status {
+  MALIO_OK = 0,
+  MALIO_ERR_INVALID_ARG = 1,
+  MALIO_ERR_CUDA = 2,          /* CUDA runtime / driver failure (no GPU, OOM, launch error) */
+  MALIO_ERR_NCCL = 3,
+  MALIO_ERR_NO_EFFECTIVE_POINTS = 4, /* N_eff == 0: reference sets valid=false (laserMapping.cpp:635-639) */
+  MALIO_ERR_STATE = 5,         /* call order violated (e.g. measure before upload) */
+  MALIO_ERR_TREE_TOO_DEEP = 6,
+  MALIO_ERR_CAPACITY = 7
+} malio_status;
+
+/* ---- map snapshot: one record per live ikd-Tree node, DFS pre-order ---------------------------
+ * Mirrors what KD_TREE::Search reads per visit (ikd_Tree.cpp:1073-1255): the node's point, its
+ * point_deleted flag, and both children's node_range_* boxes (KD_TREE_NODE, ikd_Tree.h:59-82),
+ * after Push_Down (ikd_Tree.cpp:1371-1466).  tree_deleted subtrees are not exported (Search
+ * returns immediately on them, :1075).  The left child of node i, when present, is node i+1. */
+typedef struct malio_map_node {
+  float x, y, z;
+  uint32_t link;      /* bits 0..27 index of the right child; bit 31 has_left; bit 30 has_right;
+                         bit 29 point_deleted */
+  float lbox[6];      /* left child's {x_min,x_max,y_min,y_max,z_min,z_max}; undefined if !has_left */
+  float rbox[6];      /* right child's */
+} malio_map_node;     /* 64 bytes */
+
+#define MALIO_LINK_HAS_LEFT  0x80000000u
+#define MALIO_LINK_HAS_RIGHT 0x40000000u
+#define MALIO_LINK_POINT_DELETED 0x20000000u
+#define MALIO_LINK_INDEX_MASK 0x0FFFFFFFu
+
+/* ---- scan point: feats_down_body entry as h_share_model reads it (laserMapping.cpp:565-570,694) */
+typedef struct malio_scan_pt {
+  float x, y, z;        /* point in its own LiDAR frame */
+  uint16_t lidar;       /* PointType::intensity after laserMapping.cpp:975 */
+  uint16_t table_idx;   /* int(PointType::normal_x), laserMapping.cpp:694,737 */
+} malio_scan_pt;        /* 16 bytes */
+
+/* ---- one entry of pose_unc[l][j] (struct Pose, common_lib.h:57-63): only T_ and cov_ are read by
+ * evalPointUncertainty (associate_uct.hpp:153-175) */
+typedef struct malio_pose_entry {
+  double T[16];        /* row-major 4x4 */
+  double cov[36];      /* row-major 6x6 */
+} malio_pose_entry;
+
+typedef struct malio_rigid {
+  double q[4];         /* w, x, y, z */
+  double t[3];
+} malio_rigid;
+
+/* ---- pose part of state_ikfom read by h_share_model (use-ikfom.hpp:14-27; extrinsic_update,
+ * laserMapping.cpp:291-308) */
+typedef struct malio_pass_state {
+  double rot[4];       /* s.rot, (w,x,y,z) */
+  double pos[3];       /* s.pos */
+  malio_rigid ext[MALIO_MAX_LIDAR];   /* offset_R_l / offset_T_l */
+} malio_pass_state;
+
+/* ---- run-time parameters (parameters.cpp:17-66; launch/mapping_city.launch:9-15; City.yaml:41-50) */
+typedef struct malio_params {
+  int32_t n_lidar;            /* L, 1..3 */
+  int32_t extrinsic_est_en;   /* laserMapping.cpp:681 */
+  float plane_th;             /* esti_plane threshold, common_lib.h:184 */
+  float knn_max_sqdist;       /* 5.0f, laserMapping.cpp:587 */
+  double cov_threshold;
+  double point_cov_max, point_cov_min;
+  double plane_cov_max, plane_cov_min;
+  double localize_cov_max, localize_cov_min;
+  double localize_thresh_max, localize_thresh_min;
+  double range_min, range_max;
+} malio_params;
+
+typedef struct malio_config {
+  malio_params params;
+  int32_t device;             /* CUDA device ordinal */
+  int32_t sort_queries;       /* 1: Morton-order the scan on the device (internal; outputs stay in caller order) */
+  uint32_t max_points;        /* capacity hints; buffers grow on demand when 0 */
+  uint32_t max_map_nodes;
+} malio_config;
+
+typedef struct malio_pass_stats {
+  uint32_t n_points;          /* N of this rank's shard */
+  uint32_t n_eff;             /* effct_feat_num, summed over ranks */
+  int32_t valid;              /* dyn_share.valid */
+  int32_t searched;           /* 1 if this pass ran the k-NN */
+  double u_min, u_max;        /* min/max_unit_cov, laserMapping.cpp:615-628 */
+  double tau_min, tau_max;    /* min/max_cov, laserMapping.cpp:646-703 */
+  double sigma[3];            /* singular values of h_x[:,0:3] before the localization weight */
+  double loc_weight;          /* weight, laserMapping.cpp:749-756 */
+  float ms_knn, ms_plane, ms_reduce, ms_total;   /* device time of this pass (CUDA events) */
+} malio_pass_stats;
+
+typedef struct malio_handle malio_handle;
+
+/* fill p with the reference defaults for L LiDARs (City.yaml / mapping_city.launch values) */
+void malio_default_params(malio_params* p, int n_lidar);
+
+int malio_create(malio_handle** out, const malio_config* cfg);
+void malio_destroy(malio_handle* h);
+const char* malio_last_error(const malio_handle* h);   /* static storage when h == NULL */
+const char* malio_version(void);
+
+/* multi-GPU: one process per GPU.  Rank 0 calls malio_get_nccl_unique_id and ships the bytes to the
+ * other ranks (torch.distributed / MPI / a socket — plumbing); every rank then calls malio_comm_init.
+ * With a communicator attached, malio_measure all-reduces {min,max} and the reduced system over the
+ * ranks; each rank uploads only its own block of scan points. */
+int malio_get_nccl_unique_id(uint8_t id[MALIO_NCCL_UNIQUE_ID_BYTES]);
+int malio_comm_init(malio_handle* h, const uint8_t id[MALIO_NCCL_UNIQUE_ID_BYTES], int rank, int world);
+
+/* once per scan: flattened ikd-Tree snapshot (include/malio_flatten.hpp produces it) and the map-side
+ * weight normal_y of every node (quirk: an input field).  root is node 0. */
+int malio_upload_map(malio_handle* h, const malio_map_node* nodes, const float* node_cov,
+                     uint32_t n_nodes, uint32_t max_depth);
+
+/* once per scan: this rank's block of the down-sampled merged scan + the pose tables.
+ * table holds pose_unc[0], pose_unc[1], ... back to back; pose_unc[l] = table[table_off[l] .. table_off[l+1]).
+ * temporal_comp[l-1] is kf.temporal_comp[l-1] (IMU_Processing.hpp:517-519), l = 1..L-1. */
+int malio_upload_scan(malio_handle* h, const malio_scan_pt* pts, uint32_t n_pts,
+                      const malio_pose_entry* table, const uint32_t* table_off /* L+1 */,
+                      const malio_rigid* temporal_comp /* L-1, may be NULL when L==1 */);
+
+/* one pass of h_share_model + esekfom.hpp:622-635.
+ *   HtRinvH : c x c row-major, = h_x^T diag(1/R) h_x   (HTH, esekfom.hpp:629)
+ *   HtRinvh : c,              = h_x^T diag(1/R) h     (HT * dyn_share.h, esekfom.hpp:635)
+ * redo_knn = dyn_share.converge on entry (laserMapping.cpp:583).
+ * Returns MALIO_ERR_NO_EFFECTIVE_POINTS (stats->valid = 0) when N_eff == 0. */
+int malio_measure(malio_handle* h, const malio_pass_state* s, int redo_knn,
+                  double* HtRinvH, double* HtRinvh, malio_pass_stats* stats);
+
+/* rows of the last pass for the degenerate branch n > N_eff (esekfom.hpp:574-582): up to cap rows of
+ * h_x (row-major, c columns) and h, in scan order, already scaled by plane and localization weight. */
+int malio_download_rows(malio_handle* h, double* h_x, double* hvec, uint32_t cap, uint32_t* n_rows);
+
+/* side outputs of the last pass, caller order; any pointer may be NULL.
+ *   normal_y : trace of the point covariance for all N points (laserMapping.cpp:699,730,741)
+ *   nn_idx   : N x 5 snapshot node indices, ascending by (distance, x) as Nearest_Search returns them;
+ *              0xFFFFFFFF where fewer than 5 were found
+ *   nn_sqdist: N x 5
+ *   selected : point_selected_surf after the pass
+ *   world    : N x 3 feats_down_world (laserMapping.cpp:576-578) */
+int malio_download_aux(malio_handle* h, float* normal_y, uint32_t* nn_idx, float* nn_sqdist,
+                       uint8_t* selected, float* world);
+
+/* stand-alone k-NN (BASELINE config C5, the microbench): queries are world-frame points. */
+int malio_knn(malio_handle* h, const float* queries_xyz, uint32_t n_queries,
+              uint32_t* nn_idx, float* nn_sqdist, float* ms_device);
+
+/* ---- host IESKF -----------------------------------------------------------------------------
+ * state_ikfom for L LiDARs (use-ikfom.hpp:14-27): DOF n = 17+6L laid out as
+ *   pos 0-2 | rot 3-5 | offset_R_l 6+3l | offset_T_l 6+3L+3l | vel | bg | ba | grav (S2, 2 DOF). */
+typedef struct malio_state {
+  double pos[3];
+  double rot[4];                       /* w,x,y,z */
+  malio_rigid ext[MALIO_MAX_LIDAR];    /* offset_R_l, offset_T_l */
+  double vel[3], bg[3], ba[3];
+  double grav[3];                      /* S2, |grav| = 9.809 */
+} malio_state;
+
+typedef struct malio_update_report {
+  int32_t passes;               /* passes run (<= max_iter+1) */
+  int32_t searches;             /* passes that ran the k-NN */
+  int32_t converged_count;      /* t in esekfom.hpp:658 */
+  int32_t last_status;
+  uint32_t n_eff_last;
+  float ms_device_total;        /* sum of device time over the passes */
+  float ms_host_solve;          /* host 35x35 algebra */
+  double dx_last[MALIO_MAX_DOF];  /* last state increment dx_ (esekfom.hpp:642) */
+} malio_update_report;
+
+/* esekf::update_iterated_dyn_share_modified (esekfom.hpp:495-721): iterates malio_measure and the host
+ * algebra; x and P (n x n row-major) are updated in place.  R is LASER_POINT_COV (laserMapping.cpp:38),
+ * only used by the degenerate branch. */
+int malio_ieskf_update(malio_handle* h, malio_state* x, double* P, int max_iter, double R,
+                       malio_update_report* report);
+
+/* ---- host utility: static snapshot builder --------------------------------------------------
+ * Builds a balanced k-d tree over points (median split on the longest axis, as KD_TREE::BuildTree,
+ * ikd_Tree.cpp:696-735) directly in snapshot form, for callers without a live ikd-Tree (benchmarks,
+ * the k-NN microbench).  order_out[i] = index into xyz of the point stored in node i. */
+int malio_build_static_snapshot(const float* xyz, uint32_t n, malio_map_node* nodes_out,
+                                uint32_t* order_out, uint32_t* max_depth_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MALIO_B200_H_ */
