@@ -1,0 +1,1249 @@
+// malio_b200.cu — sm_100a kernels + device-side state of libmalio_b200.so.
+//
+// Hot path of MA-LIO's measurement update, B200-native (DESIGN.md has the data layout and rooflines):
+//   K1 knn_kernel      KD_TREE::Nearest_Search / Search   (ikd_Tree.cpp:426-461, 1073-1255)
+//   K2 plane_kernel    h_share_model S1 + esti_plane + evalPointUncertainty
+//                      (laserMapping.cpp:559-612, 725-743; common_lib.h:144-190; associate_uct.hpp:153-175)
+//   K3 reduce_kernel   h_share_model S3-S4 rows fused with esekfom.hpp:622-635 (H^T R^-1 H, H^T R^-1 h)
+// Compiled with -fmad=false: every float/double expression below is evaluated with the same IEEE operations,
+// in the same order, as the reference's x86-64 build (no FMA, CMakeLists.txt:8) so that k-NN index sets are
+// bit-exact and the selection gates do not flip; explicit fma() is used only in the FP64 accumulation of K3.
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "malio_internal.h"
+
+#define CUDA_TRY(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      h->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                          \
+      return MALIO_ERR_CUDA;                                                               \
+    }                                                                                      \
+  } while (0)
+
+namespace {
+
+constexpr int KNN_THREADS = 128;
+constexpr int PLANE_THREADS = 128;
+constexpr int RED_THREADS = 128;          // one tile = 128 points
+constexpr int RED_HS_STRIDE = 26;         // doubles per staged row of h/rho (24 + pad)
+constexpr int RED_HX_STRIDE = 28;         // doubles per staged row of [h | z | rho*h_0..2]
+constexpr int TABLE_DOUBLES = 52;         // malio_pose_entry
+
+struct PassConst {
+  double rot[4], pos[3];
+  double eq[MALIO_MAX_LIDAR][4], et[MALIO_MAX_LIDAR][3];   // extrinsics (state)
+  double cq[MALIO_MAX_LIDAR][4], ct[MALIO_MAX_LIDAR][3];   // temporal compensation, index l (entry 0 unused)
+  uint32_t table_off[MALIO_MAX_LIDAR + 1];
+  int L;
+  int ext_en;
+};
+
+struct ParamConst {
+  float plane_th, knn_max_sqdist;
+  double cov_threshold, point_cov_max, point_cov_min, plane_cov_max, plane_cov_min, range_min, range_max;
+};
+
+// ------------------------------------------------------------------ small device algebra (mirrors Eigen's op order)
+__device__ __forceinline__ void cross3(const double a[3], const double b[3], double o[3]) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+// Quaternion * vector as Eigen's _transformVector: v + w*uv + qv x uv, uv = 2 (qv x v); q = (w,x,y,z)
+__device__ __forceinline__ void q_rot(const double q[4], const double v[3], double o[3]) {
+  const double qv[3] = {q[1], q[2], q[3]};
+  double uv[3], c2[3];
+  cross3(qv, v, uv);
+  uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+  cross3(qv, uv, c2);
+  o[0] = v[0] + q[0] * uv[0] + c2[0];
+  o[1] = v[1] + q[0] * uv[1] + c2[1];
+  o[2] = v[2] + q[0] * uv[2] + c2[2];
+}
+__device__ __forceinline__ void q_rot_conj(const double q[4], const double v[3], double o[3]) {
+  const double qc[4] = {q[0], -q[1], -q[2], -q[3]};
+  q_rot(qc, v, o);
+}
+// toRotationMatrix of the conjugate of q, row-major
+__device__ __forceinline__ void q_conj_to_R(const double q[4], double R[9]) {
+  const double w = q[0], x = -q[1], y = -q[2], z = -q[3];
+  const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+  R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+
+// laserMapping.cpp:569-579: point in its LiDAR frame -> LiDAR-0 body frame b, IMU frame m, world g
+__device__ __forceinline__ void transform_point(const PassConst& pc, float px, float py, float pz, int lid,
+                                                double b[3], double m[3], double g[3]) {
+  b[0] = px; b[1] = py; b[2] = pz;
+  if (lid != 0) {
+    double a[3], t[3], d[3];
+    q_rot(pc.eq[lid], b, a);
+    a[0] += pc.et[lid][0]; a[1] += pc.et[lid][1]; a[2] += pc.et[lid][2];
+    q_rot(pc.cq[lid], a, t);
+    d[0] = (t[0] + pc.ct[lid][0]) - pc.et[0][0];
+    d[1] = (t[1] + pc.ct[lid][1]) - pc.et[0][1];
+    d[2] = (t[2] + pc.ct[lid][2]) - pc.et[0][2];
+    q_rot_conj(pc.eq[0], d, b);
+  }
+  q_rot(pc.eq[0], b, m);
+  m[0] += pc.et[0][0]; m[1] += pc.et[0][1]; m[2] += pc.et[0][2];
+  q_rot(pc.rot, m, g);
+  g[0] += pc.pos[0]; g[1] += pc.pos[1]; g[2] += pc.pos[2];
+}
+
+// ------------------------------------------------------------------ K1: k-NN over the flattened ikd-Tree snapshot
+// calc_box_dist (ikd_Tree.cpp:1702-1720)
+__device__ __forceinline__ float box_dist(float px, float py, float pz, float x0, float x1, float y0, float y1,
+                                          float z0, float z1) {
+  float m = 0.0f;
+  if (px < x0) m += (px - x0) * (px - x0);
+  if (px > x1) m += (px - x1) * (px - x1);
+  if (py < y0) m += (py - y0) * (py - y0);
+  if (py > y1) m += (py - y1) * (py - y1);
+  if (pz < z0) m += (pz - z0) * (pz - z0);
+  if (pz > z1) m += (pz - z1) * (pz - z1);
+  return m;
+}
+// PointType_CMP::operator< (ikd_Tree.h:102-108)
+__device__ __forceinline__ bool cmp_lt(float d1, float x1, float d2, float x2) {
+  return (fabs((double)(d1 - d2)) < 1e-10) ? (x1 < x2) : (d1 < d2);
+}
+
+// MANUAL_HEAP (ikd_Tree.h:111-201) of k=5 items per thread, kept in shared memory, [slot][thread] layout
+struct SmemHeap {
+  float (*d)[KNN_THREADS];
+  float (*x)[KNN_THREADS];
+  uint32_t (*i)[KNN_THREADS];
+  int t;
+  int cnt;
+  __device__ __forceinline__ void pop() {   // heap[0] = heap[size-1]; size--; MoveDown(0)
+    const int n = cnt - 1;
+    const float td = d[n][t], tx = x[n][t];
+    const uint32_t ti = i[n][t];
+    int idx = 0, l = 1;
+    while (l < n) {
+      if (l + 1 < n && cmp_lt(d[l][t], x[l][t], d[l + 1][t], x[l + 1][t])) l++;
+      if (cmp_lt(td, tx, d[l][t], x[l][t])) {
+        d[idx][t] = d[l][t]; x[idx][t] = x[l][t]; i[idx][t] = i[l][t];
+        idx = l;
+        l = idx * 2 + 1;
+      } else
+        break;
+    }
+    d[idx][t] = td; x[idx][t] = tx; i[idx][t] = ti;
+    cnt = n;
+  }
+  __device__ __forceinline__ void push(float nd, float nx, uint32_t ni) {   // FloatUp
+    int idx = cnt;
+    while (idx > 0) {
+      const int anc = (idx - 1) / 2;
+      if (cmp_lt(d[anc][t], x[anc][t], nd, nx)) {
+        d[idx][t] = d[anc][t]; x[idx][t] = x[anc][t]; i[idx][t] = i[anc][t];
+        idx = anc;
+      } else
+        break;
+    }
+    d[idx][t] = nd; x[idx][t] = nx; i[idx][t] = ni;
+    cnt++;
+  }
+};
+
+// One query per thread.  Traversal order, pruning and heap behaviour are exactly KD_TREE::Search's
+// (near child first when dist_left <= dist_right, strict '<' everywhere, first-visited wins ties), so the
+// returned index lists are the reference's, bit for bit.  The far child is kept on a per-thread stack
+// together with its box distance and re-tested against the then-current heap top when popped.
+//   MODE 0: queries come from the scan (transform with pc), also writes world + the k-NN gate
+//   MODE 1: stand-alone queries (world-frame float3), no gate
+template <int MODE>
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const malio_scan_pt* __restrict__ pts,
+           const uint32_t* __restrict__ perm, const float* __restrict__ queries, uint32_t N, PassConst pc,
+           float max_sqdist, float4* __restrict__ world, uint32_t* __restrict__ nn_idx,
+           float* __restrict__ nn_d2, uint8_t* __restrict__ sel) {
+  __shared__ float s_d[MALIO_K][KNN_THREADS];
+  __shared__ float s_x[MALIO_K][KNN_THREADS];
+  __shared__ uint32_t s_i[MALIO_K][KNN_THREADS];
+  const uint32_t p = blockIdx.x * KNN_THREADS + threadIdx.x;
+  if (p >= N) return;
+  float qx, qy, qz;
+  if (MODE == 0) {
+    const malio_scan_pt pt = pts[perm ? perm[p] : p];
+    double b[3], m[3], g[3];
+    transform_point(pc, pt.x, pt.y, pt.z, pt.lidar, b, m, g);
+    qx = (float)g[0]; qy = (float)g[1]; qz = (float)g[2];
+    world[p] = make_float4(qx, qy, qz, 0.f);
+  } else {
+    const uint32_t src = perm ? perm[p] : p;
+    qx = queries[3 * (size_t)src]; qy = queries[3 * (size_t)src + 1]; qz = queries[3 * (size_t)src + 2];
+  }
+  SmemHeap hp{s_d, s_x, s_i, (int)threadIdx.x, 0};
+  uint32_t st_n[MALIO_MAX_TREE_DEPTH];
+  float st_d[MALIO_MAX_TREE_DEPTH];
+  int sp = 0;
+  float top = INFINITY;           // q.top().dist once the heap holds k items
+  uint32_t cur = 0;
+  bool go = n_nodes > 0;
+  while (go) {
+    const float4* nd = nodes + 4 * (size_t)cur;
+    const float4 a = __ldg(nd), b4 = __ldg(nd + 1), c4 = __ldg(nd + 2), d4 = __ldg(nd + 3);
+    const uint32_t link = __float_as_uint(a.w);
+    if (!(link & MALIO_LINK_POINT_DELETED)) {
+      // calc_dist (ikd_Tree.cpp:1694-1699)
+      const float dist = (qx - a.x) * (qx - a.x) + (qy - a.y) * (qy - a.y) + (qz - a.z) * (qz - a.z);
+      if (hp.cnt < MALIO_K || dist < top) {
+        if (hp.cnt >= MALIO_K) hp.pop();
+        hp.push(dist, a.x, cur);
+        if (hp.cnt == MALIO_K) top = s_d[0][threadIdx.x];
+      }
+    }
+    const bool hl = link & MALIO_LINK_HAS_LEFT, hr = link & MALIO_LINK_HAS_RIGHT;
+    const float dl = hl ? box_dist(qx, qy, qz, b4.x, b4.y, b4.z, b4.w, c4.x, c4.y) : INFINITY;
+    const float dr = hr ? box_dist(qx, qy, qz, c4.z, c4.w, d4.x, d4.y, d4.z, d4.w) : INFINITY;
+    const uint32_t li = cur + 1, ri = link & MALIO_LINK_INDEX_MASK;
+    const bool left_first = dl <= dr;
+    const uint32_t n_near = left_first ? li : ri, n_far = left_first ? ri : li;
+    const float d_near = left_first ? dl : dr, d_far = left_first ? dr : dl;
+    const bool p_near = left_first ? hl : hr, p_far = left_first ? hr : hl;
+    const bool open = hp.cnt < MALIO_K;
+    if (p_far && (open || d_far < top)) { st_n[sp] = n_far; st_d[sp] = d_far; sp++; }
+    if (p_near && (open || d_near < top)) { cur = n_near; continue; }
+    go = false;
+    while (sp > 0) {
+      --sp;
+      if (hp.cnt < MALIO_K || st_d[sp] < top) { cur = st_n[sp]; go = true; break; }
+    }
+  }
+  // Nearest_Search (ikd_Tree.cpp:451-459): pop into ascending order
+  const int found = hp.cnt;
+  uint32_t oi[MALIO_K];
+  float od[MALIO_K];
+#pragma unroll
+  for (int j = MALIO_K - 1; j >= 0; --j) {
+    if (j < found) {
+      oi[j] = s_i[0][threadIdx.x];
+      od[j] = s_d[0][threadIdx.x];
+      hp.pop();
+    } else {
+      oi[j] = 0xFFFFFFFFu;
+      od[j] = INFINITY;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MALIO_K; ++j) {
+    nn_idx[(size_t)j * N + p] = oi[j];
+    nn_d2[(size_t)j * N + p] = od[j];
+  }
+  if (MODE == 0) sel[p] = (found < MALIO_K) ? 0 : (od[MALIO_K - 1] > max_sqdist ? 0 : 1);   // laserMapping.cpp:587
+}
+
+// ------------------------------------------------------------------ Morton keys for query coherence (internal order only)
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+  v &= 1023u;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+template <int MODE>
+__global__ void morton_kernel(const malio_scan_pt* __restrict__ pts, const float* __restrict__ queries, uint32_t N,
+                              PassConst pc, uint32_t* __restrict__ keys, uint32_t* __restrict__ ids) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float x, y, z;
+  if (MODE == 0) {
+    const malio_scan_pt pt = pts[i];
+    double b[3], m[3], g[3];
+    transform_point(pc, pt.x, pt.y, pt.z, pt.lidar, b, m, g);
+    x = (float)g[0]; y = (float)g[1]; z = (float)g[2];
+  } else {
+    x = queries[3 * (size_t)i]; y = queries[3 * (size_t)i + 1]; z = queries[3 * (size_t)i + 2];
+  }
+  // 1 m cells, 10 bits per axis (wraps every 1024 m: only locality matters)
+  const uint32_t ix = (uint32_t)(int)floorf(x), iy = (uint32_t)(int)floorf(y), iz = (uint32_t)(int)floorf(z);
+  keys[i] = spread10(ix) | (spread10(iy) << 1) | (spread10(iz) << 2);
+  ids[i] = i;
+}
+
+// ------------------------------------------------------------------ K2: plane fit, gates, point-wise uncertainty
+// Eigen::ColPivHouseholderQR<Matrix<float,5,3>>::solve(b) with b = -1 (common_lib.h:156-157,174), float, no FMA.
+__device__ __forceinline__ void qr_solve_5x3(float A[5][3], float x[3]) {
+  const float eps = 1.1920928955078125e-07f;   // FLT_EPSILON
+  float hC[3] = {0.f, 0.f, 0.f};
+  int perm[3] = {0, 1, 2};
+  float nU[3], nD[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) s += A[i][k] * A[i][k];
+    nD[k] = sqrtf(s);
+    nU[k] = nD[k];
+  }
+  const float maxn = fmaxf(nU[0], fmaxf(nU[1], nU[2]));
+  const float threshold_helper = (maxn * eps) * (maxn * eps) / 5.0f;
+  const float downdate_thr = sqrtf(eps);
+  int nonzero = 3;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    int biggest = k;
+#pragma unroll
+    for (int j = k + 1; j < 3; ++j) {
+      float cur = nU[k];
+#pragma unroll
+      for (int jj = k + 1; jj < 3; ++jj) if (biggest == jj) cur = nU[jj];
+      if (nU[j] > cur) biggest = j;
+    }
+    float bn = nU[k];
+#pragma unroll
+    for (int jj = k + 1; jj < 3; ++jj) if (biggest == jj) bn = nU[jj];
+    if (nonzero == 3 && bn * bn < threshold_helper * (float)(5 - k)) nonzero = k;
+#pragma unroll
+    for (int j = k + 1; j < 3; ++j) {
+      if (biggest == j) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { float t = A[i][k]; A[i][k] = A[i][j]; A[i][j] = t; }
+        float t = nU[k]; nU[k] = nU[j]; nU[j] = t;
+        t = nD[k]; nD[k] = nD[j]; nD[j] = t;
+        int ti = perm[k]; perm[k] = perm[j]; perm[j] = ti;
+      }
+    }
+    float tailSq = 0.f;
+#pragma unroll
+    for (int i = k + 1; i < 5; ++i) tailSq += A[i][k] * A[i][k];
+    const float c0 = A[k][k];
+    float beta, tau;
+    if (tailSq <= 1.17549435e-38f) {   // numeric_limits<float>::min()
+      tau = 0.f; beta = c0;
+#pragma unroll
+      for (int i = k + 1; i < 5; ++i) A[i][k] = 0.f;
+    } else {
+      beta = sqrtf(c0 * c0 + tailSq);
+      if (c0 >= 0.f) beta = -beta;
+#pragma unroll
+      for (int i = k + 1; i < 5; ++i) A[i][k] = A[i][k] / (c0 - beta);
+      tau = (beta - c0) / beta;
+    }
+    A[k][k] = beta;
+    hC[k] = tau;
+    if (tau != 0.f) {
+#pragma unroll
+      for (int j = k + 1; j < 3; ++j) {
+        float tmp = 0.f;
+#pragma unroll
+        for (int i = k + 1; i < 5; ++i) tmp += A[i][k] * A[i][j];
+        tmp += A[k][j];
+        A[k][j] -= tau * tmp;
+#pragma unroll
+        for (int i = k + 1; i < 5; ++i) A[i][j] -= tau * A[i][k] * tmp;
+      }
+    }
+#pragma unroll
+    for (int j = k + 1; j < 3; ++j) {
+      if (nU[j] != 0.f) {
+        float temp = fabsf(A[k][j]) / nU[j];
+        temp = (1.f + temp) * (1.f - temp);
+        temp = temp < 0.f ? 0.f : temp;
+        const float r = nU[j] / nD[j];
+        const float temp2 = temp * r * r;
+        if (temp2 <= downdate_thr) {
+          float s = 0.f;
+#pragma unroll
+          for (int i = k + 1; i < 5; ++i) s += A[i][j] * A[i][j];
+          nD[j] = sqrtf(s);
+          nU[j] = nD[j];
+        } else {
+          nU[j] *= sqrtf(temp);
+        }
+      }
+    }
+  }
+  float c[5] = {-1.f, -1.f, -1.f, -1.f, -1.f};
+  x[0] = x[1] = x[2] = 0.f;
+  if (nonzero == 0) return;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (k < nonzero && hC[k] != 0.f) {
+      float tmp = 0.f;
+#pragma unroll
+      for (int i = k + 1; i < 5; ++i) tmp += A[i][k] * c[i];
+      tmp += c[k];
+      c[k] -= hC[k] * tmp;
+#pragma unroll
+      for (int i = k + 1; i < 5; ++i) c[i] -= hC[k] * A[i][k] * tmp;
+    }
+  }
+#pragma unroll
+  for (int i = 2; i >= 0; --i) {
+    if (i < nonzero) {
+      float s = c[i];
+#pragma unroll
+      for (int j = i + 1; j < 3; ++j) if (j < nonzero) s -= A[i][j] * c[j];
+      c[i] = s / A[i][i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i < nonzero) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) if (perm[i] == q) x[q] = c[i];
+    }
+  }
+}
+
+// trace of evalPointUncertainty's 3x3 (associate_uct.hpp:153-175) in closed form:
+//   G = [ q_w I | -[q]x | T(0:3,0:3) ], q = T (0.05 p, 1);  Sigma_in = blkdiag(1e4 cov, 0.1 I)
+//   trace = sum_{i<3} (F (1e4 cov) F^T)_ii + 0.1 |T(0:3,0:3)|_F^2,  F = [ q_w I | -[q]x ]
+__device__ __forceinline__ double point_cov_trace(float px, float py, float pz, const double* __restrict__ e) {
+  const double pc0 = px * 0.05, pc1 = py * 0.05, pc2 = pz * 0.05;
+  double q[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = e[4 * i] * pc0 + e[4 * i + 1] * pc1 + e[4 * i + 2] * pc2 + e[4 * i + 3] * 1.0;
+  // F rows (3x6): [q3 0 0 | 0 q2 -q1], [0 q3 0 | -q2 0 q0], [0 0 q3 | q1 -q0 0]   (-skew(q))
+  double F[3][6] = {{q[3], 0, 0, 0, q[2], -q[1]}, {0, q[3], 0, -q[2], 0, q[0]}, {0, 0, q[3], q[1], -q[0], 0}};
+  const double* cov = e + 16;
+  double tr = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      double m = 0.0;   // (F cov)_ij
+#pragma unroll
+      for (int k = 0; k < 6; ++k) m += F[i][k] * (cov[6 * k + j] * 10000.0);
+      tr += m * F[i][j];
+    }
+  }
+  double fro = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) fro += (e[4 * i + j] * 0.1) * e[4 * i + j];
+  return tr + fro;
+}
+
+struct MinMax4 { double umin, umax, tmin, tmax; uint32_t cnt; };
+
+__device__ __forceinline__ MinMax4 warp_reduce(MinMax4 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.umin = fmin(v.umin, __shfl_xor_sync(0xffffffffu, v.umin, o));
+    v.umax = fmax(v.umax, __shfl_xor_sync(0xffffffffu, v.umax, o));
+    v.tmin = fmin(v.tmin, __shfl_xor_sync(0xffffffffu, v.tmin, o));
+    v.tmax = fmax(v.tmax, __shfl_xor_sync(0xffffffffu, v.tmax, o));
+    v.cnt += __shfl_xor_sync(0xffffffffu, v.cnt, o);
+  }
+  return v;
+}
+
+// d_mm layout: {min_u, -max_u, min_tau, -max_tau} so that one MIN all-reduce serves all four
+__global__ void __launch_bounds__(PLANE_THREADS)
+plane_kernel(const float4* __restrict__ nodes, const float* __restrict__ node_cov,
+             const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t N, PassConst pc,
+             ParamConst prm, const double* __restrict__ table, const uint32_t* __restrict__ nn_idx,
+             uint8_t* __restrict__ sel, float4* __restrict__ world, float4* __restrict__ plane,
+             double* __restrict__ ucov, double* __restrict__ tau, float* __restrict__ normal_y,
+             double* __restrict__ block_mm, uint32_t* __restrict__ block_cnt, uint32_t* __restrict__ counter,
+             double* __restrict__ d_mm, uint32_t* __restrict__ d_cnt) {
+  const uint32_t p = blockIdx.x * PLANE_THREADS + threadIdx.x;
+  MinMax4 mm{1000.0, 0.0, 9999.0, 0.0, 0u};   // laserMapping.cpp:615-616, 646-647
+  if (p < N) {
+    const malio_scan_pt pt = pts[perm ? perm[p] : p];
+    const int lid = pt.lidar;
+    double b[3], m[3], g[3];
+    transform_point(pc, pt.x, pt.y, pt.z, lid, b, m, g);
+    const float wx = (float)g[0], wy = (float)g[1], wz = (float)g[2];
+    world[p] = make_float4(wx, wy, wz, 0.f);
+    bool selected = sel[p] != 0;
+    double unit_cov = 0.0;
+    if (selected) {
+      selected = false;
+      float A[5][3], W[5];
+#pragma unroll
+      for (int j = 0; j < MALIO_K; ++j) {
+        const uint32_t idx = nn_idx[(size_t)j * N + p];
+        const float4 a = __ldg(nodes + 4 * (size_t)idx);
+        A[j][0] = a.x; A[j][1] = a.y; A[j][2] = a.z;
+        W[j] = __ldg(node_cov + idx);
+      }
+      // esti_plane (common_lib.h:144-190)
+      double cov_sum = 0.0;
+#pragma unroll
+      for (int j = 0; j < MALIO_K; ++j) cov_sum += fabs(prm.cov_threshold - (double)W[j]);
+      if ((double)W[0] > 0.00001) {
+#pragma unroll
+        for (int j = 0; j < MALIO_K; ++j)
+          unit_cov += ((prm.cov_threshold - (double)W[j]) / cov_sum) * ((prm.cov_threshold - (double)W[j]) / cov_sum) * (double)W[j];
+      }
+      float Aq[5][3];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) { Aq[j][0] = A[j][0]; Aq[j][1] = A[j][1]; Aq[j][2] = A[j][2]; }
+      float nv[3];
+      qr_solve_5x3(Aq, nv);
+      const float n = sqrtf(nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2]);
+      const float pa = nv[0] / n, pb = nv[1] / n, pcn = nv[2] / n;
+      const float pd = (float)(1.0 / (double)n);
+      bool ok = true;
+#pragma unroll
+      for (int j = 0; j < MALIO_K; ++j)
+        if (fabsf(pa * A[j][0] + pb * A[j][1] + pcn * A[j][2] + pd) > prm.plane_th) ok = false;
+      if (ok) {
+        const float pd2 = pa * wx + pb * wy + pcn * wz + pd;                        // laserMapping.cpp:598
+        const double nb = sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+        const float s = (float)(1 - 0.9 * (double)fabsf(pd2) / sqrt(nb));          // :599
+        if ((double)s > 0.1) {
+          selected = true;
+          plane[p] = make_float4(pa, pb, pcn, pd2);
+          ucov[p] = unit_cov;
+        }
+      }
+    }
+    sel[p] = selected ? 1 : 0;
+    // point-wise uncertainty: selected points use the :694-696 clamp, the others :737-739
+    const int tsize = (int)(pc.table_off[lid + 1] - pc.table_off[lid]);
+    int ti = (int)pt.table_idx;
+    if (selected) { if (ti >= tsize) ti = tsize - 2; }
+    else { if (ti >= tsize - 1) ti = tsize - 2; }
+    if (!selected || pc.ext_en) {
+      const double tr = point_cov_trace(pt.x, pt.y, pt.z, table + (size_t)(pc.table_off[lid] + ti) * TABLE_DOUBLES);
+      tau[p] = tr;
+      normal_y[p] = (float)tr;
+      if (selected) { mm.tmin = fmin(mm.tmin, tr); mm.tmax = fmax(mm.tmax, tr); }
+    }
+    if (selected) { mm.umin = fmin(mm.umin, unit_cov); mm.umax = fmax(mm.umax, unit_cov); mm.cnt = 1; }
+  }
+  // block reduction -> per-block slot; the last block to finish folds all slots (deterministic order)
+  __shared__ MinMax4 s_w[PLANE_THREADS / 32];
+  __shared__ bool s_last;
+  mm = warp_reduce(mm);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = mm;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    MinMax4 r = s_w[0];
+    for (int w = 1; w < PLANE_THREADS / 32; ++w) {
+      r.umin = fmin(r.umin, s_w[w].umin); r.umax = fmax(r.umax, s_w[w].umax);
+      r.tmin = fmin(r.tmin, s_w[w].tmin); r.tmax = fmax(r.tmax, s_w[w].tmax);
+      r.cnt += s_w[w].cnt;
+    }
+    double* o = block_mm + 4 * (size_t)blockIdx.x;
+    o[0] = r.umin; o[1] = r.umax; o[2] = r.tmin; o[3] = r.tmax;
+    block_cnt[blockIdx.x] = r.cnt;
+    __threadfence();
+    const uint32_t done = atomicAdd(counter, 1u);
+    s_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    MinMax4 r{1000.0, 0.0, 9999.0, 0.0, 0u};
+    for (uint32_t bk = threadIdx.x; bk < gridDim.x; bk += PLANE_THREADS) {
+      const double* o = block_mm + 4 * (size_t)bk;
+      r.umin = fmin(r.umin, __ldcg(o)); r.umax = fmax(r.umax, __ldcg(o + 1));
+      r.tmin = fmin(r.tmin, __ldcg(o + 2)); r.tmax = fmax(r.tmax, __ldcg(o + 3));
+      r.cnt += __ldcg(block_cnt + bk);
+    }
+    r = warp_reduce(r);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      MinMax4 f = s_w[0];
+      for (int w = 1; w < PLANE_THREADS / 32; ++w) {
+        f.umin = fmin(f.umin, s_w[w].umin); f.umax = fmax(f.umax, s_w[w].umax);
+        f.tmin = fmin(f.tmin, s_w[w].tmin); f.tmax = fmax(f.tmax, s_w[w].tmax);
+        f.cnt += s_w[w].cnt;
+      }
+      d_mm[0] = f.umin; d_mm[1] = -f.umax; d_mm[2] = f.tmin; d_mm[3] = -f.tmax;
+      *d_cnt = f.cnt;
+      *counter = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K3: rows + fused H^T R^-1 [H | h] reduction
+// Per selected point (laserMapping.cpp:649-722): plane weight a_i, Jacobian row J_i, noise rho_i; the row
+// h = a_i J_i, z = -a_i pd2.  Accumulates  sum (h_a / rho^) * [h | z | rho^ h_0..2]_b  (esekfom.hpp:622-635).
+// The localization weight (a scalar, :745-759) factors out and is applied on the host.
+// Returns the unscaled row in r[24], z, rho^ ; false if the point is not selected.
+__device__ __forceinline__ bool build_row(uint32_t p, uint32_t N, const malio_scan_pt* __restrict__ pts,
+                                          const uint32_t* __restrict__ perm, const PassConst& pc,
+                                          const ParamConst& prm, const uint8_t* __restrict__ sel,
+                                          const float4* __restrict__ plane, const double* __restrict__ ucov,
+                                          const double* __restrict__ tau, const double* __restrict__ d_mm,
+                                          double r[24], double& z, double& rho) {
+  if (p >= N || !sel[p]) return false;
+  const malio_scan_pt pt = pts[perm ? perm[p] : p];
+  const int lid = pt.lidar;
+  const double umin = d_mm[0], umax = -d_mm[1], tmin = d_mm[2], tmax = -d_mm[3];
+  // :651-656
+  double a = ucov[p];
+  if (a == 0) a = 1;
+  else if (umax == umin) a = (prm.plane_cov_max + prm.plane_cov_min) / 2;
+  else a = 1 / ((prm.plane_cov_max - prm.plane_cov_min) * (a - umin) / (umax - umin) + prm.plane_cov_min);
+  double b[3], m[3], g[3];
+  transform_point(pc, pt.x, pt.y, pt.z, lid, b, m, g);
+  const float4 pl = plane[p];
+  const double nvec[3] = {(double)pl.x, (double)pl.y, (double)pl.z};
+  double C[3], A[3], B[3];
+  q_rot_conj(pc.rot, nvec, C);                    // :676  s.rot.conjugate() * norm_vec
+  cross3(m, C, A);                                // :677  [point_this]x * C
+#pragma unroll
+  for (int k = 0; k < 24; ++k) r[k] = 0.0;
+  r[0] = nvec[0]; r[1] = nvec[1]; r[2] = nvec[2]; r[3] = A[0]; r[4] = A[1]; r[5] = A[2];
+  double R = 0.0;
+  if (pc.ext_en) {
+    double Rq[9], v[3];
+    if (lid == 0) {   // :684  ([b]x R(qE0^T)) C
+      q_conj_to_R(pc.eq[0], Rq);
+      v[0] = b[0]; v[1] = b[1]; v[2] = b[2];
+    } else {          // :687-690
+      double C2[3];
+      q_rot_conj(pc.cq[lid], C, C2);
+      C[0] = C2[0]; C[1] = C2[1]; C[2] = C2[2];
+      q_conj_to_R(pc.eq[lid], Rq);
+      v[0] = pt.x; v[1] = pt.y; v[2] = pt.z;
+    }
+    // M = skew(v) * Rq, then B = M * C  (same association as the reference's M3D * Quaternion * V3D)
+    const double S[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double Mi[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Mi[j] = S[3 * i] * Rq[j] + S[3 * i + 1] * Rq[3 + j] + S[3 * i + 2] * Rq[6 + j];
+      B[i] = Mi[0] * C[0] + Mi[1] * C[1] + Mi[2] * C[2];
+    }
+#pragma unroll
+    for (int l = 0; l < MALIO_MAX_LIDAR; ++l) {
+      if (l == lid) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { r[6 + 3 * l + k] = B[k]; r[15 + 3 * l + k] = C[k]; }
+      }
+    }
+    R = tau[p];
+  }
+  // :716-721 (FIC).  Degenerate 0/0 defined as mid-range (the reference yields NaN)
+  if (R < tmin + (tmax - tmin) * prm.range_min) R = prm.point_cov_min;
+  else if (R > tmin + (tmax - tmin) * prm.range_max) R = prm.point_cov_max;
+  else {
+    const double den = (prm.range_max - prm.range_min) * (tmax - tmin);
+    if (den == 0.0) R = (prm.point_cov_max + prm.point_cov_min) / 2;
+    else R = (prm.point_cov_max - prm.point_cov_min) * (R - (tmin + (tmax - tmin) * prm.range_min)) / den + prm.point_cov_min;
+  }
+  if (R < 0.0001) R = 0.001;   // esekfom.hpp:624-626
+  rho = R;
+#pragma unroll
+  for (int k = 0; k < 24; ++k) r[k] = r[k] * a;   // :714
+  z = ((-1) * (double)pl.w) * a;                  // :707,715
+  return true;
+}
+
+// task t (0..26) -> upper-triangular 4x4 block (row group gi, col group gj >= gi) of the 24 x 28 system
+__device__ __forceinline__ void red_task(int t, int& gi, int& gj) {
+  int i = 0, rem = t;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int len = 7 - k;
+    if (rem >= len && i == k) { rem -= len; i = k + 1; }
+  }
+  gi = i; gj = i + rem;
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+reduce_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t N, PassConst pc,
+              ParamConst prm, const uint8_t* __restrict__ sel, const float4* __restrict__ plane,
+              const double* __restrict__ ucov, const double* __restrict__ tau, const double* __restrict__ d_mm,
+              uint32_t n_tiles, double* __restrict__ block_red, uint32_t* __restrict__ counter,
+              double* __restrict__ d_res) {
+  extern __shared__ double smem[];
+  double* s_hs = smem;                                   // [128][26]  h / rho^
+  double* s_hx = smem + RED_THREADS * RED_HS_STRIDE;     // [128][28]  [h | z | rho^ h0..2]
+  const int task = threadIdx.x >> 2, ks = threadIdx.x & 3;
+  int gi = 0, gj = 0;
+  if (task < MALIO_RED_BLOCKS) red_task(task, gi, gj);
+  double acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+  uint32_t cnt = 0;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t p = tile * RED_THREADS + threadIdx.x;
+    double r[24], z = 0.0, rho = 1.0;
+    const bool ok = build_row(p, N, pts, perm, pc, prm, sel, plane, ucov, tau, d_mm, r, z, rho);
+    double* hs = s_hs + threadIdx.x * RED_HS_STRIDE;
+    double* hx = s_hx + threadIdx.x * RED_HX_STRIDE;
+    if (ok) {
+      cnt++;
+#pragma unroll
+      for (int k = 0; k < 24; ++k) { hs[k] = r[k] / rho; hx[k] = r[k]; }
+      hx[24] = z; hx[25] = rho * r[0]; hx[26] = rho * r[1]; hx[27] = rho * r[2];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 24; ++k) { hs[k] = 0.0; hx[k] = 0.0; }
+      hx[24] = 0.0; hx[25] = 0.0; hx[26] = 0.0; hx[27] = 0.0;
+    }
+    __syncthreads();
+    if (task < MALIO_RED_BLOCKS) {
+#pragma unroll 4
+      for (int q = ks; q < RED_THREADS; q += 4) {
+        const double* a = s_hs + q * RED_HS_STRIDE + 4 * gi;
+        const double* bq = s_hx + q * RED_HX_STRIDE + 4 * gj;
+        const double a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
+        const double b0 = bq[0], b1 = bq[1], b2 = bq[2], b3 = bq[3];
+        acc[0] = fma(a0, b0, acc[0]);  acc[1] = fma(a0, b1, acc[1]);  acc[2] = fma(a0, b2, acc[2]);  acc[3] = fma(a0, b3, acc[3]);
+        acc[4] = fma(a1, b0, acc[4]);  acc[5] = fma(a1, b1, acc[5]);  acc[6] = fma(a1, b2, acc[6]);  acc[7] = fma(a1, b3, acc[7]);
+        acc[8] = fma(a2, b0, acc[8]);  acc[9] = fma(a2, b1, acc[9]);  acc[10] = fma(a2, b2, acc[10]); acc[11] = fma(a2, b3, acc[11]);
+        acc[12] = fma(a3, b0, acc[12]); acc[13] = fma(a3, b1, acc[13]); acc[14] = fma(a3, b2, acc[14]); acc[15] = fma(a3, b3, acc[15]);
+      }
+    }
+    __syncthreads();
+  }
+  // fold the 4 k-splits of each task with warp shuffles (lanes 4t..4t+3), then per-block slot
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
+    acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2);
+  }
+  // selected-point count of this block
+  __shared__ uint32_t s_cnt[RED_THREADS / 32];
+  __shared__ bool s_last;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  double* slot = block_red + (size_t)blockIdx.x * MALIO_RED_DOUBLES;
+  if (task < MALIO_RED_BLOCKS && ks == 0) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) slot[task * 16 + k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t c = 0;
+    for (int w = 0; w < RED_THREADS / 32; ++w) c += s_cnt[w];
+    slot[MALIO_RED_BLOCKS * 16] = (double)c;
+    slot[MALIO_RED_BLOCKS * 16 + 1] = 0.0;
+    __threadfence();
+    const uint32_t done = atomicAdd(counter, 1u);
+    s_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int e = threadIdx.x; e < MALIO_RED_DOUBLES; e += RED_THREADS) {
+      double s = 0.0;
+      for (uint32_t bk = 0; bk < gridDim.x; ++bk) s += __ldcg(block_red + (size_t)bk * MALIO_RED_DOUBLES + e);
+      d_res[e] = s;
+    }
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
+// rows for the degenerate branch (esekfom.hpp:574-582): positions of the first `cap` selected points are
+// found by one block; rows are written un-weighted by the localization weight (the host applies it)
+__global__ void rows_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t N,
+                            PassConst pc, ParamConst prm, const uint8_t* __restrict__ sel,
+                            const float4* __restrict__ plane, const double* __restrict__ ucov,
+                            const double* __restrict__ tau, const double* __restrict__ d_mm, uint32_t cap,
+                            double* __restrict__ rows /* cap x 25 */, uint32_t* __restrict__ n_rows) {
+  __shared__ uint32_t s_base;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (uint32_t start = 0; start < N; start += blockDim.x) {
+    const uint32_t p = start + threadIdx.x;
+    double r[24], z = 0.0, rho = 1.0;
+    const bool ok = build_row(p, N, pts, perm, pc, prm, sel, plane, ucov, tau, d_mm, r, z, rho);
+    // block-wide exclusive scan of ok via warp ballots
+    __shared__ uint32_t s_wcnt[32];
+    const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) s_wcnt[w] = __popc(bal);
+    __syncthreads();
+    uint32_t off = s_base;
+    for (int k = 0; k < w; ++k) off += s_wcnt[k];
+    off += __popc(bal & ((1u << lane) - 1u));
+    if (ok && off < cap) {
+      for (int k = 0; k < 24; ++k) rows[(size_t)off * 25 + k] = r[k];
+      rows[(size_t)off * 25 + 24] = z;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t tot = 0;
+      for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += s_wcnt[k];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_rows = s_base;
+}
+
+// position space -> caller order
+__global__ void scatter_aux_kernel(const uint32_t* __restrict__ perm, uint32_t N, const float* __restrict__ normal_y,
+                                   const uint32_t* __restrict__ nn_idx, const float* __restrict__ nn_d2,
+                                   const uint8_t* __restrict__ sel, const float4* __restrict__ world,
+                                   float* __restrict__ o_ny, uint32_t* __restrict__ o_idx, float* __restrict__ o_d2,
+                                   uint8_t* __restrict__ o_sel, float* __restrict__ o_world) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  const uint32_t i = perm ? perm[p] : p;
+  if (o_ny) o_ny[i] = normal_y[p];
+  if (o_sel) o_sel[i] = sel[p];
+  if (o_world) { const float4 w = world[p]; o_world[3 * (size_t)i] = w.x; o_world[3 * (size_t)i + 1] = w.y; o_world[3 * (size_t)i + 2] = w.z; }
+  if (o_idx) {
+#pragma unroll
+    for (int j = 0; j < MALIO_K; ++j) o_idx[(size_t)i * MALIO_K + j] = nn_idx[(size_t)j * N + p];
+  }
+  if (o_d2) {
+#pragma unroll
+    for (int j = 0; j < MALIO_K; ++j) o_d2[(size_t)i * MALIO_K + j] = nn_d2[(size_t)j * N + p];
+  }
+}
+
+// ------------------------------------------------------------------ NCCL through dlopen (no link-time dependency)
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) { err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "NCCL symbols missing"; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+
+struct DeviceState {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // map
+  float4* d_nodes = nullptr; float* d_cov = nullptr;
+  uint32_t n_nodes = 0, cap_nodes = 0, depth = 0;
+  // scan (caller order) + internal order
+  malio_scan_pt* d_pts = nullptr; uint32_t N = 0, capN = 0;
+  uint32_t* d_perm = nullptr; bool perm_valid = false;
+  uint32_t *d_keys = nullptr, *d_keys_out = nullptr, *d_ids = nullptr;
+  void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
+  double* d_table = nullptr; uint32_t cap_table = 0;
+  uint32_t table_off[MALIO_MAX_LIDAR + 1] = {0, 0, 0, 0};
+  malio_rigid tcomp[MALIO_MAX_LIDAR];
+  bool scan_ready = false, map_ready = false, pass_done = false, searched_once = false;
+  // per point, position space
+  uint32_t* d_nn_idx = nullptr; float* d_nn_d2 = nullptr; uint8_t* d_sel = nullptr;
+  float4 *d_world = nullptr, *d_plane = nullptr; double *d_ucov = nullptr, *d_tau = nullptr; float* d_normal_y = nullptr;
+  // aux staging (caller order)
+  float* d_o_ny = nullptr; uint32_t* d_o_idx = nullptr; float* d_o_d2 = nullptr; uint8_t* d_o_sel = nullptr; float* d_o_world = nullptr;
+  // reductions
+  double* d_block_mm = nullptr; uint32_t* d_block_cnt = nullptr; uint32_t cap_blocks = 0;
+  uint32_t* d_counters = nullptr;   // [0] plane, [1] reduce, [2] n_eff local, [3] n_rows
+  double* d_mm = nullptr;           // 4
+  double* d_block_red = nullptr; uint32_t red_grid = 0;
+  double* d_res = nullptr;          // MALIO_RED_DOUBLES
+  double* d_rows = nullptr;         // MALIO_MAX_DOF x 25
+  double* h_res = nullptr;          // pinned: res | mm(4) | cnt
+  PassConst last_pc{};
+  // stand-alone queries
+  float* d_queries = nullptr; uint32_t capQ = 0;
+  // multi-GPU
+  ncclComm_t comm = nullptr; int rank = 0, world = 1;
+};
+
+template <class T>
+int ensure(malio_handle* h, T*& ptr, size_t count) {
+  if (ptr) { cudaFree(ptr); ptr = nullptr; }
+  CUDA_TRY(cudaMalloc((void**)&ptr, count * sizeof(T)));
+  return MALIO_OK;
+}
+
+PassConst make_pass_const(const malio_handle* h, const DeviceState* D, const malio_pass_state* s) {
+  PassConst pc{};
+  std::memcpy(pc.rot, s->rot, sizeof(pc.rot));
+  std::memcpy(pc.pos, s->pos, sizeof(pc.pos));
+  for (int l = 0; l < MALIO_MAX_LIDAR; ++l) {
+    std::memcpy(pc.eq[l], s->ext[l].q, sizeof(pc.eq[l]));
+    std::memcpy(pc.et[l], s->ext[l].t, sizeof(pc.et[l]));
+    std::memcpy(pc.cq[l], D->tcomp[l].q, sizeof(pc.cq[l]));
+    std::memcpy(pc.ct[l], D->tcomp[l].t, sizeof(pc.ct[l]));
+  }
+  for (int l = 0; l <= MALIO_MAX_LIDAR; ++l) pc.table_off[l] = D->table_off[l];
+  pc.L = h->cfg.params.n_lidar;
+  pc.ext_en = h->cfg.params.extrinsic_est_en;
+  return pc;
+}
+ParamConst make_param_const(const malio_params& p) {
+  ParamConst c{};
+  c.plane_th = p.plane_th; c.knn_max_sqdist = p.knn_max_sqdist;
+  c.cov_threshold = p.cov_threshold; c.point_cov_max = p.point_cov_max; c.point_cov_min = p.point_cov_min;
+  c.plane_cov_max = p.plane_cov_max; c.plane_cov_min = p.plane_cov_min; c.range_min = p.range_min; c.range_max = p.range_max;
+  return c;
+}
+
+int sort_queries(malio_handle* h, DeviceState* D, uint32_t n) {
+  size_t need = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, need, D->d_keys, D->d_keys_out, D->d_ids, D->d_perm, (int)n, 0, 30, D->stream);
+  if (need > D->sort_tmp_bytes) {
+    if (D->d_sort_tmp) cudaFree(D->d_sort_tmp);
+    D->d_sort_tmp = nullptr;
+    CUDA_TRY(cudaMalloc(&D->d_sort_tmp, need));
+    D->sort_tmp_bytes = need;
+  }
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(D->d_sort_tmp, need, D->d_keys, D->d_keys_out, D->d_ids, D->d_perm, (int)n, 0, 30, D->stream));
+  return MALIO_OK;
+}
+
+}  // namespace
+
+// =================================================================== host-facing entry points
+namespace malio_dev {
+
+int create(malio_handle* h) {
+  DeviceState* D = new DeviceState;
+  h->dev = D;
+  D->device = h->cfg.device;
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (ndev <= 0 || D->device >= ndev) { h->err = "no such CUDA device"; return MALIO_ERR_CUDA; }
+  CUDA_TRY(cudaSetDevice(D->device));
+  cudaDeviceProp prop{};
+  CUDA_TRY(cudaGetDeviceProperties(&prop, D->device));
+  D->sm_count = prop.multiProcessorCount;
+  CUDA_TRY(cudaStreamCreateWithFlags(&D->stream, cudaStreamNonBlocking));
+  for (auto& e : D->ev) CUDA_TRY(cudaEventCreate(&e));
+  CUDA_TRY(cudaMalloc((void**)&D->d_counters, 8 * sizeof(uint32_t)));
+  CUDA_TRY(cudaMemset(D->d_counters, 0, 8 * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc((void**)&D->d_mm, 4 * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void**)&D->d_res, MALIO_RED_DOUBLES * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void**)&D->d_rows, (size_t)MALIO_MAX_DOF * 25 * sizeof(double)));
+  D->red_grid = (uint32_t)D->sm_count * 2;
+  CUDA_TRY(cudaMalloc((void**)&D->d_block_red, (size_t)D->red_grid * MALIO_RED_DOUBLES * sizeof(double)));
+  CUDA_TRY(cudaMallocHost((void**)&D->h_res, (MALIO_RED_DOUBLES + 8 + MALIO_MAX_DOF * 25) * sizeof(double)));
+  CUDA_TRY(cudaFuncSetAttribute(reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                RED_THREADS * (RED_HS_STRIDE + RED_HX_STRIDE) * (int)sizeof(double)));
+  for (int l = 0; l < MALIO_MAX_LIDAR; ++l) { D->tcomp[l] = malio_rigid{{1, 0, 0, 0}, {0, 0, 0}}; }
+  return MALIO_OK;
+}
+
+void destroy(malio_handle* h) {
+  DeviceState* D = (DeviceState*)h->dev;
+  if (!D) return;
+  cudaSetDevice(D->device);
+  if (D->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(D->comm);
+  void* ptrs[] = {D->d_nodes, D->d_cov, D->d_pts, D->d_perm, D->d_keys, D->d_keys_out, D->d_ids, D->d_sort_tmp,
+                  D->d_table, D->d_nn_idx, D->d_nn_d2, D->d_sel, D->d_world, D->d_plane, D->d_ucov, D->d_tau,
+                  D->d_normal_y, D->d_o_ny, D->d_o_idx, D->d_o_d2, D->d_o_sel, D->d_o_world, D->d_block_mm,
+                  D->d_block_cnt, D->d_counters, D->d_mm, D->d_block_red, D->d_res, D->d_rows, D->d_queries};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (D->h_res) cudaFreeHost(D->h_res);
+  for (auto& e : D->ev) if (e) cudaEventDestroy(e);
+  if (D->stream) cudaStreamDestroy(D->stream);
+  delete D;
+  h->dev = nullptr;
+}
+
+int upload_map(malio_handle* h, const malio_map_node* nodes, const float* cov, uint32_t n, uint32_t depth) {
+  DeviceState* D = (DeviceState*)h->dev;
+  CUDA_TRY(cudaSetDevice(D->device));
+  if (depth > MALIO_MAX_TREE_DEPTH) { h->err = "snapshot deeper than MALIO_MAX_TREE_DEPTH"; return MALIO_ERR_TREE_TOO_DEEP; }
+  if (n > D->cap_nodes) {
+    uint32_t cap = n + n / 8 + 1024;
+    if (cap < h->cfg.max_map_nodes) cap = h->cfg.max_map_nodes;
+    if (int rc = ensure(h, D->d_nodes, (size_t)cap * 4)) return rc;
+    if (int rc = ensure(h, D->d_cov, (size_t)cap)) return rc;
+    D->cap_nodes = cap;
+  }
+  CUDA_TRY(cudaMemcpyAsync(D->d_nodes, nodes, (size_t)n * sizeof(malio_map_node), cudaMemcpyHostToDevice, D->stream));
+  CUDA_TRY(cudaMemcpyAsync(D->d_cov, cov, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, D->stream));
+  CUDA_TRY(cudaStreamSynchronize(D->stream));
+  D->n_nodes = n; D->depth = depth; D->map_ready = true;
+  return MALIO_OK;
+}
+
+static int ensure_point_buffers(malio_handle* h, DeviceState* D, uint32_t n) {
+  if (n <= D->capN) return MALIO_OK;
+  uint32_t cap = n + n / 8 + 1024;
+  if (cap < h->cfg.max_points) cap = h->cfg.max_points;
+  int rc = 0;
+  if ((rc = ensure(h, D->d_pts, cap))) return rc;
+  if ((rc = ensure(h, D->d_perm, cap))) return rc;
+  if ((rc = ensure(h, D->d_keys, cap))) return rc;
+  if ((rc = ensure(h, D->d_keys_out, cap))) return rc;
+  if ((rc = ensure(h, D->d_ids, cap))) return rc;
+  if ((rc = ensure(h, D->d_nn_idx, (size_t)cap * MALIO_K))) return rc;
+  if ((rc = ensure(h, D->d_nn_d2, (size_t)cap * MALIO_K))) return rc;
+  if ((rc = ensure(h, D->d_sel, cap))) return rc;
+  if ((rc = ensure(h, D->d_world, cap))) return rc;
+  if ((rc = ensure(h, D->d_plane, cap))) return rc;
+  if ((rc = ensure(h, D->d_ucov, cap))) return rc;
+  if ((rc = ensure(h, D->d_tau, cap))) return rc;
+  if ((rc = ensure(h, D->d_normal_y, cap))) return rc;
+  if ((rc = ensure(h, D->d_o_ny, cap))) return rc;
+  if ((rc = ensure(h, D->d_o_idx, (size_t)cap * MALIO_K))) return rc;
+  if ((rc = ensure(h, D->d_o_d2, (size_t)cap * MALIO_K))) return rc;
+  if ((rc = ensure(h, D->d_o_sel, cap))) return rc;
+  if ((rc = ensure(h, D->d_o_world, (size_t)cap * 3))) return rc;
+  const uint32_t blocks = (cap + PLANE_THREADS - 1) / PLANE_THREADS;
+  if ((rc = ensure(h, D->d_block_mm, (size_t)blocks * 4))) return rc;
+  if ((rc = ensure(h, D->d_block_cnt, blocks))) return rc;
+  D->cap_blocks = blocks;
+  D->capN = cap;
+  return MALIO_OK;
+}
+
+int upload_scan(malio_handle* h, const malio_scan_pt* pts, uint32_t n, const malio_pose_entry* table,
+                const uint32_t* table_off, const malio_rigid* tcomp) {
+  DeviceState* D = (DeviceState*)h->dev;
+  CUDA_TRY(cudaSetDevice(D->device));
+  const int L = h->cfg.params.n_lidar;
+  for (int l = 0; l < L; ++l)
+    if (table_off[l + 1] < table_off[l] + 2) { h->err = "pose table of each LiDAR needs >= 2 entries"; return MALIO_ERR_INVALID_ARG; }
+  if (int rc = ensure_point_buffers(h, D, n > 0 ? n : 1)) return rc;
+  const uint32_t n_tab = table_off[L];
+  if (n_tab > D->cap_table) {
+    if (int rc = ensure(h, D->d_table, (size_t)(n_tab + 64) * TABLE_DOUBLES)) return rc;
+    D->cap_table = n_tab + 64;
+  }
+  if (n) CUDA_TRY(cudaMemcpyAsync(D->d_pts, pts, (size_t)n * sizeof(malio_scan_pt), cudaMemcpyHostToDevice, D->stream));
+  CUDA_TRY(cudaMemcpyAsync(D->d_table, table, (size_t)n_tab * sizeof(malio_pose_entry), cudaMemcpyHostToDevice, D->stream));
+  CUDA_TRY(cudaMemsetAsync(D->d_sel, 0, D->capN, D->stream));
+  CUDA_TRY(cudaMemsetAsync(D->d_normal_y, 0, (size_t)D->capN * sizeof(float), D->stream));
+  CUDA_TRY(cudaMemsetAsync(D->d_nn_idx, 0xFF, (size_t)D->capN * MALIO_K * sizeof(uint32_t), D->stream));
+  CUDA_TRY(cudaStreamSynchronize(D->stream));
+  for (int l = 0; l <= MALIO_MAX_LIDAR; ++l) D->table_off[l] = (l <= L) ? table_off[l] : table_off[L];
+  for (int l = 1; l < L; ++l) D->tcomp[l] = tcomp[l - 1];
+  D->N = n; D->scan_ready = true; D->perm_valid = false; D->pass_done = false; D->searched_once = false;
+  return MALIO_OK;
+}
+
+int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* HtRinvH, double* HtRinvh,
+            malio_pass_stats* st) {
+  DeviceState* D = (DeviceState*)h->dev;
+  if (!D->map_ready || !D->scan_ready) { h->err = "measure before upload_map/upload_scan"; return MALIO_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(D->device));
+  const malio_params& P = h->cfg.params;
+  const int L = P.n_lidar, c = 6 * (L + 1);
+  const uint32_t N = D->N;
+  const PassConst pc = make_pass_const(h, D, s);
+  const ParamConst prm = make_param_const(P);
+  D->last_pc = pc;
+  cudaStream_t st_ = D->stream;
+  const uint32_t* perm = nullptr;
+  CUDA_TRY(cudaEventRecord(D->ev[0], st_));
+  if (N > 0) {
+    if (h->cfg.sort_queries) {
+      if (!D->perm_valid) {
+        morton_kernel<0><<<(N + 255) / 256, 256, 0, st_>>>(D->d_pts, nullptr, N, pc, D->d_keys, D->d_ids);
+        if (int rc = sort_queries(h, D, N)) return rc;
+        D->perm_valid = true;
+      }
+      perm = D->d_perm;
+    }
+    if (redo_knn) {
+      knn_kernel<0><<<(N + KNN_THREADS - 1) / KNN_THREADS, KNN_THREADS, 0, st_>>>(
+          D->d_nodes, D->n_nodes, D->d_pts, perm, nullptr, N, pc, P.knn_max_sqdist, D->d_world, D->d_nn_idx,
+          D->d_nn_d2, D->d_sel);
+      D->searched_once = true;
+    }
+  }
+  CUDA_TRY(cudaEventRecord(D->ev[1], st_));
+  const uint32_t pblocks = N > 0 ? (N + PLANE_THREADS - 1) / PLANE_THREADS : 1;
+  plane_kernel<<<pblocks, PLANE_THREADS, 0, st_>>>(D->d_nodes, D->d_cov, D->d_pts, perm, N, pc, prm, D->d_table,
+                                                     D->d_nn_idx, D->d_sel, D->d_world, D->d_plane, D->d_ucov,
+                                                     D->d_tau, D->d_normal_y, D->d_block_mm, D->d_block_cnt,
+                                                     D->d_counters + 0, D->d_mm, D->d_counters + 2);
+  if (D->comm)   // {min_u, -max_u, min_tau, -max_tau}: one MIN all-reduce (laserMapping.cpp:615-628, 700-703)
+    if (g_nccl.AllReduce(D->d_mm, D->d_mm, 4, ncclDouble, ncclMin, D->comm, st_) != ncclSuccess) { h->err = "ncclAllReduce(min) failed"; return MALIO_ERR_NCCL; }
+  CUDA_TRY(cudaEventRecord(D->ev[2], st_));
+  const uint32_t n_tiles = (N + RED_THREADS - 1) / RED_THREADS;
+  uint32_t grid = n_tiles < D->red_grid ? n_tiles : D->red_grid;
+  if (grid == 0) grid = 1;
+  reduce_kernel<<<grid, RED_THREADS, RED_THREADS * (RED_HS_STRIDE + RED_HX_STRIDE) * sizeof(double), st_>>>(
+      D->d_pts, perm, N, pc, prm, D->d_sel, D->d_plane, D->d_ucov, D->d_tau, D->d_mm, n_tiles, D->d_block_red,
+      D->d_counters + 1, D->d_res);
+  if (D->comm)   // the reduced system + n_eff: one SUM all-reduce
+    if (g_nccl.AllReduce(D->d_res, D->d_res, MALIO_RED_DOUBLES, ncclDouble, ncclSum, D->comm, st_) != ncclSuccess) { h->err = "ncclAllReduce(sum) failed"; return MALIO_ERR_NCCL; }
+  CUDA_TRY(cudaEventRecord(D->ev[3], st_));
+  CUDA_TRY(cudaMemcpyAsync(D->h_res, D->d_res, MALIO_RED_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, st_));
+  CUDA_TRY(cudaMemcpyAsync(D->h_res + MALIO_RED_DOUBLES, D->d_mm, 4 * sizeof(double), cudaMemcpyDeviceToHost, st_));
+  CUDA_TRY(cudaEventRecord(D->ev[4], st_));
+  CUDA_TRY(cudaStreamSynchronize(st_));
+  CUDA_TRY(cudaGetLastError());
+  D->pass_done = true;
+
+  // ---- host epilogue: un-block, localization weight (laserMapping.cpp:745-759), compact to c x c
+  const double* res = D->h_res;
+  const double* mm = D->h_res + MALIO_RED_DOUBLES;
+  double G[MALIO_RED_ROWS][MALIO_RED_COLS];
+  std::memset(G, 0, sizeof(G));
+  int t = 0;
+  for (int gi = 0; gi < 6; ++gi)
+    for (int gj = gi; gj < 7; ++gj, ++t)
+      for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) G[4 * gi + a][4 * gj + b] = res[t * 16 + a * 4 + b];
+  for (int a = 0; a < 24; ++a) for (int b = 0; b < a; ++b) G[a][b] = G[b][a];   // symmetric part
+  const uint32_t n_eff = (uint32_t)(res[MALIO_RED_BLOCKS * 16] + 0.5);
+  malio_pass_stats S{};
+  S.n_points = N; S.n_eff = n_eff; S.searched = redo_knn ? 1 : 0;
+  S.u_min = mm[0]; S.u_max = -mm[1]; S.tau_min = mm[2]; S.tau_max = -mm[3];
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, D->ev[0], D->ev[1]); S.ms_knn = ms;
+  cudaEventElapsedTime(&ms, D->ev[1], D->ev[2]); S.ms_plane = ms;
+  cudaEventElapsedTime(&ms, D->ev[2], D->ev[3]); S.ms_reduce = ms;
+  cudaEventElapsedTime(&ms, D->ev[0], D->ev[4]); S.ms_total = ms;
+  if (n_eff < 1) {
+    S.valid = 0;
+    if (st) *st = S;
+    return MALIO_ERR_NO_EFFECTIVE_POINTS;
+  }
+  S.valid = 1;
+  const double Ssym[6] = {G[0][25], G[0][26], G[0][27], G[1][26], G[1][27], G[2][27]};
+  malio_host::sym3_singular_values(Ssym, S.sigma);
+  double weight = S.sigma[2] / S.sigma[0];
+  if (weight > P.localize_thresh_max) weight = P.localize_cov_max;
+  else if (weight < P.localize_thresh_min) weight = P.localize_cov_min;
+  else weight = (P.localize_cov_max - P.localize_cov_min) * (weight - P.localize_thresh_min) / (P.localize_thresh_max - P.localize_thresh_min) + P.localize_cov_min;
+  S.loc_weight = weight;
+  const double w2 = weight * weight;
+  // padded (L=3 positions) -> compact c columns: 0-5 | 6+3l | 6+3L+3l
+  int map[MALIO_MAX_COLS];
+  for (int k = 0; k < 6; ++k) map[k] = k;
+  for (int l = 0; l < L; ++l)
+    for (int k = 0; k < 3; ++k) { map[6 + 3 * l + k] = 6 + 3 * l + k; map[6 + 3 * L + 3 * l + k] = 15 + 3 * l + k; }
+  for (int a = 0; a < c; ++a) {
+    for (int b = 0; b < c; ++b) HtRinvH[a * c + b] = w2 * G[map[a]][map[b]];
+    HtRinvh[a] = w2 * G[map[a]][24];
+  }
+  if (st) *st = S;
+  return MALIO_OK;
+}
+
+int download_rows(malio_handle* h, double* h_x, double* hvec, uint32_t cap, uint32_t* n_rows) {
+  DeviceState* D = (DeviceState*)h->dev;
+  if (!D->pass_done) { h->err = "download_rows before measure"; return MALIO_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(D->device));
+  const malio_params& P = h->cfg.params;
+  const int L = P.n_lidar, c = 6 * (L + 1);
+  if (cap > MALIO_MAX_DOF) cap = MALIO_MAX_DOF;
+  const uint32_t* perm = (h->cfg.sort_queries && D->perm_valid) ? D->d_perm : nullptr;
+  rows_kernel<<<1, 256, 0, D->stream>>>(D->d_pts, perm, D->N, D->last_pc, make_param_const(P), D->d_sel, D->d_plane,
+                                          D->d_ucov, D->d_tau, D->d_mm, cap, D->d_rows, D->d_counters + 3);
+  double* hr = D->h_res + MALIO_RED_DOUBLES + 8;
+  CUDA_TRY(cudaMemcpyAsync(hr, D->d_rows, (size_t)cap * 25 * sizeof(double), cudaMemcpyDeviceToHost, D->stream));
+  uint32_t nr = 0;
+  CUDA_TRY(cudaMemcpyAsync(&nr, D->d_counters + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, D->stream));
+  CUDA_TRY(cudaStreamSynchronize(D->stream));
+  if (nr > cap) nr = cap;
+  int map[MALIO_MAX_COLS];
+  for (int k = 0; k < 6; ++k) map[k] = k;
+  for (int l = 0; l < L; ++l)
+    for (int k = 0; k < 3; ++k) { map[6 + 3 * l + k] = 6 + 3 * l + k; map[6 + 3 * L + 3 * l + k] = 15 + 3 * l + k; }
+  for (uint32_t r = 0; r < nr; ++r) {
+    for (int k = 0; k < c; ++k) h_x[(size_t)r * c + k] = hr[(size_t)r * 25 + map[k]];
+    hvec[r] = hr[(size_t)r * 25 + 24];
+  }
+  *n_rows = nr;
+  return MALIO_OK;
+}
+
+int download_aux(malio_handle* h, float* normal_y, uint32_t* nn_idx, float* nn_d2, uint8_t* sel, float* world) {
+  DeviceState* D = (DeviceState*)h->dev;
+  if (!D->pass_done) { h->err = "download_aux before measure"; return MALIO_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(D->device));
+  const uint32_t N = D->N;
+  if (N == 0) return MALIO_OK;
+  const uint32_t* perm = (h->cfg.sort_queries && D->perm_valid) ? D->d_perm : nullptr;
+  scatter_aux_kernel<<<(N + 255) / 256, 256, 0, D->stream>>>(
+      perm, N, D->d_normal_y, D->d_nn_idx, D->d_nn_d2, D->d_sel, D->d_world, normal_y ? D->d_o_ny : nullptr,
+      nn_idx ? D->d_o_idx : nullptr, nn_d2 ? D->d_o_d2 : nullptr, sel ? D->d_o_sel : nullptr,
+      world ? D->d_o_world : nullptr);
+  if (normal_y) CUDA_TRY(cudaMemcpyAsync(normal_y, D->d_o_ny, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, D->stream));
+  if (nn_idx) CUDA_TRY(cudaMemcpyAsync(nn_idx, D->d_o_idx, (size_t)N * MALIO_K * sizeof(uint32_t), cudaMemcpyDeviceToHost, D->stream));
+  if (nn_d2) CUDA_TRY(cudaMemcpyAsync(nn_d2, D->d_o_d2, (size_t)N * MALIO_K * sizeof(float), cudaMemcpyDeviceToHost, D->stream));
+  if (sel) CUDA_TRY(cudaMemcpyAsync(sel, D->d_o_sel, (size_t)N, cudaMemcpyDeviceToHost, D->stream));
+  if (world) CUDA_TRY(cudaMemcpyAsync(world, D->d_o_world, (size_t)N * 3 * sizeof(float), cudaMemcpyDeviceToHost, D->stream));
+  CUDA_TRY(cudaStreamSynchronize(D->stream));
+  CUDA_TRY(cudaGetLastError());
+  return MALIO_OK;
+}
+
+int knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* idx, float* d2, float* ms_out) {
+  DeviceState* D = (DeviceState*)h->dev;
+  if (!D->map_ready) { h->err = "knn before upload_map"; return MALIO_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(D->device));
+  if (nq == 0) return MALIO_OK;
+  if (int rc = ensure_point_buffers(h, D, nq)) return rc;
+  if (nq > D->capQ) {
+    if (int rc = ensure(h, D->d_queries, (size_t)(nq + 1024) * 3)) return rc;
+    D->capQ = nq + 1024;
+  }
+  D->scan_ready = false;   // point buffers are shared with the scan path
+  D->pass_done = false;
+  CUDA_TRY(cudaMemcpyAsync(D->d_queries, q, (size_t)nq * 3 * sizeof(float), cudaMemcpyHostToDevice, D->stream));
+  PassConst pc{};
+  const uint32_t* perm = nullptr;
+  if (h->cfg.sort_queries) {
+    morton_kernel<1><<<(nq + 255) / 256, 256, 0, D->stream>>>(nullptr, D->d_queries, nq, pc, D->d_keys, D->d_ids);
+    if (int rc = sort_queries(h, D, nq)) return rc;
+    perm = D->d_perm;
+  }
+  CUDA_TRY(cudaEventRecord(D->ev[0], D->stream));
+  knn_kernel<1><<<(nq + KNN_THREADS - 1) / KNN_THREADS, KNN_THREADS, 0, D->stream>>>(
+      D->d_nodes, D->n_nodes, nullptr, perm, D->d_queries, nq, pc, 0.f, nullptr, D->d_nn_idx, D->d_nn_d2, nullptr);
+  CUDA_TRY(cudaEventRecord(D->ev[1], D->stream));
+  scatter_aux_kernel<<<(nq + 255) / 256, 256, 0, D->stream>>>(perm, nq, nullptr, D->d_nn_idx, D->d_nn_d2, nullptr,
+                                                               nullptr, nullptr, idx ? D->d_o_idx : nullptr,
+                                                               d2 ? D->d_o_d2 : nullptr, nullptr, nullptr);
+  if (idx) CUDA_TRY(cudaMemcpyAsync(idx, D->d_o_idx, (size_t)nq * MALIO_K * sizeof(uint32_t), cudaMemcpyDeviceToHost, D->stream));
+  if (d2) CUDA_TRY(cudaMemcpyAsync(d2, D->d_o_d2, (size_t)nq * MALIO_K * sizeof(float), cudaMemcpyDeviceToHost, D->stream));
+  CUDA_TRY(cudaStreamSynchronize(D->stream));
+  CUDA_TRY(cudaGetLastError());
+  if (ms_out) cudaEventElapsedTime(ms_out, D->ev[0], D->ev[1]);
+  return MALIO_OK;
+}
+
+int get_unique_id(uint8_t* id) {
+  std::string err;
+  if (!g_nccl.load(err)) return MALIO_ERR_NCCL;
+  ncclUniqueId uid;
+  if (g_nccl.GetUniqueId(&uid) != ncclSuccess) return MALIO_ERR_NCCL;
+  static_assert(sizeof(ncclUniqueId) == MALIO_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  std::memcpy(id, &uid, sizeof(uid));
+  return MALIO_OK;
+}
+
+int comm_init(malio_handle* h, const uint8_t* id, int rank, int world) {
+  DeviceState* D = (DeviceState*)h->dev;
+  CUDA_TRY(cudaSetDevice(D->device));
+  if (!g_nccl.load(h->err)) return MALIO_ERR_NCCL;
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, sizeof(uid));
+  ncclResult_t r = g_nccl.CommInitRank(&D->comm, world, uid, rank);
+  if (r != ncclSuccess) {
+    h->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    D->comm = nullptr;
+    return MALIO_ERR_NCCL;
+  }
+  D->rank = rank; D->world = world;
+  return MALIO_OK;
+}
+
+}  // namespace malio_dev

@@ -1,0 +1,608 @@
+// malio_host.cpp — host C++ side of libmalio_b200.so: the C-ABI wrappers, the iterated error-state Kalman
+// update on the state manifold, and the static snapshot builder.  No CUDA here; the device work is behind
+// malio_dev:: (malio_b200.cu).  There is NO CPU fallback for the measurement: without a usable GPU
+// malio_create fails with MALIO_ERR_CUDA.
+//
+// Reference interface mirrored (paths relative to /root/reference/MA_LIO):
+//   esekf::update_iterated_dyn_share_modified   include/IKFoM_toolkit/esekfom/esekfom.hpp:495-721
+//   state_ikfom manifold                        src/use-ikfom.hpp:14-27
+//   MTK SO3 / S2 / vect boxplus, boxminus       include/IKFoM_toolkit/mtk/types/{SOn,S2,vect}.hpp
+//   MTK::A_matrix, exp, log                     include/IKFoM_toolkit/mtk/src/mtkmath.hpp:235-289
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <vector>
+
+#include "malio_internal.h"
+
+namespace {
+
+thread_local std::string g_err = "";
+
+// ---------------------------------------------------------------- tiny dense matrix (row-major, run-time n <= 35)
+struct Mat {
+  int r = 0, c = 0;
+  std::vector<double> a;
+  Mat() {}
+  Mat(int r_, int c_) : r(r_), c(c_), a((size_t)r_ * c_, 0.0) {}
+  double& operator()(int i, int j) { return a[(size_t)i * c + j]; }
+  double operator()(int i, int j) const { return a[(size_t)i * c + j]; }
+};
+
+// LU with partial pivoting, in place; returns false on an exactly singular pivot
+bool lu_factor(Mat& A, std::vector<int>& piv) {
+  const int n = A.r;
+  piv.resize(n);
+  std::iota(piv.begin(), piv.end(), 0);
+  for (int k = 0; k < n; ++k) {
+    int p = k;
+    double best = std::fabs(A(k, k));
+    for (int i = k + 1; i < n; ++i)
+      if (std::fabs(A(i, k)) > best) { best = std::fabs(A(i, k)); p = i; }
+    if (best == 0.0) return false;
+    if (p != k) {
+      for (int j = 0; j < n; ++j) std::swap(A(k, j), A(p, j));
+      std::swap(piv[k], piv[p]);
+    }
+    const double inv = 1.0 / A(k, k);
+    for (int i = k + 1; i < n; ++i) {
+      const double f = A(i, k) * inv;
+      A(i, k) = f;
+      if (f != 0.0)
+        for (int j = k + 1; j < n; ++j) A(i, j) -= f * A(k, j);
+    }
+  }
+  return true;
+}
+// X = A^{-1} B for B given column-block wise (B: n x m)
+void lu_solve(const Mat& LU, const std::vector<int>& piv, const Mat& B, Mat& X) {
+  const int n = LU.r, m = B.c;
+  X = Mat(n, m);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < m; ++j) X(i, j) = B(piv[i], j);
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < i; ++k) {
+      const double f = LU(i, k);
+      if (f != 0.0) for (int j = 0; j < m; ++j) X(i, j) -= f * X(k, j);
+    }
+  for (int i = n - 1; i >= 0; --i) {
+    for (int k = i + 1; k < n; ++k) {
+      const double f = LU(i, k);
+      if (f != 0.0) for (int j = 0; j < m; ++j) X(i, j) -= f * X(k, j);
+    }
+    const double inv = 1.0 / LU(i, i);
+    for (int j = 0; j < m; ++j) X(i, j) *= inv;
+  }
+}
+bool invert(const Mat& A, Mat& Ainv) {
+  Mat LU = A;
+  std::vector<int> piv;
+  if (!lu_factor(LU, piv)) return false;
+  Mat I(A.r, A.r);
+  for (int i = 0; i < A.r; ++i) I(i, i) = 1.0;
+  lu_solve(LU, piv, I, Ainv);
+  return true;
+}
+
+// ---------------------------------------------------------------- rotations
+struct Quat { double w, x, y, z; };
+inline Quat qload(const double* q) { return Quat{q[0], q[1], q[2], q[3]}; }
+inline void qstore(const Quat& q, double* o) { o[0] = q.w; o[1] = q.x; o[2] = q.y; o[3] = q.z; }
+inline Quat qconj(const Quat& q) { return Quat{q.w, -q.x, -q.y, -q.z}; }
+inline Quat qmul(const Quat& a, const Quat& b) {
+  return Quat{a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+              a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z, a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x};
+}
+struct M3 { double m[3][3]; };
+inline M3 hat3(const double v[3]) { return M3{{{0, -v[2], v[1]}, {v[2], 0, -v[0]}, {-v[1], v[0], 0}}}; }
+inline M3 mul3(const M3& A, const M3& B) {
+  M3 C{};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) C.m[i][j] = A.m[i][0] * B.m[0][j] + A.m[i][1] * B.m[1][j] + A.m[i][2] * B.m[2][j];
+  return C;
+}
+inline M3 rotmat(const Quat& q) {
+  const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w, txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+  const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  return M3{{{1 - (tyy + tzz), txy - twz, txz + twy}, {txy + twz, 1 - (txx + tzz), tyz - twx}, {txz - twy, tyz + twx, 1 - (txx + tyy)}}};
+}
+
+const double kTol = 1e-11;                    // MTK::tolerance<double>() (mtkmath.hpp:122)
+const double kGrav = 98090.0 / 10000.0;       // S2<double,98090,10000,1> (use-ikfom.hpp:8)
+
+// cos(sqrt(x2)), sinc(sqrt(x2))  (mtkmath.hpp:141-171)
+void cos_sinc_sqrt(double x2, double& c, double& sc) {
+  const double b0 = std::numeric_limits<double>::epsilon();
+  const double bn = std::sqrt(std::sqrt(b0));
+  if (x2 >= bn) {
+    const double x = std::sqrt(x2);
+    c = std::cos(x);
+    sc = std::sin(x) / x;
+    return;
+  }
+  static const double inv[] = {1 / 3., 1 / 4., 1 / 5., 1 / 6., 1 / 7., 1 / 8., 1 / 9.};
+  double ci = 1., si = 1., term = -1 / 2. * x2;
+  for (int i = 0; i < 3; ++i) {
+    ci += term;
+    term *= inv[2 * i];
+    si += term;
+    term *= -inv[2 * i + 1] * x2;
+  }
+  c = ci;
+  sc = si;
+}
+// quaternion of MTK::exp(vec, scale) (mtkmath.hpp:249-256)
+Quat exp_quat(const double v[3], double scale) {
+  double c, sc;
+  cos_sinc_sqrt(scale * scale * (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), c, sc);
+  const double m = sc * scale;
+  return Quat{c, m * v[0], m * v[1], m * v[2]};
+}
+// SO3::log (SOn.hpp:341-345 -> mtkmath.hpp:268-289, scale 2, +-periodic)
+void so3_log(const Quat& q, double out[3]) {
+  double nv = std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z);
+  if (nv < kTol) nv = kTol;
+  const double s = 2.0 / nv * std::atan(nv / q.w);
+  out[0] = s * q.x; out[1] = s * q.y; out[2] = s * q.z;
+}
+// MTK::A_matrix (mtkmath.hpp:235-247)
+M3 A_matrix(const double v[3]) {
+  const double sq = v[0] * v[0] + v[1] * v[1] + v[2] * v[2], nrm = std::sqrt(sq);
+  M3 R{{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}};
+  if (nrm < kTol) return R;
+  const M3 H = hat3(v), HH = mul3(H, H);
+  const double a = (1 - std::cos(nrm)) / sq, b = (1 - std::sin(nrm) / nrm) / sq;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R.m[i][j] += a * H.m[i][j] + b * HH.m[i][j];
+  return R;
+}
+inline M3 transpose3(const M3& A) {
+  M3 T{};
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) T.m[i][j] = A.m[j][i];
+  return T;
+}
+
+// S2 chart with the x axis as pole (S2_typ == 1, S2.hpp:225-243): Bx is 3x2
+void S2_Bx(const double v[3], double B[3][2]) {
+  const double L = kGrav;
+  if (v[0] + L > kTol) {
+    const double d = L + v[0];
+    B[0][0] = -v[1];              B[0][1] = -v[2];
+    B[1][0] = L - v[1] * v[1] / d; B[1][1] = -v[2] * v[1] / d;
+    B[2][0] = -v[2] * v[1] / d;    B[2][1] = L - v[2] * v[2] / d;
+    for (int i = 0; i < 3; ++i) { B[i][0] /= L; B[i][1] /= L; }
+  } else {
+    for (int i = 0; i < 3; ++i) B[i][0] = B[i][1] = 0;
+    B[1][1] = -1;
+    B[2][0] = 1;
+  }
+}
+void S2_boxplus(double v[3], const double d[2]) {   // S2.hpp:136-142
+  double B[3][2];
+  S2_Bx(v, B);
+  const double Bu[3] = {B[0][0] * d[0] + B[0][1] * d[1], B[1][0] * d[0] + B[1][1] * d[1], B[2][0] * d[0] + B[2][1] * d[1]};
+  const M3 R = rotmat(exp_quat(Bu, 0.5));
+  const double o[3] = {R.m[0][0] * v[0] + R.m[0][1] * v[1] + R.m[0][2] * v[2], R.m[1][0] * v[0] + R.m[1][1] * v[1] + R.m[1][2] * v[2],
+                       R.m[2][0] * v[0] + R.m[2][1] * v[1] + R.m[2][2] * v[2]};
+  v[0] = o[0]; v[1] = o[1]; v[2] = o[2];
+}
+void S2_boxminus(const double v[3], const double o[3], double res[2]) {   // S2.hpp:144-168
+  const double cr[3] = {v[1] * o[2] - v[2] * o[1], v[2] * o[0] - v[0] * o[2], v[0] * o[1] - v[1] * o[0]};
+  const double v_sin = std::sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+  const double v_cos = v[0] * o[0] + v[1] * o[1] + v[2] * o[2];
+  const double theta = std::atan2(v_sin, v_cos);
+  if (v_sin < kTol) {
+    res[0] = (std::fabs(theta) > kTol) ? 3.1415926 : 0.0;
+    res[1] = 0.0;
+    return;
+  }
+  double B[3][2];
+  S2_Bx(o, B);
+  const double u[3] = {o[1] * v[2] - o[2] * v[1], o[2] * v[0] - o[0] * v[2], o[0] * v[1] - o[1] * v[0]};   // hat(o) v
+  const double f = theta / v_sin;
+  res[0] = f * (B[0][0] * u[0] + B[1][0] * u[1] + B[2][0] * u[2]);
+  res[1] = f * (B[0][1] * u[0] + B[1][1] * u[1] + B[2][1] * u[2]);
+}
+// J = Nx(x) * Mx(x0, delta), the 2x2 projection of the S2 block (esekfom.hpp:560-564; S2.hpp:269-291).
+// Mx's exp_delta uses scalar(1/2) == 0 in the reference, i.e. the identity rotation.
+void S2_projection(const double x[3], const double x0[3], const double delta[2], double J[2][2]) {
+  double Bx[3][2], B0[3][2];
+  S2_Bx(x, Bx);
+  S2_Bx(x0, B0);
+  const M3 Hx = hat3(x), H0 = hat3(x0);
+  double Nx[2][3];
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 3; ++j) Nx[i][j] = (Bx[0][i] * Hx.m[0][j] + Bx[1][i] * Hx.m[1][j] + Bx[2][i] * Hx.m[2][j]) / kGrav / kGrav;
+  double Mx[3][2];
+  if (std::sqrt(delta[0] * delta[0] + delta[1] * delta[1]) < kTol) {
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 2; ++j) Mx[i][j] = -(H0.m[i][0] * B0[0][j] + H0.m[i][1] * B0[1][j] + H0.m[i][2] * B0[2][j]);
+  } else {
+    const double Bu[3] = {B0[0][0] * delta[0] + B0[0][1] * delta[1], B0[1][0] * delta[0] + B0[1][1] * delta[1],
+                          B0[2][0] * delta[0] + B0[2][1] * delta[1]};
+    const M3 HA = mul3(H0, transpose3(A_matrix(Bu)));
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 2; ++j) Mx[i][j] = -(HA.m[i][0] * B0[0][j] + HA.m[i][1] * B0[1][j] + HA.m[i][2] * B0[2][j]);
+  }
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) J[i][j] = Nx[i][0] * Mx[0][j] + Nx[i][1] * Mx[1][j] + Nx[i][2] * Mx[2][j];
+}
+
+// ---------------------------------------------------------------- state manifold
+struct StateLayout {
+  int L, n, c, rot, vel, bg, ba, grav;
+  int offR[MALIO_MAX_LIDAR], offT[MALIO_MAX_LIDAR];
+  int so3[1 + MALIO_MAX_LIDAR];
+  explicit StateLayout(int L_) : L(L_) {
+    n = 17 + 6 * L; c = 6 * (L + 1); rot = 3;
+    so3[0] = rot;
+    for (int l = 0; l < L; ++l) { offR[l] = 6 + 3 * l; offT[l] = 6 + 3 * L + 3 * l; so3[1 + l] = offR[l]; }
+    vel = 6 + 6 * L; bg = vel + 3; ba = bg + 3; grav = ba + 3;
+  }
+};
+void boxminus(const StateLayout& ly, const malio_state& x, const malio_state& x0, double* d) {
+  for (int k = 0; k < 3; ++k) d[k] = x.pos[k] - x0.pos[k];
+  so3_log(qmul(qconj(qload(x0.rot)), qload(x.rot)), d + ly.rot);
+  for (int l = 0; l < ly.L; ++l) {
+    so3_log(qmul(qconj(qload(x0.ext[l].q)), qload(x.ext[l].q)), d + ly.offR[l]);
+    for (int k = 0; k < 3; ++k) d[ly.offT[l] + k] = x.ext[l].t[k] - x0.ext[l].t[k];
+  }
+  for (int k = 0; k < 3; ++k) {
+    d[ly.vel + k] = x.vel[k] - x0.vel[k];
+    d[ly.bg + k] = x.bg[k] - x0.bg[k];
+    d[ly.ba + k] = x.ba[k] - x0.ba[k];
+  }
+  S2_boxminus(x.grav, x0.grav, d + ly.grav);
+}
+void boxplus(const StateLayout& ly, malio_state& x, const double* d) {
+  for (int k = 0; k < 3; ++k) x.pos[k] += d[k];
+  qstore(qmul(qload(x.rot), exp_quat(d + ly.rot, 0.5)), x.rot);
+  for (int l = 0; l < ly.L; ++l) {
+    qstore(qmul(qload(x.ext[l].q), exp_quat(d + ly.offR[l], 0.5)), x.ext[l].q);
+    for (int k = 0; k < 3; ++k) x.ext[l].t[k] += d[ly.offT[l] + k];
+  }
+  for (int k = 0; k < 3; ++k) {
+    x.vel[k] += d[ly.vel + k];
+    x.bg[k] += d[ly.bg + k];
+    x.ba[k] += d[ly.ba + k];
+  }
+  S2_boxplus(x.grav, d + ly.grav);
+}
+
+// rows [idx, idx+bs) <- J * rows ; cols likewise with J^T  (block sizes 3 and 2)
+template <int BS>
+void left_block(Mat& M, int idx, const double J[BS][BS], int ncols) {
+  for (int j = 0; j < ncols; ++j) {
+    double v[BS], o[BS];
+    for (int a = 0; a < BS; ++a) v[a] = M(idx + a, j);
+    for (int a = 0; a < BS; ++a) { o[a] = 0; for (int b = 0; b < BS; ++b) o[a] += J[a][b] * v[b]; }
+    for (int a = 0; a < BS; ++a) M(idx + a, j) = o[a];
+  }
+}
+template <int BS>
+void right_block_T(Mat& M, int idx, const double J[BS][BS]) {
+  for (int i = 0; i < M.r; ++i) {
+    double v[BS], o[BS];
+    for (int a = 0; a < BS; ++a) v[a] = M(i, idx + a);
+    for (int a = 0; a < BS; ++a) { o[a] = 0; for (int b = 0; b < BS; ++b) o[a] += v[b] * J[a][b]; }
+    for (int a = 0; a < BS; ++a) M(i, idx + a) = o[a];
+  }
+}
+
+}  // namespace
+
+namespace malio_host {
+// singular values of the N x 3 matrix whose Gram matrix is S (descending) = sqrt(eig(S)); closed-form
+// trigonometric solution of the symmetric 3x3 characteristic polynomial, refined by one Jacobi sweep set
+void sym3_singular_values(const double S[6], double sv[3]) {
+  double A[3][3] = {{S[0], S[1], S[2]}, {S[1], S[3], S[4]}, {S[2], S[4], S[5]}};
+  for (int sweep = 0; sweep < 50; ++sweep) {
+    const double off = std::fabs(A[0][1]) + std::fabs(A[0][2]) + std::fabs(A[1][2]);
+    if (off == 0.0) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (A[p][q] == 0.0) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2 * A[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
+        const double c = 1 / std::sqrt(t * t + 1), s = t * c;
+        for (int k = 0; k < 3; ++k) { const double a = A[k][p], b = A[k][q]; A[k][p] = c * a - s * b; A[k][q] = s * a + c * b; }
+        for (int k = 0; k < 3; ++k) { const double a = A[p][k], b = A[q][k]; A[p][k] = c * a - s * b; A[q][k] = s * a + c * b; }
+      }
+  }
+  double e[3] = {A[0][0], A[1][1], A[2][2]};
+  std::sort(e, e + 3);
+  sv[0] = std::sqrt(std::max(e[2], 0.0));
+  sv[1] = std::sqrt(std::max(e[1], 0.0));
+  sv[2] = std::sqrt(std::max(e[0], 0.0));
+}
+}  // namespace malio_host
+
+// =================================================================== C-ABI
+extern "C" {
+
+const char* malio_version(void) { return "malio_b200 0.1 (sm_100a)"; }
+
+void malio_default_params(malio_params* p, int n_lidar) {
+  std::memset(p, 0, sizeof(*p));
+  p->n_lidar = n_lidar;
+  p->extrinsic_est_en = 1;          // config/City.yaml:23
+  p->plane_th = 0.4f;               // launch/mapping_city.launch:13
+  p->knn_max_sqdist = 5.0f;         // laserMapping.cpp:587
+  p->cov_threshold = 0.5;           // City.yaml:50
+  p->point_cov_max = 0.00125; p->point_cov_min = 0.00075;   // City.yaml:42-43
+  p->plane_cov_max = 1.0; p->plane_cov_min = 0.8;           // City.yaml:44-45
+  p->localize_cov_max = 2.0; p->localize_cov_min = 0.3;     // City.yaml:46-47
+  p->localize_thresh_max = 0.7; p->localize_thresh_min = 0.2;   // City.yaml:48-49
+  p->range_min = 0.0; p->range_max = 1.0;                   // mapping_city.launch:14-15
+}
+
+const char* malio_last_error(const malio_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int malio_create(malio_handle** out, const malio_config* cfg) {
+  if (!out || !cfg) { g_err = "null argument"; return MALIO_ERR_INVALID_ARG; }
+  *out = nullptr;
+  if (cfg->params.n_lidar < 1 || cfg->params.n_lidar > MALIO_MAX_LIDAR) { g_err = "n_lidar must be 1..3"; return MALIO_ERR_INVALID_ARG; }
+  malio_handle* h = new malio_handle;
+  h->cfg = *cfg;
+  const int rc = malio_dev::create(h);
+  if (rc != MALIO_OK) {
+    g_err = h->err;
+    malio_dev::destroy(h);
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return MALIO_OK;
+}
+void malio_destroy(malio_handle* h) {
+  if (!h) return;
+  malio_dev::destroy(h);
+  delete h;
+}
+int malio_get_nccl_unique_id(uint8_t id[MALIO_NCCL_UNIQUE_ID_BYTES]) { return malio_dev::get_unique_id(id); }
+int malio_comm_init(malio_handle* h, const uint8_t id[MALIO_NCCL_UNIQUE_ID_BYTES], int rank, int world) {
+  if (!h || !id || world < 1 || rank < 0 || rank >= world) return MALIO_ERR_INVALID_ARG;
+  return malio_dev::comm_init(h, id, rank, world);
+}
+int malio_upload_map(malio_handle* h, const malio_map_node* nodes, const float* node_cov, uint32_t n_nodes, uint32_t max_depth) {
+  if (!h || (n_nodes && (!nodes || !node_cov))) return MALIO_ERR_INVALID_ARG;
+  return malio_dev::upload_map(h, nodes, node_cov, n_nodes, max_depth);
+}
+int malio_upload_scan(malio_handle* h, const malio_scan_pt* pts, uint32_t n_pts, const malio_pose_entry* table,
+                      const uint32_t* table_off, const malio_rigid* temporal_comp) {
+  if (!h || (n_pts && !pts) || !table || !table_off) return MALIO_ERR_INVALID_ARG;
+  if (h->cfg.params.n_lidar > 1 && !temporal_comp) { h->err = "temporal_comp required for L > 1"; return MALIO_ERR_INVALID_ARG; }
+  return malio_dev::upload_scan(h, pts, n_pts, table, table_off, temporal_comp);
+}
+int malio_measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* HtRinvH, double* HtRinvh, malio_pass_stats* stats) {
+  if (!h || !s || !HtRinvH || !HtRinvh) return MALIO_ERR_INVALID_ARG;
+  return malio_dev::measure(h, s, redo_knn, HtRinvH, HtRinvh, stats);
+}
+int malio_download_rows(malio_handle* h, double* h_x, double* hvec, uint32_t cap, uint32_t* n_rows) {
+  if (!h || !h_x || !hvec || !n_rows) return MALIO_ERR_INVALID_ARG;
+  return malio_dev::download_rows(h, h_x, hvec, cap, n_rows);
+}
+int malio_download_aux(malio_handle* h, float* normal_y, uint32_t* nn_idx, float* nn_sqdist, uint8_t* selected, float* world) {
+  if (!h) return MALIO_ERR_INVALID_ARG;
+  return malio_dev::download_aux(h, normal_y, nn_idx, nn_sqdist, selected, world);
+}
+int malio_knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* nn_idx, float* nn_sqdist, float* ms_device) {
+  if (!h || (nq && !q)) return MALIO_ERR_INVALID_ARG;
+  return malio_dev::knn(h, q, nq, nn_idx, nn_sqdist, ms_device);
+}
+
+// ---------------------------------------------------------------- IESKF (esekfom.hpp:495-721)
+int malio_ieskf_update(malio_handle* h, malio_state* x, double* Pio, int max_iter, double R, malio_update_report* rep) {
+  if (!h || !x || !Pio || max_iter < 0) return MALIO_ERR_INVALID_ARG;
+  const StateLayout ly(h->cfg.params.n_lidar);
+  const int n = ly.n, c = ly.c;
+  malio_update_report rp{};
+  const malio_state x_prop = *x;
+  Mat P_prop(n, n);
+  std::memcpy(P_prop.a.data(), Pio, sizeof(double) * n * n);
+  Mat P = P_prop, Kx(n, c), G(c, c);
+  std::vector<double> g(c), dx(n), dxn(n), Kh(n), step(n);
+  bool redo = true;   // dyn_share.converge
+  int t = 0, rc_last = MALIO_OK;
+  double host_ms = 0.0;
+  for (int it = -1; it < max_iter; ++it) {
+    malio_pass_state ps;
+    std::memcpy(ps.rot, x->rot, sizeof(ps.rot));
+    std::memcpy(ps.pos, x->pos, sizeof(ps.pos));
+    std::memcpy(ps.ext, x->ext, sizeof(ps.ext));
+    malio_pass_stats st{};
+    const int rc = malio_dev::measure(h, &ps, redo ? 1 : 0, G.a.data(), g.data(), &st);   // h_dyn_share, :512
+    rp.passes++;
+    if (redo) rp.searches++;
+    rp.ms_device_total += st.ms_total;
+    rc_last = rc;
+    if (rc == MALIO_ERR_NO_EFFECTIVE_POINTS) continue;   // :514-517
+    if (rc != MALIO_OK) { if (rep) *rep = rp; return rc; }
+    const auto t0 = std::chrono::steady_clock::now();
+    rp.n_eff_last = st.n_eff;
+    boxminus(ly, *x, x_prop, dx.data());   // :526
+    dxn = dx;
+    P = P_prop;   // :530
+    for (int s = 0; s <= ly.L; ++s) {      // SO3 blocks, :534-549
+      const int idx = ly.so3[s];
+      const M3 Jt = transpose3(A_matrix(&dx[idx]));
+      double o[3];
+      for (int a = 0; a < 3; ++a) o[a] = Jt.m[a][0] * dxn[idx] + Jt.m[a][1] * dxn[idx + 1] + Jt.m[a][2] * dxn[idx + 2];
+      dxn[idx] = o[0]; dxn[idx + 1] = o[1]; dxn[idx + 2] = o[2];
+      left_block<3>(P, idx, Jt.m, n);
+      right_block_T<3>(P, idx, Jt.m);
+    }
+    {                                       // S2 block, :553-572
+      double J2[2][2];
+      S2_projection(x->grav, x_prop.grav, &dx[ly.grav], J2);
+      const double d0 = dxn[ly.grav], d1 = dxn[ly.grav + 1];
+      dxn[ly.grav] = J2[0][0] * d0 + J2[0][1] * d1;
+      dxn[ly.grav + 1] = J2[1][0] * d0 + J2[1][1] * d1;
+      left_block<2>(P, ly.grav, J2, n);
+      right_block_T<2>(P, ly.grav, J2);
+    }
+    if (n > (int)st.n_eff) {   // degenerate branch :574-582 — needs the rows, scalar R
+      const int m = (int)st.n_eff;
+      std::vector<double> rows((size_t)MALIO_MAX_DOF * c), hv(MALIO_MAX_DOF);
+      uint32_t nr = 0;
+      const int rc2 = malio_dev::download_rows(h, rows.data(), hv.data(), (uint32_t)m, &nr);
+      if (rc2 != MALIO_OK) { if (rep) *rep = rp; return rc2; }
+      Mat H(m, n);
+      for (int r = 0; r < m; ++r) {
+        for (int k = 0; k < c; ++k) H(r, k) = rows[(size_t)r * c + k] * st.loc_weight;
+        hv[r] *= st.loc_weight;
+      }
+      Mat PHt(n, m), Sm(m, m), Si;
+      for (int a = 0; a < n; ++a) for (int r = 0; r < m; ++r) { double s = 0; for (int k = 0; k < c; ++k) s += P(a, k) * H(r, k); PHt(a, r) = s; }
+      for (int r = 0; r < m; ++r) for (int q = 0; q < m; ++q) { double s = 0; for (int k = 0; k < c; ++k) s += H(r, k) * PHt(k, q); Sm(r, q) = s / R + (r == q ? 1.0 : 0.0); }
+      if (!invert(Sm, Si)) { h->err = "singular innovation matrix"; if (rep) *rep = rp; return MALIO_ERR_INVALID_ARG; }
+      Mat K(n, m);
+      for (int a = 0; a < n; ++a) for (int q = 0; q < m; ++q) { double s = 0; for (int r = 0; r < m; ++r) s += PHt(a, r) * Si(r, q); K(a, q) = s / R; }
+      for (int a = 0; a < n; ++a) { double s = 0; for (int r = 0; r < m; ++r) s += K(a, r) * hv[r]; Kh[a] = s; }
+      for (int a = 0; a < n; ++a) for (int b = 0; b < c; ++b) { double s = 0; for (int r = 0; r < m; ++r) s += K(a, r) * H(r, b); Kx(a, b) = s; }
+    } else {                   // :621-637
+      Mat Pinv0, Q;
+      if (!invert(P, Pinv0)) { h->err = "singular covariance"; if (rep) *rep = rp; return MALIO_ERR_INVALID_ARG; }
+      for (int a = 0; a < c; ++a) for (int b = 0; b < c; ++b) Pinv0(a, b) += G(a, b);
+      if (!invert(Pinv0, Q)) { h->err = "singular information matrix"; if (rep) *rep = rp; return MALIO_ERR_INVALID_ARG; }
+      for (int a = 0; a < n; ++a) {
+        double s = 0;
+        for (int k = 0; k < c; ++k) s += Q(a, k) * g[k];
+        Kh[a] = s;
+        for (int b = 0; b < c; ++b) { double v = 0; for (int k = 0; k < c; ++k) v += Q(a, k) * G(k, b); Kx(a, b) = v; }
+      }
+    }
+    for (int a = 0; a < n; ++a) {          // dx_ = K_h + (K_x - I) dx_new, :642
+      double s = Kh[a] - dxn[a];
+      for (int b = 0; b < c; ++b) s += Kx(a, b) * dxn[b];
+      step[a] = s;
+    }
+    std::memcpy(rp.dx_last, step.data(), sizeof(double) * n);
+    boxplus(ly, *x, step.data());          // :646
+    redo = true;                           // :649-657
+    for (int k = 0; k < n; ++k) if (std::fabs(step[k]) > 0.001) { redo = false; break; }
+    if (redo) t++;
+    if (!t && it == max_iter - 2) redo = true;   // :660-663
+    if (t > 1 || it == max_iter - 1) {     // final covariance, :665-718
+      Mat Lm = P;
+      for (int s = 0; s <= ly.L; ++s) {
+        const int idx = ly.so3[s];
+        const M3 Jt = transpose3(A_matrix(&step[idx]));
+        // L rows from P rows (identical at this point for rows idx..idx+2), K_x rows, then L and P columns
+        for (int j = 0; j < n; ++j) {
+          double v[3] = {P(idx, j), P(idx + 1, j), P(idx + 2, j)};
+          for (int a = 0; a < 3; ++a) Lm(idx + a, j) = Jt.m[a][0] * v[0] + Jt.m[a][1] * v[1] + Jt.m[a][2] * v[2];
+        }
+        left_block<3>(Kx, idx, Jt.m, c);
+        right_block_T<3>(Lm, idx, Jt.m);
+        right_block_T<3>(P, idx, Jt.m);
+      }
+      {
+        double J2[2][2];
+        S2_projection(x->grav, x_prop.grav, &step[ly.grav], J2);
+        for (int j = 0; j < n; ++j) {
+          const double v0 = P(ly.grav, j), v1 = P(ly.grav + 1, j);
+          Lm(ly.grav, j) = J2[0][0] * v0 + J2[0][1] * v1;
+          Lm(ly.grav + 1, j) = J2[1][0] * v0 + J2[1][1] * v1;
+        }
+        left_block<2>(Kx, ly.grav, J2, c);
+        right_block_T<2>(Lm, ly.grav, J2);
+        right_block_T<2>(P, ly.grav, J2);
+      }
+      for (int a = 0; a < n; ++a)          // P_ = L_ - K_x[:,0:c] P_[0:c,:], :714
+        for (int b = 0; b < n; ++b) {
+          double s = 0;
+          for (int k = 0; k < c; ++k) s += Kx(a, k) * P(k, b);
+          Pio[(size_t)a * n + b] = Lm(a, b) - s;
+        }
+      host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      rp.converged_count = t;
+      rp.last_status = MALIO_OK;
+      rp.ms_host_solve = (float)host_ms;
+      if (rep) *rep = rp;
+      return MALIO_OK;
+    }
+    host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
+  // every remaining pass was invalid: the reference leaves P_ at its last projected value
+  std::memcpy(Pio, P.a.data(), sizeof(double) * n * n);
+  rp.converged_count = t;
+  rp.last_status = rc_last;
+  rp.ms_host_solve = (float)host_ms;
+  if (rep) *rep = rp;
+  return rc_last == MALIO_OK ? MALIO_OK : MALIO_ERR_NO_EFFECTIVE_POINTS;
+}
+
+// ---------------------------------------------------------------- static snapshot builder
+namespace {
+struct BuildCtx {
+  const float* xyz;
+  malio_map_node* out;
+  uint32_t* order;     // work array of point indices, permuted in place
+  uint32_t* order_out;
+  uint32_t max_depth;
+};
+// builds the subtree over order[l..r] rooted at slot `slot`; returns its AABB in box[6]
+void build_rec(BuildCtx& C, int64_t l, int64_t r, uint32_t slot, uint32_t depth, float box[6], uint32_t& max_depth) {
+  if (depth > max_depth) max_depth = depth;
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int64_t i = l; i <= r; ++i) {
+    const float* p = C.xyz + 3 * (size_t)C.order[i];
+    for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], p[k]); mx[k] = std::max(mx[k], p[k]); }
+  }
+  int axis = 0;   // longest extent (ikd_Tree.cpp:712-716)
+  for (int k = 1; k < 3; ++k) if (mx[k] - mn[k] > mx[axis] - mn[axis]) axis = k;
+  const int64_t mid = (l + r) >> 1;
+  std::nth_element(C.order + l, C.order + mid, C.order + r + 1, [&](uint32_t a, uint32_t b) {
+    return C.xyz[3 * (size_t)a + axis] < C.xyz[3 * (size_t)b + axis];
+  });
+  malio_map_node& o = C.out[slot];
+  const float* p = C.xyz + 3 * (size_t)C.order[mid];
+  o.x = p[0]; o.y = p[1]; o.z = p[2];
+  C.order_out[slot] = C.order[mid];
+  uint32_t link = 0;
+  for (int k = 0; k < 6; ++k) { o.lbox[k] = 0.f; o.rbox[k] = 0.f; }
+  const int64_t nl = mid - l, nr = r - mid;
+  if (nl > 0) { link |= MALIO_LINK_HAS_LEFT; }
+  if (nr > 0) { link |= MALIO_LINK_HAS_RIGHT | (uint32_t)(slot + 1 + nl); }
+  o.link = link;
+  for (int k = 0; k < 3; ++k) { box[2 * k] = mn[k]; box[2 * k + 1] = mx[k]; }
+  float lb[6], rb[6];
+  uint32_t dl = depth, dr = depth;
+  const bool spawn = (r - l) > 65536;
+  if (nl > 0 && nr > 0 && spawn) {
+#pragma omp task shared(C, lb, dl) firstprivate(l, mid, slot, depth)
+    build_rec(C, l, mid - 1, slot + 1, depth + 1, lb, dl);
+#pragma omp task shared(C, rb, dr) firstprivate(r, mid, slot, depth, nl)
+    build_rec(C, mid + 1, r, (uint32_t)(slot + 1 + nl), depth + 1, rb, dr);
+#pragma omp taskwait
+  } else {
+    if (nl > 0) build_rec(C, l, mid - 1, slot + 1, depth + 1, lb, dl);
+    if (nr > 0) build_rec(C, mid + 1, r, (uint32_t)(slot + 1 + nl), depth + 1, rb, dr);
+  }
+  if (nl > 0) std::memcpy(o.lbox, lb, sizeof(lb));
+  if (nr > 0) std::memcpy(o.rbox, rb, sizeof(rb));
+  max_depth = std::max(max_depth, std::max(dl, dr));
+}
+}  // namespace
+
+int malio_build_static_snapshot(const float* xyz, uint32_t n, malio_map_node* nodes_out, uint32_t* order_out, uint32_t* max_depth_out) {
+  if (n == 0) { if (max_depth_out) *max_depth_out = 0; return MALIO_OK; }
+  if (!xyz || !nodes_out || !order_out || n > MALIO_LINK_INDEX_MASK) return MALIO_ERR_INVALID_ARG;
+  std::vector<uint32_t> order(n);
+  std::iota(order.begin(), order.end(), 0u);
+  BuildCtx C{xyz, nodes_out, order.data(), order_out, 0};
+  float box[6];
+  uint32_t md = 0;
+#pragma omp parallel
+#pragma omp single
+  build_rec(C, 0, (int64_t)n - 1, 0, 1, box, md);
+  if (max_depth_out) *max_depth_out = md;
+  return MALIO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,48 @@
+// malio_internal.h — shared between the CUDA translation unit and the host C++ of libmalio_b200.so.
+#ifndef MALIO_INTERNAL_H_
+#define MALIO_INTERNAL_H_
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "malio_b200.h"
+
+// Reduced system as the device produces it: fixed, L=3-shaped and padded so that one kernel serves L=1..3.
+//   rows  : 24  (Jacobian columns, always at their L=3 positions: 0-5 | 6+3l | 15+3l)
+//   cols  : 28  = 24 Jacobian columns | 1 residual column (-> H^T R^-1 h) | 3 "rho*h_0..2" columns
+//           (-> the un-weighted 3x3 normal scatter that JacobiSVD's singular values come from)
+// Only the 27 upper-triangular 4x4 blocks (row group i <= col group j) are computed and stored.
+#define MALIO_RED_ROWS 24
+#define MALIO_RED_COLS 28
+#define MALIO_RED_BLOCKS 27
+#define MALIO_RED_DOUBLES (MALIO_RED_BLOCKS * 16 + 2)   // + n_eff + spare
+
+struct malio_handle {
+  malio_config cfg{};
+  std::string err;
+  void* dev = nullptr;   // DeviceState*, owned by the CUDA TU
+};
+
+// CUDA TU entry points used by the C-ABI wrappers
+namespace malio_dev {
+int create(malio_handle* h);
+void destroy(malio_handle* h);
+int upload_map(malio_handle* h, const malio_map_node* nodes, const float* cov, uint32_t n, uint32_t depth);
+int upload_scan(malio_handle* h, const malio_scan_pt* pts, uint32_t n, const malio_pose_entry* table,
+                const uint32_t* table_off, const malio_rigid* tcomp);
+int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* HtRinvH, double* HtRinvh,
+            malio_pass_stats* st);
+int download_rows(malio_handle* h, double* h_x, double* hvec, uint32_t cap, uint32_t* n_rows);
+int download_aux(malio_handle* h, float* normal_y, uint32_t* nn_idx, float* nn_d2, uint8_t* sel, float* world);
+int knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* idx, float* d2, float* ms);
+int comm_init(malio_handle* h, const uint8_t* id, int rank, int world);
+int get_unique_id(uint8_t* id);
+}  // namespace malio_dev
+
+// host math shared by measure() (localization weight) and the IESKF
+namespace malio_host {
+void sym3_singular_values(const double S[6] /* xx,xy,xz,yy,yz,zz */, double sv[3]);
+}
+
+#endif

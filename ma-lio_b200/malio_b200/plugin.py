@@ -1,0 +1,163 @@
+"""Host-side mirror of the reference's measurement plug-in, over the C-ABI.
+
+Names follow the reference (paths relative to /root/reference/MA_LIO):
+  MeasurementModel.h_share_model(state, converge)        src/laserMapping.cpp:552-760  (+ esekfom.hpp:622-635)
+  MeasurementModel.update_iterated_dyn_share_modified()  include/IKFoM_toolkit/esekfom/esekfom.hpp:495-721
+  MeasurementModel.Nearest_Search(points)                include/ikd-Tree/ikd_Tree.cpp:426-461
+Everything heavy happens inside libmalio_b200.so on the GPU; this file is marshalling only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+
+
+@dataclass
+class MapSnapshot:
+    """Flattened ikd-Tree (include/malio_flatten.hpp or malio_build_static_snapshot)."""
+    nodes: np.ndarray        # capi.MAP_NODE[M]
+    node_cov: np.ndarray     # float32[M]  map-side weight normal_y (common_lib.h:164)
+    node_ids: np.ndarray     # int32/uint32[M] caller's id of the point stored in each node
+    max_depth: int
+
+    @property
+    def n_nodes(self) -> int:
+        return int(self.nodes.shape[0])
+
+
+def build_static_snapshot(xyz: np.ndarray, normal_y: np.ndarray | float = 0.001) -> MapSnapshot:
+    """Balanced k-d tree over xyz directly in snapshot form (median split on the longest axis, like
+    KD_TREE::BuildTree, ikd_Tree.cpp:696-735).  Host C++ inside the product library."""
+    lib = capi.load()
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    n = xyz.shape[0]
+    nodes = np.zeros(n, dtype=capi.MAP_NODE)
+    order = np.zeros(n, dtype=np.uint32)
+    depth = C.c_uint32(0)
+    rc = lib.malio_build_static_snapshot(capi.ptr(xyz), n, capi.ptr(nodes), capi.ptr(order), C.byref(depth))
+    if rc != capi.OK:
+        raise capi.MalioError(rc, "malio_build_static_snapshot")
+    if np.isscalar(normal_y):
+        cov = np.full(n, normal_y, dtype=np.float32)
+    else:
+        cov = np.ascontiguousarray(np.asarray(normal_y, dtype=np.float32)[order])
+    return MapSnapshot(nodes, cov, order.astype(np.int64), int(depth.value))
+
+
+class MeasurementModel:
+    """One handle = one GPU.  Mirrors the life cycle of one scan in laserMapping.cpp:935-1082."""
+
+    def __init__(self, n_lidar: int = 3, device: int = 0, sort_queries: bool = True, params: capi.Params | None = None):
+        self.lib = capi.load()
+        cfg = capi.Config()
+        cfg.params = params if params is not None else capi.default_params(n_lidar)
+        cfg.params.n_lidar = n_lidar
+        cfg.device = device
+        cfg.sort_queries = 1 if sort_queries else 0
+        self.n_lidar = n_lidar
+        self.n_dof = 17 + 6 * n_lidar
+        self.n_cols = 6 * (n_lidar + 1)
+        self._h = C.c_void_p()
+        rc = self.lib.malio_create(C.byref(self._h), C.byref(cfg))
+        if rc != capi.OK:
+            raise capi.MalioError(rc, self.lib.malio_last_error(None).decode())
+        self.n_points = 0
+        self._keep = []   # host buffers must outlive the (synchronous) calls only; kept for clarity
+
+    def close(self):
+        if self._h:
+            self.lib.malio_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, allow=()):
+        if rc != capi.OK and rc not in allow:
+            raise capi.MalioError(rc, self.lib.malio_last_error(self._h).decode())
+        return rc
+
+    # ---- multi-GPU plumbing
+    @staticmethod
+    def nccl_unique_id() -> np.ndarray:
+        uid = np.zeros(capi.NCCL_UNIQUE_ID_BYTES, dtype=np.uint8)
+        rc = capi.load().malio_get_nccl_unique_id(capi.ptr(uid))
+        if rc != capi.OK:
+            raise capi.MalioError(rc, "malio_get_nccl_unique_id")
+        return uid
+
+    def comm_init(self, uid: np.ndarray, rank: int, world: int):
+        uid = np.ascontiguousarray(uid, dtype=np.uint8)
+        self._check(self.lib.malio_comm_init(self._h, capi.ptr(uid), rank, world))
+
+    # ---- per scan
+    def upload_map(self, snap: MapSnapshot):
+        nodes = np.ascontiguousarray(snap.nodes)
+        cov = np.ascontiguousarray(snap.node_cov, dtype=np.float32)
+        self._check(self.lib.malio_upload_map(self._h, capi.ptr(nodes), capi.ptr(cov), nodes.shape[0], snap.max_depth))
+
+    def upload_scan(self, pts: np.ndarray, table: np.ndarray, table_off: np.ndarray, temporal_comp: np.ndarray | None):
+        pts = np.ascontiguousarray(pts)
+        assert pts.dtype == capi.SCAN_PT
+        table = np.ascontiguousarray(table)
+        assert table.dtype == capi.POSE_ENTRY
+        table_off = np.ascontiguousarray(table_off, dtype=np.uint32)
+        tc = None if temporal_comp is None else np.ascontiguousarray(temporal_comp)
+        self._check(self.lib.malio_upload_scan(self._h, capi.ptr(pts), pts.shape[0], capi.ptr(table),
+                                               capi.ptr(table_off), capi.ptr(tc)))
+        self.n_points = int(pts.shape[0])
+
+    def h_share_model(self, s: capi.PassState | capi.State, converge: bool):
+        """One measurement pass.  Returns (valid, HTH[c,c], HTh[c], stats)."""
+        ps = s.pass_state() if isinstance(s, capi.State) else s
+        c = self.n_cols
+        HTH = np.zeros((c, c))
+        HTh = np.zeros(c)
+        st = capi.PassStats()
+        rc = self._check(self.lib.malio_measure(self._h, C.byref(ps), 1 if converge else 0, capi.ptr(HTH),
+                                                capi.ptr(HTh), C.byref(st)), allow=(capi.ERR_NO_EFFECTIVE_POINTS,))
+        return rc == capi.OK, HTH, HTh, st
+
+    def rows(self, cap: int | None = None):
+        cap = capi.MAX_DOF if cap is None else cap
+        hx = np.zeros((cap, self.n_cols))
+        hv = np.zeros(cap)
+        n = C.c_uint32(0)
+        self._check(self.lib.malio_download_rows(self._h, capi.ptr(hx), capi.ptr(hv), cap, C.byref(n)))
+        return hx[: n.value], hv[: n.value]
+
+    def aux(self, normal_y=True, nn_idx=True, nn_sqdist=True, selected=True, world=True):
+        n = self.n_points
+        o_ny = np.zeros(n, np.float32) if normal_y else None
+        o_idx = np.zeros((n, capi.K), np.uint32) if nn_idx else None
+        o_d2 = np.zeros((n, capi.K), np.float32) if nn_sqdist else None
+        o_sel = np.zeros(n, np.uint8) if selected else None
+        o_w = np.zeros((n, 3), np.float32) if world else None
+        self._check(self.lib.malio_download_aux(self._h, capi.ptr(o_ny), capi.ptr(o_idx), capi.ptr(o_d2),
+                                                capi.ptr(o_sel), capi.ptr(o_w)))
+        return dict(normal_y=o_ny, nn_idx=o_idx, nn_sqdist=o_d2, selected=o_sel, world=o_w)
+
+    def update_iterated_dyn_share_modified(self, x: capi.State, P: np.ndarray, max_iter: int, R: float = 0.001):
+        """IESKF update; x and P are updated in place.  Returns the report (status in report.last_status)."""
+        assert P.shape == (self.n_dof, self.n_dof) and P.dtype == np.float64 and P.flags["C_CONTIGUOUS"]
+        rep = capi.UpdateReport()
+        rc = self.lib.malio_ieskf_update(self._h, C.byref(x), capi.ptr(P), max_iter, R, C.byref(rep))
+        self._check(rc, allow=(capi.ERR_NO_EFFECTIVE_POINTS,))
+        return rep
+
+    # ---- stand-alone k-NN (BASELINE config C5)
+    def Nearest_Search(self, queries: np.ndarray):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        n = q.shape[0]
+        idx = np.zeros((n, capi.K), np.uint32)
+        d2 = np.zeros((n, capi.K), np.float32)
+        ms = C.c_float(0)
+        self._check(self.lib.malio_knn(self._h, capi.ptr(q), n, capi.ptr(idx), capi.ptr(d2), C.byref(ms)))
+        return idx, d2, float(ms.value)
