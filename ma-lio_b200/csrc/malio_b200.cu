@@ -2,7 +2,7 @@
 //
 // Hot path of MA-LIO's measurement update, B200-native (DESIGN.md has the data layout and rooflines):
 //   K1 knn_kernel      KD_TREE::Nearest_Search / Search   (ikd_Tree.cpp:426-461, 1073-1255)
-//   K2 plane_kernel    h_share_model S1 + esti_plane + evalPointUncertainty
+//   K2 fit/tau/gate    h_share_model S1 + esti_plane (once per search) + evalPointUncertainty (once per scan)
 //                      (laserMapping.cpp:559-612, 725-743; common_lib.h:144-190; associate_uct.hpp:153-175)
 //   K3 reduce_kernel   h_share_model S3-S4 rows fused with esekfom.hpp:622-635 (H^T R^-1 H, H^T R^-1 h)
 // Compiled with -fmad=false: every float/double expression below is evaluated with the same IEEE operations,
@@ -15,6 +15,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -31,8 +32,9 @@
 
 namespace {
 
-constexpr int KNN_THREADS = 128;
-constexpr int PLANE_THREADS = 128;
+constexpr int KNN_THREADS = 64;
+constexpr int PLANE_THREADS = 64;
+constexpr int GATE_THREADS = 256;
 constexpr int RED_THREADS = 128;          // one tile = 128 points
 constexpr int RED_HS_STRIDE = 26;         // doubles per staged row of h/rho (24 + pad)
 constexpr int RED_HX_STRIDE = 28;         // doubles per staged row of [h | z | rho*h_0..2]
@@ -106,79 +108,168 @@ __device__ __forceinline__ void transform_point(const PassConst& pc, float px, f
 }
 
 // ------------------------------------------------------------------ K1: k-NN over the flattened ikd-Tree snapshot
-// calc_box_dist (ikd_Tree.cpp:1702-1720)
+// calc_box_dist (ikd_Tree.cpp:1702-1720).  For lo <= hi at most one of `p < lo`, `p > hi` fires per axis and
+// (p-lo)^2 == (lo-p)^2 exactly, so  t = max(lo-p, p-hi, 0);  m += t*t  (in x,y,z order, adding an exact 0 when
+// neither fires) gives the reference's float result bit for bit with fewer, branch-free instructions.
 __device__ __forceinline__ float box_dist(float px, float py, float pz, float x0, float x1, float y0, float y1,
                                           float z0, float z1) {
-  float m = 0.0f;
-  if (px < x0) m += (px - x0) * (px - x0);
-  if (px > x1) m += (px - x1) * (px - x1);
-  if (py < y0) m += (py - y0) * (py - y0);
-  if (py > y1) m += (py - y1) * (py - y1);
-  if (pz < z0) m += (pz - z0) * (pz - z0);
-  if (pz > z1) m += (pz - z1) * (pz - z1);
+  const float tx = fmaxf(fmaxf(x0 - px, px - x1), 0.0f);
+  const float ty = fmaxf(fmaxf(y0 - py, py - y1), 0.0f);
+  const float tz = fmaxf(fmaxf(z0 - pz, pz - z1), 0.0f);
+  float m = tx * tx;
+  m += ty * ty;
+  m += tz * tz;
   return m;
 }
-// PointType_CMP::operator< (ikd_Tree.h:102-108)
-__device__ __forceinline__ bool cmp_lt(float d1, float x1, float d2, float x2) {
-  return (fabs((double)(d1 - d2)) < 1e-10) ? (x1 < x2) : (d1 < d2);
+// PointType_CMP::operator< (ikd_Tree.h:102-108):  fabs(dist - a.dist) < 1e-10 ? point.x < a.point.x : dist < a.dist.
+// The reference promotes the float difference to double before comparing with 1e-10; 1e-10f rounds UP
+// (1.0000000134e-10), so for a float v:  (double)v < 1e-10  <=>  v < 1e-10f.  Pure-float compare, same truth table.
+struct HItem { float d, x; uint32_t i; };
+__device__ __forceinline__ bool h_lt(const HItem& a, const HItem& b) {
+  return (fabsf(a.d - b.d) < 1e-10f) ? (a.x < b.x) : (a.d < b.d);
 }
 
-// MANUAL_HEAP (ikd_Tree.h:111-201) of k=5 items per thread, kept in shared memory, [slot][thread] layout
-struct SmemHeap {
-  float (*d)[KNN_THREADS];
-  float (*x)[KNN_THREADS];
-  uint32_t (*i)[KNN_THREADS];
-  int t;
+// MANUAL_HEAP (ikd_Tree.h:111-201) specialised to capacity k = 5 and held in registers: slots h0..h4 with the
+// binary-heap shape {0:(1,2), 1:(3,4)}.  Each routine below is MoveDown / FloatUp written out for one heap size,
+// comparison for comparison, so the slot contents match the reference's array at every step.
+struct Heap5 {
+  HItem h0, h1, h2, h3, h4;
   int cnt;
-  __device__ __forceinline__ void pop() {   // heap[0] = heap[size-1]; size--; MoveDown(0)
-    const int n = cnt - 1;
-    const float td = d[n][t], tx = x[n][t];
-    const uint32_t ti = i[n][t];
-    int idx = 0, l = 1;
-    while (l < n) {
-      if (l + 1 < n && cmp_lt(d[l][t], x[l][t], d[l + 1][t], x[l + 1][t])) l++;
-      if (cmp_lt(td, tx, d[l][t], x[l][t])) {
-        d[idx][t] = d[l][t]; x[idx][t] = x[l][t]; i[idx][t] = i[l][t];
-        idx = l;
-        l = idx * 2 + 1;
-      } else
-        break;
+  // push while cnt < 5: heap[cnt] = p; FloatUp(cnt)
+  __device__ __forceinline__ void push_fill(const HItem& p) {
+    if (cnt == 0) { h0 = p; }
+    else if (cnt == 1) { if (h_lt(h0, p)) { h1 = h0; h0 = p; } else h1 = p; }
+    else if (cnt == 2) { if (h_lt(h0, p)) { h2 = h0; h0 = p; } else h2 = p; }
+    else if (cnt == 3) {
+      if (h_lt(h1, p)) { h3 = h1; if (h_lt(h0, p)) { h1 = h0; h0 = p; } else h1 = p; } else h3 = p;
+    } else {
+      if (h_lt(h1, p)) { h4 = h1; if (h_lt(h0, p)) { h1 = h0; h0 = p; } else h1 = p; } else h4 = p;
     }
-    d[idx][t] = td; x[idx][t] = tx; i[idx][t] = ti;
-    cnt = n;
-  }
-  __device__ __forceinline__ void push(float nd, float nx, uint32_t ni) {   // FloatUp
-    int idx = cnt;
-    while (idx > 0) {
-      const int anc = (idx - 1) / 2;
-      if (cmp_lt(d[anc][t], x[anc][t], nd, nx)) {
-        d[idx][t] = d[anc][t]; x[idx][t] = x[anc][t]; i[idx][t] = i[anc][t];
-        idx = anc;
-      } else
-        break;
-    }
-    d[idx][t] = nd; x[idx][t] = nx; i[idx][t] = ni;
     cnt++;
+  }
+  // pop() at size 5: heap[0] = heap[4]; size = 4; MoveDown(0)
+  __device__ __forceinline__ void pop5() {
+    const HItem tmp = h4;
+    const bool c12 = h_lt(h1, h2);            // l = 1; if (l+1 < 4 && heap[1] < heap[2]) l = 2
+    const HItem hl = c12 ? h2 : h1;
+    if (h_lt(tmp, hl)) {
+      h0 = hl;
+      if (c12) { h2 = tmp; }                  // idx = 2, l = 5 >= 4
+      else {                                  // idx = 1, l = 3 < 4, l+1 = 4 not < 4
+        if (h_lt(tmp, h3)) { h1 = h3; h3 = tmp; } else h1 = tmp;
+      }
+    } else h0 = tmp;
+    cnt = 4;
+  }
+  // steady state: pop() then push(p) with the heap full
+  __device__ __forceinline__ void replace_top(const HItem& p) {
+    pop5();
+    if (h_lt(h1, p)) { h4 = h1; if (h_lt(h0, p)) { h1 = h0; h0 = p; } else h1 = p; } else h4 = p;   // FloatUp(4)
+    cnt = 5;
+  }
+  __device__ __forceinline__ void pop4() {   // size 4 -> 3
+    const HItem tmp = h3;
+    const bool c12 = h_lt(h1, h2);            // l+1 = 2 < 3
+    const HItem hl = c12 ? h2 : h1;
+    if (h_lt(tmp, hl)) { h0 = hl; if (c12) h2 = tmp; else h1 = tmp; }   // next l = 3 or 5, both >= 3
+    else h0 = tmp;
+    cnt = 3;
+  }
+  __device__ __forceinline__ void pop3() {   // size 3 -> 2: l = 1 < 2, l+1 = 2 not < 2
+    const HItem tmp = h2;
+    if (h_lt(tmp, h1)) { h0 = h1; h1 = tmp; } else h0 = tmp;
+    cnt = 2;
+  }
+  __device__ __forceinline__ void pop2() { h0 = h1; cnt = 1; }   // size 2 -> 1: l = 1 not < 1
+  __device__ __forceinline__ void pop_any() {
+    if (cnt == 5) pop5(); else if (cnt == 4) pop4(); else if (cnt == 3) pop3(); else if (cnt == 2) pop2(); else cnt = 0;
   }
 };
 
-// One query per thread.  Traversal order, pruning and heap behaviour are exactly KD_TREE::Search's
-// (near child first when dist_left <= dist_right, strict '<' everywhere, first-visited wins ties), so the
-// returned index lists are the reference's, bit for bit.  The far child is kept on a per-thread stack
-// together with its box distance and re-tested against the then-current heap top when popped.
+// Exact emulation of one Nearest_Search call: KD_TREE::Search's traversal with the MANUAL_HEAP emulated slot
+// for slot.  Used for the (rare) queries on which the fast path below saw a tie hazard.
+__device__ __noinline__ void knn_exact_query(const float4* __restrict__ nodes, float qx, float qy, float qz,
+                                             uint32_t oi[MALIO_K], float od[MALIO_K], int& found_out) {
+  Heap5 hp;
+  hp.cnt = 0;
+  hp.h0 = hp.h1 = hp.h2 = hp.h3 = hp.h4 = HItem{INFINITY, 0.f, 0xFFFFFFFFu};
+  uint32_t st_n[MALIO_MAX_TREE_DEPTH];
+  float st_d[MALIO_MAX_TREE_DEPTH];
+  int sp = 0;
+  float top = INFINITY;           // q.top().dist once the heap holds k items; +inf (accept all) before
+  uint32_t cur = 0;
+  bool go = true;
+  while (go) {
+    const float4* nd = nodes + 4 * (size_t)cur;
+    const float4 a = __ldg(nd), b4 = __ldg(nd + 1), c4 = __ldg(nd + 2), d4 = __ldg(nd + 3);
+    const uint32_t link = __float_as_uint(a.w);
+    if (!(link & MALIO_LINK_POINT_DELETED)) {
+      const float dist = (qx - a.x) * (qx - a.x) + (qy - a.y) * (qy - a.y) + (qz - a.z) * (qz - a.z);
+      if (hp.cnt < MALIO_K) {
+        hp.push_fill(HItem{dist, a.x, cur});
+        if (hp.cnt == MALIO_K) top = hp.h0.d;
+      } else if (dist < top) {
+        hp.replace_top(HItem{dist, a.x, cur});
+        top = hp.h0.d;
+      }
+    }
+    const bool hl = link & MALIO_LINK_HAS_LEFT, hr = link & MALIO_LINK_HAS_RIGHT;
+    const float dl = hl ? box_dist(qx, qy, qz, b4.x, b4.y, b4.z, b4.w, c4.x, c4.y) : INFINITY;
+    const float dr = hr ? box_dist(qx, qy, qz, c4.z, c4.w, d4.x, d4.y, d4.z, d4.w) : INFINITY;
+    const uint32_t li = cur + 1, ri = link & MALIO_LINK_INDEX_MASK;
+    const bool left_first = dl <= dr;
+    const uint32_t n_near = left_first ? li : ri, n_far = left_first ? ri : li;
+    const float d_near = left_first ? dl : dr, d_far = left_first ? dr : dl;
+    if (d_far < top) { st_n[sp] = n_far; st_d[sp] = d_far; sp++; }
+    if (d_near < top) { cur = n_near; continue; }
+    go = false;
+    while (sp > 0) {
+      --sp;
+      if (st_d[sp] < top) { cur = st_n[sp]; go = true; break; }
+    }
+  }
+  const int found = hp.cnt;
+#pragma unroll
+  for (int j = MALIO_K - 1; j >= 0; --j) {
+    if (j < found) { oi[j] = hp.h0.i; od[j] = hp.h0.d; hp.pop_any(); }
+    else { oi[j] = 0xFFFFFFFFu; od[j] = INFINITY; }
+  }
+  found_out = found;
+}
+
+// One query per active lane.  Traversal order and pruning are exactly KD_TREE::Search's (near child first
+// when dist_left <= dist_right, strict '<' everywhere, first-visited wins), the far child waits on a
+// per-thread stack with its box distance and is re-tested against the then-current k-th distance when popped.
+//
+// Fast path / exact path.  The reference keeps candidates in a binary max-heap ordered by PointType_CMP.  As long
+// as no two candidates held at the same time have |d_a - d_b| < 1e-10 (in particular no equal distances), that
+// comparator is the plain order on d, the heap is a priority queue over a strict total order, and its
+// observable behaviour (top().dist, what pop() evicts, the ascending output) is that of a sorted list.  The fast
+// path keeps the 5 best in registers sorted by d, checks every accepted candidate against the 5 held distances
+// for the 1e-10 window, and on a hit re-runs that query through knn_exact_query (slot-for-slot heap emulation).
+// Results are therefore the reference's, bit for bit, in every case; hazards are ~1e-6 per query on jittered data.
+//
+// Only the first `lanes` lanes of every warp carry a query (narrow logical warps for very small N).
 //   MODE 0: queries come from the scan (transform with pc), also writes world + the k-NN gate
 //   MODE 1: stand-alone queries (world-frame float3), no gate
-template <int MODE>
+// Traversal stack: SMEM_STACK = true keeps it in shared memory ([depth][thread] layout, 8 B entries; snapshots up to
+// KNN_SMEM_DEPTH-1 levels deep) — the unwinding loop is a chain of dependent stack reads, and in local memory those
+// reads fall out of L1 behind the node traffic and cost an L2 round trip each; SMEM_STACK = false is the
+// local-memory fallback for deeper trees.
+struct StackEnt { uint32_t n; float d; };
+constexpr int KNN_SMEM_DEPTH = 32;
+template <int MODE, bool SMEM_STACK>
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const malio_scan_pt* __restrict__ pts,
-           const uint32_t* __restrict__ perm, const float* __restrict__ queries, uint32_t N, PassConst pc,
+           const uint32_t* __restrict__ perm, const float* __restrict__ queries, uint32_t N, int lanes, PassConst pc,
            float max_sqdist, float4* __restrict__ world, uint32_t* __restrict__ nn_idx,
            float* __restrict__ nn_d2, uint8_t* __restrict__ sel) {
-  __shared__ float s_d[MALIO_K][KNN_THREADS];
-  __shared__ float s_x[MALIO_K][KNN_THREADS];
-  __shared__ uint32_t s_i[MALIO_K][KNN_THREADS];
-  const uint32_t p = blockIdx.x * KNN_THREADS + threadIdx.x;
-  if (p >= N) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * KNN_THREADS + threadIdx.x) >> 5;
+  const uint32_t p = warp * (uint32_t)lanes + lane;
+  const bool valid = ((int)lane < lanes) && (p < N);
+  const unsigned wmask = __ballot_sync(0xffffffffu, valid);
+  if (!valid) return;
   float qx, qy, qz;
   if (MODE == 0) {
     const malio_scan_pt pt = pts[perm ? perm[p] : p];
@@ -190,57 +281,73 @@ knn_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const malio_scan_
     const uint32_t src = perm ? perm[p] : p;
     qx = queries[3 * (size_t)src]; qy = queries[3 * (size_t)src + 1]; qz = queries[3 * (size_t)src + 2];
   }
-  SmemHeap hp{s_d, s_x, s_i, (int)threadIdx.x, 0};
-  uint32_t st_n[MALIO_MAX_TREE_DEPTH];
-  float st_d[MALIO_MAX_TREE_DEPTH];
-  int sp = 0;
-  float top = INFINITY;           // q.top().dist once the heap holds k items
-  uint32_t cur = 0;
-  bool go = n_nodes > 0;
-  while (go) {
-    const float4* nd = nodes + 4 * (size_t)cur;
-    const float4 a = __ldg(nd), b4 = __ldg(nd + 1), c4 = __ldg(nd + 2), d4 = __ldg(nd + 3);
-    const uint32_t link = __float_as_uint(a.w);
-    if (!(link & MALIO_LINK_POINT_DELETED)) {
-      // calc_dist (ikd_Tree.cpp:1694-1699)
-      const float dist = (qx - a.x) * (qx - a.x) + (qy - a.y) * (qy - a.y) + (qz - a.z) * (qz - a.z);
-      if (hp.cnt < MALIO_K || dist < top) {
-        if (hp.cnt >= MALIO_K) hp.pop();
-        hp.push(dist, a.x, cur);
-        if (hp.cnt == MALIO_K) top = s_d[0][threadIdx.x];
-      }
-    }
-    const bool hl = link & MALIO_LINK_HAS_LEFT, hr = link & MALIO_LINK_HAS_RIGHT;
-    const float dl = hl ? box_dist(qx, qy, qz, b4.x, b4.y, b4.z, b4.w, c4.x, c4.y) : INFINITY;
-    const float dr = hr ? box_dist(qx, qy, qz, c4.z, c4.w, d4.x, d4.y, d4.z, d4.w) : INFINITY;
-    const uint32_t li = cur + 1, ri = link & MALIO_LINK_INDEX_MASK;
-    const bool left_first = dl <= dr;
-    const uint32_t n_near = left_first ? li : ri, n_far = left_first ? ri : li;
-    const float d_near = left_first ? dl : dr, d_far = left_first ? dr : dl;
-    const bool p_near = left_first ? hl : hr, p_far = left_first ? hr : hl;
-    const bool open = hp.cnt < MALIO_K;
-    if (p_far && (open || d_far < top)) { st_n[sp] = n_far; st_d[sp] = d_far; sp++; }
-    if (p_near && (open || d_near < top)) { cur = n_near; continue; }
-    go = false;
-    while (sp > 0) {
-      --sp;
-      if (hp.cnt < MALIO_K || st_d[sp] < top) { cur = st_n[sp]; go = true; break; }
-    }
-  }
-  // Nearest_Search (ikd_Tree.cpp:451-459): pop into ascending order
-  const int found = hp.cnt;
   uint32_t oi[MALIO_K];
   float od[MALIO_K];
-#pragma unroll
-  for (int j = MALIO_K - 1; j >= 0; --j) {
-    if (j < found) {
-      oi[j] = s_i[0][threadIdx.x];
-      od[j] = s_d[0][threadIdx.x];
-      hp.pop();
-    } else {
-      oi[j] = 0xFFFFFFFFu;
-      od[j] = INFINITY;
+  int found = 0;
+  if (n_nodes > 0) {
+    // 5 best so far, ascending; +inf sentinels make the fill phase (q.size() < k) the same code path
+    float d0 = INFINITY, d1 = INFINITY, d2 = INFINITY, d3 = INFINITY, d4 = INFINITY;
+    uint32_t i0 = 0xFFFFFFFFu, i1 = 0xFFFFFFFFu, i2 = 0xFFFFFFFFu, i3 = 0xFFFFFFFFu, i4 = 0xFFFFFFFFu;
+    bool hazard = false;
+    __shared__ uint2 s_stack[SMEM_STACK ? KNN_SMEM_DEPTH * KNN_THREADS : 1];
+    uint2 l_stack[SMEM_STACK ? 1 : MALIO_MAX_TREE_DEPTH + 1];
+#define ST(k) (SMEM_STACK ? s_stack[(k) * KNN_THREADS + threadIdx.x] : l_stack[(k)])
+    ST(0) = make_uint2(0xFFFFFFFFu, __float_as_uint(-1.0f));   // sentinel: always passes `d < top`, ends the traversal
+    int sp = 1;
+    uint32_t cur = 0;
+    bool done = false;
+    // One node visit per iteration for every unfinished lane; the vote at the bottom makes the warp reconverge
+    // each iteration (lanes that descend would otherwise run ahead of lanes that are unwinding their stack).
+    for (;;) {
+     if (!done) {
+      const float4* nd = nodes + 4 * (size_t)cur;
+      const float4 a = __ldg(nd), b4 = __ldg(nd + 1), c4 = __ldg(nd + 2), e4 = __ldg(nd + 3);
+      const uint32_t link = __float_as_uint(a.w);
+      // calc_dist (ikd_Tree.cpp:1694-1699)
+      const float dist = (qx - a.x) * (qx - a.x) + (qy - a.y) * (qy - a.y) + (qz - a.z) * (qz - a.z);
+      // both children's box distances, unconditionally (absent children carry a zero box and are masked below):
+      // straight-line code lets the box arithmetic overlap the candidate insertion instead of sitting behind branches
+      const float bl = box_dist(qx, qy, qz, b4.x, b4.y, b4.z, b4.w, c4.x, c4.y);
+      const float br = box_dist(qx, qy, qz, c4.z, c4.w, e4.x, e4.y, e4.z, e4.w);
+      // candidate: accepted iff the point is live and dist < k-th best (d4 == +inf while q.size() < k).
+      // Branch-free sorted insertion; with acc == false every select keeps its old value.
+      const bool acc = !(link & MALIO_LINK_POINT_DELETED) && (dist < d4);
+      hazard |= acc & ((fabsf(dist - d0) < 1e-10f) | (fabsf(dist - d1) < 1e-10f) | (fabsf(dist - d2) < 1e-10f) |
+                       (fabsf(dist - d3) < 1e-10f) | (fabsf(dist - d4) < 1e-10f));
+      const bool c0 = acc & (dist < d0), c1 = acc & (dist < d1), c2 = acc & (dist < d2), c3 = acc & (dist < d3);
+      d4 = acc ? (c3 ? d3 : dist) : d4;   i4 = acc ? (c3 ? i3 : cur) : i4;
+      d3 = c3 ? (c2 ? d2 : dist) : d3;    i3 = c3 ? (c2 ? i2 : cur) : i3;
+      d2 = c2 ? (c1 ? d1 : dist) : d2;    i2 = c2 ? (c1 ? i1 : cur) : i2;
+      d1 = c1 ? (c0 ? d0 : dist) : d1;    i1 = c1 ? (c0 ? i0 : cur) : i1;
+      d0 = c0 ? dist : d0;                i0 = c0 ? cur : i0;
+      const float dl = (link & MALIO_LINK_HAS_LEFT) ? bl : INFINITY;
+      const float dr = (link & MALIO_LINK_HAS_RIGHT) ? br : INFINITY;
+      const uint32_t li = cur + 1, ri = link & MALIO_LINK_INDEX_MASK;
+      const bool left_first = dl <= dr;
+      const uint32_t n_near = left_first ? li : ri, n_far = left_first ? ri : li;
+      const float d_near = left_first ? dl : dr, d_far = left_first ? dr : dl;
+      // d4 == +inf while fewer than k are held, so `d < d4` also covers `q.size() < k` for present children
+      if (d_far < d4) { ST(sp) = make_uint2(n_far, __float_as_uint(d_far)); sp++; }
+      if (d_near < d4) { cur = n_near; }
+      else {
+        uint2 e;
+        do { --sp; e = ST(sp); } while (!(__uint_as_float(e.y) < d4));
+        cur = e.x;
+        done = (e.x == 0xFFFFFFFFu);
+      }
+     }
+     if (__all_sync(wmask, done)) break;
     }
+    if (!hazard) {
+      oi[0] = i0; oi[1] = i1; oi[2] = i2; oi[3] = i3; oi[4] = i4;
+      od[0] = d0; od[1] = d1; od[2] = d2; od[3] = d3; od[4] = d4;
+      found = (i0 != 0xFFFFFFFFu) + (i1 != 0xFFFFFFFFu) + (i2 != 0xFFFFFFFFu) + (i3 != 0xFFFFFFFFu) + (i4 != 0xFFFFFFFFu);
+    } else {
+      knn_exact_query(nodes, qx, qy, qz, oi, od, found);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < MALIO_K; ++j) { oi[j] = 0xFFFFFFFFu; od[j] = INFINITY; }
   }
 #pragma unroll
   for (int j = 0; j < MALIO_K; ++j) {
@@ -248,6 +355,7 @@ knn_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const malio_scan_
     nn_d2[(size_t)j * N + p] = od[j];
   }
   if (MODE == 0) sel[p] = (found < MALIO_K) ? 0 : (od[MALIO_K - 1] > max_sqdist ? 0 : 1);   // laserMapping.cpp:587
+#undef ST
 }
 
 // ------------------------------------------------------------------ Morton keys for query coherence (internal order only)
@@ -408,23 +516,26 @@ __device__ __forceinline__ void qr_solve_5x3(float A[5][3], float x[3]) {
 // trace of evalPointUncertainty's 3x3 (associate_uct.hpp:153-175) in closed form:
 //   G = [ q_w I | -[q]x | T(0:3,0:3) ], q = T (0.05 p, 1);  Sigma_in = blkdiag(1e4 cov, 0.1 I)
 //   trace = sum_{i<3} (F (1e4 cov) F^T)_ii + 0.1 |T(0:3,0:3)|_F^2,  F = [ q_w I | -[q]x ]
+// Row i of F has three non-zeros, so (F S F^T)_ii is a 3x3 quadratic form: 27 terms instead of the dense 9x9
+// product.  `e` is one table entry as uploaded: T (16) then cov (36).
 __device__ __forceinline__ double point_cov_trace(float px, float py, float pz, const double* __restrict__ e) {
   const double pc0 = px * 0.05, pc1 = py * 0.05, pc2 = pz * 0.05;
   double q[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) q[i] = e[4 * i] * pc0 + e[4 * i + 1] * pc1 + e[4 * i + 2] * pc2 + e[4 * i + 3] * 1.0;
-  // F rows (3x6): [q3 0 0 | 0 q2 -q1], [0 q3 0 | -q2 0 q0], [0 0 q3 | q1 -q0 0]   (-skew(q))
-  double F[3][6] = {{q[3], 0, 0, 0, q[2], -q[1]}, {0, q[3], 0, -q[2], 0, q[0]}, {0, 0, q[3], q[1], -q[0], 0}};
   const double* cov = e + 16;
+  // non-zero columns / values of the rows of F = [q3 I | -skew(q)]
+  const int col[3][3] = {{0, 4, 5}, {1, 3, 5}, {2, 3, 4}};
+  const double val[3][3] = {{q[3], q[2], -q[1]}, {q[3], -q[2], q[0]}, {q[3], q[1], -q[0]}};
   double tr = 0.0;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      double m = 0.0;   // (F cov)_ij
+    for (int a = 0; a < 3; ++a) {
+      double m = 0.0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) m += F[i][k] * (cov[6 * k + j] * 10000.0);
-      tr += m * F[i][j];
+      for (int b = 0; b < 3; ++b) m += val[i][b] * (cov[6 * col[i][b] + col[i][a]] * 10000.0);
+      tr += m * val[i][a];
     }
   }
   double fro = 0.0;
@@ -436,6 +547,19 @@ __device__ __forceinline__ double point_cov_trace(float px, float py, float pz, 
 }
 
 struct MinMax4 { double umin, umax, tmin, tmax; uint32_t cnt; };
+
+// order-preserving map double <-> uint64 (so that min/max can use integer atomics: exact and order-independent)
+__host__ __device__ __forceinline__ unsigned long long dkey(double v) {
+  unsigned long long b;
+  memcpy(&b, &v, 8);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double dkey_inv(unsigned long long k) {
+  const unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+  double v;
+  memcpy(&v, &b, 8);
+  return v;
+}
 
 __device__ __forceinline__ MinMax4 warp_reduce(MinMax4 v) {
 #pragma unroll
@@ -449,125 +573,126 @@ __device__ __forceinline__ MinMax4 warp_reduce(MinMax4 v) {
   return v;
 }
 
-// d_mm layout: {min_u, -max_u, min_tau, -max_tau} so that one MIN all-reduce serves all four
+// ---- K2a (search passes only): plane fit of the 5 neighbours.  esti_plane depends on the neighbours alone, not on
+// the state, so its result is computed once per search and reused by the passes that re-use Nearest_Points
+// (the reference recomputes it every pass, laserMapping.cpp:596, with the same outcome).
+//   plane[p] = (n_x, n_y, n_z, d) ;  ucov[p] = plane_cov ;  sel[p] &= plane ok
 __global__ void __launch_bounds__(PLANE_THREADS)
-plane_kernel(const float4* __restrict__ nodes, const float* __restrict__ node_cov,
-             const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t N, PassConst pc,
-             ParamConst prm, const double* __restrict__ table, const uint32_t* __restrict__ nn_idx,
-             uint8_t* __restrict__ sel, float4* __restrict__ world, float4* __restrict__ plane,
-             double* __restrict__ ucov, double* __restrict__ tau, float* __restrict__ normal_y,
-             double* __restrict__ block_mm, uint32_t* __restrict__ block_cnt, uint32_t* __restrict__ counter,
-             double* __restrict__ d_mm, uint32_t* __restrict__ d_cnt) {
+fit_kernel(const float4* __restrict__ nodes, const float* __restrict__ node_cov, uint32_t N, ParamConst prm,
+           const uint32_t* __restrict__ nn_idx, uint8_t* __restrict__ sel, float4* __restrict__ plane,
+           double* __restrict__ ucov) {
   const uint32_t p = blockIdx.x * PLANE_THREADS + threadIdx.x;
+  if (p >= N || !sel[p]) return;
+  float A[5][3], W[5];
+#pragma unroll
+  for (int j = 0; j < MALIO_K; ++j) {
+    const uint32_t idx = nn_idx[(size_t)j * N + p];
+    const float4 a = __ldg(nodes + 4 * (size_t)idx);
+    A[j][0] = a.x; A[j][1] = a.y; A[j][2] = a.z;
+    W[j] = __ldg(node_cov + idx);
+  }
+  // esti_plane (common_lib.h:144-190)
+  double cov_sum = 0.0, unit_cov = 0.0;
+#pragma unroll
+  for (int j = 0; j < MALIO_K; ++j) cov_sum += fabs(prm.cov_threshold - (double)W[j]);
+  if ((double)W[0] > 0.00001) {
+#pragma unroll
+    for (int j = 0; j < MALIO_K; ++j)
+      unit_cov += ((prm.cov_threshold - (double)W[j]) / cov_sum) * ((prm.cov_threshold - (double)W[j]) / cov_sum) * (double)W[j];
+  }
+  float Aq[5][3];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) { Aq[j][0] = A[j][0]; Aq[j][1] = A[j][1]; Aq[j][2] = A[j][2]; }
+  float nv[3];
+  qr_solve_5x3(Aq, nv);
+  const float n = sqrtf(nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2]);
+  const float pa = nv[0] / n, pb = nv[1] / n, pcn = nv[2] / n;
+  const float pd = (float)(1.0 / (double)n);
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < MALIO_K; ++j)
+    if (fabsf(pa * A[j][0] + pb * A[j][1] + pcn * A[j][2] + pd) > prm.plane_th) ok = false;
+  plane[p] = make_float4(pa, pb, pcn, pd);
+  ucov[p] = unit_cov;
+  if (!ok) sel[p] = 0;
+}
+
+// ---- K2b (once per scan): point-wise uncertainty.  evalPointUncertainty depends on the point and its table entry
+// only; the entry index is clamped differently for selected (:694-696) and non-selected (:737-739) points, so both
+// traces are kept:  tau2[p] = (tau_selected, tau_not_selected).
+__global__ void __launch_bounds__(PLANE_THREADS)
+tau_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t N, PassConst pc,
+           const double* __restrict__ table, double2* __restrict__ tau2) {
+  const uint32_t p = blockIdx.x * PLANE_THREADS + threadIdx.x;
+  if (p >= N) return;
+  const malio_scan_pt pt = pts[perm ? perm[p] : p];
+  const int lid = pt.lidar;
+  const int tsize = (int)(pc.table_off[lid + 1] - pc.table_off[lid]);
+  const int ti = (int)pt.table_idx;
+  const int ti_sel = (ti >= tsize) ? tsize - 2 : ti;
+  const int ti_non = (ti >= tsize - 1) ? tsize - 2 : ti;
+  const double t_sel = point_cov_trace(pt.x, pt.y, pt.z, table + (size_t)(pc.table_off[lid] + ti_sel) * TABLE_DOUBLES);
+  const double t_non = (ti_non == ti_sel) ? t_sel
+                       : point_cov_trace(pt.x, pt.y, pt.z, table + (size_t)(pc.table_off[lid] + ti_non) * TABLE_DOUBLES);
+  tau2[p] = make_double2(t_sel, t_non);
+}
+
+// ---- K2c (every pass): transform, point-to-plane residual, residual gate, min/max of the two weights.
+// d_mmkey layout: dkey of {min_u, -max_u, min_tau, -max_tau}: one (integer) MIN all-reduce serves all four
+__global__ void __launch_bounds__(GATE_THREADS)
+gate_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t N, PassConst pc,
+            const float4* __restrict__ plane, const double* __restrict__ ucov, const double2* __restrict__ tau2,
+            uint8_t* __restrict__ sel, float4* __restrict__ world, float* __restrict__ pd2_out,
+            double* __restrict__ tau, float* __restrict__ normal_y,
+            unsigned long long* __restrict__ d_mmkey, uint32_t* __restrict__ d_cnt) {
+  const uint32_t p = blockIdx.x * GATE_THREADS + threadIdx.x;
   MinMax4 mm{1000.0, 0.0, 9999.0, 0.0, 0u};   // laserMapping.cpp:615-616, 646-647
   if (p < N) {
     const malio_scan_pt pt = pts[perm ? perm[p] : p];
-    const int lid = pt.lidar;
     double b[3], m[3], g[3];
-    transform_point(pc, pt.x, pt.y, pt.z, lid, b, m, g);
+    transform_point(pc, pt.x, pt.y, pt.z, pt.lidar, b, m, g);
     const float wx = (float)g[0], wy = (float)g[1], wz = (float)g[2];
     world[p] = make_float4(wx, wy, wz, 0.f);
     bool selected = sel[p] != 0;
-    double unit_cov = 0.0;
     if (selected) {
-      selected = false;
-      float A[5][3], W[5];
-#pragma unroll
-      for (int j = 0; j < MALIO_K; ++j) {
-        const uint32_t idx = nn_idx[(size_t)j * N + p];
-        const float4 a = __ldg(nodes + 4 * (size_t)idx);
-        A[j][0] = a.x; A[j][1] = a.y; A[j][2] = a.z;
-        W[j] = __ldg(node_cov + idx);
-      }
-      // esti_plane (common_lib.h:144-190)
-      double cov_sum = 0.0;
-#pragma unroll
-      for (int j = 0; j < MALIO_K; ++j) cov_sum += fabs(prm.cov_threshold - (double)W[j]);
-      if ((double)W[0] > 0.00001) {
-#pragma unroll
-        for (int j = 0; j < MALIO_K; ++j)
-          unit_cov += ((prm.cov_threshold - (double)W[j]) / cov_sum) * ((prm.cov_threshold - (double)W[j]) / cov_sum) * (double)W[j];
-      }
-      float Aq[5][3];
-#pragma unroll
-      for (int j = 0; j < 5; ++j) { Aq[j][0] = A[j][0]; Aq[j][1] = A[j][1]; Aq[j][2] = A[j][2]; }
-      float nv[3];
-      qr_solve_5x3(Aq, nv);
-      const float n = sqrtf(nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2]);
-      const float pa = nv[0] / n, pb = nv[1] / n, pcn = nv[2] / n;
-      const float pd = (float)(1.0 / (double)n);
-      bool ok = true;
-#pragma unroll
-      for (int j = 0; j < MALIO_K; ++j)
-        if (fabsf(pa * A[j][0] + pb * A[j][1] + pcn * A[j][2] + pd) > prm.plane_th) ok = false;
-      if (ok) {
-        const float pd2 = pa * wx + pb * wy + pcn * wz + pd;                        // laserMapping.cpp:598
-        const double nb = sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
-        const float s = (float)(1 - 0.9 * (double)fabsf(pd2) / sqrt(nb));          // :599
-        if ((double)s > 0.1) {
-          selected = true;
-          plane[p] = make_float4(pa, pb, pcn, pd2);
-          ucov[p] = unit_cov;
-        }
-      }
+      const float4 pl = plane[p];
+      const float pd2 = pl.x * wx + pl.y * wy + pl.z * wz + pl.w;                  // laserMapping.cpp:598
+      const double nb = sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+      const float s = (float)(1 - 0.9 * (double)fabsf(pd2) / sqrt(nb));           // :599
+      selected = (double)s > 0.1;
+      pd2_out[p] = pd2;
+      if (!selected) sel[p] = 0;
     }
-    sel[p] = selected ? 1 : 0;
-    // point-wise uncertainty: selected points use the :694-696 clamp, the others :737-739
-    const int tsize = (int)(pc.table_off[lid + 1] - pc.table_off[lid]);
-    int ti = (int)pt.table_idx;
-    if (selected) { if (ti >= tsize) ti = tsize - 2; }
-    else { if (ti >= tsize - 1) ti = tsize - 2; }
-    if (!selected || pc.ext_en) {
-      const double tr = point_cov_trace(pt.x, pt.y, pt.z, table + (size_t)(pc.table_off[lid] + ti) * TABLE_DOUBLES);
-      tau[p] = tr;
-      normal_y[p] = (float)tr;
-      if (selected) { mm.tmin = fmin(mm.tmin, tr); mm.tmax = fmax(mm.tmax, tr); }
+    const double2 t2 = tau2[p];
+    if (selected) {
+      const double u = ucov[p];
+      mm.umin = fmin(mm.umin, u); mm.umax = fmax(mm.umax, u); mm.cnt = 1;
+      if (pc.ext_en) {   // :694-703; with extrinsic_est_en == false R and normal_y are left untouched
+        tau[p] = t2.x;
+        normal_y[p] = (float)t2.x;
+        mm.tmin = fmin(mm.tmin, t2.x); mm.tmax = fmax(mm.tmax, t2.x);
+      }
+    } else {
+      normal_y[p] = (float)t2.y;   // :735-741
     }
-    if (selected) { mm.umin = fmin(mm.umin, unit_cov); mm.umax = fmax(mm.umax, unit_cov); mm.cnt = 1; }
   }
-  // block reduction -> per-block slot; the last block to finish folds all slots (deterministic order)
-  __shared__ MinMax4 s_w[PLANE_THREADS / 32];
-  __shared__ bool s_last;
+  // block reduction, then one integer atomicMin per quantity and block on the order-preserving keys:
+  // min/max are exact under any ordering, so this is deterministic without a serial fold.
+  __shared__ MinMax4 s_w[GATE_THREADS / 32];
   mm = warp_reduce(mm);
   if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = mm;
   __syncthreads();
   if (threadIdx.x == 0) {
     MinMax4 r = s_w[0];
-    for (int w = 1; w < PLANE_THREADS / 32; ++w) {
+    for (int w = 1; w < GATE_THREADS / 32; ++w) {
       r.umin = fmin(r.umin, s_w[w].umin); r.umax = fmax(r.umax, s_w[w].umax);
       r.tmin = fmin(r.tmin, s_w[w].tmin); r.tmax = fmax(r.tmax, s_w[w].tmax);
       r.cnt += s_w[w].cnt;
     }
-    double* o = block_mm + 4 * (size_t)blockIdx.x;
-    o[0] = r.umin; o[1] = r.umax; o[2] = r.tmin; o[3] = r.tmax;
-    block_cnt[blockIdx.x] = r.cnt;
-    __threadfence();
-    const uint32_t done = atomicAdd(counter, 1u);
-    s_last = (done == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    MinMax4 r{1000.0, 0.0, 9999.0, 0.0, 0u};
-    for (uint32_t bk = threadIdx.x; bk < gridDim.x; bk += PLANE_THREADS) {
-      const double* o = block_mm + 4 * (size_t)bk;
-      r.umin = fmin(r.umin, __ldcg(o)); r.umax = fmax(r.umax, __ldcg(o + 1));
-      r.tmin = fmin(r.tmin, __ldcg(o + 2)); r.tmax = fmax(r.tmax, __ldcg(o + 3));
-      r.cnt += __ldcg(block_cnt + bk);
-    }
-    r = warp_reduce(r);
-    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = r;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      MinMax4 f = s_w[0];
-      for (int w = 1; w < PLANE_THREADS / 32; ++w) {
-        f.umin = fmin(f.umin, s_w[w].umin); f.umax = fmax(f.umax, s_w[w].umax);
-        f.tmin = fmin(f.tmin, s_w[w].tmin); f.tmax = fmax(f.tmax, s_w[w].tmax);
-        f.cnt += s_w[w].cnt;
-      }
-      d_mm[0] = f.umin; d_mm[1] = -f.umax; d_mm[2] = f.tmin; d_mm[3] = -f.tmax;
-      *d_cnt = f.cnt;
-      *counter = 0;
+    if (r.cnt) {
+      atomicMin(d_mmkey + 0, dkey(r.umin)); atomicMin(d_mmkey + 1, dkey(-r.umax));
+      atomicMin(d_mmkey + 2, dkey(r.tmin)); atomicMin(d_mmkey + 3, dkey(-r.tmax));
+      atomicAdd(d_cnt, r.cnt);
     }
   }
 }
@@ -580,13 +705,14 @@ plane_kernel(const float4* __restrict__ nodes, const float* __restrict__ node_co
 __device__ __forceinline__ bool build_row(uint32_t p, uint32_t N, const malio_scan_pt* __restrict__ pts,
                                           const uint32_t* __restrict__ perm, const PassConst& pc,
                                           const ParamConst& prm, const uint8_t* __restrict__ sel,
-                                          const float4* __restrict__ plane, const double* __restrict__ ucov,
-                                          const double* __restrict__ tau, const double* __restrict__ d_mm,
+                                          const float4* __restrict__ plane, const float* __restrict__ pd2v,
+                                          const double* __restrict__ ucov,
+                                          const double* __restrict__ tau, const unsigned long long* __restrict__ d_mm,
                                           double r[24], double& z, double& rho) {
   if (p >= N || !sel[p]) return false;
   const malio_scan_pt pt = pts[perm ? perm[p] : p];
   const int lid = pt.lidar;
-  const double umin = d_mm[0], umax = -d_mm[1], tmin = d_mm[2], tmax = -d_mm[3];
+  const double umin = dkey_inv(d_mm[0]), umax = -dkey_inv(d_mm[1]), tmin = dkey_inv(d_mm[2]), tmax = -dkey_inv(d_mm[3]);
   // :651-656
   double a = ucov[p];
   if (a == 0) a = 1;
@@ -645,7 +771,7 @@ __device__ __forceinline__ bool build_row(uint32_t p, uint32_t N, const malio_sc
   rho = R;
 #pragma unroll
   for (int k = 0; k < 24; ++k) r[k] = r[k] * a;   // :714
-  z = ((-1) * (double)pl.w) * a;                  // :707,715
+  z = ((-1) * (double)pd2v[p]) * a;               // :707,715
   return true;
 }
 
@@ -663,8 +789,8 @@ __device__ __forceinline__ void red_task(int t, int& gi, int& gj) {
 __global__ void __launch_bounds__(RED_THREADS)
 reduce_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t N, PassConst pc,
               ParamConst prm, const uint8_t* __restrict__ sel, const float4* __restrict__ plane,
-              const double* __restrict__ ucov, const double* __restrict__ tau, const double* __restrict__ d_mm,
-              uint32_t n_tiles, double* __restrict__ block_red, uint32_t* __restrict__ counter,
+              const float* __restrict__ pd2v, const double* __restrict__ ucov, const double* __restrict__ tau,
+              const unsigned long long* __restrict__ d_mm, uint32_t n_tiles, double* __restrict__ block_red, uint32_t* __restrict__ counter,
               double* __restrict__ d_res) {
   extern __shared__ double smem[];
   double* s_hs = smem;                                   // [128][26]  h / rho^
@@ -679,13 +805,14 @@ reduce_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict_
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t p = tile * RED_THREADS + threadIdx.x;
     double r[24], z = 0.0, rho = 1.0;
-    const bool ok = build_row(p, N, pts, perm, pc, prm, sel, plane, ucov, tau, d_mm, r, z, rho);
+    const bool ok = build_row(p, N, pts, perm, pc, prm, sel, plane, pd2v, ucov, tau, d_mm, r, z, rho);
     double* hs = s_hs + threadIdx.x * RED_HS_STRIDE;
     double* hx = s_hx + threadIdx.x * RED_HX_STRIDE;
     if (ok) {
       cnt++;
+      const double inv_rho = 1.0 / rho;   // HT(:,i) / R_i (esekfom.hpp:627) as a multiply: <= 1 ulp per term
 #pragma unroll
-      for (int k = 0; k < 24; ++k) { hs[k] = r[k] / rho; hx[k] = r[k]; }
+      for (int k = 0; k < 24; ++k) { hs[k] = r[k] * inv_rho; hx[k] = r[k]; }
       hx[24] = z; hx[25] = rho * r[0]; hx[26] = rho * r[1]; hx[27] = rho * r[2];
     } else {
 #pragma unroll
@@ -716,7 +843,6 @@ reduce_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict_
   }
   // selected-point count of this block
   __shared__ uint32_t s_cnt[RED_THREADS / 32];
-  __shared__ bool s_last;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
@@ -731,28 +857,35 @@ reduce_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict_
     for (int w = 0; w < RED_THREADS / 32; ++w) c += s_cnt[w];
     slot[MALIO_RED_BLOCKS * 16] = (double)c;
     slot[MALIO_RED_BLOCKS * 16 + 1] = 0.0;
-    __threadfence();
-    const uint32_t done = atomicAdd(counter, 1u);
-    s_last = (done == gridDim.x - 1);
   }
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    for (int e = threadIdx.x; e < MALIO_RED_DOUBLES; e += RED_THREADS) {
-      double s = 0.0;
-      for (uint32_t bk = 0; bk < gridDim.x; ++bk) s += __ldcg(block_red + (size_t)bk * MALIO_RED_DOUBLES + e);
-      d_res[e] = s;
-    }
-    if (threadIdx.x == 0) *counter = 0;
+}
+
+// second stage: one warp per entry of the reduced system folds the per-block slots in a fixed order
+// (lane-strided partial sums, then a shuffle tree) -> bit-reproducible result, no FP64 atomics
+__global__ void __launch_bounds__(256)
+fold_kernel(const double* __restrict__ block_red, uint32_t n_slots, double* __restrict__ d_res,
+            unsigned long long* __restrict__ next_mmkey, uint32_t* __restrict__ next_cnt) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {   // arm the other parity's min/max cell for the next pass
+    next_mmkey[0] = dkey(1000.0); next_mmkey[1] = dkey(-0.0);    // laserMapping.cpp:615-616
+    next_mmkey[2] = dkey(9999.0); next_mmkey[3] = dkey(-0.0);    // :646-647
+    *next_cnt = 0;
   }
+  const uint32_t e = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (e >= MALIO_RED_DOUBLES) return;
+  double s = 0.0;
+  for (uint32_t bk = lane; bk < n_slots; bk += 32) s += block_red[(size_t)bk * MALIO_RED_DOUBLES + e];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) d_res[e] = s;
 }
 
 // rows for the degenerate branch (esekfom.hpp:574-582): positions of the first `cap` selected points are
 // found by one block; rows are written un-weighted by the localization weight (the host applies it)
 __global__ void rows_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t N,
                             PassConst pc, ParamConst prm, const uint8_t* __restrict__ sel,
-                            const float4* __restrict__ plane, const double* __restrict__ ucov,
-                            const double* __restrict__ tau, const double* __restrict__ d_mm, uint32_t cap,
+                            const float4* __restrict__ plane, const float* __restrict__ pd2v,
+                            const double* __restrict__ ucov,
+                            const double* __restrict__ tau, const unsigned long long* __restrict__ d_mm, uint32_t cap,
                             double* __restrict__ rows /* cap x 25 */, uint32_t* __restrict__ n_rows) {
   __shared__ uint32_t s_base;
   if (threadIdx.x == 0) s_base = 0;
@@ -760,7 +893,7 @@ __global__ void rows_kernel(const malio_scan_pt* __restrict__ pts, const uint32_
   for (uint32_t start = 0; start < N; start += blockDim.x) {
     const uint32_t p = start + threadIdx.x;
     double r[24], z = 0.0, rho = 1.0;
-    const bool ok = build_row(p, N, pts, perm, pc, prm, sel, plane, ucov, tau, d_mm, r, z, rho);
+    const bool ok = build_row(p, N, pts, perm, pc, prm, sel, plane, pd2v, ucov, tau, d_mm, r, z, rho);
     // block-wide exclusive scan of ok via warp ballots
     __shared__ uint32_t s_wcnt[32];
     const uint32_t bal = __ballot_sync(0xffffffffu, ok);
@@ -851,12 +984,14 @@ struct DeviceState {
   // per point, position space
   uint32_t* d_nn_idx = nullptr; float* d_nn_d2 = nullptr; uint8_t* d_sel = nullptr;
   float4 *d_world = nullptr, *d_plane = nullptr; double *d_ucov = nullptr, *d_tau = nullptr; float* d_normal_y = nullptr;
+  double2* d_tau2 = nullptr; float* d_pd2 = nullptr; bool tau_valid = false;
   // aux staging (caller order)
   float* d_o_ny = nullptr; uint32_t* d_o_idx = nullptr; float* d_o_d2 = nullptr; uint8_t* d_o_sel = nullptr; float* d_o_world = nullptr;
   // reductions
   double* d_block_mm = nullptr; uint32_t* d_block_cnt = nullptr; uint32_t cap_blocks = 0;
   uint32_t* d_counters = nullptr;   // [0] plane, [1] reduce, [2] n_eff local, [3] n_rows
-  double* d_mm = nullptr;           // 4
+  unsigned long long* d_mmkey = nullptr;   // 2 parities x 4 keys (+ counts in d_counters[4+parity])
+  int parity = 0, last_parity = 0;
   double* d_block_red = nullptr; uint32_t red_grid = 0;
   double* d_res = nullptr;          // MALIO_RED_DOUBLES
   double* d_rows = nullptr;         // MALIO_MAX_DOF x 25
@@ -898,6 +1033,21 @@ ParamConst make_param_const(const malio_params& p) {
   return c;
 }
 
+// queries per warp for knn_kernel: halve the logical warp width while fewer than ~8 warps per SM would be resident
+// (MALIO_KNN_LANES overrides, for experiments)
+int pick_lanes(uint32_t n, int sm_count) {
+  static const int forced = [] { const char* e = getenv("MALIO_KNN_LANES"); return e ? atoi(e) : 0; }();
+  if (forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
+  const uint64_t target = (uint64_t)sm_count * 8;
+  int lanes = 32;
+  while (lanes > 4 && (n + lanes - 1) / lanes < target) lanes >>= 1;
+  return lanes;
+}
+uint32_t knn_blocks(uint32_t n, int lanes) {
+  const uint32_t warps = (n + lanes - 1) / lanes;
+  return (warps + KNN_THREADS / 32 - 1) / (KNN_THREADS / 32);
+}
+
 int sort_queries(malio_handle* h, DeviceState* D, uint32_t n) {
   size_t need = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, need, D->d_keys, D->d_keys_out, D->d_ids, D->d_perm, (int)n, 0, 30, D->stream);
@@ -931,10 +1081,14 @@ int create(malio_handle* h) {
   for (auto& e : D->ev) CUDA_TRY(cudaEventCreate(&e));
   CUDA_TRY(cudaMalloc((void**)&D->d_counters, 8 * sizeof(uint32_t)));
   CUDA_TRY(cudaMemset(D->d_counters, 0, 8 * sizeof(uint32_t)));
-  CUDA_TRY(cudaMalloc((void**)&D->d_mm, 4 * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void**)&D->d_mmkey, 8 * sizeof(unsigned long long)));
+  {
+    const unsigned long long init[8] = {dkey(1000.0), dkey(-0.0), dkey(9999.0), dkey(-0.0), dkey(1000.0), dkey(-0.0), dkey(9999.0), dkey(-0.0)};
+    CUDA_TRY(cudaMemcpy(D->d_mmkey, init, sizeof(init), cudaMemcpyHostToDevice));
+  }
   CUDA_TRY(cudaMalloc((void**)&D->d_res, MALIO_RED_DOUBLES * sizeof(double)));
   CUDA_TRY(cudaMalloc((void**)&D->d_rows, (size_t)MALIO_MAX_DOF * 25 * sizeof(double)));
-  D->red_grid = (uint32_t)D->sm_count * 2;
+  D->red_grid = (uint32_t)D->sm_count * 3;   // 156 registers x 128 threads: 3 blocks per SM are co-resident
   CUDA_TRY(cudaMalloc((void**)&D->d_block_red, (size_t)D->red_grid * MALIO_RED_DOUBLES * sizeof(double)));
   CUDA_TRY(cudaMallocHost((void**)&D->h_res, (MALIO_RED_DOUBLES + 8 + MALIO_MAX_DOF * 25) * sizeof(double)));
   CUDA_TRY(cudaFuncSetAttribute(reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -949,9 +1103,9 @@ void destroy(malio_handle* h) {
   cudaSetDevice(D->device);
   if (D->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(D->comm);
   void* ptrs[] = {D->d_nodes, D->d_cov, D->d_pts, D->d_perm, D->d_keys, D->d_keys_out, D->d_ids, D->d_sort_tmp,
-                  D->d_table, D->d_nn_idx, D->d_nn_d2, D->d_sel, D->d_world, D->d_plane, D->d_ucov, D->d_tau,
+                  D->d_table, D->d_nn_idx, D->d_nn_d2, D->d_sel, D->d_world, D->d_plane, D->d_ucov, D->d_tau, D->d_tau2, D->d_pd2,
                   D->d_normal_y, D->d_o_ny, D->d_o_idx, D->d_o_d2, D->d_o_sel, D->d_o_world, D->d_block_mm,
-                  D->d_block_cnt, D->d_counters, D->d_mm, D->d_block_red, D->d_res, D->d_rows, D->d_queries};
+                  D->d_block_cnt, D->d_counters, D->d_mmkey, D->d_block_red, D->d_res, D->d_rows, D->d_queries};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (D->h_res) cudaFreeHost(D->h_res);
   for (auto& e : D->ev) if (e) cudaEventDestroy(e);
@@ -995,6 +1149,8 @@ static int ensure_point_buffers(malio_handle* h, DeviceState* D, uint32_t n) {
   if ((rc = ensure(h, D->d_plane, cap))) return rc;
   if ((rc = ensure(h, D->d_ucov, cap))) return rc;
   if ((rc = ensure(h, D->d_tau, cap))) return rc;
+  if ((rc = ensure(h, D->d_tau2, cap))) return rc;
+  if ((rc = ensure(h, D->d_pd2, cap))) return rc;
   if ((rc = ensure(h, D->d_normal_y, cap))) return rc;
   if ((rc = ensure(h, D->d_o_ny, cap))) return rc;
   if ((rc = ensure(h, D->d_o_idx, (size_t)cap * MALIO_K))) return rc;
@@ -1030,7 +1186,7 @@ int upload_scan(malio_handle* h, const malio_scan_pt* pts, uint32_t n, const mal
   CUDA_TRY(cudaStreamSynchronize(D->stream));
   for (int l = 0; l <= MALIO_MAX_LIDAR; ++l) D->table_off[l] = (l <= L) ? table_off[l] : table_off[L];
   for (int l = 1; l < L; ++l) D->tcomp[l] = tcomp[l - 1];
-  D->N = n; D->scan_ready = true; D->perm_valid = false; D->pass_done = false; D->searched_once = false;
+  D->N = n; D->scan_ready = true; D->perm_valid = false; D->tau_valid = false; D->pass_done = false; D->searched_once = false;
   return MALIO_OK;
 }
 
@@ -1058,32 +1214,51 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
       perm = D->d_perm;
     }
     if (redo_knn) {
-      knn_kernel<0><<<(N + KNN_THREADS - 1) / KNN_THREADS, KNN_THREADS, 0, st_>>>(
-          D->d_nodes, D->n_nodes, D->d_pts, perm, nullptr, N, pc, P.knn_max_sqdist, D->d_world, D->d_nn_idx,
-          D->d_nn_d2, D->d_sel);
+      const int lanes = pick_lanes(N, D->sm_count);
+      if (D->depth < (uint32_t)KNN_SMEM_DEPTH)
+        knn_kernel<0, true><<<knn_blocks(N, lanes), KNN_THREADS, 0, st_>>>(
+            D->d_nodes, D->n_nodes, D->d_pts, perm, nullptr, N, lanes, pc, P.knn_max_sqdist, D->d_world, D->d_nn_idx,
+            D->d_nn_d2, D->d_sel);
+      else
+        knn_kernel<0, false><<<knn_blocks(N, lanes), KNN_THREADS, 0, st_>>>(
+            D->d_nodes, D->n_nodes, D->d_pts, perm, nullptr, N, lanes, pc, P.knn_max_sqdist, D->d_world, D->d_nn_idx,
+            D->d_nn_d2, D->d_sel);
       D->searched_once = true;
     }
   }
   CUDA_TRY(cudaEventRecord(D->ev[1], st_));
   const uint32_t pblocks = N > 0 ? (N + PLANE_THREADS - 1) / PLANE_THREADS : 1;
-  plane_kernel<<<pblocks, PLANE_THREADS, 0, st_>>>(D->d_nodes, D->d_cov, D->d_pts, perm, N, pc, prm, D->d_table,
-                                                     D->d_nn_idx, D->d_sel, D->d_world, D->d_plane, D->d_ucov,
-                                                     D->d_tau, D->d_normal_y, D->d_block_mm, D->d_block_cnt,
-                                                     D->d_counters + 0, D->d_mm, D->d_counters + 2);
-  if (D->comm)   // {min_u, -max_u, min_tau, -max_tau}: one MIN all-reduce (laserMapping.cpp:615-628, 700-703)
-    if (g_nccl.AllReduce(D->d_mm, D->d_mm, 4, ncclDouble, ncclMin, D->comm, st_) != ncclSuccess) { h->err = "ncclAllReduce(min) failed"; return MALIO_ERR_NCCL; }
+  if (N > 0 && !D->tau_valid) {   // once per scan
+    tau_kernel<<<pblocks, PLANE_THREADS, 0, st_>>>(D->d_pts, perm, N, pc, D->d_table, D->d_tau2);
+    D->tau_valid = true;
+  }
+  if (N > 0 && redo_knn)           // once per search
+    fit_kernel<<<pblocks, PLANE_THREADS, 0, st_>>>(D->d_nodes, D->d_cov, N, prm, D->d_nn_idx, D->d_sel, D->d_plane, D->d_ucov);
+  unsigned long long* mmkey = D->d_mmkey + 4 * D->parity;
+  unsigned long long* mmkey_next = D->d_mmkey + 4 * (1 - D->parity);
+  uint32_t* cnt_cell = D->d_counters + 4 + D->parity;
+  uint32_t* cnt_next = D->d_counters + 4 + (1 - D->parity);
+  const uint32_t gblocks = N > 0 ? (N + GATE_THREADS - 1) / GATE_THREADS : 1;
+  gate_kernel<<<gblocks, GATE_THREADS, 0, st_>>>(D->d_pts, perm, N, pc, D->d_plane, D->d_ucov, D->d_tau2, D->d_sel,
+                                                   D->d_world, D->d_pd2, D->d_tau, D->d_normal_y, mmkey, cnt_cell);
+  if (D->comm)   // keys of {min_u, -max_u, min_tau, -max_tau}: one MIN all-reduce (laserMapping.cpp:615-628, 700-703)
+    if (g_nccl.AllReduce(mmkey, mmkey, 4, ncclUint64, ncclMin, D->comm, st_) != ncclSuccess) { h->err = "ncclAllReduce(min) failed"; return MALIO_ERR_NCCL; }
   CUDA_TRY(cudaEventRecord(D->ev[2], st_));
   const uint32_t n_tiles = (N + RED_THREADS - 1) / RED_THREADS;
-  uint32_t grid = n_tiles < D->red_grid ? n_tiles : D->red_grid;
-  if (grid == 0) grid = 1;
+  // one resident wave, every block the same number of tiles (+-1): no straggler blocks
+  const uint32_t per_block = n_tiles ? (n_tiles + D->red_grid - 1) / D->red_grid : 1;
+  uint32_t grid = n_tiles ? (n_tiles + per_block - 1) / per_block : 1;
   reduce_kernel<<<grid, RED_THREADS, RED_THREADS * (RED_HS_STRIDE + RED_HX_STRIDE) * sizeof(double), st_>>>(
-      D->d_pts, perm, N, pc, prm, D->d_sel, D->d_plane, D->d_ucov, D->d_tau, D->d_mm, n_tiles, D->d_block_red,
+      D->d_pts, perm, N, pc, prm, D->d_sel, D->d_plane, D->d_pd2, D->d_ucov, D->d_tau, mmkey, n_tiles, D->d_block_red,
       D->d_counters + 1, D->d_res);
+  fold_kernel<<<(MALIO_RED_DOUBLES * 32 + 255) / 256, 256, 0, st_>>>(D->d_block_red, grid, D->d_res, mmkey_next, cnt_next);
   if (D->comm)   // the reduced system + n_eff: one SUM all-reduce
     if (g_nccl.AllReduce(D->d_res, D->d_res, MALIO_RED_DOUBLES, ncclDouble, ncclSum, D->comm, st_) != ncclSuccess) { h->err = "ncclAllReduce(sum) failed"; return MALIO_ERR_NCCL; }
   CUDA_TRY(cudaEventRecord(D->ev[3], st_));
   CUDA_TRY(cudaMemcpyAsync(D->h_res, D->d_res, MALIO_RED_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, st_));
-  CUDA_TRY(cudaMemcpyAsync(D->h_res + MALIO_RED_DOUBLES, D->d_mm, 4 * sizeof(double), cudaMemcpyDeviceToHost, st_));
+  CUDA_TRY(cudaMemcpyAsync(D->h_res + MALIO_RED_DOUBLES, mmkey, 4 * sizeof(double), cudaMemcpyDeviceToHost, st_));
+  D->last_parity = D->parity;
+  D->parity = 1 - D->parity;
   CUDA_TRY(cudaEventRecord(D->ev[4], st_));
   CUDA_TRY(cudaStreamSynchronize(st_));
   CUDA_TRY(cudaGetLastError());
@@ -1091,7 +1266,8 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
 
   // ---- host epilogue: un-block, localization weight (laserMapping.cpp:745-759), compact to c x c
   const double* res = D->h_res;
-  const double* mm = D->h_res + MALIO_RED_DOUBLES;
+  double mm[4];
+  for (int k = 0; k < 4; ++k) { unsigned long long key; std::memcpy(&key, D->h_res + MALIO_RED_DOUBLES + k, 8); mm[k] = dkey_inv(key); }
   double G[MALIO_RED_ROWS][MALIO_RED_COLS];
   std::memset(G, 0, sizeof(G));
   int t = 0;
@@ -1145,7 +1321,7 @@ int download_rows(malio_handle* h, double* h_x, double* hvec, uint32_t cap, uint
   if (cap > MALIO_MAX_DOF) cap = MALIO_MAX_DOF;
   const uint32_t* perm = (h->cfg.sort_queries && D->perm_valid) ? D->d_perm : nullptr;
   rows_kernel<<<1, 256, 0, D->stream>>>(D->d_pts, perm, D->N, D->last_pc, make_param_const(P), D->d_sel, D->d_plane,
-                                          D->d_ucov, D->d_tau, D->d_mm, cap, D->d_rows, D->d_counters + 3);
+                                          D->d_pd2, D->d_ucov, D->d_tau, D->d_mmkey + 4 * D->last_parity, cap, D->d_rows, D->d_counters + 3);
   double* hr = D->h_res + MALIO_RED_DOUBLES + 8;
   CUDA_TRY(cudaMemcpyAsync(hr, D->d_rows, (size_t)cap * 25 * sizeof(double), cudaMemcpyDeviceToHost, D->stream));
   uint32_t nr = 0;
@@ -1206,8 +1382,13 @@ int knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* idx, float* d2, 
     perm = D->d_perm;
   }
   CUDA_TRY(cudaEventRecord(D->ev[0], D->stream));
-  knn_kernel<1><<<(nq + KNN_THREADS - 1) / KNN_THREADS, KNN_THREADS, 0, D->stream>>>(
-      D->d_nodes, D->n_nodes, nullptr, perm, D->d_queries, nq, pc, 0.f, nullptr, D->d_nn_idx, D->d_nn_d2, nullptr);
+  const int lanes = pick_lanes(nq, D->sm_count);
+  if (D->depth < (uint32_t)KNN_SMEM_DEPTH)
+    knn_kernel<1, true><<<knn_blocks(nq, lanes), KNN_THREADS, 0, D->stream>>>(
+        D->d_nodes, D->n_nodes, nullptr, perm, D->d_queries, nq, lanes, pc, 0.f, nullptr, D->d_nn_idx, D->d_nn_d2, nullptr);
+  else
+    knn_kernel<1, false><<<knn_blocks(nq, lanes), KNN_THREADS, 0, D->stream>>>(
+        D->d_nodes, D->n_nodes, nullptr, perm, D->d_queries, nq, lanes, pc, 0.f, nullptr, D->d_nn_idx, D->d_nn_d2, nullptr);
   CUDA_TRY(cudaEventRecord(D->ev[1], D->stream));
   scatter_aux_kernel<<<(nq + 255) / 256, 256, 0, D->stream>>>(perm, nq, nullptr, D->d_nn_idx, D->d_nn_d2, nullptr,
                                                                nullptr, nullptr, idx ? D->d_o_idx : nullptr,

@@ -90,3 +90,41 @@ def test_three_lidar_churned_tree_varied_cov():
     assert rep.passes == rep_o.passes and rep.searches == rep_o.searches
     assert np.abs(synth.state_to_vec(xg, 3) - synth.state_to_vec(xo, 3)).max() < STATE_TOL
     assert H.rel_err(Pg, Po) < 1e-6
+
+
+def test_knn_exact_ties_and_duplicates():
+    """Adversarial k-NN: a perfect 0.5 m lattice (exact float ties at the k-th boundary everywhere), duplicated
+    points (comparator-equivalent heap items) and near-coincident queries (|d_a - d_b| < 1e-10 window).  The
+    first-visited-wins / MANUAL_HEAP behaviour of the reference must be reproduced index for index."""
+    import pyoracle as po
+    from malio_b200 import plugin
+    rng = np.random.default_rng(5)
+    g = np.arange(-20, 20, dtype=np.float32) * 0.5
+    X, Y, Z = np.meshgrid(g, g, g[:8], indexing="ij")
+    lattice = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1).astype(np.float32)
+    dup = lattice[rng.integers(0, lattice.shape[0], 2000)]
+    tiny = lattice[rng.integers(0, lattice.shape[0], 500)] + rng.normal(0, 2e-6, (500, 3)).astype(np.float32)
+    xyz = np.concatenate([lattice, dup, tiny], axis=0)
+    xyz = xyz[rng.permutation(xyz.shape[0])]
+    if po.ref_available():
+        tree = po.RefTree()
+        tree.build(xyz)
+        nodes, cov, ids, depth, _ = tree.snapshot()
+        snap = plugin.MapSnapshot(nodes, cov, ids, depth)
+    else:
+        snap = plugin.build_static_snapshot(xyz)
+    q = np.concatenate([
+        lattice[rng.integers(0, lattice.shape[0], 3000)] + np.float32(0.25),          # cell centres: 8-way ties
+        lattice[rng.integers(0, lattice.shape[0], 3000)],                             # on lattice points: 6-way ties
+        lattice[rng.integers(0, lattice.shape[0], 3000)] + rng.normal(0, 1e-6, (3000, 3)).astype(np.float32),
+        rng.uniform(-10, 10, (3000, 3)).astype(np.float32),
+    ]).astype(np.float32)
+    model = plugin.MeasurementModel(1)
+    model.upload_map(snap)
+    idx, d2, _ = model.Nearest_Search(q)
+    o_idx, o_d2, o_found, _ = po.knn_snapshot(snap.nodes, snap.node_cov, q, nthreads=4)
+    assert np.array_equal(idx.astype(np.int64), o_idx.astype(np.int64))
+    assert np.array_equal(d2, o_d2)
+    if po.ref_available():   # and the restated search is itself the real reference's
+        r_ids, r_d2, _, _ = tree.knn(q[:2000])
+        assert np.array_equal(snap.node_ids[o_idx[:2000]], r_ids)
