@@ -128,7 +128,8 @@ typedef struct malio_pass_stats {
   double tau_min, tau_max;    /* min/max_cov, laserMapping.cpp:646-703 */
   double sigma[3];            /* singular values of h_x[:,0:3] before the localization weight */
   double loc_weight;          /* weight, laserMapping.cpp:749-756 */
-  float ms_knn, ms_plane, ms_reduce, ms_total;   /* device time of this pass (CUDA events) */
+  float ms_sort;              /* Morton keys + sort of the scan (first pass of a scan only, else 0) */
+  float ms_knn, ms_plane, ms_reduce, ms_total;   /* device time of this pass (CUDA events); ms_knn = the k-NN kernel alone */
 } malio_pass_stats;
 
 typedef struct malio_handle malio_handle;
@@ -160,6 +161,11 @@ int malio_upload_scan(malio_handle* h, const malio_scan_pt* pts, uint32_t n_pts,
                       const malio_pose_entry* table, const uint32_t* table_off /* L+1 */,
                       const malio_rigid* temporal_comp /* L-1, may be NULL when L==1 */);
 
+/* re-arm the scan that is already resident on the device (same points / tables as the last malio_upload_scan):
+ * resets the per-scan state (Nearest_Points, point_selected_surf, internal ordering) without any host copy.
+ * Lets a caller time the device path with inputs resident in HBM. */
+int malio_rearm_scan(malio_handle* h);
+
 /* one pass of h_share_model + esekfom.hpp:622-635.
  *   HtRinvH : c x c row-major, = h_x^T diag(1/R) h_x   (HTH, esekfom.hpp:629)
  *   HtRinvh : c,              = h_x^T diag(1/R) h     (HT * dyn_share.h, esekfom.hpp:635)
@@ -181,6 +187,17 @@ int malio_download_rows(malio_handle* h, double* h_x, double* hvec, uint32_t cap
  *   world    : N x 3 feats_down_world (laserMapping.cpp:576-578) */
 int malio_download_aux(malio_handle* h, float* normal_y, uint32_t* nn_idx, float* nn_sqdist,
                        uint8_t* selected, float* world);
+
+/* cumulative counters since malio_create: kernels launched by this library, k-NN kernel launches, queries they
+ * processed and their summed device time (CUDA events) — what bench.py's roofline is computed from. */
+typedef struct malio_counters {
+  uint64_t kernel_launches;
+  uint64_t knn_launches;
+  uint64_t knn_queries;
+  double knn_ms;
+  uint64_t h2d_bytes, d2h_bytes;
+} malio_counters;
+int malio_get_counters(malio_handle* h, malio_counters* out);
 
 /* stand-alone k-NN (BASELINE config C5, the microbench): queries are world-frame points. */
 int malio_knn(malio_handle* h, const float* queries_xyz, uint32_t n_queries,

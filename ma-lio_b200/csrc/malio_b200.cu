@@ -968,7 +968,8 @@ struct DeviceState {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [5] after sort, [6] after knn kernel
+  malio_counters ctr{};
   // map
   float4* d_nodes = nullptr; float* d_cov = nullptr;
   uint32_t n_nodes = 0, cap_nodes = 0, depth = 0;
@@ -1129,6 +1130,7 @@ int upload_map(malio_handle* h, const malio_map_node* nodes, const float* cov, u
   CUDA_TRY(cudaMemcpyAsync(D->d_cov, cov, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, D->stream));
   CUDA_TRY(cudaStreamSynchronize(D->stream));
   D->n_nodes = n; D->depth = depth; D->map_ready = true;
+  D->ctr.h2d_bytes += (uint64_t)n * (sizeof(malio_map_node) + sizeof(float));
   return MALIO_OK;
 }
 
@@ -1187,6 +1189,23 @@ int upload_scan(malio_handle* h, const malio_scan_pt* pts, uint32_t n, const mal
   for (int l = 0; l <= MALIO_MAX_LIDAR; ++l) D->table_off[l] = (l <= L) ? table_off[l] : table_off[L];
   for (int l = 1; l < L; ++l) D->tcomp[l] = tcomp[l - 1];
   D->N = n; D->scan_ready = true; D->perm_valid = false; D->tau_valid = false; D->pass_done = false; D->searched_once = false;
+  D->ctr.h2d_bytes += (uint64_t)n * sizeof(malio_scan_pt) + (uint64_t)n_tab * sizeof(malio_pose_entry);
+  return MALIO_OK;
+}
+
+int rearm_scan(malio_handle* h) {
+  DeviceState* D = (DeviceState*)h->dev;
+  if (!D->scan_ready) { h->err = "rearm_scan before upload_scan"; return MALIO_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(D->device));
+  CUDA_TRY(cudaMemsetAsync(D->d_sel, 0, D->capN, D->stream));
+  CUDA_TRY(cudaMemsetAsync(D->d_normal_y, 0, (size_t)D->capN * sizeof(float), D->stream));
+  CUDA_TRY(cudaMemsetAsync(D->d_nn_idx, 0xFF, (size_t)D->capN * MALIO_K * sizeof(uint32_t), D->stream));
+  D->perm_valid = false; D->tau_valid = false; D->pass_done = false; D->searched_once = false;
+  return MALIO_OK;
+}
+
+int get_counters(malio_handle* h, malio_counters* out) {
+  *out = ((DeviceState*)h->dev)->ctr;
   return MALIO_OK;
 }
 
@@ -1204,16 +1223,22 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
   cudaStream_t st_ = D->stream;
   const uint32_t* perm = nullptr;
   CUDA_TRY(cudaEventRecord(D->ev[0], st_));
+  bool sorted_now = false, knn_now = false;
   if (N > 0) {
     if (h->cfg.sort_queries) {
       if (!D->perm_valid) {
         morton_kernel<0><<<(N + 255) / 256, 256, 0, st_>>>(D->d_pts, nullptr, N, pc, D->d_keys, D->d_ids);
         if (int rc = sort_queries(h, D, N)) return rc;
         D->perm_valid = true;
+        sorted_now = true;
+        D->ctr.kernel_launches += 7;   // keys + CUB histogram / exclusive-sum / 4 onesweep passes (30 key bits)
       }
       perm = D->d_perm;
     }
+    CUDA_TRY(cudaEventRecord(D->ev[5], st_));
     if (redo_knn) {
+      knn_now = true;
+      D->ctr.kernel_launches += 1;
       const int lanes = pick_lanes(N, D->sm_count);
       if (D->depth < (uint32_t)KNN_SMEM_DEPTH)
         knn_kernel<0, true><<<knn_blocks(N, lanes), KNN_THREADS, 0, st_>>>(
@@ -1224,6 +1249,7 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
             D->d_nodes, D->n_nodes, D->d_pts, perm, nullptr, N, lanes, pc, P.knn_max_sqdist, D->d_world, D->d_nn_idx,
             D->d_nn_d2, D->d_sel);
       D->searched_once = true;
+      CUDA_TRY(cudaEventRecord(D->ev[6], st_));
     }
   }
   CUDA_TRY(cudaEventRecord(D->ev[1], st_));
@@ -1231,9 +1257,13 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
   if (N > 0 && !D->tau_valid) {   // once per scan
     tau_kernel<<<pblocks, PLANE_THREADS, 0, st_>>>(D->d_pts, perm, N, pc, D->d_table, D->d_tau2);
     D->tau_valid = true;
+    D->ctr.kernel_launches += 1;
   }
-  if (N > 0 && redo_knn)           // once per search
+  if (N > 0 && redo_knn) {         // once per search
     fit_kernel<<<pblocks, PLANE_THREADS, 0, st_>>>(D->d_nodes, D->d_cov, N, prm, D->d_nn_idx, D->d_sel, D->d_plane, D->d_ucov);
+    D->ctr.kernel_launches += 1;
+  }
+  D->ctr.kernel_launches += 3;     // gate, reduce, fold
   unsigned long long* mmkey = D->d_mmkey + 4 * D->parity;
   unsigned long long* mmkey_next = D->d_mmkey + 4 * (1 - D->parity);
   uint32_t* cnt_cell = D->d_counters + 4 + D->parity;
@@ -1281,7 +1311,12 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
   S.n_points = N; S.n_eff = n_eff; S.searched = redo_knn ? 1 : 0;
   S.u_min = mm[0]; S.u_max = -mm[1]; S.tau_min = mm[2]; S.tau_max = -mm[3];
   float ms = 0.f;
-  cudaEventElapsedTime(&ms, D->ev[0], D->ev[1]); S.ms_knn = ms;
+  if (N > 0 && sorted_now) { cudaEventElapsedTime(&ms, D->ev[0], D->ev[5]); S.ms_sort = ms; }
+  if (knn_now) {
+    cudaEventElapsedTime(&ms, D->ev[5], D->ev[6]); S.ms_knn = ms;
+    D->ctr.knn_launches += 1; D->ctr.knn_queries += N; D->ctr.knn_ms += ms;
+  }
+  D->ctr.d2h_bytes += (MALIO_RED_DOUBLES + 4) * sizeof(double);
   cudaEventElapsedTime(&ms, D->ev[1], D->ev[2]); S.ms_plane = ms;
   cudaEventElapsedTime(&ms, D->ev[2], D->ev[3]); S.ms_reduce = ms;
   cudaEventElapsedTime(&ms, D->ev[0], D->ev[4]); S.ms_total = ms;
@@ -1356,6 +1391,8 @@ int download_aux(malio_handle* h, float* normal_y, uint32_t* nn_idx, float* nn_d
   if (nn_d2) CUDA_TRY(cudaMemcpyAsync(nn_d2, D->d_o_d2, (size_t)N * MALIO_K * sizeof(float), cudaMemcpyDeviceToHost, D->stream));
   if (sel) CUDA_TRY(cudaMemcpyAsync(sel, D->d_o_sel, (size_t)N, cudaMemcpyDeviceToHost, D->stream));
   if (world) CUDA_TRY(cudaMemcpyAsync(world, D->d_o_world, (size_t)N * 3 * sizeof(float), cudaMemcpyDeviceToHost, D->stream));
+  D->ctr.kernel_launches += 1;
+  D->ctr.d2h_bytes += (uint64_t)N * ((normal_y ? 4 : 0) + (nn_idx ? 20 : 0) + (nn_d2 ? 20 : 0) + (sel ? 1 : 0) + (world ? 12 : 0));
   CUDA_TRY(cudaStreamSynchronize(D->stream));
   CUDA_TRY(cudaGetLastError());
   return MALIO_OK;
@@ -1397,7 +1434,13 @@ int knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* idx, float* d2, 
   if (d2) CUDA_TRY(cudaMemcpyAsync(d2, D->d_o_d2, (size_t)nq * MALIO_K * sizeof(float), cudaMemcpyDeviceToHost, D->stream));
   CUDA_TRY(cudaStreamSynchronize(D->stream));
   CUDA_TRY(cudaGetLastError());
-  if (ms_out) cudaEventElapsedTime(ms_out, D->ev[0], D->ev[1]);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, D->ev[0], D->ev[1]);
+  if (ms_out) *ms_out = ms;
+  D->ctr.kernel_launches += 2 + (h->cfg.sort_queries ? 7 : 0);
+  D->ctr.knn_launches += 1; D->ctr.knn_queries += nq; D->ctr.knn_ms += ms;
+  D->ctr.h2d_bytes += (uint64_t)nq * 12;
+  D->ctr.d2h_bytes += (uint64_t)nq * ((idx ? 20 : 0) + (d2 ? 20 : 0));
   return MALIO_OK;
 }
 

@@ -378,6 +378,8 @@ int malio_upload_scan(malio_handle* h, const malio_scan_pt* pts, uint32_t n_pts,
   if (h->cfg.params.n_lidar > 1 && !temporal_comp) { h->err = "temporal_comp required for L > 1"; return MALIO_ERR_INVALID_ARG; }
   return malio_dev::upload_scan(h, pts, n_pts, table, table_off, temporal_comp);
 }
+int malio_rearm_scan(malio_handle* h) { return h ? malio_dev::rearm_scan(h) : MALIO_ERR_INVALID_ARG; }
+int malio_get_counters(malio_handle* h, malio_counters* out) { return (h && out) ? malio_dev::get_counters(h, out) : MALIO_ERR_INVALID_ARG; }
 int malio_measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* HtRinvH, double* HtRinvh, malio_pass_stats* stats) {
   if (!h || !s || !HtRinvH || !HtRinvh) return MALIO_ERR_INVALID_ARG;
   return malio_dev::measure(h, s, redo_knn, HtRinvH, HtRinvh, stats);

@@ -56,7 +56,7 @@ class Config(C.Structure):
 class PassStats(C.Structure):
     _fields_ = [("n_points", C.c_uint32), ("n_eff", C.c_uint32), ("valid", C.c_int32), ("searched", C.c_int32),
                 ("u_min", C.c_double), ("u_max", C.c_double), ("tau_min", C.c_double), ("tau_max", C.c_double),
-                ("sigma", C.c_double * 3), ("loc_weight", C.c_double), ("ms_knn", C.c_float),
+                ("sigma", C.c_double * 3), ("loc_weight", C.c_double), ("ms_sort", C.c_float), ("ms_knn", C.c_float),
                 ("ms_plane", C.c_float), ("ms_reduce", C.c_float), ("ms_total", C.c_float)]
 
 
@@ -79,6 +79,11 @@ class State(C.Structure):
         return ps
 
 
+class Counters(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("knn_launches", C.c_uint64), ("knn_queries", C.c_uint64),
+                ("knn_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
 class UpdateReport(C.Structure):
     _fields_ = [("passes", C.c_int32), ("searches", C.c_int32), ("converged_count", C.c_int32),
                 ("last_status", C.c_int32), ("n_eff_last", C.c_uint32), ("ms_device_total", C.c_float),
@@ -92,6 +97,7 @@ EXPORTS = [
     "malio_default_params", "malio_create", "malio_destroy", "malio_last_error", "malio_version",
     "malio_get_nccl_unique_id", "malio_comm_init", "malio_upload_map", "malio_upload_scan", "malio_measure",
     "malio_download_rows", "malio_download_aux", "malio_knn", "malio_ieskf_update", "malio_build_static_snapshot",
+    "malio_rearm_scan", "malio_get_counters",
 ]
 
 
@@ -128,6 +134,8 @@ def load() -> C.CDLL:
     lib.malio_knn.argtypes = [vp, vp, u32, vp, vp, C.POINTER(C.c_float)]
     lib.malio_ieskf_update.argtypes = [vp, C.POINTER(State), vp, i32, C.c_double, C.POINTER(UpdateReport)]
     lib.malio_build_static_snapshot.argtypes = [vp, u32, vp, vp, C.POINTER(u32)]
+    lib.malio_rearm_scan.argtypes = [vp]
+    lib.malio_get_counters.argtypes = [vp, C.POINTER(Counters)]
     _lib = lib
     return lib
 

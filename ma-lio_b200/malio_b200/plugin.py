@@ -114,6 +114,15 @@ class MeasurementModel:
                                                capi.ptr(table_off), capi.ptr(tc)))
         self.n_points = int(pts.shape[0])
 
+    def rearm_scan(self):
+        """Reset the per-scan state of the scan already resident on the device (no host copy)."""
+        self._check(self.lib.malio_rearm_scan(self._h))
+
+    def counters(self) -> capi.Counters:
+        c = capi.Counters()
+        self._check(self.lib.malio_get_counters(self._h, C.byref(c)))
+        return c
+
     def h_share_model(self, s: capi.PassState | capi.State, converge: bool):
         """One measurement pass.  Returns (valid, HTH[c,c], HTh[c], stats)."""
         ps = s.pass_state() if isinstance(s, capi.State) else s
