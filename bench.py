@@ -194,7 +194,8 @@ def run_ours(args, rank, world):
     case = synth.case_C2()
     N_total = case.pts.shape[0]
     # contiguous block of the merged scan per rank; map, tables and state are replicated
-    lo, hi = (N_total * rank) // world, (N_total * (rank + 1)) // world
+    from malio_b200 import dist as mdist
+    lo, hi = mdist.shard_bounds(N_total, rank, world)
     snap = plugin.build_static_snapshot(case.map_xyz, case.map_normal_y)
 
     def pinned(a):
@@ -211,10 +212,7 @@ def run_ours(args, rank, world):
 
     model = plugin.MeasurementModel(case.n_lidar, device=local_rank, sort_queries=not args.no_sort, params=case.params)
     if world > 1:
-        uid = torch.from_numpy(plugin.MeasurementModel.nccl_unique_id() if rank == 0
-                               else np.zeros(capi.NCCL_UNIQUE_ID_BYTES, np.uint8)).cuda()
-        dist.broadcast(uid, 0)
-        model.comm_init(uid.cpu().numpy(), rank, world)
+        mdist.init_comm(model, rank, world, device=torch.device("cuda", local_rank))
     model.upload_map(snap_p)
     model.upload_scan(h_pts, case.table, case.table_off, case.temporal_comp)
 

@@ -694,6 +694,10 @@ struct orc_ctx {
   std::vector<double> h_x, h, R;
   int n_eff = 0;
   malio_pass_stats st{};
+  // multi-rank protocol tests: global min/max injected between the two phases (what the MIN all-reduce delivers)
+  bool mm_override = false;
+  double ov_umin = 0, ov_umax = 0, ov_tmin = 0, ov_tmax = 0;
+  double raw_min_cov = 9999, raw_max_cov = 0;   // local min/max trace of the selected points of the last pass
 };
 
 extern "C" {
@@ -859,6 +863,7 @@ int orc_h_share_model(void* vc, const malio_pass_state* s, int converge, int nth
   c->st.n_points = (uint32_t)N;
   c->st.n_eff = (uint32_t)effct;
   c->st.searched = converge ? 1 : 0;
+  if (c->mm_override) { min_unit_cov = c->ov_umin; max_unit_cov = c->ov_umax; }
   if (effct < 1) {   // :635-639
     c->st.valid = 0;
     return 0;
@@ -934,6 +939,8 @@ int orc_h_share_model(void* vc, const malio_pass_state* s, int converge, int nth
     }
     c->h[i] = (-1) * np_[3];   // :707
   }
+  c->raw_min_cov = min_cov; c->raw_max_cov = max_cov;
+  if (c->mm_override) { min_cov = c->ov_tmin; max_cov = c->ov_tmax; }
   c->st.u_min = min_unit_cov; c->st.u_max = max_unit_cov;
   c->st.tau_min = min_cov; c->st.tau_max = max_cov;
 
@@ -1005,6 +1012,35 @@ void orc_reduce(void* vc, double* HTH, double* HTh) {
     for (int i = 0; i < c->n_eff; ++i) s += HT[(size_t)a * c->n_eff + i] * c->h[i];
     HTh[a] = s;
   }
+}
+
+// ---- helpers for the multi-rank protocol tests (tests/test_multirank_gloo.py)
+void orc_set_minmax_override(void* vc, int enable, double umin, double umax, double tmin, double tmax) {
+  orc_ctx* c = (orc_ctx*)vc;
+  c->mm_override = enable != 0;
+  c->ov_umin = umin; c->ov_umax = umax; c->ov_tmin = tmin; c->ov_tmax = tmax;
+}
+// local min/max as the first phase of a rank sees them: {u_min, u_max, tau_min, tau_max} before any override
+void orc_get_local_minmax(void* vc, double out[4]) {
+  orc_ctx* c = (orc_ctx*)vc;
+  out[0] = c->st.u_min; out[1] = c->st.u_max; out[2] = c->raw_min_cov; out[3] = c->raw_max_cov;
+}
+// the additive partials of one rank with the (scalar) localization weight divided out:
+//   G = sum h_x^T/R h_x / w^2 ; g = sum h_x^T/R h / w^2 ; S = h_x[:,0:3]^T h_x[:,0:3] / w^2 (xx,xy,xz,yy,yz,zz)
+void orc_partials(void* vc, double* G, double* g, double* S) {
+  orc_ctx* c = (orc_ctx*)vc;
+  const int ncol = 6 * (c->prm.n_lidar + 1);
+  const double w2 = c->st.loc_weight * c->st.loc_weight;
+  orc_reduce(vc, G, g);
+  for (int k = 0; k < ncol * ncol; ++k) G[k] /= w2;
+  for (int k = 0; k < ncol; ++k) g[k] /= w2;
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < c->n_eff; ++i) {
+    const double* r = &c->h_x[(size_t)i * ncol];
+    s[0] += r[0] * r[0]; s[1] += r[0] * r[1]; s[2] += r[0] * r[2];
+    s[3] += r[1] * r[1]; s[4] += r[1] * r[2]; s[5] += r[2] * r[2];
+  }
+  for (int k = 0; k < 6; ++k) S[k] = s[k] / w2;
 }
 
 // accessors

@@ -53,6 +53,9 @@ def oracle_lib() -> C.CDLL:
         L.orc_h_share_model.argtypes = [vp, C.POINTER(capi.PassState), C.c_int, C.c_int]
         L.orc_reduce.argtypes = [vp, vp, vp]
         L.orc_n_eff.argtypes = [vp]
+        L.orc_set_minmax_override.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.orc_get_local_minmax.argtypes = [vp, vp]
+        L.orc_partials.argtypes = [vp, vp, vp, vp]
         L.orc_get_stats.argtypes = [vp, C.POINTER(capi.PassStats)]
         L.orc_get_dense.argtypes = [vp, vp, vp, vp]
         L.orc_get_aux.argtypes = [vp, vp, vp, vp, vp, vp, vp]
@@ -238,6 +241,19 @@ class Oracle:
 
     def n_eff(self):
         return self.L.orc_n_eff(self.c)
+
+    def set_minmax_override(self, enable, umin=0.0, umax=0.0, tmin=0.0, tmax=0.0):
+        self.L.orc_set_minmax_override(self.c, 1 if enable else 0, umin, umax, tmin, tmax)
+
+    def local_minmax(self):
+        out = np.zeros(4)
+        self.L.orc_get_local_minmax(self.c, ptr(out))
+        return out
+
+    def partials(self):
+        G = np.zeros((self.n_cols, self.n_cols)); g = np.zeros(self.n_cols); S = np.zeros(6)
+        self.L.orc_partials(self.c, ptr(G), ptr(g), ptr(S))
+        return G, g, S
 
     def stats(self):
         st = capi.PassStats()

@@ -1,0 +1,346 @@
+"""CPU tests (no GPU): the oracle against the reference's golden vectors / the real reference ikd-Tree, the oracle's
+hand-rolled algebra against numpy/scipy, host-side logic, and the C-ABI surface of the product library."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import helpers as H
+import np_oracle as npo
+import pyoracle as po
+from malio_b200 import capi, plugin, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "ikd_knn_golden.npz")
+
+
+def load_golden():
+    g = np.load(GOLD)
+    nodes = g["nodes"].view(capi.MAP_NODE).reshape(-1)
+    return g, nodes
+
+
+# ------------------------------------------------------------------ K / N: pinned by the real reference
+def test_restated_search_matches_reference_golden():
+    """oracle's restated KD_TREE::Search + MANUAL_HEAP on the flattened snapshot == the real Nearest_Search
+    (fixture produced by tests/golden/make_golden.py from the reference ikd_Tree.cpp)."""
+    g, nodes = load_golden()
+    ids, d2, found, visits = po.knn_snapshot(nodes, g["node_cov"], g["queries"], nthreads=2)
+    assert np.array_equal(found, g["ref_found"])
+    m = ids >= 0
+    mapped = np.where(m, g["node_ids"][np.clip(ids, 0, None)], -1)
+    assert np.array_equal(mapped, g["ref_ids"])
+    assert np.array_equal(d2[m], g["ref_d2"][m])
+    assert visits > 0
+
+
+def test_flattener_semantics_golden():
+    g, nodes = load_golden()
+    live = (nodes["link"] & capi.LINK_POINT_DELETED) == 0
+    assert int(live.sum()) == int(g["n_live"]) == int(g["tree_valid"])
+    # DFS pre-order: live points come out exactly in KD_TREE::flatten order (ikd_Tree.cpp:1638-1648)
+    assert np.array_equal(g["node_ids"][live], g["flat_ids"])
+    # links: left child is i+1, right index in range, boxes contain their child point
+    n = nodes.shape[0]
+    hl = (nodes["link"] & capi.LINK_HAS_LEFT) != 0
+    hr = (nodes["link"] & capi.LINK_HAS_RIGHT) != 0
+    ri = (nodes["link"] & capi.LINK_INDEX_MASK).astype(np.int64)
+    idx = np.arange(n)
+    assert np.all(idx[hl] + 1 < n) and np.all(ri[hr] < n) and np.all(ri[hr] > idx[hr])
+    lc = nodes["xyz"][idx[hl] + 1]
+    lb = nodes["lbox"][hl]
+    child_live = live[idx[hl] + 1]
+    inside = (lc[:, 0] >= lb[:, 0]) & (lc[:, 0] <= lb[:, 1]) & (lc[:, 1] >= lb[:, 2]) & (lc[:, 1] <= lb[:, 3]) & \
+             (lc[:, 2] >= lb[:, 4]) & (lc[:, 2] <= lb[:, 5])
+    assert np.all(inside[child_live])
+
+
+@pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref (real ikd_Tree.cpp) only exists in the build container")
+def test_restated_search_vs_real_tree_after_churn():
+    case = synth.make_case("t", 3000, 40000, 1, 3, varied_map_cov=True)
+    snap, tree = H.snapshot_for(case, churn=True)
+    rng = np.random.default_rng(1)
+    q = case.map_xyz[rng.integers(0, 40000, 4000)] + rng.normal(0, 0.3, (4000, 3)).astype(np.float32)
+    r_ids, r_d2, r_pts, r_found = tree.knn(q, 5, nthreads=4)
+    ids, d2, found, _ = po.knn_snapshot(snap.nodes, snap.node_cov, q, nthreads=4)
+    assert np.array_equal(found, r_found)
+    assert np.array_equal(snap.node_ids[ids], r_ids)
+    assert np.array_equal(d2, r_d2)
+    assert np.array_equal(snap.node_cov[ids], r_pts[:, :, 3])
+
+
+def test_search_is_exact_knn_bruteforce():
+    rng = np.random.default_rng(3)
+    xyz = (rng.random((5000, 3)) * [40, 40, 4]).astype(np.float32)
+    snap = plugin.build_static_snapshot(xyz)
+    q = (rng.random((300, 3)) * [40, 40, 4]).astype(np.float32)
+    ids, d2, found, _ = po.knn_snapshot(snap.nodes, snap.node_cov, q)
+    d = q[:, None, :] - xyz[None, :, :]
+    bd = (d[:, :, 0] * d[:, :, 0] + d[:, :, 1] * d[:, :, 1]) + d[:, :, 2] * d[:, :, 2]
+    bi = np.argsort(bd, axis=1, kind="stable")[:, :5]
+    assert np.array_equal(np.sort(snap.node_ids[ids], 1), np.sort(bi, 1))
+    assert np.array_equal(d2, np.take_along_axis(bd, bi, 1))
+
+
+def test_static_snapshot_builder_invariants():
+    xyz = synth.make_world(20000, seed=5)
+    snap = plugin.build_static_snapshot(xyz, np.linspace(0.001, 0.01, 20000, dtype=np.float32))
+    assert sorted(snap.node_ids.tolist()) == list(range(20000))
+    assert np.array_equal(snap.nodes["xyz"], xyz[snap.node_ids])
+    assert np.allclose(snap.node_cov, np.linspace(0.001, 0.01, 20000, dtype=np.float32)[snap.node_ids])
+    assert snap.max_depth == 15   # ceil(log2(20001))
+    # subtree sizes implied by the links are consistent: right child index = i + 1 + size(left)
+    n = 20000
+    link = snap.nodes["link"]
+    hr = (link & capi.LINK_HAS_RIGHT) != 0
+    ri = (link & capi.LINK_INDEX_MASK)[hr]
+    assert np.all(ri > np.arange(n)[hr])
+
+
+# ------------------------------------------------------------------ P / U / algebra vs numpy
+def test_esti_plane_vs_scipy_qr():
+    L = po.oracle_lib()
+    rng = np.random.default_rng(0)
+    for trial in range(300):
+        nrm = rng.normal(size=3); nrm /= np.linalg.norm(nrm)
+        base = rng.normal(size=3) * 8
+        u = np.cross(nrm, rng.normal(size=3)); u /= np.linalg.norm(u)
+        v = np.cross(nrm, u)
+        pts = base + rng.uniform(-1, 1, (5, 1)) * u + rng.uniform(-1, 1, (5, 1)) * v + rng.normal(0, 0.02 if trial % 3 else 0.3, (5, 1)) * nrm
+        near = np.zeros((5, 4), np.float32)
+        near[:, :3] = pts
+        near[:, 3] = rng.uniform(0, 0.02, 5) if trial % 5 else 0.0
+        pab = np.zeros(4, np.float32)
+        pc = C.c_double(0)
+        ok = L.orc_esti_plane(po.ptr(near), C.c_float(0.4), C.c_double(0.5), po.ptr(pab), C.byref(pc))
+        ok2, pab2, pc2 = npo.esti_plane(near, np.float32(0.4), 0.5)
+        resid = np.abs(near[:, :3].astype(np.float64) @ pab[:3] + pab[3])
+        if abs(resid.max() - 0.4) > 1e-3:
+            assert bool(ok) == ok2
+        # float32 LSQ of A n = -1 is conditioned like |p|^2: two valid float QRs agree to ~1e-3 here
+        np.testing.assert_allclose(pab, pab2, rtol=3e-3, atol=3e-4)
+        assert pc.value == pytest.approx(pc2, rel=1e-12, abs=1e-18)
+
+
+def test_eval_point_uncertainty_vs_numpy():
+    L = po.oracle_lib()
+    rng = np.random.default_rng(1)
+    table, _ = synth.make_tables(1, 6, rng)
+    for j in range(6):
+        p = rng.normal(0, 30, 3).astype(np.float32)
+        cov = np.zeros(9)
+        L.orc_eval_point_uncertainty(po.ptr(p), po.ptr(table[j:j + 1]), po.ptr(cov))
+        ref = npo.eval_point_uncertainty(p, table[j]["T"], table[j]["cov"])
+        np.testing.assert_allclose(cov.reshape(3, 3), ref, rtol=1e-12)
+
+
+def test_inverse_and_singular_values_vs_numpy():
+    L = po.oracle_lib()
+    rng = np.random.default_rng(2)
+    A = rng.normal(size=(35, 35))
+    A = A @ A.T + np.eye(35)
+    inv = np.zeros((35, 35))
+    assert L.orc_inverse(po.ptr(A), 35, po.ptr(inv)) == 1
+    np.testing.assert_allclose(inv, np.linalg.inv(A), rtol=1e-9, atol=1e-12)
+    M = rng.normal(size=(500, 24)) * [3, 1, 0.2] + [0] * 24 if False else rng.normal(size=(500, 24))
+    M[:, :3] *= [3.0, 1.0, 0.2]
+    sv = np.zeros(3)
+    L.orc_singular_values_Nx3(po.ptr(M), 500, 24, po.ptr(sv))
+    np.testing.assert_allclose(sv, np.linalg.svd(M[:, :3], compute_uv=False), rtol=1e-10)
+
+
+def test_manifold_ops_vs_numpy_and_roundtrip():
+    L = po.oracle_lib()
+    case = synth.make_case("m", 100, 5000, 3, 3)
+    rng = np.random.default_rng(4)
+    for _ in range(20):
+        d = rng.normal(0, 0.05, 35)
+        x = case.x_prop.copy()
+        L.orc_state_boxplus(3, C.byref(x), po.ptr(d))
+        back = np.zeros(35)
+        L.orc_state_boxminus(3, C.byref(x), C.byref(case.x_prop), po.ptr(back))
+        np.testing.assert_allclose(back, d, atol=1e-9)
+        xn = npo.NpState(case.x_prop, 3)
+        npo.boxplus(xn, d)
+        np.testing.assert_allclose(synth.state_to_vec(x, 3), xn.vec(), atol=1e-12)
+        v = rng.normal(0, 0.3, 3)
+        A = np.zeros(9)
+        L.orc_A_matrix(po.ptr(v), po.ptr(A))
+        np.testing.assert_allclose(A.reshape(3, 3), npo.A_matrix(v), atol=1e-14)
+        g = np.array(x.grav[:])
+        Nx = np.zeros(6); Mx = np.zeros(6)
+        dl = rng.normal(0, 0.01, 2)
+        L.orc_S2_Nx_yy(po.ptr(g), po.ptr(Nx)); L.orc_S2_Mx(po.ptr(g), po.ptr(dl), po.ptr(Mx))
+        np.testing.assert_allclose(Nx.reshape(2, 3), npo.S2_Nx_yy(g), atol=1e-13)
+        np.testing.assert_allclose(Mx.reshape(3, 2), npo.S2_Mx(g, dl), atol=1e-12)
+
+
+# ------------------------------------------------------------------ B / A on a small case
+@pytest.fixture(scope="module")
+def small():
+    case = synth.make_case("small-3L", 3000, 40000, 3, 3, varied_map_cov=True)
+    snap = plugin.build_static_snapshot(case.map_xyz, case.map_normal_y)
+    return case, snap
+
+
+def test_oracle_reduction_equals_dense(small):
+    case, snap = small
+    orc = H.make_oracle(case, snap)
+    assert orc.h_share_model(case.x_prop, True, 2)
+    hx, h, R = orc.dense()
+    Rc = np.where(R < 1e-4, 1e-3, R)
+    HTH, HTh = orc.reduce()
+    np.testing.assert_allclose(HTH, (hx.T / Rc) @ hx, rtol=1e-10)
+    np.testing.assert_allclose(HTh, (hx.T / Rc) @ h, rtol=1e-10)
+    st = orc.stats()
+    assert st.n_eff == hx.shape[0] > 2000
+    assert 0.3 <= st.loc_weight <= 2.0
+    # each row has at most 12 non-zeros: cols 0-5, 6+3l, 6+3(L+l) of its LiDAR
+    sel = orc.aux()["selected"].astype(bool)
+    lid = case.pts["lidar"][sel]
+    for l in range(3):
+        rows = hx[lid == l]
+        mask = np.ones(24, bool)
+        mask[0:6] = False; mask[6 + 3 * l:9 + 3 * l] = False; mask[15 + 3 * l:18 + 3 * l] = False
+        assert np.all(rows[:, mask] == 0)
+        assert np.all(np.abs(rows[:, ~mask]).sum(1) > 0)
+
+
+def test_jacobian_rows_match_finite_differences(small):
+    """h_x (laserMapping.cpp:665-693) against d(pd2)/d(delta x) by central differences on the manifold, with the
+    neighbours / planes frozen (converge = false)."""
+    case, snap = small
+    L_ = po.oracle_lib()
+    orc = H.make_oracle(case, snap)
+    x0 = case.x_prop.copy()
+    assert orc.h_share_model(x0, True, 2)
+
+    def unweighted(state):
+        assert orc.h_share_model(state, False, 2)
+        hx, h, _ = orc.dense()
+        sel = np.flatnonzero(orc.aux()["selected"])
+        w = np.linalg.norm(hx[:, :3], axis=1)          # = plane weight * localization weight (|n| = 1)
+        return sel, hx / w[:, None], -h / w
+
+    sel0, J0, pd0 = unweighted(x0)
+    eps = 1e-6
+    for k in list(range(0, 24)):
+        d = np.zeros(35); d[k] = eps
+        xp, xm = x0.copy(), x0.copy()
+        L_.orc_state_boxplus(3, C.byref(xp), po.ptr(d))
+        L_.orc_state_boxplus(3, C.byref(xm), po.ptr(-d))
+        sp, _, pdp = unweighted(xp)
+        sm, _, pdm = unweighted(xm)
+        common = np.intersect1d(np.intersect1d(sp, sm), sel0)
+        fd = (pdp[np.searchsorted(sp, common)] - pdm[np.searchsorted(sm, common)]) / (2 * eps)
+        an = J0[np.searchsorted(sel0, common), k]
+        # pd2 is evaluated in float32 on float32 world points: ~1e-6 m noise / 2e-6 => O(1) absolute noise per
+        # point; compare in aggregate (robust) form
+        err = np.abs(fd - an)
+        assert np.median(err) < 0.6, (k, np.median(err))
+        scale = max(np.abs(an).max(), 1.0)
+        assert np.corrcoef(fd, an)[0, 1] > 0.99 or np.abs(an).max() < 1.0, k
+
+
+def test_ieskf_update_vs_numpy_restatement(small):
+    """oracle A (C++) against the numpy restatement fed with the same dense rows."""
+    case, snap = small
+    orc = H.make_oracle(case, snap)
+    xo, Po = case.x_prop.copy(), case.P_prop.copy()
+    rc, dx_log, flags, rep = orc.update_iterated(xo, Po, case.max_iter, nthreads=2)
+    assert rc == 0
+    orc2 = H.make_oracle(case, snap)
+
+    def measure(xn, converge):
+        s = capi.PassState()
+        s.rot[:] = list(xn.rot); s.pos[:] = list(xn.pos)
+        for l in range(3):
+            s.ext[l].q[:] = list(xn.eq[l]); s.ext[l].t[:] = list(xn.et[l])
+        ok = orc2.h_share_model(s, converge, 2)
+        if not ok:
+            return False, None, None, None
+        return (True,) + orc2.dense()
+
+    xn, Pn, dxn_log = npo.ieskf_update(measure, npo.NpState(case.x_prop, 3), case.P_prop.copy(), case.max_iter)
+    np.testing.assert_allclose(synth.state_to_vec(xo, 3), xn.vec(), atol=1e-9)
+    np.testing.assert_allclose(Po, Pn, rtol=1e-6, atol=1e-14)
+    for a, b in zip(dx_log, dxn_log):
+        if b is not None:
+            np.testing.assert_allclose(a, b, atol=1e-9)
+    assert rep.passes == len(dxn_log)
+
+
+def test_degenerate_cases(small):
+    case, snap = small
+    # no effective points: empty map far away -> valid = false on every pass, state untouched
+    far = plugin.build_static_snapshot(case.map_xyz[:50] + np.float32(1e4))
+    orc = H.make_oracle(case, far)
+    assert not orc.h_share_model(case.x_prop, True, 1)
+    x, P = case.x_prop.copy(), case.P_prop.copy()
+    rc, _, flags, rep = orc.update_iterated(x, P, 3)
+    assert rc == 1 and np.all(flags & 1 == 0)
+    assert np.array_equal(synth.state_to_vec(x, 3), synth.state_to_vec(case.x_prop, 3))
+    # fewer effective points than state DOF: the dense branch (esekfom.hpp:574-582)
+    sub = synth.make_case("tiny", 25, 40000, 3, 3, map_xyz=case.map_xyz)
+    orc = H.make_oracle(sub, snap)
+    assert orc.h_share_model(sub.x_prop, True, 1)
+    assert 1 <= orc.n_eff() < 35
+    x, P = sub.x_prop.copy(), sub.P_prop.copy()
+    rc, dx_log, flags, rep = orc.update_iterated(x, P, 3)
+    assert rc == 0 and np.all(np.isfinite(synth.state_to_vec(x, 3))) and np.all(np.isfinite(P))
+    # all-equal point covariances: FIC 0/0 defined as mid-range
+    eq = synth.make_case("eqcov", 500, 40000, 1, 3, map_xyz=case.map_xyz)
+    eq.table["cov"][:] = 0.0
+    eq.pts["xyz"][:] = eq.pts["xyz"][0]          # same point, same table entry -> identical traces
+    eq.pts["table_idx"][:] = 0
+    orc = po.Oracle(eq.params)
+    orc.set_map_snapshot(snap.nodes, snap.node_cov)
+    orc.set_scan(eq.pts, eq.table, eq.table_off, eq.temporal_comp)
+    if orc.h_share_model(eq.x_prop, True, 1):
+        _, _, R = orc.dense()
+        assert np.all(R == (eq.params.point_cov_max + eq.params.point_cov_min) / 2)
+
+
+# ------------------------------------------------------------------ the product library's surface (no compute calls)
+def test_cabi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "malio_b200.h")).read()
+    declared = set(re.findall(r"\b(malio_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"malio_flatten"}
+    lib = capi.load()
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert set(capi.EXPORTS) <= declared
+    assert lib.malio_version().startswith(b"malio_b200")
+    # struct layouts shared with the C side
+    assert C.sizeof(capi.PassState) == 8 * (4 + 3 + 3 * 7)
+    assert C.sizeof(capi.Rigid) == 56 and capi.MAP_NODE.itemsize == 64 and capi.SCAN_PT.itemsize == 16
+    p = capi.default_params(3)
+    assert p.n_lidar == 3 and p.plane_th == pytest.approx(0.4) and p.knn_max_sqdist == 5.0 and p.cov_threshold == 0.5
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.MalioError) as e:
+        plugin.MeasurementModel(1)
+    assert e.value.status == capi.ERR_CUDA
+    cfg = capi.Config(); cfg.params = capi.default_params(5); cfg.params.n_lidar = 5
+    h = C.c_void_p()
+    assert capi.load().malio_create(C.byref(h), C.byref(cfg)) == capi.ERR_INVALID_ARG
+
+
+def test_product_does_not_link_or_import_the_oracle():
+    """The product must never route through oracle/ (no CPU fallback): no source under ma-lio_b200/ mentions it,
+    and the shared library has no dependency on the checker libraries."""
+    pkg = os.path.join(ROOT, "ma-lio_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cpp", ".cu", ".h", ".hpp")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "pyoracle" not in txt and "liboracle" not in txt and "libikd_ref" not in txt, f
+    import subprocess
+    out = subprocess.run(["ldd", capi.lib_path()], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "ikd_ref" not in out
