@@ -199,6 +199,10 @@ typedef struct malio_counters {
 } malio_counters;
 int malio_get_counters(malio_handle* h, malio_counters* out);
 
+/* per-pass CUDA-event timing (the ms_* fields of malio_pass_stats and knn_ms of the counters); on by default,
+ * costs ~7 event records per pass on the host when enabled. */
+int malio_set_timing(malio_handle* h, int enable);
+
 /* stand-alone k-NN (BASELINE config C5, the microbench): queries are world-frame points. */
 int malio_knn(malio_handle* h, const float* queries_xyz, uint32_t n_queries,
               uint32_t* nn_idx, float* nn_sqdist, float* ms_device);

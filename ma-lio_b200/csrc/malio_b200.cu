@@ -9,10 +9,10 @@
 // in the same order, as the reference's x86-64 build (no FMA, CMakeLists.txt:8) so that k-NN index sets are
 // bit-exact and the selection gates do not flip; explicit fma() is used only in the FP64 accumulation of K3.
 #include <cuda_runtime.h>
-#include <cub/device/device_radix_sort.cuh>
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -36,8 +36,11 @@ constexpr int KNN_THREADS = 64;
 constexpr int PLANE_THREADS = 64;
 constexpr int GATE_THREADS = 256;
 constexpr int RED_THREADS = 128;          // one tile = 128 points
-constexpr int RED_HS_STRIDE = 26;         // doubles per staged row of h/rho (24 + pad)
-constexpr int RED_HX_STRIDE = 28;         // doubles per staged row of [h | z | rho*h_0..2]
+constexpr int RED_HS_STRIDE = 13;         // doubles per staged row of a*J12/rho (12 + 1: odd stride, conflict-free)
+constexpr int RED_HX_STRIDE = 17;         // doubles per staged row of [a*J12 | z | rho*a*J12_0..2] (16 + 1)
+constexpr int RED_TASKS = 9;              // upper-triangular 4x4 blocks of the 12 x 16 compact system
+constexpr int RED_KS = 14;                // row-splits per task: 9 x 14 = 126 of the 128 threads work
+constexpr int RED_SMEM_DOUBLES = RED_THREADS * (RED_HS_STRIDE + RED_HX_STRIDE) + MALIO_MAX_LIDAR * RED_TASKS * RED_KS * 16;
 constexpr int TABLE_DOUBLES = 52;         // malio_pose_entry
 
 struct PassConst {
@@ -358,18 +361,27 @@ knn_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const malio_scan_
 #undef ST
 }
 
-// ------------------------------------------------------------------ Morton keys for query coherence (internal order only)
-__device__ __forceinline__ uint32_t spread10(uint32_t v) {
-  v &= 1023u;
-  v = (v | (v << 16)) & 0x030000FFu;
-  v = (v | (v << 8)) & 0x0300F00Fu;
-  v = (v | (v << 4)) & 0x030C30C3u;
-  v = (v | (v << 2)) & 0x09249249u;
+// ------------------------------------------------------------------ query ordering (internal only; outputs stay in caller order)
+// Spatially coherent warps matter (neighbouring queries walk the same upper tree levels: L1 hits, similar visit
+// counts), the exact order does not.  A general radix sort of ~1e5 keys is launch/latency-bound (CUB: 6 kernels,
+// ~57 us here), so this is a hand-written counting sort on a 16-bit cell key:
+//   cell = 2 m; key = z(2 bits) | Morton(x 7 bits, y 7 bits)   (wraps every 256 m / 8 m: only locality matters)
+//   count_kernel   key per point + histogram (integer atomics)
+//   scan_kernel    exclusive prefix over the 65 536 bins (64 block-local scans + 64 totals)
+//   scatter_kernel slot = offset[key] + atomic cursor  -> tmp (order inside a bin is arrival order ...)
+//   rank_kernel    ... so each point re-derives its slot as its rank among its bin-mates by point index: the final
+//                  permutation is a pure function of the input (bit-reproducible reduction order downstream)
+constexpr int SORT_BINS = 1 << 16;
+__device__ __forceinline__ uint32_t spread7(uint32_t v) {   // 7 bits -> every other bit
+  v &= 0x7Fu;
+  v = (v | (v << 4)) & 0x070Fu;
+  v = (v | (v << 2)) & 0x1333u;
+  v = (v | (v << 1)) & 0x1555u;
   return v;
 }
 template <int MODE>
-__global__ void morton_kernel(const malio_scan_pt* __restrict__ pts, const float* __restrict__ queries, uint32_t N,
-                              PassConst pc, uint32_t* __restrict__ keys, uint32_t* __restrict__ ids) {
+__global__ void count_kernel(const malio_scan_pt* __restrict__ pts, const float* __restrict__ queries, uint32_t N,
+                             PassConst pc, uint16_t* __restrict__ keys, uint32_t* __restrict__ hist) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   float x, y, z;
@@ -381,10 +393,74 @@ __global__ void morton_kernel(const malio_scan_pt* __restrict__ pts, const float
   } else {
     x = queries[3 * (size_t)i]; y = queries[3 * (size_t)i + 1]; z = queries[3 * (size_t)i + 2];
   }
-  // 1 m cells, 10 bits per axis (wraps every 1024 m: only locality matters)
-  const uint32_t ix = (uint32_t)(int)floorf(x), iy = (uint32_t)(int)floorf(y), iz = (uint32_t)(int)floorf(z);
-  keys[i] = spread10(ix) | (spread10(iy) << 1) | (spread10(iz) << 2);
-  ids[i] = i;
+  const uint32_t ix = (uint32_t)(int)floorf(x * 0.5f), iy = (uint32_t)(int)floorf(y * 0.5f), iz = (uint32_t)(int)floorf(z * 0.5f);
+  const uint32_t key = ((iz & 3u) << 14) | (spread7(iy) << 1) | spread7(ix);
+  keys[i] = (uint16_t)key;
+  atomicAdd(hist + key, 1u);
+}
+// 64 blocks x 1024 bins: block-local exclusive scan (coalesced uint4 loads) + the block's total; consumers add the
+// prefix of the 64 totals themselves (bin_base below) — no second scan kernel, no grid-wide dependency
+constexpr int SCAN_BLOCKS = 64, SCAN_THREADS = 256;
+static_assert(SCAN_BLOCKS * SCAN_THREADS * 4 == SORT_BINS, "scan tiling");
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ offs,
+                                                            uint32_t* __restrict__ cursor, uint32_t* __restrict__ btot) {
+  __shared__ uint32_t s_w[SCAN_THREADS / 32];
+  const uint32_t base = (blockIdx.x * SCAN_THREADS + threadIdx.x) * 4;
+  const uint4 v = *reinterpret_cast<const uint4*>(hist + base);
+  const uint32_t sum = v.x + v.y + v.z + v.w;
+  uint32_t inc = sum;   // inclusive warp scan
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= (unsigned)o) inc += t; }
+  if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = inc;
+  __syncthreads();
+  uint32_t wbase = 0;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += s_w[w];
+  uint32_t run = wbase + inc - sum;
+  uint4 o4;
+  o4.x = run; run += v.x; o4.y = run; run += v.y; o4.z = run; run += v.z; o4.w = run;
+  *reinterpret_cast<uint4*>(offs + base) = o4;
+  *reinterpret_cast<uint4*>(cursor + base) = make_uint4(0u, 0u, 0u, 0u);
+  if (threadIdx.x == SCAN_THREADS - 1) btot[blockIdx.x] = wbase + inc;
+}
+// prefix of the 64 block totals into shared memory (every consumer block recomputes it: 64 adds)
+__device__ __forceinline__ void load_bin_base(const uint32_t* __restrict__ btot, uint32_t* s_base) {
+  if (threadIdx.x < 32) {
+    const uint32_t a = btot[threadIdx.x], b = btot[32 + threadIdx.x];
+    uint32_t ia = a, ib = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+      if (threadIdx.x >= (unsigned)o) { ia += ta; ib += tb; }
+    }
+    const uint32_t tot_a = __shfl_sync(0xffffffffu, ia, 31);
+    s_base[threadIdx.x] = ia - a;
+    s_base[32 + threadIdx.x] = tot_a + ib - b;
+  }
+  __syncthreads();
+}
+__global__ void scatter_kernel(const uint16_t* __restrict__ keys, uint32_t N, const uint32_t* __restrict__ offs,
+                               const uint32_t* __restrict__ btot, uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm) {
+  __shared__ uint32_t s_base[SCAN_BLOCKS];
+  load_bin_base(btot, s_base);
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const uint32_t key = keys[i];
+  perm[s_base[key >> 10] + offs[key] + atomicAdd(cursor + key, 1u)] = i;
+}
+// one thread per point: its final slot inside its bin is the number of bin-mates with a smaller index
+// (bins hold ~10 points, at most a few dozen: a short, fully parallel O(cnt) scan per point)
+__global__ void rank_kernel(const uint16_t* __restrict__ keys, uint32_t N, const uint32_t* __restrict__ offs,
+                            const uint32_t* __restrict__ btot, const uint32_t* __restrict__ hist,
+                            const uint32_t* __restrict__ tmp, uint32_t* __restrict__ perm) {
+  __shared__ uint32_t s_base[SCAN_BLOCKS];
+  load_bin_base(btot, s_base);
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const uint32_t key = keys[i];
+  const uint32_t off = s_base[key >> 10] + offs[key], cnt = hist[key];
+  uint32_t rank = 0;
+  for (uint32_t j = 0; j < cnt; ++j) rank += (tmp[off + j] < i) ? 1u : 0u;
+  perm[off + rank] = i;
 }
 
 // ------------------------------------------------------------------ K2: plane fit, gates, point-wise uncertainty
@@ -643,8 +719,8 @@ __global__ void __launch_bounds__(GATE_THREADS)
 gate_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t N, PassConst pc,
             const float4* __restrict__ plane, const double* __restrict__ ucov, const double2* __restrict__ tau2,
             uint8_t* __restrict__ sel, float4* __restrict__ world, float* __restrict__ pd2_out,
-            double* __restrict__ tau, float* __restrict__ normal_y,
-            unsigned long long* __restrict__ d_mmkey, uint32_t* __restrict__ d_cnt) {
+            double* __restrict__ tau, float* __restrict__ normal_y, double* __restrict__ rows12,
+            uint8_t* __restrict__ lid8, unsigned long long* __restrict__ d_mmkey, uint32_t* __restrict__ d_cnt) {
   const uint32_t p = blockIdx.x * GATE_THREADS + threadIdx.x;
   MinMax4 mm{1000.0, 0.0, 9999.0, 0.0, 0u};   // laserMapping.cpp:615-616, 646-647
   if (p < N) {
@@ -662,6 +738,42 @@ gate_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ 
       selected = (double)s > 0.1;
       pd2_out[p] = pd2;
       if (!selected) sel[p] = 0;
+      if (selected) {
+        // un-weighted Jacobian row, compact: [ n | A | B | C ]  (laserMapping.cpp:665-693)
+        const int lid = pt.lidar;
+        const double nvec[3] = {(double)pl.x, (double)pl.y, (double)pl.z};
+        double C[3], A[3], B[3] = {0.0, 0.0, 0.0};
+        q_rot_conj(pc.rot, nvec, C);                    // :676  s.rot.conjugate() * norm_vec
+        cross3(m, C, A);                                // :677  [point_this]x * C
+        double Cc[3] = {0.0, 0.0, 0.0};
+        if (pc.ext_en) {
+          double Rq[9], v[3];
+          if (lid == 0) {   // :684  ([b]x R(qE0^T)) C
+            q_conj_to_R(pc.eq[0], Rq);
+            v[0] = b[0]; v[1] = b[1]; v[2] = b[2];
+          } else {          // :687-690
+            double C2[3];
+            q_rot_conj(pc.cq[lid], C, C2);
+            C[0] = C2[0]; C[1] = C2[1]; C[2] = C2[2];
+            q_conj_to_R(pc.eq[lid], Rq);
+            v[0] = pt.x; v[1] = pt.y; v[2] = pt.z;
+          }
+          // M = skew(v) * Rq, then B = M * C  (same association as the reference's M3D * Quaternion * V3D)
+          const double S[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            double Mi[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Mi[j] = S[3 * i] * Rq[j] + S[3 * i + 1] * Rq[3 + j] + S[3 * i + 2] * Rq[6 + j];
+            B[i] = Mi[0] * C[0] + Mi[1] * C[1] + Mi[2] * C[2];
+          }
+          Cc[0] = C[0]; Cc[1] = C[1]; Cc[2] = C[2];
+        }
+        double2* dst = reinterpret_cast<double2*>(rows12 + (size_t)p * 12);
+        dst[0] = make_double2(nvec[0], nvec[1]); dst[1] = make_double2(nvec[2], A[0]); dst[2] = make_double2(A[1], A[2]);
+        dst[3] = make_double2(B[0], B[1]);       dst[4] = make_double2(B[2], Cc[0]);   dst[5] = make_double2(Cc[1], Cc[2]);
+        lid8[p] = (uint8_t)lid;
+      }
     }
     const double2 t2 = tau2[p];
     if (selected) {
@@ -697,69 +809,25 @@ gate_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ 
   }
 }
 
-// ------------------------------------------------------------------ K3: rows + fused H^T R^-1 [H | h] reduction
-// Per selected point (laserMapping.cpp:649-722): plane weight a_i, Jacobian row J_i, noise rho_i; the row
-// h = a_i J_i, z = -a_i pd2.  Accumulates  sum (h_a / rho^) * [h | z | rho^ h_0..2]_b  (esekfom.hpp:622-635).
+// ------------------------------------------------------------------ K3: weights + fused H^T R^-1 [H | h] reduction
+// The gate kernel leaves, per selected point, the un-weighted Jacobian row in compact form
+//   J12 = [ n | [m]x C0 | B | C ]     (laserMapping.cpp:665-693; 12 of the 24 columns are non-zero)
+// and the LiDAR id that says where B and C sit (columns 6+3l and 6+3(L+l)).  Here each row gets its plane weight
+// a_i (:651-656) and noise rho_i (:716-721, clamp esekfom.hpp:624-626) and the block accumulates, per LiDAR l,
+//     Gc_l = sum_{i in l} (a J12 / rho^)_a * [ a J12 | z | rho^ a J12_0..2 ]_b          (12 x 16, upper 4x4 blocks)
+// i.e. esekfom.hpp:622-635 restricted to the non-zero columns (3.7x fewer FP64 operations than the dense 24 x 28
+// form; FP64 issue is the limiter of this kernel).  The host scatters the three compact systems into the c x c one.
 // The localization weight (a scalar, :745-759) factors out and is applied on the host.
-// Returns the unscaled row in r[24], z, rho^ ; false if the point is not selected.
-__device__ __forceinline__ bool build_row(uint32_t p, uint32_t N, const malio_scan_pt* __restrict__ pts,
-                                          const uint32_t* __restrict__ perm, const PassConst& pc,
-                                          const ParamConst& prm, const uint8_t* __restrict__ sel,
-                                          const float4* __restrict__ plane, const float* __restrict__ pd2v,
-                                          const double* __restrict__ ucov,
-                                          const double* __restrict__ tau, const unsigned long long* __restrict__ d_mm,
-                                          double r[24], double& z, double& rho) {
-  if (p >= N || !sel[p]) return false;
-  const malio_scan_pt pt = pts[perm ? perm[p] : p];
-  const int lid = pt.lidar;
-  const double umin = dkey_inv(d_mm[0]), umax = -dkey_inv(d_mm[1]), tmin = dkey_inv(d_mm[2]), tmax = -dkey_inv(d_mm[3]);
+__device__ __forceinline__ void point_weights(const ParamConst& prm, double u, double tau_i, int ext_en,
+                                              double umin, double umax, double tmin, double tmax,
+                                              double& a, double& rho) {
   // :651-656
-  double a = ucov[p];
+  a = u;
   if (a == 0) a = 1;
   else if (umax == umin) a = (prm.plane_cov_max + prm.plane_cov_min) / 2;
   else a = 1 / ((prm.plane_cov_max - prm.plane_cov_min) * (a - umin) / (umax - umin) + prm.plane_cov_min);
-  double b[3], m[3], g[3];
-  transform_point(pc, pt.x, pt.y, pt.z, lid, b, m, g);
-  const float4 pl = plane[p];
-  const double nvec[3] = {(double)pl.x, (double)pl.y, (double)pl.z};
-  double C[3], A[3], B[3];
-  q_rot_conj(pc.rot, nvec, C);                    // :676  s.rot.conjugate() * norm_vec
-  cross3(m, C, A);                                // :677  [point_this]x * C
-#pragma unroll
-  for (int k = 0; k < 24; ++k) r[k] = 0.0;
-  r[0] = nvec[0]; r[1] = nvec[1]; r[2] = nvec[2]; r[3] = A[0]; r[4] = A[1]; r[5] = A[2];
-  double R = 0.0;
-  if (pc.ext_en) {
-    double Rq[9], v[3];
-    if (lid == 0) {   // :684  ([b]x R(qE0^T)) C
-      q_conj_to_R(pc.eq[0], Rq);
-      v[0] = b[0]; v[1] = b[1]; v[2] = b[2];
-    } else {          // :687-690
-      double C2[3];
-      q_rot_conj(pc.cq[lid], C, C2);
-      C[0] = C2[0]; C[1] = C2[1]; C[2] = C2[2];
-      q_conj_to_R(pc.eq[lid], Rq);
-      v[0] = pt.x; v[1] = pt.y; v[2] = pt.z;
-    }
-    // M = skew(v) * Rq, then B = M * C  (same association as the reference's M3D * Quaternion * V3D)
-    const double S[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      double Mi[3];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) Mi[j] = S[3 * i] * Rq[j] + S[3 * i + 1] * Rq[3 + j] + S[3 * i + 2] * Rq[6 + j];
-      B[i] = Mi[0] * C[0] + Mi[1] * C[1] + Mi[2] * C[2];
-    }
-#pragma unroll
-    for (int l = 0; l < MALIO_MAX_LIDAR; ++l) {
-      if (l == lid) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { r[6 + 3 * l + k] = B[k]; r[15 + 3 * l + k] = C[k]; }
-      }
-    }
-    R = tau[p];
-  }
   // :716-721 (FIC).  Degenerate 0/0 defined as mid-range (the reference yields NaN)
+  double R = ext_en ? tau_i : 0.0;
   if (R < tmin + (tmax - tmin) * prm.range_min) R = prm.point_cov_min;
   else if (R > tmin + (tmax - tmin) * prm.range_max) R = prm.point_cov_max;
   else {
@@ -769,95 +837,109 @@ __device__ __forceinline__ bool build_row(uint32_t p, uint32_t N, const malio_sc
   }
   if (R < 0.0001) R = 0.001;   // esekfom.hpp:624-626
   rho = R;
-#pragma unroll
-  for (int k = 0; k < 24; ++k) r[k] = r[k] * a;   // :714
-  z = ((-1) * (double)pd2v[p]) * a;               // :707,715
-  return true;
 }
 
-// task t (0..26) -> upper-triangular 4x4 block (row group gi, col group gj >= gi) of the 24 x 28 system
+// task t (0..8) -> upper-triangular 4x4 block (row group gi < 3, col group gj >= gi, gj < 4) of a 12 x 16 system
 __device__ __forceinline__ void red_task(int t, int& gi, int& gj) {
-  int i = 0, rem = t;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const int len = 7 - k;
-    if (rem >= len && i == k) { rem -= len; i = k + 1; }
-  }
-  gi = i; gj = i + rem;
+  gi = (t >= 4) + (t >= 7);
+  gj = t - (gi == 0 ? 0 : (gi == 1 ? 3 : 5));
 }
 
 __global__ void __launch_bounds__(RED_THREADS)
-reduce_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t N, PassConst pc,
-              ParamConst prm, const uint8_t* __restrict__ sel, const float4* __restrict__ plane,
-              const float* __restrict__ pd2v, const double* __restrict__ ucov, const double* __restrict__ tau,
-              const unsigned long long* __restrict__ d_mm, uint32_t n_tiles, double* __restrict__ block_red, uint32_t* __restrict__ counter,
-              double* __restrict__ d_res) {
+reduce_kernel(uint32_t N, ParamConst prm, int ext_en, const uint8_t* __restrict__ sel, const uint8_t* __restrict__ lid8,
+              const double* __restrict__ rows12, const float* __restrict__ pd2v, const double* __restrict__ ucov,
+              const double* __restrict__ tau, const unsigned long long* __restrict__ d_mm, uint32_t n_tiles,
+              double* __restrict__ block_red) {
   extern __shared__ double smem[];
-  double* s_hs = smem;                                   // [128][26]  h / rho^
-  double* s_hx = smem + RED_THREADS * RED_HS_STRIDE;     // [128][28]  [h | z | rho^ h0..2]
-  const int task = threadIdx.x >> 2, ks = threadIdx.x & 3;
+  double* s_hs = smem;                                       // [128][RED_HS_STRIDE]  a J12 / rho^
+  double* s_hx = s_hs + RED_THREADS * RED_HS_STRIDE;         // [128][RED_HX_STRIDE]  [a J12 | z | rho^ a J12_0..2]
+  double* s_acc = s_hx + RED_THREADS * RED_HX_STRIDE;        // [3 lidar][16][RED_TASKS * RED_KS]  (entry-major: conflict-free)
+  __shared__ uint32_t s_wcnt[MALIO_MAX_LIDAR][RED_THREADS / 32];
+  __shared__ uint32_t s_seg[MALIO_MAX_LIDAR + 1];
+  __shared__ uint32_t s_cnt_total;
+  const int task = threadIdx.x / RED_KS, ks = threadIdx.x % RED_KS;
+  const bool worker = task < RED_TASKS;
   int gi = 0, gj = 0;
-  if (task < MALIO_RED_BLOCKS) red_task(task, gi, gj);
-  double acc[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) acc[k] = 0.0;
-  uint32_t cnt = 0;
+  if (worker) red_task(task, gi, gj);
+  for (int k = threadIdx.x; k < MALIO_MAX_LIDAR * RED_TASKS * RED_KS * 16; k += RED_THREADS) s_acc[k] = 0.0;
+  if (threadIdx.x == 0) s_cnt_total = 0;
+  const double umin = dkey_inv(d_mm[0]), umax = -dkey_inv(d_mm[1]), tmin = dkey_inv(d_mm[2]), tmax = -dkey_inv(d_mm[3]);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // ---- phase A: weight this thread's row, then place it in the tile's LiDAR-sorted order
     const uint32_t p = tile * RED_THREADS + threadIdx.x;
-    double r[24], z = 0.0, rho = 1.0;
-    const bool ok = build_row(p, N, pts, perm, pc, prm, sel, plane, pd2v, ucov, tau, d_mm, r, z, rho);
-    double* hs = s_hs + threadIdx.x * RED_HS_STRIDE;
-    double* hx = s_hx + threadIdx.x * RED_HX_STRIDE;
+    const bool ok = (p < N) && sel[p];
+    const int l = ok ? (int)lid8[p] : -1;
+    double h[12], z = 0.0, rho = 1.0, a = 0.0;
     if (ok) {
-      cnt++;
-      const double inv_rho = 1.0 / rho;   // HT(:,i) / R_i (esekfom.hpp:627) as a multiply: <= 1 ulp per term
+      point_weights(prm, ucov[p], ext_en ? tau[p] : 0.0, ext_en, umin, umax, tmin, tmax, a, rho);
+      const double2* src = reinterpret_cast<const double2*>(rows12 + (size_t)p * 12);
 #pragma unroll
-      for (int k = 0; k < 24; ++k) { hs[k] = r[k] * inv_rho; hx[k] = r[k]; }
-      hx[24] = z; hx[25] = rho * r[0]; hx[26] = rho * r[1]; hx[27] = rho * r[2];
-    } else {
-#pragma unroll
-      for (int k = 0; k < 24; ++k) { hs[k] = 0.0; hx[k] = 0.0; }
-      hx[24] = 0.0; hx[25] = 0.0; hx[26] = 0.0; hx[27] = 0.0;
+      for (int k = 0; k < 6; ++k) { const double2 v = src[k]; h[2 * k] = v.x * a; h[2 * k + 1] = v.y * a; }   // :714
+      z = ((-1) * (double)pd2v[p]) * a;                                                                  // :707,715
+    }
+    const uint32_t b0 = __ballot_sync(0xffffffffu, l == 0), b1 = __ballot_sync(0xffffffffu, l == 1),
+                   b2 = __ballot_sync(0xffffffffu, l == 2);
+    if (lane == 0) { s_wcnt[0][wid] = __popc(b0); s_wcnt[1][wid] = __popc(b1); s_wcnt[2][wid] = __popc(b2); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t run = 0;
+      for (int ll = 0; ll < MALIO_MAX_LIDAR; ++ll) {
+        s_seg[ll] = run;
+        for (int w = 0; w < RED_THREADS / 32; ++w) { const uint32_t c = s_wcnt[ll][w]; s_wcnt[ll][w] = run; run += c; }
+      }
+      s_seg[MALIO_MAX_LIDAR] = run;
+      s_cnt_total += run;
     }
     __syncthreads();
-    if (task < MALIO_RED_BLOCKS) {
-#pragma unroll 4
-      for (int q = ks; q < RED_THREADS; q += 4) {
-        const double* a = s_hs + q * RED_HS_STRIDE + 4 * gi;
-        const double* bq = s_hx + q * RED_HX_STRIDE + 4 * gj;
-        const double a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
-        const double b0 = bq[0], b1 = bq[1], b2 = bq[2], b3 = bq[3];
-        acc[0] = fma(a0, b0, acc[0]);  acc[1] = fma(a0, b1, acc[1]);  acc[2] = fma(a0, b2, acc[2]);  acc[3] = fma(a0, b3, acc[3]);
-        acc[4] = fma(a1, b0, acc[4]);  acc[5] = fma(a1, b1, acc[5]);  acc[6] = fma(a1, b2, acc[6]);  acc[7] = fma(a1, b3, acc[7]);
-        acc[8] = fma(a2, b0, acc[8]);  acc[9] = fma(a2, b1, acc[9]);  acc[10] = fma(a2, b2, acc[10]); acc[11] = fma(a2, b3, acc[11]);
-        acc[12] = fma(a3, b0, acc[12]); acc[13] = fma(a3, b1, acc[13]); acc[14] = fma(a3, b2, acc[14]); acc[15] = fma(a3, b3, acc[15]);
+    if (ok) {
+      const uint32_t bal = l == 0 ? b0 : (l == 1 ? b1 : b2);
+      const uint32_t dst = s_wcnt[l][wid] + __popc(bal & ((1u << lane) - 1u));
+      double* hs = s_hs + dst * RED_HS_STRIDE;
+      double* hx = s_hx + dst * RED_HX_STRIDE;
+      const double inv_rho = 1.0 / rho;   // HT(:,i) / R_i (esekfom.hpp:627) as a multiply: <= 1 ulp per term
+#pragma unroll
+      for (int k = 0; k < 12; ++k) { hs[k] = h[k] * inv_rho; hx[k] = h[k]; }
+      hx[12] = z; hx[13] = rho * h[0]; hx[14] = rho * h[1]; hx[15] = rho * h[2];
+    }
+    __syncthreads();
+    // ---- phase B: per LiDAR segment, 9 block tasks x RED_KS row-splits
+    if (worker) {
+#pragma unroll 1
+      for (int ll = 0; ll < MALIO_MAX_LIDAR; ++ll) {
+        const uint32_t beg = s_seg[ll], end = s_seg[ll + 1];
+        if (beg == end) continue;
+        double acc[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+        for (uint32_t q = beg + ks; q < end; q += RED_KS) {
+          const double* aa = s_hs + q * RED_HS_STRIDE + 4 * gi;
+          const double* bb = s_hx + q * RED_HX_STRIDE + 4 * gj;
+          const double a0 = aa[0], a1 = aa[1], a2 = aa[2], a3 = aa[3];
+          const double c0 = bb[0], c1 = bb[1], c2 = bb[2], c3 = bb[3];
+          acc[0] = fma(a0, c0, acc[0]);   acc[1] = fma(a0, c1, acc[1]);   acc[2] = fma(a0, c2, acc[2]);   acc[3] = fma(a0, c3, acc[3]);
+          acc[4] = fma(a1, c0, acc[4]);   acc[5] = fma(a1, c1, acc[5]);   acc[6] = fma(a1, c2, acc[6]);   acc[7] = fma(a1, c3, acc[7]);
+          acc[8] = fma(a2, c0, acc[8]);   acc[9] = fma(a2, c1, acc[9]);   acc[10] = fma(a2, c2, acc[10]); acc[11] = fma(a2, c3, acc[11]);
+          acc[12] = fma(a3, c0, acc[12]); acc[13] = fma(a3, c1, acc[13]); acc[14] = fma(a3, c2, acc[14]); acc[15] = fma(a3, c3, acc[15]);
+        }
+        double* sa = s_acc + (size_t)ll * 16 * (RED_TASKS * RED_KS) + threadIdx.x;   // this thread's own cells
+#pragma unroll
+        for (int k = 0; k < 16; ++k) sa[k * (RED_TASKS * RED_KS)] += acc[k];
       }
     }
     __syncthreads();
   }
-  // fold the 4 k-splits of each task with warp shuffles (lanes 4t..4t+3), then per-block slot
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
-    acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2);
-  }
-  // selected-point count of this block
-  __shared__ uint32_t s_cnt[RED_THREADS / 32];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  // ---- fold the RED_KS row-splits (fixed order) and write this block's slot
   double* slot = block_red + (size_t)blockIdx.x * MALIO_RED_DOUBLES;
-  if (task < MALIO_RED_BLOCKS && ks == 0) {
+  for (int e = threadIdx.x; e < MALIO_MAX_LIDAR * RED_TASKS * 16; e += RED_THREADS) {
+    const int lt = e / 16, k = e % 16, ll = lt / RED_TASKS, tk = lt % RED_TASKS;
+    double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) slot[task * 16 + k] = acc[k];
+    for (int q = 0; q < RED_KS; ++q) s += s_acc[((size_t)ll * 16 + k) * (RED_TASKS * RED_KS) + tk * RED_KS + q];
+    slot[e] = s;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t c = 0;
-    for (int w = 0; w < RED_THREADS / 32; ++w) c += s_cnt[w];
-    slot[MALIO_RED_BLOCKS * 16] = (double)c;
-    slot[MALIO_RED_BLOCKS * 16 + 1] = 0.0;
-  }
+  if (threadIdx.x == 0) { slot[MALIO_RED_BLOCKS * 16] = (double)s_cnt_total; slot[MALIO_RED_BLOCKS * 16 + 1] = 0.0; }
 }
 
 // second stage: one warp per entry of the reduced system folds the per-block slots in a fixed order
@@ -879,23 +961,21 @@ fold_kernel(const double* __restrict__ block_red, uint32_t n_slots, double* __re
   if (lane == 0) d_res[e] = s;
 }
 
-// rows for the degenerate branch (esekfom.hpp:574-582): positions of the first `cap` selected points are
-// found by one block; rows are written un-weighted by the localization weight (the host applies it)
-__global__ void rows_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t N,
-                            PassConst pc, ParamConst prm, const uint8_t* __restrict__ sel,
-                            const float4* __restrict__ plane, const float* __restrict__ pd2v,
-                            const double* __restrict__ ucov,
+// rows for the degenerate branch (esekfom.hpp:574-582): the first `cap` selected points in position order, one
+// block; rows are written in the padded 24-column layout + z, un-weighted by the localization weight
+__global__ void rows_kernel(uint32_t N, ParamConst prm, int ext_en, const uint8_t* __restrict__ sel,
+                            const uint8_t* __restrict__ lid8, const double* __restrict__ rows12,
+                            const float* __restrict__ pd2v, const double* __restrict__ ucov,
                             const double* __restrict__ tau, const unsigned long long* __restrict__ d_mm, uint32_t cap,
                             double* __restrict__ rows /* cap x 25 */, uint32_t* __restrict__ n_rows) {
   __shared__ uint32_t s_base;
+  __shared__ uint32_t s_wcnt[32];
   if (threadIdx.x == 0) s_base = 0;
+  const double umin = dkey_inv(d_mm[0]), umax = -dkey_inv(d_mm[1]), tmin = dkey_inv(d_mm[2]), tmax = -dkey_inv(d_mm[3]);
   __syncthreads();
   for (uint32_t start = 0; start < N; start += blockDim.x) {
     const uint32_t p = start + threadIdx.x;
-    double r[24], z = 0.0, rho = 1.0;
-    const bool ok = build_row(p, N, pts, perm, pc, prm, sel, plane, pd2v, ucov, tau, d_mm, r, z, rho);
-    // block-wide exclusive scan of ok via warp ballots
-    __shared__ uint32_t s_wcnt[32];
+    const bool ok = (p < N) && sel[p];
     const uint32_t bal = __ballot_sync(0xffffffffu, ok);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (lane == 0) s_wcnt[w] = __popc(bal);
@@ -904,8 +984,15 @@ __global__ void rows_kernel(const malio_scan_pt* __restrict__ pts, const uint32_
     for (int k = 0; k < w; ++k) off += s_wcnt[k];
     off += __popc(bal & ((1u << lane) - 1u));
     if (ok && off < cap) {
-      for (int k = 0; k < 24; ++k) rows[(size_t)off * 25 + k] = r[k];
-      rows[(size_t)off * 25 + 24] = z;
+      double a, rho;
+      point_weights(prm, ucov[p], ext_en ? tau[p] : 0.0, ext_en, umin, umax, tmin, tmax, a, rho);
+      const int l = lid8[p];
+      double* o = rows + (size_t)off * 25;
+      for (int k = 0; k < 24; ++k) o[k] = 0.0;
+      const double* j = rows12 + (size_t)p * 12;
+      for (int k = 0; k < 6; ++k) o[k] = j[k] * a;
+      for (int k = 0; k < 3; ++k) { o[6 + 3 * l + k] = j[6 + k] * a; o[15 + 3 * l + k] = j[9 + k] * a; }
+      o[24] = ((-1) * (double)pd2v[p]) * a;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -970,14 +1057,15 @@ struct DeviceState {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [5] after sort, [6] after knn kernel
   malio_counters ctr{};
+  bool timing = true;   // per-pass CUDA-event timing (malio_set_timing)
+  double host_launch_us = 0, host_wait_us = 0; uint64_t host_passes = 0;   // MALIO_HOST_PROF=1 prints them at destroy
   // map
   float4* d_nodes = nullptr; float* d_cov = nullptr;
   uint32_t n_nodes = 0, cap_nodes = 0, depth = 0;
   // scan (caller order) + internal order
   malio_scan_pt* d_pts = nullptr; uint32_t N = 0, capN = 0;
   uint32_t* d_perm = nullptr; bool perm_valid = false;
-  uint32_t *d_keys = nullptr, *d_keys_out = nullptr, *d_ids = nullptr;
-  void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
+  uint16_t* d_keys16 = nullptr; uint32_t *d_hist = nullptr, *d_offs = nullptr, *d_cursor = nullptr, *d_btot = nullptr, *d_tmp_ids = nullptr;   // counting sort
   double* d_table = nullptr; uint32_t cap_table = 0;
   uint32_t table_off[MALIO_MAX_LIDAR + 1] = {0, 0, 0, 0};
   malio_rigid tcomp[MALIO_MAX_LIDAR];
@@ -986,6 +1074,7 @@ struct DeviceState {
   uint32_t* d_nn_idx = nullptr; float* d_nn_d2 = nullptr; uint8_t* d_sel = nullptr;
   float4 *d_world = nullptr, *d_plane = nullptr; double *d_ucov = nullptr, *d_tau = nullptr; float* d_normal_y = nullptr;
   double2* d_tau2 = nullptr; float* d_pd2 = nullptr; bool tau_valid = false;
+  double* d_rows12 = nullptr; uint8_t* d_lid8 = nullptr;
   // aux staging (caller order)
   float* d_o_ny = nullptr; uint32_t* d_o_idx = nullptr; float* d_o_d2 = nullptr; uint8_t* d_o_sel = nullptr; float* d_o_world = nullptr;
   // reductions
@@ -1049,16 +1138,17 @@ uint32_t knn_blocks(uint32_t n, int lanes) {
   return (warps + KNN_THREADS / 32 - 1) / (KNN_THREADS / 32);
 }
 
-int sort_queries(malio_handle* h, DeviceState* D, uint32_t n) {
-  size_t need = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, need, D->d_keys, D->d_keys_out, D->d_ids, D->d_perm, (int)n, 0, 30, D->stream);
-  if (need > D->sort_tmp_bytes) {
-    if (D->d_sort_tmp) cudaFree(D->d_sort_tmp);
-    D->d_sort_tmp = nullptr;
-    CUDA_TRY(cudaMalloc(&D->d_sort_tmp, need));
-    D->sort_tmp_bytes = need;
-  }
-  CUDA_TRY(cub::DeviceRadixSort::SortPairs(D->d_sort_tmp, need, D->d_keys, D->d_keys_out, D->d_ids, D->d_perm, (int)n, 0, 30, D->stream));
+// keys + counting sort of n queries into D->d_perm (MODE 0: scan points through pc, MODE 1: D->d_queries)
+template <int MODE>
+int sort_queries(malio_handle* h, DeviceState* D, uint32_t n, const PassConst& pc) {
+  cudaStream_t st = D->stream;
+  CUDA_TRY(cudaMemsetAsync(D->d_hist, 0, SORT_BINS * sizeof(uint32_t), st));
+  count_kernel<MODE><<<(n + 255) / 256, 256, 0, st>>>(D->d_pts, D->d_queries, n, pc, D->d_keys16, D->d_hist);
+  scan_kernel<<<SCAN_BLOCKS, SCAN_THREADS, 0, st>>>(D->d_hist, D->d_offs, D->d_cursor, D->d_btot);
+  scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(D->d_keys16, n, D->d_offs, D->d_btot, D->d_cursor, D->d_tmp_ids);
+  rank_kernel<<<(n + 255) / 256, 256, 0, st>>>(D->d_keys16, n, D->d_offs, D->d_btot, D->d_hist, D->d_tmp_ids, D->d_perm);
+  CUDA_TRY(cudaGetLastError());
+  D->ctr.kernel_launches += 4;
   return MALIO_OK;
 }
 
@@ -1088,12 +1178,17 @@ int create(malio_handle* h) {
     CUDA_TRY(cudaMemcpy(D->d_mmkey, init, sizeof(init), cudaMemcpyHostToDevice));
   }
   CUDA_TRY(cudaMalloc((void**)&D->d_res, MALIO_RED_DOUBLES * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void**)&D->d_hist, SORT_BINS * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc((void**)&D->d_offs, SORT_BINS * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc((void**)&D->d_cursor, SORT_BINS * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc((void**)&D->d_btot, SCAN_BLOCKS * sizeof(uint32_t)));
+  CUDA_TRY(cudaMemset(D->d_hist, 0, SORT_BINS * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc((void**)&D->d_rows, (size_t)MALIO_MAX_DOF * 25 * sizeof(double)));
-  D->red_grid = (uint32_t)D->sm_count * 3;   // 156 registers x 128 threads: 3 blocks per SM are co-resident
+  D->red_grid = (uint32_t)D->sm_count * 2;   // 81 KB of shared memory per block: 2 blocks per SM are co-resident
   CUDA_TRY(cudaMalloc((void**)&D->d_block_red, (size_t)D->red_grid * MALIO_RED_DOUBLES * sizeof(double)));
   CUDA_TRY(cudaMallocHost((void**)&D->h_res, (MALIO_RED_DOUBLES + 8 + MALIO_MAX_DOF * 25) * sizeof(double)));
   CUDA_TRY(cudaFuncSetAttribute(reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                RED_THREADS * (RED_HS_STRIDE + RED_HX_STRIDE) * (int)sizeof(double)));
+                                RED_SMEM_DOUBLES * (int)sizeof(double)));
   for (int l = 0; l < MALIO_MAX_LIDAR; ++l) { D->tcomp[l] = malio_rigid{{1, 0, 0, 0}, {0, 0, 0}}; }
   return MALIO_OK;
 }
@@ -1101,10 +1196,13 @@ int create(malio_handle* h) {
 void destroy(malio_handle* h) {
   DeviceState* D = (DeviceState*)h->dev;
   if (!D) return;
+  if (getenv("MALIO_HOST_PROF") && D->host_passes)
+    fprintf(stderr, "[malio] passes %llu: host launch %.1f us/pass, host wait-for-device %.1f us/pass\n",
+            (unsigned long long)D->host_passes, D->host_launch_us / D->host_passes, D->host_wait_us / D->host_passes);
   cudaSetDevice(D->device);
   if (D->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(D->comm);
-  void* ptrs[] = {D->d_nodes, D->d_cov, D->d_pts, D->d_perm, D->d_keys, D->d_keys_out, D->d_ids, D->d_sort_tmp,
-                  D->d_table, D->d_nn_idx, D->d_nn_d2, D->d_sel, D->d_world, D->d_plane, D->d_ucov, D->d_tau, D->d_tau2, D->d_pd2,
+  void* ptrs[] = {D->d_nodes, D->d_cov, D->d_pts, D->d_perm, D->d_keys16, D->d_hist, D->d_offs, D->d_cursor, D->d_btot, D->d_tmp_ids,
+                  D->d_table, D->d_nn_idx, D->d_nn_d2, D->d_sel, D->d_world, D->d_plane, D->d_ucov, D->d_tau, D->d_tau2, D->d_pd2, D->d_rows12, D->d_lid8,
                   D->d_normal_y, D->d_o_ny, D->d_o_idx, D->d_o_d2, D->d_o_sel, D->d_o_world, D->d_block_mm,
                   D->d_block_cnt, D->d_counters, D->d_mmkey, D->d_block_red, D->d_res, D->d_rows, D->d_queries};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -1141,9 +1239,8 @@ static int ensure_point_buffers(malio_handle* h, DeviceState* D, uint32_t n) {
   int rc = 0;
   if ((rc = ensure(h, D->d_pts, cap))) return rc;
   if ((rc = ensure(h, D->d_perm, cap))) return rc;
-  if ((rc = ensure(h, D->d_keys, cap))) return rc;
-  if ((rc = ensure(h, D->d_keys_out, cap))) return rc;
-  if ((rc = ensure(h, D->d_ids, cap))) return rc;
+  if ((rc = ensure(h, D->d_keys16, cap))) return rc;
+  if ((rc = ensure(h, D->d_tmp_ids, cap))) return rc;
   if ((rc = ensure(h, D->d_nn_idx, (size_t)cap * MALIO_K))) return rc;
   if ((rc = ensure(h, D->d_nn_d2, (size_t)cap * MALIO_K))) return rc;
   if ((rc = ensure(h, D->d_sel, cap))) return rc;
@@ -1153,6 +1250,8 @@ static int ensure_point_buffers(malio_handle* h, DeviceState* D, uint32_t n) {
   if ((rc = ensure(h, D->d_tau, cap))) return rc;
   if ((rc = ensure(h, D->d_tau2, cap))) return rc;
   if ((rc = ensure(h, D->d_pd2, cap))) return rc;
+  if ((rc = ensure(h, D->d_rows12, (size_t)cap * 12))) return rc;
+  if ((rc = ensure(h, D->d_lid8, cap))) return rc;
   if ((rc = ensure(h, D->d_normal_y, cap))) return rc;
   if ((rc = ensure(h, D->d_o_ny, cap))) return rc;
   if ((rc = ensure(h, D->d_o_idx, (size_t)cap * MALIO_K))) return rc;
@@ -1204,6 +1303,11 @@ int rearm_scan(malio_handle* h) {
   return MALIO_OK;
 }
 
+int set_timing(malio_handle* h, int enable) {
+  ((DeviceState*)h->dev)->timing = enable != 0;
+  return MALIO_OK;
+}
+
 int get_counters(malio_handle* h, malio_counters* out) {
   *out = ((DeviceState*)h->dev)->ctr;
   return MALIO_OK;
@@ -1217,25 +1321,24 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
   const malio_params& P = h->cfg.params;
   const int L = P.n_lidar, c = 6 * (L + 1);
   const uint32_t N = D->N;
+  const auto hp0 = std::chrono::steady_clock::now();
   const PassConst pc = make_pass_const(h, D, s);
   const ParamConst prm = make_param_const(P);
   D->last_pc = pc;
   cudaStream_t st_ = D->stream;
   const uint32_t* perm = nullptr;
-  CUDA_TRY(cudaEventRecord(D->ev[0], st_));
+  if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[0], st_));
   bool sorted_now = false, knn_now = false;
   if (N > 0) {
     if (h->cfg.sort_queries) {
       if (!D->perm_valid) {
-        morton_kernel<0><<<(N + 255) / 256, 256, 0, st_>>>(D->d_pts, nullptr, N, pc, D->d_keys, D->d_ids);
-        if (int rc = sort_queries(h, D, N)) return rc;
+        if (int rc = sort_queries<0>(h, D, N, pc)) return rc;
         D->perm_valid = true;
         sorted_now = true;
-        D->ctr.kernel_launches += 7;   // keys + CUB histogram / exclusive-sum / 4 onesweep passes (30 key bits)
       }
       perm = D->d_perm;
     }
-    CUDA_TRY(cudaEventRecord(D->ev[5], st_));
+    if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[5], st_));
     if (redo_knn) {
       knn_now = true;
       D->ctr.kernel_launches += 1;
@@ -1249,10 +1352,10 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
             D->d_nodes, D->n_nodes, D->d_pts, perm, nullptr, N, lanes, pc, P.knn_max_sqdist, D->d_world, D->d_nn_idx,
             D->d_nn_d2, D->d_sel);
       D->searched_once = true;
-      CUDA_TRY(cudaEventRecord(D->ev[6], st_));
+      if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[6], st_));
     }
   }
-  CUDA_TRY(cudaEventRecord(D->ev[1], st_));
+  if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[1], st_));
   const uint32_t pblocks = N > 0 ? (N + PLANE_THREADS - 1) / PLANE_THREADS : 1;
   if (N > 0 && !D->tau_valid) {   // once per scan
     tau_kernel<<<pblocks, PLANE_THREADS, 0, st_>>>(D->d_pts, perm, N, pc, D->d_table, D->d_tau2);
@@ -1270,47 +1373,64 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
   uint32_t* cnt_next = D->d_counters + 4 + (1 - D->parity);
   const uint32_t gblocks = N > 0 ? (N + GATE_THREADS - 1) / GATE_THREADS : 1;
   gate_kernel<<<gblocks, GATE_THREADS, 0, st_>>>(D->d_pts, perm, N, pc, D->d_plane, D->d_ucov, D->d_tau2, D->d_sel,
-                                                   D->d_world, D->d_pd2, D->d_tau, D->d_normal_y, mmkey, cnt_cell);
+                                                   D->d_world, D->d_pd2, D->d_tau, D->d_normal_y, D->d_rows12, D->d_lid8, mmkey, cnt_cell);
   if (D->comm)   // keys of {min_u, -max_u, min_tau, -max_tau}: one MIN all-reduce (laserMapping.cpp:615-628, 700-703)
     if (g_nccl.AllReduce(mmkey, mmkey, 4, ncclUint64, ncclMin, D->comm, st_) != ncclSuccess) { h->err = "ncclAllReduce(min) failed"; return MALIO_ERR_NCCL; }
-  CUDA_TRY(cudaEventRecord(D->ev[2], st_));
+  if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[2], st_));
   const uint32_t n_tiles = (N + RED_THREADS - 1) / RED_THREADS;
   // one resident wave, every block the same number of tiles (+-1): no straggler blocks
   const uint32_t per_block = n_tiles ? (n_tiles + D->red_grid - 1) / D->red_grid : 1;
   uint32_t grid = n_tiles ? (n_tiles + per_block - 1) / per_block : 1;
-  reduce_kernel<<<grid, RED_THREADS, RED_THREADS * (RED_HS_STRIDE + RED_HX_STRIDE) * sizeof(double), st_>>>(
-      D->d_pts, perm, N, pc, prm, D->d_sel, D->d_plane, D->d_pd2, D->d_ucov, D->d_tau, mmkey, n_tiles, D->d_block_red,
-      D->d_counters + 1, D->d_res);
+  reduce_kernel<<<grid, RED_THREADS, RED_SMEM_DOUBLES * sizeof(double), st_>>>(
+      N, prm, pc.ext_en, D->d_sel, D->d_lid8, D->d_rows12, D->d_pd2, D->d_ucov, D->d_tau, mmkey, n_tiles, D->d_block_red);
   fold_kernel<<<(MALIO_RED_DOUBLES * 32 + 255) / 256, 256, 0, st_>>>(D->d_block_red, grid, D->d_res, mmkey_next, cnt_next);
   if (D->comm)   // the reduced system + n_eff: one SUM all-reduce
     if (g_nccl.AllReduce(D->d_res, D->d_res, MALIO_RED_DOUBLES, ncclDouble, ncclSum, D->comm, st_) != ncclSuccess) { h->err = "ncclAllReduce(sum) failed"; return MALIO_ERR_NCCL; }
-  CUDA_TRY(cudaEventRecord(D->ev[3], st_));
+  if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[3], st_));
   CUDA_TRY(cudaMemcpyAsync(D->h_res, D->d_res, MALIO_RED_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, st_));
   CUDA_TRY(cudaMemcpyAsync(D->h_res + MALIO_RED_DOUBLES, mmkey, 4 * sizeof(double), cudaMemcpyDeviceToHost, st_));
   D->last_parity = D->parity;
   D->parity = 1 - D->parity;
-  CUDA_TRY(cudaEventRecord(D->ev[4], st_));
+  if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[4], st_));
+  const auto hp1 = std::chrono::steady_clock::now();
   CUDA_TRY(cudaStreamSynchronize(st_));
+  const auto hp2 = std::chrono::steady_clock::now();
   CUDA_TRY(cudaGetLastError());
   D->pass_done = true;
+  D->host_launch_us += std::chrono::duration<double, std::micro>(hp1 - hp0).count();
+  D->host_wait_us += std::chrono::duration<double, std::micro>(hp2 - hp1).count();
+  D->host_passes += 1;
 
   // ---- host epilogue: un-block, localization weight (laserMapping.cpp:745-759), compact to c x c
   const double* res = D->h_res;
   double mm[4];
   for (int k = 0; k < 4; ++k) { unsigned long long key; std::memcpy(&key, D->h_res + MALIO_RED_DOUBLES + k, 8); mm[k] = dkey_inv(key); }
+  // res holds, per LiDAR l, the 9 upper-triangular 4x4 blocks of the compact 12 x 16 system Gc_l; scatter into the
+  // padded 24 x 28 one (columns at their L=3 positions: 0-5 | 6+3l | 15+3l ; 24 = residual ; 25-27 = normal scatter)
   double G[MALIO_RED_ROWS][MALIO_RED_COLS];
   std::memset(G, 0, sizeof(G));
-  int t = 0;
-  for (int gi = 0; gi < 6; ++gi)
-    for (int gj = gi; gj < 7; ++gj, ++t)
-      for (int a = 0; a < 4; ++a)
-        for (int b = 0; b < 4; ++b) G[4 * gi + a][4 * gj + b] = res[t * 16 + a * 4 + b];
-  for (int a = 0; a < 24; ++a) for (int b = 0; b < a; ++b) G[a][b] = G[b][a];   // symmetric part
+  for (int l = 0; l < MALIO_MAX_LIDAR; ++l) {
+    double Gc[12][16];
+    std::memset(Gc, 0, sizeof(Gc));
+    int t = 0;
+    for (int gi = 0; gi < 3; ++gi)
+      for (int gj = gi; gj < 4; ++gj, ++t)
+        for (int a = 0; a < 4; ++a)
+          for (int b = 0; b < 4; ++b) Gc[4 * gi + a][4 * gj + b] = res[(l * 9 + t) * 16 + a * 4 + b];
+    for (int a = 0; a < 12; ++a) for (int b = 0; b < a; ++b) Gc[a][b] = Gc[b][a];
+    int col[16];
+    for (int k = 0; k < 6; ++k) col[k] = k;
+    for (int k = 0; k < 3; ++k) { col[6 + k] = 6 + 3 * l + k; col[9 + k] = 15 + 3 * l + k; }
+    col[12] = 24; col[13] = 25; col[14] = 26; col[15] = 27;
+    for (int a = 0; a < 12; ++a)
+      for (int b = 0; b < 16; ++b) G[col[a]][col[b]] += Gc[a][b];
+  }
   const uint32_t n_eff = (uint32_t)(res[MALIO_RED_BLOCKS * 16] + 0.5);
   malio_pass_stats S{};
   S.n_points = N; S.n_eff = n_eff; S.searched = redo_knn ? 1 : 0;
   S.u_min = mm[0]; S.u_max = -mm[1]; S.tau_min = mm[2]; S.tau_max = -mm[3];
   float ms = 0.f;
+  if (D->timing) {
   if (N > 0 && sorted_now) { cudaEventElapsedTime(&ms, D->ev[0], D->ev[5]); S.ms_sort = ms; }
   if (knn_now) {
     cudaEventElapsedTime(&ms, D->ev[5], D->ev[6]); S.ms_knn = ms;
@@ -1320,6 +1440,7 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
   cudaEventElapsedTime(&ms, D->ev[1], D->ev[2]); S.ms_plane = ms;
   cudaEventElapsedTime(&ms, D->ev[2], D->ev[3]); S.ms_reduce = ms;
   cudaEventElapsedTime(&ms, D->ev[0], D->ev[4]); S.ms_total = ms;
+  }
   if (n_eff < 1) {
     S.valid = 0;
     if (st) *st = S;
@@ -1355,8 +1476,9 @@ int download_rows(malio_handle* h, double* h_x, double* hvec, uint32_t cap, uint
   const int L = P.n_lidar, c = 6 * (L + 1);
   if (cap > MALIO_MAX_DOF) cap = MALIO_MAX_DOF;
   const uint32_t* perm = (h->cfg.sort_queries && D->perm_valid) ? D->d_perm : nullptr;
-  rows_kernel<<<1, 256, 0, D->stream>>>(D->d_pts, perm, D->N, D->last_pc, make_param_const(P), D->d_sel, D->d_plane,
-                                          D->d_pd2, D->d_ucov, D->d_tau, D->d_mmkey + 4 * D->last_parity, cap, D->d_rows, D->d_counters + 3);
+  rows_kernel<<<1, 256, 0, D->stream>>>(D->N, make_param_const(P), D->last_pc.ext_en, D->d_sel, D->d_lid8, D->d_rows12,
+                                          D->d_pd2, D->d_ucov, D->d_tau, D->d_mmkey + 4 * D->last_parity, cap, D->d_rows,
+                                          D->d_counters + 3);
   double* hr = D->h_res + MALIO_RED_DOUBLES + 8;
   CUDA_TRY(cudaMemcpyAsync(hr, D->d_rows, (size_t)cap * 25 * sizeof(double), cudaMemcpyDeviceToHost, D->stream));
   uint32_t nr = 0;
@@ -1414,8 +1536,7 @@ int knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* idx, float* d2, 
   PassConst pc{};
   const uint32_t* perm = nullptr;
   if (h->cfg.sort_queries) {
-    morton_kernel<1><<<(nq + 255) / 256, 256, 0, D->stream>>>(nullptr, D->d_queries, nq, pc, D->d_keys, D->d_ids);
-    if (int rc = sort_queries(h, D, nq)) return rc;
+    if (int rc = sort_queries<1>(h, D, nq, pc)) return rc;
     perm = D->d_perm;
   }
   CUDA_TRY(cudaEventRecord(D->ev[0], D->stream));
@@ -1437,7 +1558,7 @@ int knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* idx, float* d2, 
   float ms = 0.f;
   cudaEventElapsedTime(&ms, D->ev[0], D->ev[1]);
   if (ms_out) *ms_out = ms;
-  D->ctr.kernel_launches += 2 + (h->cfg.sort_queries ? 7 : 0);
+  D->ctr.kernel_launches += 2;   // k-NN + scatter (the sort counts its own)
   D->ctr.knn_launches += 1; D->ctr.knn_queries += nq; D->ctr.knn_ms += ms;
   D->ctr.h2d_bytes += (uint64_t)nq * 12;
   D->ctr.d2h_bytes += (uint64_t)nq * ((idx ? 20 : 0) + (d2 ? 20 : 0));

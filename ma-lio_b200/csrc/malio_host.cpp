@@ -379,6 +379,7 @@ int malio_upload_scan(malio_handle* h, const malio_scan_pt* pts, uint32_t n_pts,
   return malio_dev::upload_scan(h, pts, n_pts, table, table_off, temporal_comp);
 }
 int malio_rearm_scan(malio_handle* h) { return h ? malio_dev::rearm_scan(h) : MALIO_ERR_INVALID_ARG; }
+int malio_set_timing(malio_handle* h, int enable) { return h ? malio_dev::set_timing(h, enable) : MALIO_ERR_INVALID_ARG; }
 int malio_get_counters(malio_handle* h, malio_counters* out) { return (h && out) ? malio_dev::get_counters(h, out) : MALIO_ERR_INVALID_ARG; }
 int malio_measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* HtRinvH, double* HtRinvh, malio_pass_stats* stats) {
   if (!h || !s || !HtRinvH || !HtRinvh) return MALIO_ERR_INVALID_ARG;
@@ -467,15 +468,65 @@ int malio_ieskf_update(malio_handle* h, malio_state* x, double* Pio, int max_ite
       for (int a = 0; a < n; ++a) { double s = 0; for (int r = 0; r < m; ++r) s += K(a, r) * hv[r]; Kh[a] = s; }
       for (int a = 0; a < n; ++a) for (int b = 0; b < c; ++b) { double s = 0; for (int r = 0; r < m; ++r) s += K(a, r) * H(r, b); Kx(a, b) = s; }
     } else {                   // :621-637
-      Mat Pinv0, Q;
-      if (!invert(P, Pinv0)) { h->err = "singular covariance"; if (rep) *rep = rp; return MALIO_ERR_INVALID_ARG; }
-      for (int a = 0; a < c; ++a) for (int b = 0; b < c; ++b) Pinv0(a, b) += G(a, b);
-      if (!invert(Pinv0, Q)) { h->err = "singular information matrix"; if (rep) *rep = rp; return MALIO_ERR_INVALID_ARG; }
+      // The reference forms Q = (P^-1 + E^T G E)^-1 with two n x n inversions (E = [I_c 0]) and uses only Q[:, 0:c].
+      // By the push-through identity  Q E^T = P E^T (I_c + G P_cc)^-1 : one c x c factorisation instead.
+      // I + G P_cc has eigenvalues >= 1 (product of two PSD matrices), so the solve is well conditioned.
+      // Fixed-size scratch, unit-stride inner loops (this runs once per pass between two kernel sequences, with
+      // the GPU idle: every microsecond here is a microsecond of scan latency).
+      //   Mt = (I + G P_cc)^T  (row a, col b) = delta_ab + sum_k G(b,k) P(a,k)   [P is symmetric after the
+      //   congruence projections above];  solve Mt * Yt = (P[:,0:c])^T  =>  Y = Yt^T = Q[:, 0:c]
+      constexpr int CM = MALIO_MAX_COLS, NM = MALIO_MAX_DOF;
+      double Mt[CM][CM], Yt[CM][NM];
+      const double* Gd = G.a.data();
+      const double* Pd = P.a.data();
+      for (int a = 0; a < c; ++a)
+        for (int b = 0; b < c; ++b) {
+          const double* gr = Gd + (size_t)b * c;
+          const double* pr = Pd + (size_t)a * n;
+          double s = 0.0;
+          for (int k = 0; k < c; ++k) s += gr[k] * pr[k];
+          Mt[a][b] = s + ((a == b) ? 1.0 : 0.0);
+        }
+      for (int a = 0; a < c; ++a) for (int j = 0; j < n; ++j) Yt[a][j] = Pd[(size_t)a * n + j];   // P(j,a) = P(a,j)
+      // LU with partial pivoting on Mt, the row operations applied to Yt as they happen
+      for (int k = 0; k < c; ++k) {
+        int p = k;
+        double best = std::fabs(Mt[k][k]);
+        for (int i = k + 1; i < c; ++i) if (std::fabs(Mt[i][k]) > best) { best = std::fabs(Mt[i][k]); p = i; }
+        if (best == 0.0) { h->err = "singular information matrix"; if (rep) *rep = rp; return MALIO_ERR_INVALID_ARG; }
+        if (p != k) {
+          for (int j = 0; j < c; ++j) std::swap(Mt[k][j], Mt[p][j]);
+          for (int j = 0; j < n; ++j) std::swap(Yt[k][j], Yt[p][j]);
+        }
+        const double inv = 1.0 / Mt[k][k];
+        for (int i = k + 1; i < c; ++i) {
+          const double f = Mt[i][k] * inv;
+          if (f == 0.0) continue;
+          for (int j = k + 1; j < c; ++j) Mt[i][j] -= f * Mt[k][j];
+          for (int j = 0; j < n; ++j) Yt[i][j] -= f * Yt[k][j];
+        }
+      }
+      for (int i = c - 1; i >= 0; --i) {
+        for (int k = i + 1; k < c; ++k) {
+          const double f = Mt[i][k];
+          if (f == 0.0) continue;
+          for (int j = 0; j < n; ++j) Yt[i][j] -= f * Yt[k][j];
+        }
+        const double inv = 1.0 / Mt[i][i];
+        for (int j = 0; j < n; ++j) Yt[i][j] *= inv;
+      }
+      double* Kxd = Kx.a.data();
       for (int a = 0; a < n; ++a) {
-        double s = 0;
-        for (int k = 0; k < c; ++k) s += Q(a, k) * g[k];
+        double s = 0.0;
+        double* kr = Kxd + (size_t)a * c;
+        for (int b = 0; b < c; ++b) kr[b] = 0.0;
+        for (int k = 0; k < c; ++k) {
+          const double y = Yt[k][a];
+          s += y * g[k];                                             // K_h = Q[:,0:c] g            (:635)
+          const double* gr = Gd + (size_t)k * c;
+          for (int b = 0; b < c; ++b) kr[b] += y * gr[b];            // K_x = Q[:,0:c] G            (:637)
+        }
         Kh[a] = s;
-        for (int b = 0; b < c; ++b) { double v = 0; for (int k = 0; k < c; ++k) v += Q(a, k) * G(k, b); Kx(a, b) = v; }
       }
     }
     for (int a = 0; a < n; ++a) {          // dx_ = K_h + (K_x - I) dx_new, :642
@@ -515,12 +566,15 @@ int malio_ieskf_update(malio_handle* h, malio_state* x, double* Pio, int max_ite
         right_block_T<2>(Lm, ly.grav, J2);
         right_block_T<2>(P, ly.grav, J2);
       }
-      for (int a = 0; a < n; ++a)          // P_ = L_ - K_x[:,0:c] P_[0:c,:], :714
-        for (int b = 0; b < n; ++b) {
-          double s = 0;
-          for (int k = 0; k < c; ++k) s += Kx(a, k) * P(k, b);
-          Pio[(size_t)a * n + b] = Lm(a, b) - s;
+      for (int a = 0; a < n; ++a) {        // P_ = L_ - K_x[:,0:c] P_[0:c,:], :714
+        double* out = Pio + (size_t)a * n;
+        for (int b = 0; b < n; ++b) out[b] = Lm(a, b);
+        for (int k = 0; k < c; ++k) {
+          const double f = Kx(a, k);
+          const double* pr = P.a.data() + (size_t)k * n;
+          for (int b = 0; b < n; ++b) out[b] -= f * pr[b];
         }
+      }
       host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
       rp.converged_count = t;
       rp.last_status = MALIO_OK;

@@ -38,6 +38,7 @@ int download_aux(malio_handle* h, float* normal_y, uint32_t* nn_idx, float* nn_d
 int knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* idx, float* d2, float* ms);
 int rearm_scan(malio_handle* h);
 int get_counters(malio_handle* h, malio_counters* out);
+int set_timing(malio_handle* h, int enable);
 int comm_init(malio_handle* h, const uint8_t* id, int rank, int world);
 int get_unique_id(uint8_t* id);
 }  // namespace malio_dev

@@ -97,7 +97,7 @@ EXPORTS = [
     "malio_default_params", "malio_create", "malio_destroy", "malio_last_error", "malio_version",
     "malio_get_nccl_unique_id", "malio_comm_init", "malio_upload_map", "malio_upload_scan", "malio_measure",
     "malio_download_rows", "malio_download_aux", "malio_knn", "malio_ieskf_update", "malio_build_static_snapshot",
-    "malio_rearm_scan", "malio_get_counters",
+    "malio_rearm_scan", "malio_get_counters", "malio_set_timing",
 ]
 
 
@@ -136,6 +136,7 @@ def load() -> C.CDLL:
     lib.malio_build_static_snapshot.argtypes = [vp, u32, vp, vp, C.POINTER(u32)]
     lib.malio_rearm_scan.argtypes = [vp]
     lib.malio_get_counters.argtypes = [vp, C.POINTER(Counters)]
+    lib.malio_set_timing.argtypes = [vp, i32]
     _lib = lib
     return lib
 

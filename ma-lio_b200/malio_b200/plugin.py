@@ -118,6 +118,10 @@ class MeasurementModel:
         """Reset the per-scan state of the scan already resident on the device (no host copy)."""
         self._check(self.lib.malio_rearm_scan(self._h))
 
+    def set_timing(self, enable: bool):
+        """Per-pass CUDA-event timing (PassStats.ms_*, Counters.knn_ms); on by default."""
+        self._check(self.lib.malio_set_timing(self._h, 1 if enable else 0))
+
     def counters(self) -> capi.Counters:
         c = capi.Counters()
         self._check(self.lib.malio_get_counters(self._h, C.byref(c)))

@@ -739,7 +739,7 @@ void orc_set_scan(void* vc, const malio_scan_pt* pts, uint32_t n, const malio_po
 // stand-alone restated search over a snapshot (K), batch form
 void orc_knn_snapshot_batch(const malio_map_node* nodes, const float* cov, uint32_t n_nodes, const float* q,
                             int64_t nq, int k, int32_t* out_ids, float* out_d2, int32_t* out_found,
-                            int64_t* visits_total, int nthreads) {
+                            int64_t* visits_total, int nthreads, int32_t* visits_per_query) {
   int64_t vt = 0;
   if (nthreads < 1) nthreads = 1;
 #pragma omp parallel for num_threads(nthreads) schedule(dynamic, 256) reduction(+ : vt)
@@ -748,6 +748,7 @@ void orc_knn_snapshot_batch(const malio_map_node* nodes, const float* cov, uint3
     int f = knn_snapshot(nodes, cov, n_nodes, q + 3 * i, k, nullptr, out_d2 ? out_d2 + i * k : nullptr,
                          out_ids ? out_ids + i * k : nullptr, &v);
     if (out_found) out_found[i] = f;
+    if (visits_per_query) visits_per_query[i] = (int32_t)v;
     vt += v;
   }
   if (visits_total) *visits_total = vt;

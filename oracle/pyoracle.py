@@ -39,7 +39,7 @@ def oracle_lib() -> C.CDLL:
         L.orc_set_map_snapshot.argtypes = [vp, vp, vp, C.c_uint32]
         L.orc_set_knn_hook.argtypes = [vp, vp, vp]
         L.orc_set_scan.argtypes = [vp, vp, C.c_uint32, vp, vp, vp]
-        L.orc_knn_snapshot_batch.argtypes = [vp, vp, C.c_uint32, vp, C.c_int64, C.c_int, vp, vp, vp, C.POINTER(C.c_int64), C.c_int]
+        L.orc_knn_snapshot_batch.argtypes = [vp, vp, C.c_uint32, vp, C.c_int64, C.c_int, vp, vp, vp, C.POINTER(C.c_int64), C.c_int, vp]
         L.orc_esti_plane.argtypes = [vp, C.c_float, C.c_double, vp, C.POINTER(C.c_double)]
         L.orc_eval_point_uncertainty.argtypes = [vp, vp, vp]
         L.orc_qr_solve_5x3.argtypes = [vp, vp, vp]
@@ -188,7 +188,7 @@ def knn_snapshot(nodes, cov, q, k=5, nthreads=1):
     nodes = np.ascontiguousarray(nodes)
     cov = np.ascontiguousarray(cov, np.float32)
     L.orc_knn_snapshot_batch(ptr(nodes), ptr(cov), nodes.shape[0], ptr(q), n, k, ptr(ids), ptr(d2), ptr(found),
-                             C.byref(visits), nthreads)
+                             C.byref(visits), nthreads, None)
     return ids, d2, found, int(visits.value)
 
 
