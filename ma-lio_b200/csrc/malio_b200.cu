@@ -260,7 +260,8 @@ __device__ __noinline__ void knn_exact_query(const float4* __restrict__ nodes, f
 // reads fall out of L1 behind the node traffic and cost an L2 round trip each; SMEM_STACK = false is the
 // local-memory fallback for deeper trees.
 struct StackEnt { uint32_t n; float d; };
-constexpr int KNN_SMEM_DEPTH = 32;
+constexpr int KNN_POP_WIDTH = 4;
+constexpr int KNN_SMEM_DEPTH = 36;   // entries per thread in shared memory, KNN_POP_WIDTH sentinels included
 template <int MODE, bool SMEM_STACK>
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const malio_scan_pt* __restrict__ pts,
@@ -293,10 +294,13 @@ knn_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const malio_scan_
     uint32_t i0 = 0xFFFFFFFFu, i1 = 0xFFFFFFFFu, i2 = 0xFFFFFFFFu, i3 = 0xFFFFFFFFu, i4 = 0xFFFFFFFFu;
     bool hazard = false;
     __shared__ uint2 s_stack[SMEM_STACK ? KNN_SMEM_DEPTH * KNN_THREADS : 1];
-    uint2 l_stack[SMEM_STACK ? 1 : MALIO_MAX_TREE_DEPTH + 1];
+    uint2 l_stack[SMEM_STACK ? 1 : MALIO_MAX_TREE_DEPTH + KNN_POP_WIDTH];
 #define ST(k) (SMEM_STACK ? s_stack[(k) * KNN_THREADS + threadIdx.x] : l_stack[(k)])
-    ST(0) = make_uint2(0xFFFFFFFFu, __float_as_uint(-1.0f));   // sentinel: always passes `d < top`, ends the traversal
-    int sp = 1;
+    // KNN_POP_WIDTH sentinels at the bottom: a sentinel always passes `d < top` and ends the traversal; having as
+    // many as the pop width lets the unwinding loop read a full group without a bounds check
+#pragma unroll
+    for (int k = 0; k < KNN_POP_WIDTH; ++k) ST(k) = make_uint2(0xFFFFFFFFu, __float_as_uint(-1.0f));
+    int sp = KNN_POP_WIDTH;
     uint32_t cur = 0;
     bool done = false;
     // One node visit per iteration for every unfinished lane; the vote at the bottom makes the warp reconverge
@@ -333,8 +337,21 @@ knn_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const malio_scan_
       if (d_far < d4) { ST(sp) = make_uint2(n_far, __float_as_uint(d_far)); sp++; }
       if (d_near < d4) { cur = n_near; }
       else {
+        // unwind: the reference re-tests one pending far child per returning recursion level; here the top
+        // KNN_POP_WIDTH entries are read together (independent shared-memory loads, one latency) and the first
+        // live one from the top is taken — same entry, same order, a quarter of the dependent round trips
         uint2 e;
-        do { --sp; e = ST(sp); } while (!(__uint_as_float(e.y) < d4));
+        for (;;) {
+          const uint2 e1 = ST(sp - 1), e2 = ST(sp - 2), e3 = ST(sp - 3), e4 = ST(sp - 4);
+          const bool k1 = __uint_as_float(e1.y) < d4, k2 = __uint_as_float(e2.y) < d4, k3 = __uint_as_float(e3.y) < d4,
+                     k4 = __uint_as_float(e4.y) < d4;
+          if (k1 | k2 | k3 | k4) {
+            e = k1 ? e1 : (k2 ? e2 : (k3 ? e3 : e4));
+            sp -= k1 ? 1 : (k2 ? 2 : (k3 ? 3 : 4));
+            break;
+          }
+          sp -= 4;
+        }
         cur = e.x;
         done = (e.x == 0xFFFFFFFFu);
       }
@@ -1343,7 +1360,7 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
       knn_now = true;
       D->ctr.kernel_launches += 1;
       const int lanes = pick_lanes(N, D->sm_count);
-      if (D->depth < (uint32_t)KNN_SMEM_DEPTH)
+      if (D->depth + KNN_POP_WIDTH <= (uint32_t)KNN_SMEM_DEPTH)
         knn_kernel<0, true><<<knn_blocks(N, lanes), KNN_THREADS, 0, st_>>>(
             D->d_nodes, D->n_nodes, D->d_pts, perm, nullptr, N, lanes, pc, P.knn_max_sqdist, D->d_world, D->d_nn_idx,
             D->d_nn_d2, D->d_sel);
@@ -1541,7 +1558,7 @@ int knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* idx, float* d2, 
   }
   CUDA_TRY(cudaEventRecord(D->ev[0], D->stream));
   const int lanes = pick_lanes(nq, D->sm_count);
-  if (D->depth < (uint32_t)KNN_SMEM_DEPTH)
+  if (D->depth + KNN_POP_WIDTH <= (uint32_t)KNN_SMEM_DEPTH)
     knn_kernel<1, true><<<knn_blocks(nq, lanes), KNN_THREADS, 0, D->stream>>>(
         D->d_nodes, D->n_nodes, nullptr, perm, D->d_queries, nq, lanes, pc, 0.f, nullptr, D->d_nn_idx, D->d_nn_d2, nullptr);
   else
