@@ -117,6 +117,9 @@ typedef struct malio_config {
   int32_t sort_queries;       /* 1: Morton-order the scan on the device (internal; outputs stay in caller order) */
   uint32_t max_points;        /* capacity hints; buffers grow on demand when 0 */
   uint32_t max_map_nodes;
+  float knn_cell_size;        /* k-NN fast path: edge of the cell-list index built over the snapshot at upload
+                                 (metres).  0 = automatic (starts at 1 m = 2 x filter_size_map), < 0 = index off:
+                                 every query walks the flattened ikd-Tree.  Results are identical either way. */
 } malio_config;
 
 typedef struct malio_pass_stats {
@@ -196,6 +199,8 @@ typedef struct malio_counters {
   uint64_t knn_queries;
   double knn_ms;
   uint64_t h2d_bytes, d2h_bytes;
+  uint64_t knn_fallback_queries;  /* queries the cell-list fast path handed to the exact ikd-Tree-order traversal */
+  uint64_t knn_ring2_queries;     /* queries that needed the 5x5x5 cell block */
 } malio_counters;
 int malio_get_counters(malio_handle* h, malio_counters* out);
 

@@ -12,6 +12,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -40,7 +41,7 @@ constexpr int RED_HS_STRIDE = 13;         // doubles per staged row of a*J12/rho
 constexpr int RED_HX_STRIDE = 17;         // doubles per staged row of [a*J12 | z | rho*a*J12_0..2] (16 + 1)
 constexpr int RED_TASKS = 9;              // upper-triangular 4x4 blocks of the 12 x 16 compact system
 constexpr int RED_KS = 14;                // row-splits per task: 9 x 14 = 126 of the 128 threads work
-constexpr int RED_SMEM_DOUBLES = RED_THREADS * (RED_HS_STRIDE + RED_HX_STRIDE) + MALIO_MAX_LIDAR * RED_TASKS * RED_KS * 16;
+constexpr int RED_SMEM_DOUBLES = RED_THREADS * (RED_HS_STRIDE + RED_HX_STRIDE) + RED_TASKS * RED_KS * 16;   // staging + flush scratch
 constexpr int TABLE_DOUBLES = 52;         // malio_pose_entry
 
 struct PassConst {
@@ -259,54 +260,32 @@ __device__ __noinline__ void knn_exact_query(const float4* __restrict__ nodes, f
 // KNN_SMEM_DEPTH-1 levels deep) — the unwinding loop is a chain of dependent stack reads, and in local memory those
 // reads fall out of L1 behind the node traffic and cost an L2 round trip each; SMEM_STACK = false is the
 // local-memory fallback for deeper trees.
-struct StackEnt { uint32_t n; float d; };
 constexpr int KNN_POP_WIDTH = 4;
 constexpr int KNN_SMEM_DEPTH = 36;   // entries per thread in shared memory, KNN_POP_WIDTH sentinels included
-template <int MODE, bool SMEM_STACK>
-__global__ void __launch_bounds__(KNN_THREADS)
-knn_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const malio_scan_pt* __restrict__ pts,
-           const uint32_t* __restrict__ perm, const float* __restrict__ queries, uint32_t N, int lanes, PassConst pc,
-           float max_sqdist, float4* __restrict__ world, uint32_t* __restrict__ nn_idx,
-           float* __restrict__ nn_d2, uint8_t* __restrict__ sel) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t warp = (blockIdx.x * KNN_THREADS + threadIdx.x) >> 5;
-  const uint32_t p = warp * (uint32_t)lanes + lane;
-  const bool valid = ((int)lane < lanes) && (p < N);
-  const unsigned wmask = __ballot_sync(0xffffffffu, valid);
-  if (!valid) return;
-  float qx, qy, qz;
-  if (MODE == 0) {
-    const malio_scan_pt pt = pts[perm ? perm[p] : p];
-    double b[3], m[3], g[3];
-    transform_point(pc, pt.x, pt.y, pt.z, pt.lidar, b, m, g);
-    qx = (float)g[0]; qy = (float)g[1]; qz = (float)g[2];
-    world[p] = make_float4(qx, qy, qz, 0.f);
-  } else {
-    const uint32_t src = perm ? perm[p] : p;
-    qx = queries[3 * (size_t)src]; qy = queries[3 * (size_t)src + 1]; qz = queries[3 * (size_t)src + 2];
-  }
-  uint32_t oi[MALIO_K];
-  float od[MALIO_K];
-  int found = 0;
-  if (n_nodes > 0) {
-    // 5 best so far, ascending; +inf sentinels make the fill phase (q.size() < k) the same code path
-    float d0 = INFINITY, d1 = INFINITY, d2 = INFINITY, d3 = INFINITY, d4 = INFINITY;
-    uint32_t i0 = 0xFFFFFFFFu, i1 = 0xFFFFFFFFu, i2 = 0xFFFFFFFFu, i3 = 0xFFFFFFFFu, i4 = 0xFFFFFFFFu;
-    bool hazard = false;
-    __shared__ uint2 s_stack[SMEM_STACK ? KNN_SMEM_DEPTH * KNN_THREADS : 1];
-    uint2 l_stack[SMEM_STACK ? 1 : MALIO_MAX_TREE_DEPTH + KNN_POP_WIDTH];
+
+// The traversal itself, called by every lane in `wmask` (converged); lanes with active == false only take part in
+// the per-iteration vote.  Returns the reference's Nearest_Search result for the lane's query in oi/od/found.
+template <bool SMEM_STACK>
+__device__ __forceinline__ void knn_tree_lane(const float4* __restrict__ nodes, float qx, float qy, float qz, bool active,
+                                              unsigned wmask, uint32_t oi[MALIO_K], float od[MALIO_K], int& found) {
+  // 5 best so far, ascending; +inf sentinels make the fill phase (q.size() < k) the same code path
+  float d0 = INFINITY, d1 = INFINITY, d2 = INFINITY, d3 = INFINITY, d4 = INFINITY;
+  uint32_t i0 = 0xFFFFFFFFu, i1 = 0xFFFFFFFFu, i2 = 0xFFFFFFFFu, i3 = 0xFFFFFFFFu, i4 = 0xFFFFFFFFu;
+  bool hazard = false;
+  __shared__ uint2 s_stack[SMEM_STACK ? KNN_SMEM_DEPTH * KNN_THREADS : 1];
+  uint2 l_stack[SMEM_STACK ? 1 : MALIO_MAX_TREE_DEPTH + KNN_POP_WIDTH];
 #define ST(k) (SMEM_STACK ? s_stack[(k) * KNN_THREADS + threadIdx.x] : l_stack[(k)])
-    // KNN_POP_WIDTH sentinels at the bottom: a sentinel always passes `d < top` and ends the traversal; having as
-    // many as the pop width lets the unwinding loop read a full group without a bounds check
+  // KNN_POP_WIDTH sentinels at the bottom: a sentinel always passes `d < top` and ends the traversal; having as
+  // many as the pop width lets the unwinding loop read a full group without a bounds check
 #pragma unroll
-    for (int k = 0; k < KNN_POP_WIDTH; ++k) ST(k) = make_uint2(0xFFFFFFFFu, __float_as_uint(-1.0f));
-    int sp = KNN_POP_WIDTH;
-    uint32_t cur = 0;
-    bool done = false;
-    // One node visit per iteration for every unfinished lane; the vote at the bottom makes the warp reconverge
-    // each iteration (lanes that descend would otherwise run ahead of lanes that are unwinding their stack).
-    for (;;) {
-     if (!done) {
+  for (int k = 0; k < KNN_POP_WIDTH; ++k) ST(k) = make_uint2(0xFFFFFFFFu, __float_as_uint(-1.0f));
+  int sp = KNN_POP_WIDTH;
+  uint32_t cur = 0;
+  bool done = !active;
+  // One node visit per iteration for every unfinished lane; the vote at the bottom makes the warp reconverge
+  // each iteration (lanes that descend would otherwise run ahead of lanes that are unwinding their stack).
+  for (;;) {
+    if (!done) {
       const float4* nd = nodes + 4 * (size_t)cur;
       const float4 a = __ldg(nd), b4 = __ldg(nd + 1), c4 = __ldg(nd + 2), e4 = __ldg(nd + 3);
       const uint32_t link = __float_as_uint(a.w);
@@ -355,16 +334,56 @@ knn_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const malio_scan_
         cur = e.x;
         done = (e.x == 0xFFFFFFFFu);
       }
-     }
-     if (__all_sync(wmask, done)) break;
     }
-    if (!hazard) {
-      oi[0] = i0; oi[1] = i1; oi[2] = i2; oi[3] = i3; oi[4] = i4;
-      od[0] = d0; od[1] = d1; od[2] = d2; od[3] = d3; od[4] = d4;
-      found = (i0 != 0xFFFFFFFFu) + (i1 != 0xFFFFFFFFu) + (i2 != 0xFFFFFFFFu) + (i3 != 0xFFFFFFFFu) + (i4 != 0xFFFFFFFFu);
-    } else {
-      knn_exact_query(nodes, qx, qy, qz, oi, od, found);
-    }
+    if (__all_sync(wmask, done)) break;
+  }
+#undef ST
+  if (!active) { found = 0; return; }
+  if (!hazard) {
+    oi[0] = i0; oi[1] = i1; oi[2] = i2; oi[3] = i3; oi[4] = i4;
+    od[0] = d0; od[1] = d1; od[2] = d2; od[3] = d3; od[4] = d4;
+    found = (i0 != 0xFFFFFFFFu) + (i1 != 0xFFFFFFFFu) + (i2 != 0xFFFFFFFFu) + (i3 != 0xFFFFFFFFu) + (i4 != 0xFFFFFFFFu);
+  } else {
+    knn_exact_query(nodes, qx, qy, qz, oi, od, found);
+  }
+}
+
+// query of position p: MODE 0 = scan point through the state (also yields the world point), MODE 1 = stand-alone
+template <int MODE>
+__device__ __forceinline__ void load_query(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm,
+                                           const float* __restrict__ queries, uint32_t p, const PassConst& pc,
+                                           float& qx, float& qy, float& qz) {
+  if (MODE == 0) {
+    const malio_scan_pt pt = pts[perm ? perm[p] : p];
+    double b[3], m[3], g[3];
+    transform_point(pc, pt.x, pt.y, pt.z, pt.lidar, b, m, g);
+    qx = (float)g[0]; qy = (float)g[1]; qz = (float)g[2];
+  } else {
+    const uint32_t src = perm ? perm[p] : p;
+    qx = queries[3 * (size_t)src]; qy = queries[3 * (size_t)src + 1]; qz = queries[3 * (size_t)src + 2];
+  }
+}
+
+template <int MODE, bool SMEM_STACK>
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const malio_scan_pt* __restrict__ pts,
+           const uint32_t* __restrict__ perm, const float* __restrict__ queries, uint32_t N, int lanes, PassConst pc,
+           float max_sqdist, float4* __restrict__ world, uint32_t* __restrict__ nn_idx,
+           float* __restrict__ nn_d2, uint8_t* __restrict__ sel) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * KNN_THREADS + threadIdx.x) >> 5;
+  const uint32_t p = warp * (uint32_t)lanes + lane;
+  const bool valid = ((int)lane < lanes) && (p < N);
+  const unsigned wmask = __ballot_sync(0xffffffffu, valid);
+  if (!valid) return;
+  float qx, qy, qz;
+  load_query<MODE>(pts, perm, queries, p, pc, qx, qy, qz);
+  if (MODE == 0) world[p] = make_float4(qx, qy, qz, 0.f);
+  uint32_t oi[MALIO_K];
+  float od[MALIO_K];
+  int found = 0;
+  if (n_nodes > 0) {
+    knn_tree_lane<SMEM_STACK>(nodes, qx, qy, qz, true, wmask, oi, od, found);
   } else {
 #pragma unroll
     for (int j = 0; j < MALIO_K; ++j) { oi[j] = 0xFFFFFFFFu; od[j] = INFINITY; }
@@ -375,14 +394,361 @@ knn_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const malio_scan_
     nn_d2[(size_t)j * N + p] = od[j];
   }
   if (MODE == 0) sel[p] = (found < MALIO_K) ? 0 : (od[MALIO_K - 1] > max_sqdist ? 0 : 1);   // laserMapping.cpp:587
-#undef ST
+}
+
+// List mode: the same traversal for the positions the cell-list fast path (below) could not settle — tie hazards,
+// queries whose 5th neighbour lies beyond the searched cell block, queries outside the grid.  A fixed grid walks
+// the list (its length is only known on the device); the world point was already written by the fast path.
+template <int MODE, bool SMEM_STACK>
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_list_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const malio_scan_pt* __restrict__ pts,
+                const uint32_t* __restrict__ perm, const float* __restrict__ queries, uint32_t N, PassConst pc,
+                float max_sqdist, const uint32_t* __restrict__ plist, const uint32_t* __restrict__ pcount,
+                uint32_t* __restrict__ nn_idx, float* __restrict__ nn_d2, uint8_t* __restrict__ sel,
+                uint32_t* __restrict__ count_out) {
+  const uint32_t count = *pcount;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { count_out[0] = count; count_out[2] = count_out[1]; }   // [1] = ring-2 counter
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lanes = 8;   // few, unrelated queries: narrow logical warps (less divergence, more warps)
+  const uint32_t warp = (blockIdx.x * KNN_THREADS + threadIdx.x) >> 5, nwarps = (gridDim.x * KNN_THREADS) >> 5;
+  for (uint32_t base = warp * lanes; base < count; base += nwarps * lanes) {
+    const bool valid = (lane < lanes) && (base + lane < count);
+    const uint32_t p = valid ? plist[base + lane] : 0u;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (valid) load_query<MODE>(pts, perm, queries, p, pc, qx, qy, qz);
+    uint32_t oi[MALIO_K];
+    float od[MALIO_K];
+    int found = 0;
+    if (n_nodes > 0) {
+      knn_tree_lane<SMEM_STACK>(nodes, qx, qy, qz, valid, 0xffffffffu, oi, od, found);
+    } else {
+#pragma unroll
+      for (int j = 0; j < MALIO_K; ++j) { oi[j] = 0xFFFFFFFFu; od[j] = INFINITY; }
+    }
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < MALIO_K; ++j) {
+        nn_idx[(size_t)j * N + p] = oi[j];
+        nn_d2[(size_t)j * N + p] = od[j];
+      }
+      if (MODE == 0) sel[p] = (found < MALIO_K) ? 0 : (od[MALIO_K - 1] > max_sqdist ? 0 : 1);   // laserMapping.cpp:587
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ K1g: cell-list k-NN, the fast path of K1
+// Nearest_Search's RESULT (the 5 smallest squared distances, ascending) does not depend on how the tree is walked
+// unless distances tie: acceptance is `dist < q.top().dist` (ikd_Tree.cpp:1099), so with pairwise distinct distances
+// among the six closest points any exact search returns the same list.  The traversal order only matters for ties
+// (first visited wins; PointType_CMP's 1e-10 window, ikd_Tree.h:102-108).  So: the live snapshot points are binned
+// once per upload into a uniform grid (cell edge h), a query scans the 3x3x3 cell block around its own cell — 9
+// contiguous x-rows of the cell-sorted point array, no dependent chain — keeping the 6 smallest distances, computed
+// with calc_dist's exact float expression.  The block contains every point closer than r = (1 + min frac) h, so if
+// the 5th distance is below r (minus a margin that covers float rounding of the cell arithmetic) and the six
+// smallest distances are pairwise more than 1e-10 apart, the list IS the reference's.  Otherwise the 5x5x5 block
+// is tried (r = (2 + min frac) h), and what is still unsettled — ties, very sparse neighbourhoods, queries outside
+// the grid — goes to knn_list_kernel, i.e. through the exact ikd-Tree-order traversal above.
+struct GridConst {
+  float ox, oy, oz, inv_h, h;
+  int nx, ny, nz;        // cells per axis (un-padded)
+  int px, py;            // padded pitches: nx + 2*GRID_PAD, ny + 2*GRID_PAD
+  uint32_t ncell;        // padded cell count
+};
+constexpr int GRID_PAD = 3;          // empty border cells: queries up to one cell outside the box still take the fast path
+constexpr int GRID_CHUNK = 4096;          // cells per scan block (1024 threads x 4)
+constexpr float GRID_MARGIN = 0.005f;     // in cells: >> rounding of (x - o) * inv_h (< 1e-3 cells for < 4096 cells/axis)
+
+__device__ __forceinline__ uint32_t grid_cell_index(const GridConst& G, int cx, int cy, int cz) {
+  return (uint32_t)(((cz + GRID_PAD) * G.py + (cy + GRID_PAD)) * G.px + (cx + GRID_PAD));
+}
+
+__global__ void grid_count_kernel(const float4* __restrict__ nodes, uint32_t n, GridConst G, uint32_t* __restrict__ cnt,
+                                  uint32_t* __restrict__ cell_of) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 a = __ldg(nodes + 4 * (size_t)i);
+  if (__float_as_uint(a.w) & MALIO_LINK_POINT_DELETED) { cell_of[i] = 0xFFFFFFFFu; return; }
+  // monotone in each coordinate (subtract, multiply by a positive constant, floor, clamp): what the radius guarantee needs
+  int cx = (int)floorf((a.x - G.ox) * G.inv_h), cy = (int)floorf((a.y - G.oy) * G.inv_h), cz = (int)floorf((a.z - G.oz) * G.inv_h);
+  cx = min(max(cx, 0), G.nx - 1); cy = min(max(cy, 0), G.ny - 1); cz = min(max(cz, 0), G.nz - 1);
+  const uint32_t c = grid_cell_index(G, cx, cy, cz);
+  cell_of[i] = c;
+  atomicAdd(cnt + c, 1u);
+}
+// exclusive scan of the cell counts, three small kernels: chunk-local scan (+ chunk totals, occupied-cell count;
+// the counts are zeroed to serve as scatter cursors), scan of the <= 8192 chunk totals, add-back
+__global__ void __launch_bounds__(1024) grid_scan_local_kernel(uint32_t* __restrict__ cnt, uint32_t* __restrict__ start,
+                                                               uint32_t* __restrict__ ctot, uint32_t* __restrict__ stats) {
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_occ[32];
+  const uint32_t base = (blockIdx.x * 1024u + threadIdx.x) * 4u;
+  const uint4 v = *reinterpret_cast<const uint4*>(cnt + base);
+  *reinterpret_cast<uint4*>(cnt + base) = make_uint4(0u, 0u, 0u, 0u);
+  const uint32_t sum = v.x + v.y + v.z + v.w;
+  uint32_t occ = (v.x != 0) + (v.y != 0) + (v.z != 0) + (v.w != 0);
+  uint32_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= (unsigned)o) inc += t; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) occ += __shfl_xor_sync(0xffffffffu, occ, o);
+  if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = inc;
+  if ((threadIdx.x & 31) == 0) s_occ[threadIdx.x >> 5] = occ;
+  __syncthreads();
+  uint32_t wbase = 0;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += s_w[w];
+  uint32_t run = wbase + inc - sum;
+  uint4 o4;
+  o4.x = run; run += v.x; o4.y = run; run += v.y; o4.z = run; run += v.z; o4.w = run;
+  *reinterpret_cast<uint4*>(start + base) = o4;
+  if (threadIdx.x == 1023) ctot[blockIdx.x] = wbase + inc;
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < 32; ++w) t += s_occ[w];
+    if (t) atomicAdd(stats, t);
+  }
+}
+__global__ void __launch_bounds__(1024) grid_scan_tot_kernel(const uint32_t* __restrict__ ctot, uint32_t nchunk,
+                                                             uint32_t* __restrict__ cbase, uint32_t* __restrict__ stats) {
+  __shared__ uint32_t s_w[32];
+  uint32_t v[8], sum = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { const uint32_t i = threadIdx.x * 8 + k; v[k] = i < nchunk ? ctot[i] : 0u; sum += v[k]; }
+  uint32_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= (unsigned)o) inc += t; }
+  if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = inc;
+  __syncthreads();
+  uint32_t wbase = 0;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += s_w[w];
+  uint32_t run = wbase + inc - sum;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { const uint32_t i = threadIdx.x * 8 + k; if (i < nchunk) cbase[i] = run; run += v[k]; }
+  if (threadIdx.x == 1023) stats[1] = run;   // number of live points
+}
+__global__ void __launch_bounds__(1024) grid_scan_add_kernel(uint32_t* __restrict__ start, const uint32_t* __restrict__ cbase) {
+  const uint32_t base = (blockIdx.x * 1024u + threadIdx.x) * 4u;
+  const uint32_t b = cbase[blockIdx.x];
+  uint4 v = *reinterpret_cast<uint4*>(start + base);
+  v.x += b; v.y += b; v.z += b; v.w += b;
+  *reinterpret_cast<uint4*>(start + base) = v;
+}
+__global__ void grid_scatter_kernel(const float4* __restrict__ nodes, uint32_t n, const uint32_t* __restrict__ cell_of,
+                                    const uint32_t* __restrict__ start, uint32_t* __restrict__ cursor,
+                                    float4* __restrict__ cell_pts) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t c = cell_of[i];
+  if (c == 0xFFFFFFFFu) return;
+  const float4 a = __ldg(nodes + 4 * (size_t)i);
+  const uint32_t slot = start[c] + atomicAdd(cursor + c, 1u);
+  cell_pts[slot] = make_float4(a.x, a.y, a.z, __uint_as_float(i));
+}
+
+// the 6 smallest squared distances seen so far (ascending) and the snapshot indices of the first 5
+struct Top6 {
+  float d0, d1, d2, d3, d4, d5;
+  uint32_t i0, i1, i2, i3, i4;
+  __device__ __forceinline__ void reset() {
+    d0 = d1 = d2 = d3 = d4 = d5 = INFINITY;
+    i0 = i1 = i2 = i3 = i4 = 0xFFFFFFFFu;
+  }
+  __device__ __forceinline__ void insert(float dist, uint32_t idx) {   // precondition: dist < d5
+    const bool c0 = dist < d0, c1 = dist < d1, c2 = dist < d2, c3 = dist < d3, c4 = dist < d4;
+    d5 = c4 ? d4 : dist;
+    d4 = c4 ? (c3 ? d3 : dist) : d4;   i4 = c4 ? (c3 ? i3 : idx) : i4;
+    d3 = c3 ? (c2 ? d2 : dist) : d3;   i3 = c3 ? (c2 ? i2 : idx) : i3;
+    d2 = c2 ? (c1 ? d1 : dist) : d2;   i2 = c2 ? (c1 ? i1 : idx) : i2;
+    d1 = c1 ? (c0 ? d0 : dist) : d1;   i1 = c1 ? (c0 ? i0 : idx) : i1;
+    d0 = c0 ? dist : d0;               i0 = c0 ? idx : i0;
+  }
+  // any two of the six within PointType_CMP's window (ascending list: adjacent gaps suffice)
+  __device__ __forceinline__ bool tie_hazard() const {
+    return (fabsf(d1 - d0) < 1e-10f) | (fabsf(d2 - d1) < 1e-10f) | (fabsf(d3 - d2) < 1e-10f) |
+           (fabsf(d4 - d3) < 1e-10f) | (fabsf(d5 - d4) < 1e-10f);
+  }
+};
+
+// Staged scan.  The candidates of one query are 9 (25) short contiguous runs of the cell-sorted point array.  Read
+// run by run with ordinary loads, every run costs a dependent memory round trip (profile: ~90 % of stall samples on the
+// first use of a loaded candidate).  Instead each thread fires cp.async (LDGSTS, 16 B) copies for ALL its candidates into
+// a private column of shared memory — they are in flight together, one round trip — and then scans them from shared
+// memory.  Column layout [slot][thread] keeps both the asynchronous writes and the LDS.128 reads conflict-free.
+constexpr int GK_THREADS = 64;
+constexpr int GK_CAP = 40;                 // staged candidates per thread and round (more: another round)
+constexpr int GK_ROWS1 = 9, GK_ROWS2 = 25;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// RING 1: one query per work item p < N (3x3x3 cells); unsettled queries go to the ring-2 list, tie hazards and
+//         out-of-grid queries to the traversal list.
+// RING 2: work items are the ring-2 list (5x5x5 cells); what is still unsettled goes to the traversal list.
+template <int MODE, int RING>
+__global__ void __launch_bounds__(GK_THREADS)
+knn_grid_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict__ cell_start, GridConst G,
+                const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm,
+                const float* __restrict__ queries, uint32_t N, PassConst pc, float max_sqdist,
+                float4* __restrict__ world, uint32_t* __restrict__ nn_idx, float* __restrict__ nn_d2,
+                uint8_t* __restrict__ sel, const uint32_t* __restrict__ in_list, const uint32_t* __restrict__ in_count,
+                uint32_t* __restrict__ r2_list, uint32_t* __restrict__ r2_count, uint32_t* __restrict__ fb_list,
+                uint32_t* __restrict__ fb_count) {
+  constexpr int ROWS = RING == 1 ? GK_ROWS1 : GK_ROWS2;
+  constexpr int HALF = RING == 1 ? 1 : 2;       // the block is (2*HALF+1)^3 cells
+  extern __shared__ float4 s_dyn[];
+  float4* s_cand = s_dyn;                                              // [GK_CAP][GK_THREADS]
+  uint2* s_rng = reinterpret_cast<uint2*>(s_dyn + GK_CAP * GK_THREADS);   // [ROWS][GK_THREADS]
+  const uint32_t n_items = RING == 1 ? N : *in_count;
+  for (uint32_t item = blockIdx.x * GK_THREADS + threadIdx.x; item < n_items; item += gridDim.x * GK_THREADS) {
+    const uint32_t p = RING == 1 ? item : in_list[item];
+    float qx, qy, qz;
+    load_query<MODE>(pts, perm, queries, p, pc, qx, qy, qz);
+    if (MODE == 0 && RING == 1) world[p] = make_float4(qx, qy, qz, 0.f);
+    const float ux = (qx - G.ox) * G.inv_h, uy = (qy - G.oy) * G.inv_h, uz = (qz - G.oz) * G.inv_h;
+    const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
+    // own cell in [-1, n] per axis: the 5x5x5 block then stays inside the GRID_PAD = 3 border of empty cells
+    const bool in_grid = flx >= -1.f && fly >= -1.f && flz >= -1.f && flx <= (float)G.nx && fly <= (float)G.ny && flz <= (float)G.nz;
+    bool settled = false, hazard = false;
+    Top6 t;
+    t.reset();
+    if (in_grid) {
+      const int cx = (int)flx, cy = (int)fly, cz = (int)flz;
+      const float fx = ux - flx, fy = uy - fly, fz = uz - flz;
+      const float fmin = fminf(fminf(fminf(fx, 1.f - fx), fminf(fy, 1.f - fy)), fminf(fz, 1.f - fz));
+      // the block's x-rows: (2*HALF+1)^2 runs of 2*HALF+1 consecutive cells
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        constexpr int W = 2 * HALF + 1;
+        const int dy = (r % W) - HALF, dz = (r / W) - HALF;
+        const uint32_t row = grid_cell_index(G, cx, cy + dy, cz + dz);
+        s_rng[r * GK_THREADS + threadIdx.x] = make_uint2(__ldg(cell_start + row - HALF), __ldg(cell_start + row + HALF + 1));
+      }
+      int r = 0;
+      uint2 cur = s_rng[threadIdx.x];
+      for (;;) {
+        // ---- stage up to GK_CAP candidates
+        int k = 0;
+        while (k < GK_CAP && r < ROWS) {
+          if (cur.x < cur.y) {
+            cp_async16(s_cand + k * GK_THREADS + threadIdx.x, cell_pts + cur.x);
+            ++cur.x; ++k;
+          } else {
+            ++r;   // past the last row the (clamped) re-read is never used: the loop ends on r == ROWS
+            cur = s_rng[min(r, ROWS - 1) * GK_THREADS + threadIdx.x];
+          }
+        }
+        cp_async_wait_all();
+        // ---- scan them
+#pragma unroll 4
+        for (int i = 0; i < k; ++i) {
+          const float4 c = s_cand[i * GK_THREADS + threadIdx.x];
+          const float dist = (qx - c.x) * (qx - c.x) + (qy - c.y) * (qy - c.y) + (qz - c.z) * (qz - c.z);   // calc_dist
+          if (dist < t.d5) t.insert(dist, __float_as_uint(c.w));
+        }
+        if (r >= ROWS) break;
+      }
+      const float rg = ((float)HALF + fmin - GRID_MARGIN) * G.h;
+      hazard = t.tie_hazard();
+      settled = (t.d4 < rg * rg) & !hazard;
+    }
+    if (settled) {
+      nn_idx[p] = t.i0;                  nn_d2[p] = t.d0;
+      nn_idx[(size_t)N + p] = t.i1;      nn_d2[(size_t)N + p] = t.d1;
+      nn_idx[(size_t)2 * N + p] = t.i2;  nn_d2[(size_t)2 * N + p] = t.d2;
+      nn_idx[(size_t)3 * N + p] = t.i3;  nn_d2[(size_t)3 * N + p] = t.d3;
+      nn_idx[(size_t)4 * N + p] = t.i4;  nn_d2[(size_t)4 * N + p] = t.d4;
+      if (MODE == 0) sel[p] = (t.d4 > max_sqdist) ? 0 : 1;   // laserMapping.cpp:587 (five were found)
+    } else if (RING == 1 && in_grid && !hazard) {
+      r2_list[atomicAdd(r2_count, 1u)] = p;
+    } else {
+      fb_list[atomicAdd(fb_count, 1u)] = p;
+    }
+  }
+}
+
+// Ring 2 (5x5x5 cells), one WARP per listed query.  These are the few queries (sparse neighbourhoods) whose 5th
+// neighbour was not proven inside the 3x3x3 block; a single thread would need ~125 candidates x a dependent
+// insertion chain (tens of microseconds of pure latency at the tail of the search), so the candidates of one query
+// are spread over the 32 lanes (coalesced row reads), every lane keeps its own 6 best, and the warp extracts the 6
+// overall smallest by six rounds of arg-min over the lane heads.  Equal heads in two lanes are a tie -> traversal.
+template <int MODE>
+__global__ void __launch_bounds__(128)
+knn_ring2_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict__ cell_start, GridConst G,
+                 const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm,
+                 const float* __restrict__ queries, uint32_t N, PassConst pc, float max_sqdist,
+                 uint32_t* __restrict__ nn_idx, float* __restrict__ nn_d2, uint8_t* __restrict__ sel,
+                 const uint32_t* __restrict__ in_list, const uint32_t* __restrict__ in_count,
+                 uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_count) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t n_items = *in_count;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n_items; item += nwarps) {
+    const uint32_t p = in_list[item];
+    float qx, qy, qz;
+    load_query<MODE>(pts, perm, queries, p, pc, qx, qy, qz);
+    const float ux = (qx - G.ox) * G.inv_h, uy = (qy - G.oy) * G.inv_h, uz = (qz - G.oz) * G.inv_h;
+    const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
+    const int cx = (int)flx, cy = (int)fly, cz = (int)flz;       // in [-1, n]: ring 1 only lists in-grid queries
+    const float fx = ux - flx, fy = uy - fly, fz = uz - flz;
+    const float fmin = fminf(fminf(fminf(fx, 1.f - fx), fminf(fy, 1.f - fy)), fminf(fz, 1.f - fz));
+    uint32_t rs = 0, re = 0;
+    if (lane < 25) {
+      const uint32_t row = grid_cell_index(G, cx, cy + (int)(lane % 5) - 2, cz + (int)(lane / 5) - 2);
+      rs = __ldg(cell_start + row - 2);
+      re = __ldg(cell_start + row + 3);
+    }
+    Top6 t;
+    t.reset();
+#pragma unroll 1
+    for (int r = 0; r < 25; ++r) {
+      const uint32_t s0 = __shfl_sync(0xffffffffu, rs, r), e0 = __shfl_sync(0xffffffffu, re, r);
+      for (uint32_t j = s0 + lane; j < e0; j += 32) {
+        const float4 c = __ldg(cell_pts + j);
+        const float dist = (qx - c.x) * (qx - c.x) + (qy - c.y) * (qy - c.y) + (qz - c.z) * (qz - c.z);   // calc_dist
+        if (dist < t.d5) t.insert(dist, __float_as_uint(c.w));
+      }
+    }
+    // six rounds: smallest lane head overall, popped from the lane that holds it
+    float od[6];
+    uint32_t oi[6];
+    bool hazard = false;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      float m = t.d0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      const uint32_t who = __ballot_sync(0xffffffffu, t.d0 == m && m < INFINITY);
+      if (__popc(who) > 1) hazard = true;
+      const int src = who ? __ffs(who) - 1 : 0;
+      od[k] = m;
+      oi[k] = __shfl_sync(0xffffffffu, t.i0, src);
+      if (who && (int)lane == src) {
+        t.d0 = t.d1; t.d1 = t.d2; t.d2 = t.d3; t.d3 = t.d4; t.d4 = t.d5; t.d5 = INFINITY;
+        t.i0 = t.i1; t.i1 = t.i2; t.i2 = t.i3; t.i3 = t.i4; t.i4 = 0xFFFFFFFFu;
+      }
+    }
+    hazard |= (fabsf(od[1] - od[0]) < 1e-10f) | (fabsf(od[2] - od[1]) < 1e-10f) | (fabsf(od[3] - od[2]) < 1e-10f) |
+              (fabsf(od[4] - od[3]) < 1e-10f) | (fabsf(od[5] - od[4]) < 1e-10f);
+    const float rg = (2.f + fmin - GRID_MARGIN) * G.h;
+    const bool settled = (od[4] < rg * rg) & !hazard;
+    if (lane == 0) {
+      if (settled) {
+#pragma unroll
+        for (int k = 0; k < MALIO_K; ++k) { nn_idx[(size_t)k * N + p] = oi[k]; nn_d2[(size_t)k * N + p] = od[k]; }
+        if (MODE == 0) sel[p] = (od[4] > max_sqdist) ? 0 : 1;   // laserMapping.cpp:587 (five were found)
+      } else {
+        fb_list[atomicAdd(fb_count, 1u)] = p;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------ query ordering (internal only; outputs stay in caller order)
 // Spatially coherent warps matter (neighbouring queries walk the same upper tree levels: L1 hits, similar visit
 // counts), the exact order does not.  A general radix sort of ~1e5 keys is launch/latency-bound (CUB: 6 kernels,
 // ~57 us here), so this is a hand-written counting sort on a 16-bit cell key:
-//   cell = 2 m; key = z(2 bits) | Morton(x 7 bits, y 7 bits)   (wraps every 256 m / 8 m: only locality matters)
+//   cell = 2 m; key = LiDAR(2 bits) | z(2 bits) | Morton(x 6 bits, y 6 bits)   (wraps every 128 m / 8 m: only locality matters)
 //   count_kernel   key per point + histogram (integer atomics)
 //   scan_kernel    exclusive prefix over the 65 536 bins (64 block-local scans + 64 totals)
 //   scatter_kernel slot = offset[key] + atomic cursor  -> tmp (order inside a bin is arrival order ...)
@@ -402,16 +768,19 @@ __global__ void count_kernel(const malio_scan_pt* __restrict__ pts, const float*
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   float x, y, z;
+  uint32_t lid_key = 0;
   if (MODE == 0) {
     const malio_scan_pt pt = pts[i];
     double b[3], m[3], g[3];
     transform_point(pc, pt.x, pt.y, pt.z, pt.lidar, b, m, g);
     x = (float)g[0]; y = (float)g[1]; z = (float)g[2];
+    lid_key = pt.lidar < 3 ? pt.lidar : 3u;
   } else {
     x = queries[3 * (size_t)i]; y = queries[3 * (size_t)i + 1]; z = queries[3 * (size_t)i + 2];
   }
   const uint32_t ix = (uint32_t)(int)floorf(x * 0.5f), iy = (uint32_t)(int)floorf(y * 0.5f), iz = (uint32_t)(int)floorf(z * 0.5f);
-  const uint32_t key = ((iz & 3u) << 14) | (spread7(iy) << 1) | spread7(ix);
+  // LiDAR id is the major key: the reduction keeps one LiDAR's accumulators in registers while it walks its tiles
+  const uint32_t key = (lid_key << 14) | ((iz & 3u) << 12) | (spread7(iy & 0x3Fu) << 1) | spread7(ix & 0x3Fu);
   keys[i] = (uint16_t)key;
   atomicAdd(hist + key, 1u);
 }
@@ -670,12 +1039,10 @@ __device__ __forceinline__ MinMax4 warp_reduce(MinMax4 v) {
 // the state, so its result is computed once per search and reused by the passes that re-use Nearest_Points
 // (the reference recomputes it every pass, laserMapping.cpp:596, with the same outcome).
 //   plane[p] = (n_x, n_y, n_z, d) ;  ucov[p] = plane_cov ;  sel[p] &= plane ok
-__global__ void __launch_bounds__(PLANE_THREADS)
-fit_kernel(const float4* __restrict__ nodes, const float* __restrict__ node_cov, uint32_t N, ParamConst prm,
-           const uint32_t* __restrict__ nn_idx, uint8_t* __restrict__ sel, float4* __restrict__ plane,
-           double* __restrict__ ucov) {
-  const uint32_t p = blockIdx.x * PLANE_THREADS + threadIdx.x;
-  if (p >= N || !sel[p]) return;
+__device__ __forceinline__ void fit_point(const float4* __restrict__ nodes, const float* __restrict__ node_cov, uint32_t N,
+                                          const ParamConst& prm, const uint32_t* __restrict__ nn_idx,
+                                          uint8_t* __restrict__ sel, float4* __restrict__ plane,
+                                          double* __restrict__ ucov, uint32_t p) {
   float A[5][3], W[5];
 #pragma unroll
   for (int j = 0; j < MALIO_K; ++j) {
@@ -709,16 +1076,20 @@ fit_kernel(const float4* __restrict__ nodes, const float* __restrict__ node_cov,
   ucov[p] = unit_cov;
   if (!ok) sel[p] = 0;
 }
+__global__ void __launch_bounds__(PLANE_THREADS)
+fit_kernel(const float4* __restrict__ nodes, const float* __restrict__ node_cov, uint32_t N, ParamConst prm,
+           const uint32_t* __restrict__ nn_idx, uint8_t* __restrict__ sel, float4* __restrict__ plane,
+           double* __restrict__ ucov) {
+  const uint32_t p = blockIdx.x * PLANE_THREADS + threadIdx.x;
+  if (p >= N || !sel[p]) return;
+  fit_point(nodes, node_cov, N, prm, nn_idx, sel, plane, ucov, p);
+}
 
 // ---- K2b (once per scan): point-wise uncertainty.  evalPointUncertainty depends on the point and its table entry
 // only; the entry index is clamped differently for selected (:694-696) and non-selected (:737-739) points, so both
 // traces are kept:  tau2[p] = (tau_selected, tau_not_selected).
-__global__ void __launch_bounds__(PLANE_THREADS)
-tau_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t N, PassConst pc,
-           const double* __restrict__ table, double2* __restrict__ tau2) {
-  const uint32_t p = blockIdx.x * PLANE_THREADS + threadIdx.x;
-  if (p >= N) return;
-  const malio_scan_pt pt = pts[perm ? perm[p] : p];
+__device__ __forceinline__ void tau_point(const malio_scan_pt& pt, const PassConst& pc, const double* __restrict__ table,
+                                          double2* __restrict__ tau2, uint32_t p) {
   const int lid = pt.lidar;
   const int tsize = (int)(pc.table_off[lid + 1] - pc.table_off[lid]);
   const int ti = (int)pt.table_idx;
@@ -729,91 +1100,99 @@ tau_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ p
                        : point_cov_trace(pt.x, pt.y, pt.z, table + (size_t)(pc.table_off[lid] + ti_non) * TABLE_DOUBLES);
   tau2[p] = make_double2(t_sel, t_non);
 }
+__global__ void __launch_bounds__(PLANE_THREADS)
+tau_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t N, PassConst pc,
+           const double* __restrict__ table, double2* __restrict__ tau2) {
+  const uint32_t p = blockIdx.x * PLANE_THREADS + threadIdx.x;
+  if (p >= N) return;
+  const malio_scan_pt pt = pts[perm ? perm[p] : p];
+  tau_point(pt, pc, table, tau2, p);
+}
 
 // ---- K2c (every pass): transform, point-to-plane residual, residual gate, min/max of the two weights.
 // d_mmkey layout: dkey of {min_u, -max_u, min_tau, -max_tau}: one (integer) MIN all-reduce serves all four
-__global__ void __launch_bounds__(GATE_THREADS)
-gate_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t N, PassConst pc,
-            const float4* __restrict__ plane, const double* __restrict__ ucov, const double2* __restrict__ tau2,
-            uint8_t* __restrict__ sel, float4* __restrict__ world, float* __restrict__ pd2_out,
-            double* __restrict__ tau, float* __restrict__ normal_y, double* __restrict__ rows12,
-            uint8_t* __restrict__ lid8, unsigned long long* __restrict__ d_mmkey, uint32_t* __restrict__ d_cnt) {
-  const uint32_t p = blockIdx.x * GATE_THREADS + threadIdx.x;
-  MinMax4 mm{1000.0, 0.0, 9999.0, 0.0, 0u};   // laserMapping.cpp:615-616, 646-647
-  if (p < N) {
-    const malio_scan_pt pt = pts[perm ? perm[p] : p];
-    double b[3], m[3], g[3];
-    transform_point(pc, pt.x, pt.y, pt.z, pt.lidar, b, m, g);
-    const float wx = (float)g[0], wy = (float)g[1], wz = (float)g[2];
-    world[p] = make_float4(wx, wy, wz, 0.f);
-    bool selected = sel[p] != 0;
+// one point of the gate: returns its contribution to the min/max of the two weights in mm
+__device__ __forceinline__ void gate_point(const malio_scan_pt& pt, uint32_t p, const PassConst& pc,
+                                           const float4* __restrict__ plane, const double* __restrict__ ucov,
+                                           const double2* __restrict__ tau2, uint8_t* __restrict__ sel,
+                                           float4* __restrict__ world, float* __restrict__ pd2_out, double* __restrict__ tau,
+                                           float* __restrict__ normal_y, double* __restrict__ rows12,
+                                           uint8_t* __restrict__ lid8, MinMax4& mm) {
+  double b[3], m[3], g[3];
+  transform_point(pc, pt.x, pt.y, pt.z, pt.lidar, b, m, g);
+  const float wx = (float)g[0], wy = (float)g[1], wz = (float)g[2];
+  world[p] = make_float4(wx, wy, wz, 0.f);
+  bool selected = sel[p] != 0;
+  if (selected) {
+    const float4 pl = plane[p];
+    const float pd2 = pl.x * wx + pl.y * wy + pl.z * wz + pl.w;                  // laserMapping.cpp:598
+    const double nb = sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+    const float s = (float)(1 - 0.9 * (double)fabsf(pd2) / sqrt(nb));           // :599
+    selected = (double)s > 0.1;
+    pd2_out[p] = pd2;
+    if (!selected) sel[p] = 0;
     if (selected) {
-      const float4 pl = plane[p];
-      const float pd2 = pl.x * wx + pl.y * wy + pl.z * wz + pl.w;                  // laserMapping.cpp:598
-      const double nb = sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
-      const float s = (float)(1 - 0.9 * (double)fabsf(pd2) / sqrt(nb));           // :599
-      selected = (double)s > 0.1;
-      pd2_out[p] = pd2;
-      if (!selected) sel[p] = 0;
-      if (selected) {
-        // un-weighted Jacobian row, compact: [ n | A | B | C ]  (laserMapping.cpp:665-693)
-        const int lid = pt.lidar;
-        const double nvec[3] = {(double)pl.x, (double)pl.y, (double)pl.z};
-        double C[3], A[3], B[3] = {0.0, 0.0, 0.0};
-        q_rot_conj(pc.rot, nvec, C);                    // :676  s.rot.conjugate() * norm_vec
-        cross3(m, C, A);                                // :677  [point_this]x * C
-        double Cc[3] = {0.0, 0.0, 0.0};
-        if (pc.ext_en) {
-          double Rq[9], v[3];
-          if (lid == 0) {   // :684  ([b]x R(qE0^T)) C
-            q_conj_to_R(pc.eq[0], Rq);
-            v[0] = b[0]; v[1] = b[1]; v[2] = b[2];
-          } else {          // :687-690
-            double C2[3];
-            q_rot_conj(pc.cq[lid], C, C2);
-            C[0] = C2[0]; C[1] = C2[1]; C[2] = C2[2];
-            q_conj_to_R(pc.eq[lid], Rq);
-            v[0] = pt.x; v[1] = pt.y; v[2] = pt.z;
-          }
-          // M = skew(v) * Rq, then B = M * C  (same association as the reference's M3D * Quaternion * V3D)
-          const double S[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            double Mi[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) Mi[j] = S[3 * i] * Rq[j] + S[3 * i + 1] * Rq[3 + j] + S[3 * i + 2] * Rq[6 + j];
-            B[i] = Mi[0] * C[0] + Mi[1] * C[1] + Mi[2] * C[2];
-          }
-          Cc[0] = C[0]; Cc[1] = C[1]; Cc[2] = C[2];
+      // un-weighted Jacobian row, compact: [ n | A | B | C ]  (laserMapping.cpp:665-693)
+      const int lid = pt.lidar;
+      const double nvec[3] = {(double)pl.x, (double)pl.y, (double)pl.z};
+      double C[3], A[3], B[3] = {0.0, 0.0, 0.0};
+      q_rot_conj(pc.rot, nvec, C);                    // :676  s.rot.conjugate() * norm_vec
+      cross3(m, C, A);                                // :677  [point_this]x * C
+      double Cc[3] = {0.0, 0.0, 0.0};
+      if (pc.ext_en) {
+        double Rq[9], v[3];
+        if (lid == 0) {   // :684  ([b]x R(qE0^T)) C
+          q_conj_to_R(pc.eq[0], Rq);
+          v[0] = b[0]; v[1] = b[1]; v[2] = b[2];
+        } else {          // :687-690
+          double C2[3];
+          q_rot_conj(pc.cq[lid], C, C2);
+          C[0] = C2[0]; C[1] = C2[1]; C[2] = C2[2];
+          q_conj_to_R(pc.eq[lid], Rq);
+          v[0] = pt.x; v[1] = pt.y; v[2] = pt.z;
         }
-        double2* dst = reinterpret_cast<double2*>(rows12 + (size_t)p * 12);
-        dst[0] = make_double2(nvec[0], nvec[1]); dst[1] = make_double2(nvec[2], A[0]); dst[2] = make_double2(A[1], A[2]);
-        dst[3] = make_double2(B[0], B[1]);       dst[4] = make_double2(B[2], Cc[0]);   dst[5] = make_double2(Cc[1], Cc[2]);
-        lid8[p] = (uint8_t)lid;
+        // M = skew(v) * Rq, then B = M * C  (same association as the reference's M3D * Quaternion * V3D)
+        const double S[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          double Mi[3];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) Mi[j] = S[3 * i] * Rq[j] + S[3 * i + 1] * Rq[3 + j] + S[3 * i + 2] * Rq[6 + j];
+          B[i] = Mi[0] * C[0] + Mi[1] * C[1] + Mi[2] * C[2];
+        }
+        Cc[0] = C[0]; Cc[1] = C[1]; Cc[2] = C[2];
       }
-    }
-    const double2 t2 = tau2[p];
-    if (selected) {
-      const double u = ucov[p];
-      mm.umin = fmin(mm.umin, u); mm.umax = fmax(mm.umax, u); mm.cnt = 1;
-      if (pc.ext_en) {   // :694-703; with extrinsic_est_en == false R and normal_y are left untouched
-        tau[p] = t2.x;
-        normal_y[p] = (float)t2.x;
-        mm.tmin = fmin(mm.tmin, t2.x); mm.tmax = fmax(mm.tmax, t2.x);
-      }
-    } else {
-      normal_y[p] = (float)t2.y;   // :735-741
+      double2* dst = reinterpret_cast<double2*>(rows12 + (size_t)p * 12);
+      dst[0] = make_double2(nvec[0], nvec[1]); dst[1] = make_double2(nvec[2], A[0]); dst[2] = make_double2(A[1], A[2]);
+      dst[3] = make_double2(B[0], B[1]);       dst[4] = make_double2(B[2], Cc[0]);   dst[5] = make_double2(Cc[1], Cc[2]);
+      lid8[p] = (uint8_t)lid;
     }
   }
-  // block reduction, then one integer atomicMin per quantity and block on the order-preserving keys:
-  // min/max are exact under any ordering, so this is deterministic without a serial fold.
-  __shared__ MinMax4 s_w[GATE_THREADS / 32];
+  const double2 t2 = tau2[p];
+  if (selected) {
+    const double u = ucov[p];
+    mm.umin = fmin(mm.umin, u); mm.umax = fmax(mm.umax, u); mm.cnt += 1;
+    if (pc.ext_en) {   // :694-703; with extrinsic_est_en == false R and normal_y are left untouched
+      tau[p] = t2.x;
+      normal_y[p] = (float)t2.x;
+      mm.tmin = fmin(mm.tmin, t2.x); mm.tmax = fmax(mm.tmax, t2.x);
+    }
+  } else {
+    normal_y[p] = (float)t2.y;   // :735-741
+  }
+}
+// block-level min/max, then one integer atomicMin per quantity and block on the order-preserving keys:
+// min/max are exact under any ordering, so this is deterministic without a serial fold.
+template <int THREADS>
+__device__ __forceinline__ void minmax_block_commit(MinMax4 mm, unsigned long long* __restrict__ d_mmkey,
+                                                    uint32_t* __restrict__ d_cnt) {
+  __shared__ MinMax4 s_w[THREADS / 32];
   mm = warp_reduce(mm);
   if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = mm;
   __syncthreads();
   if (threadIdx.x == 0) {
     MinMax4 r = s_w[0];
-    for (int w = 1; w < GATE_THREADS / 32; ++w) {
+    for (int w = 1; w < THREADS / 32; ++w) {
       r.umin = fmin(r.umin, s_w[w].umin); r.umax = fmax(r.umax, s_w[w].umax);
       r.tmin = fmin(r.tmin, s_w[w].tmin); r.tmax = fmax(r.tmax, s_w[w].tmax);
       r.cnt += s_w[w].cnt;
@@ -824,6 +1203,20 @@ gate_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ 
       atomicAdd(d_cnt, r.cnt);
     }
   }
+}
+__global__ void __launch_bounds__(GATE_THREADS)
+gate_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t N, PassConst pc,
+            const float4* __restrict__ plane, const double* __restrict__ ucov, const double2* __restrict__ tau2,
+            uint8_t* __restrict__ sel, float4* __restrict__ world, float* __restrict__ pd2_out,
+            double* __restrict__ tau, float* __restrict__ normal_y, double* __restrict__ rows12,
+            uint8_t* __restrict__ lid8, unsigned long long* __restrict__ d_mmkey, uint32_t* __restrict__ d_cnt) {
+  const uint32_t p = blockIdx.x * GATE_THREADS + threadIdx.x;
+  MinMax4 mm{1000.0, 0.0, 9999.0, 0.0, 0u};   // laserMapping.cpp:615-616, 646-647
+  if (p < N) {
+    const malio_scan_pt pt = pts[perm ? perm[p] : p];
+    gate_point(pt, p, pc, plane, ucov, tau2, sel, world, pd2_out, tau, normal_y, rows12, lid8, mm);
+  }
+  minmax_block_commit<GATE_THREADS>(mm, d_mmkey, d_cnt);
 }
 
 // ------------------------------------------------------------------ K3: weights + fused H^T R^-1 [H | h] reduction
@@ -862,28 +1255,52 @@ __device__ __forceinline__ void red_task(int t, int& gi, int& gj) {
   gj = t - (gi == 0 ? 0 : (gi == 1 ? 3 : 5));
 }
 
-__global__ void __launch_bounds__(RED_THREADS)
-reduce_kernel(uint32_t N, ParamConst prm, int ext_en, const uint8_t* __restrict__ sel, const uint8_t* __restrict__ lid8,
-              const double* __restrict__ rows12, const float* __restrict__ pd2v, const double* __restrict__ ucov,
-              const double* __restrict__ tau, const unsigned long long* __restrict__ d_mm, uint32_t n_tiles,
-              double* __restrict__ block_red) {
+// The body of the reduction for one block: tiles [tile_begin, tile_end) (contiguous, so that with the LiDAR-major
+// internal order a block sees one LiDAR for many tiles), result in the block's slot.  Each of the 126 worker threads
+// owns one 4x4 block (task) of the compact 12 x 16 system and every RED_KS-th row; its 16 accumulators stay in
+// registers for as long as the LiDAR does not change and are folded over the row-splits (fixed order) into the slot
+// only then.
+__device__ __forceinline__ void reduce_flush(const double acc[16], bool worker, int l, double* __restrict__ s_flush,
+                                             double* __restrict__ slot) {
+  if (worker) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s_flush[k * (RED_TASKS * RED_KS) + threadIdx.x] = acc[k];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < RED_TASKS * 16; e += RED_THREADS) {
+    const int tk = e / 16, k = e % 16;
+    double sum = 0.0;
+#pragma unroll
+    for (int q = 0; q < RED_KS; ++q) sum += s_flush[k * (RED_TASKS * RED_KS) + tk * RED_KS + q];
+    slot[(l * RED_TASKS + tk) * 16 + k] += sum;
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void reduce_block(uint32_t N, const ParamConst& prm, int ext_en, const uint8_t* __restrict__ sel,
+                                             const uint8_t* __restrict__ lid8, const double* __restrict__ rows12,
+                                             const float* __restrict__ pd2v, const double* __restrict__ ucov,
+                                             const double* __restrict__ tau, const unsigned long long* __restrict__ d_mm,
+                                             uint32_t tile_begin, uint32_t tile_end, double* __restrict__ slot) {
   extern __shared__ double smem[];
   double* s_hs = smem;                                       // [128][RED_HS_STRIDE]  a J12 / rho^
   double* s_hx = s_hs + RED_THREADS * RED_HS_STRIDE;         // [128][RED_HX_STRIDE]  [a J12 | z | rho^ a J12_0..2]
-  double* s_acc = s_hx + RED_THREADS * RED_HX_STRIDE;        // [3 lidar][16][RED_TASKS * RED_KS]  (entry-major: conflict-free)
+  double* s_flush = s_hx + RED_THREADS * RED_HX_STRIDE;      // [16][RED_TASKS * RED_KS]  (entry-major: conflict-free)
   __shared__ uint32_t s_wcnt[MALIO_MAX_LIDAR][RED_THREADS / 32];
   __shared__ uint32_t s_seg[MALIO_MAX_LIDAR + 1];
-  __shared__ uint32_t s_cnt_total;
   const int task = threadIdx.x / RED_KS, ks = threadIdx.x % RED_KS;
   const bool worker = task < RED_TASKS;
   int gi = 0, gj = 0;
   if (worker) red_task(task, gi, gj);
-  for (int k = threadIdx.x; k < MALIO_MAX_LIDAR * RED_TASKS * RED_KS * 16; k += RED_THREADS) s_acc[k] = 0.0;
-  if (threadIdx.x == 0) s_cnt_total = 0;
+  for (int e = threadIdx.x; e < MALIO_RED_DOUBLES; e += RED_THREADS) slot[e] = 0.0;
   const double umin = dkey_inv(d_mm[0]), umax = -dkey_inv(d_mm[1]), tmin = dkey_inv(d_mm[2]), tmax = -dkey_inv(d_mm[3]);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t cnt_total = 0;
+  int cur_l = -1;            // block-uniform: every thread derives it from s_seg
+  double acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.0;
   __syncthreads();
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
     // ---- phase A: weight this thread's row, then place it in the tile's LiDAR-sorted order
     const uint32_t p = tile * RED_THREADS + threadIdx.x;
     const bool ok = (p < N) && sel[p];
@@ -907,7 +1324,6 @@ reduce_kernel(uint32_t N, ParamConst prm, int ext_en, const uint8_t* __restrict_
         for (int w = 0; w < RED_THREADS / 32; ++w) { const uint32_t c = s_wcnt[ll][w]; s_wcnt[ll][w] = run; run += c; }
       }
       s_seg[MALIO_MAX_LIDAR] = run;
-      s_cnt_total += run;
     }
     __syncthreads();
     if (ok) {
@@ -921,15 +1337,19 @@ reduce_kernel(uint32_t N, ParamConst prm, int ext_en, const uint8_t* __restrict_
       hx[12] = z; hx[13] = rho * h[0]; hx[14] = rho * h[1]; hx[15] = rho * h[2];
     }
     __syncthreads();
+    cnt_total += s_seg[MALIO_MAX_LIDAR];
     // ---- phase B: per LiDAR segment, 9 block tasks x RED_KS row-splits
-    if (worker) {
 #pragma unroll 1
-      for (int ll = 0; ll < MALIO_MAX_LIDAR; ++ll) {
-        const uint32_t beg = s_seg[ll], end = s_seg[ll + 1];
-        if (beg == end) continue;
-        double acc[16];
+    for (int ll = 0; ll < MALIO_MAX_LIDAR; ++ll) {
+      const uint32_t beg = s_seg[ll], end = s_seg[ll + 1];
+      if (beg == end) continue;
+      if (ll != cur_l) {
+        if (cur_l >= 0) reduce_flush(acc, worker, cur_l, s_flush, slot);
+        cur_l = ll;
 #pragma unroll
         for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+      }
+      if (worker) {
         for (uint32_t q = beg + ks; q < end; q += RED_KS) {
           const double* aa = s_hs + q * RED_HS_STRIDE + 4 * gi;
           const double* bb = s_hx + q * RED_HX_STRIDE + 4 * gj;
@@ -940,31 +1360,125 @@ reduce_kernel(uint32_t N, ParamConst prm, int ext_en, const uint8_t* __restrict_
           acc[8] = fma(a2, c0, acc[8]);   acc[9] = fma(a2, c1, acc[9]);   acc[10] = fma(a2, c2, acc[10]); acc[11] = fma(a2, c3, acc[11]);
           acc[12] = fma(a3, c0, acc[12]); acc[13] = fma(a3, c1, acc[13]); acc[14] = fma(a3, c2, acc[14]); acc[15] = fma(a3, c3, acc[15]);
         }
-        double* sa = s_acc + (size_t)ll * 16 * (RED_TASKS * RED_KS) + threadIdx.x;   // this thread's own cells
-#pragma unroll
-        for (int k = 0; k < 16; ++k) sa[k * (RED_TASKS * RED_KS)] += acc[k];
       }
     }
-    __syncthreads();
+    __syncthreads();   // the staging area is rewritten by the next tile
   }
-  // ---- fold the RED_KS row-splits (fixed order) and write this block's slot
-  double* slot = block_red + (size_t)blockIdx.x * MALIO_RED_DOUBLES;
-  for (int e = threadIdx.x; e < MALIO_MAX_LIDAR * RED_TASKS * 16; e += RED_THREADS) {
-    const int lt = e / 16, k = e % 16, ll = lt / RED_TASKS, tk = lt % RED_TASKS;
-    double s = 0.0;
+  if (cur_l >= 0) reduce_flush(acc, worker, cur_l, s_flush, slot);
+  if (threadIdx.x == 0) { slot[MALIO_RED_BLOCKS * 16] = (double)cnt_total; slot[MALIO_RED_BLOCKS * 16 + 1] = 0.0; }
+}
+// contiguous tile range of block b when n_tiles are dealt to `grid` blocks (the host picks grid = ceil(n_tiles / per_block))
+__device__ __forceinline__ void block_tiles(uint32_t n_tiles, uint32_t& t0, uint32_t& t1) {
+  const uint32_t per_block = (n_tiles + gridDim.x - 1) / gridDim.x;
+  t0 = blockIdx.x * per_block;
+  t1 = t0 + per_block < n_tiles ? t0 + per_block : n_tiles;
+  if (t0 > n_tiles) t0 = n_tiles;
+}
+__global__ void __launch_bounds__(RED_THREADS)
+reduce_kernel(uint32_t N, ParamConst prm, int ext_en, const uint8_t* __restrict__ sel, const uint8_t* __restrict__ lid8,
+              const double* __restrict__ rows12, const float* __restrict__ pd2v, const double* __restrict__ ucov,
+              const double* __restrict__ tau, const unsigned long long* __restrict__ d_mm, uint32_t n_tiles,
+              double* __restrict__ block_red) {
+  uint32_t t0, t1;
+  block_tiles(n_tiles, t0, t1);
+  reduce_block(N, prm, ext_en, sel, lid8, rows12, pd2v, ucov, tau, d_mm, t0, t1, block_red + (size_t)blockIdx.x * MALIO_RED_DOUBLES);
+}
+
+// ------------------------------------------------------------------ one measurement pass in ONE cooperative launch
+// K2 + K3 fused (single-GPU path):  [tau once per scan] [plane fit once per search] gate -> grid barrier -> weights +
+// H^T R^-1 [H|h] accumulation -> grid barrier -> distributed fixed-order fold, written both to device memory and straight
+// into pinned, mapped host memory, followed by a sequence flag the host spins on.  Compared with the three launches +
+// D2H copy + stream synchronisation it replaces, this removes every launch gap and the copy/sync latency from the
+// per-pass critical path; arithmetic and summation order are unchanged (bit-identical results).
+// The kernel is launched with cudaLaunchCooperativeKernel (all blocks co-resident), the barriers are plain
+// device-scope counters that only ever grow (the host passes the value they had before the launch).
+struct PassArgs {
+  const malio_scan_pt* pts; const uint32_t* perm; uint32_t N;
+  const double* table; const float4* nodes; const float* node_cov; const uint32_t* nn_idx;
+  uint8_t* sel; float4* world; float4* plane; double* ucov; double2* tau2; float* pd2; double* tau; float* normal_y;
+  double* rows12; uint8_t* lid8;
+  int do_tau, do_fit;
+  unsigned long long *mmkey, *mmkey_next; uint32_t *cnt_cell, *cnt_next, *gstats;
+  uint32_t* bar;           // [0] barrier 1 arrivals, [1] barrier 2 arrivals, [2] folded entries  (monotone)
+  uint32_t bar_base[3];
+  uint32_t n_tiles;
+  double* block_red; double* d_res;
+  double* h_res;           // mapped host memory: MALIO_RED_DOUBLES result | 4 min/max keys | flag
+  uint32_t seq;
+};
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// all threads of all blocks call this; returns when `expected` arrivals have been counted
+__device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while ((int32_t)(ld_acquire_u32(counter) - target) < 0) { }
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(RED_THREADS, 4)
+pass_kernel(PassArgs a, PassConst pc, ParamConst prm) {
+  uint32_t t0, t1;
+  block_tiles(a.n_tiles, t0, t1);
+  // ---- phase 1: per point, same tile -> block mapping as the accumulation below
+  {
+    MinMax4 mm{1000.0, 0.0, 9999.0, 0.0, 0u};   // laserMapping.cpp:615-616, 646-647
+    for (uint32_t tile = t0; tile < t1; ++tile) {
+      const uint32_t p = tile * RED_THREADS + threadIdx.x;
+      if (p < a.N) {
+        const malio_scan_pt pt = a.pts[a.perm ? a.perm[p] : p];
+        if (a.do_tau) tau_point(pt, pc, a.table, a.tau2, p);
+        if (a.do_fit && a.sel[p]) fit_point(a.nodes, a.node_cov, a.N, prm, a.nn_idx, a.sel, a.plane, a.ucov, p);
+        gate_point(pt, p, pc, a.plane, a.ucov, a.tau2, a.sel, a.world, a.pd2, a.tau, a.normal_y, a.rows12, a.lid8, mm);
+      }
+    }
+    minmax_block_commit<RED_THREADS>(mm, a.mmkey, a.cnt_cell);
+  }
+  grid_barrier(a.bar + 0, a.bar_base[0] + gridDim.x);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {   // arm the other parity's min/max cell for the next pass
+    a.mmkey_next[0] = dkey(1000.0); a.mmkey_next[1] = dkey(-0.0);
+    a.mmkey_next[2] = dkey(9999.0); a.mmkey_next[3] = dkey(-0.0);
+    *a.cnt_next = 0;
+    a.gstats[2] = 0; a.gstats[4] = 0;
+  }
+  // ---- phase 2: weights + accumulation into this block's slot
+  reduce_block(a.N, prm, pc.ext_en, a.sel, a.lid8, a.rows12, a.pd2, a.ucov, a.tau, a.mmkey, t0, t1,
+               a.block_red + (size_t)blockIdx.x * MALIO_RED_DOUBLES);
+  grid_barrier(a.bar + 1, a.bar_base[1] + gridDim.x);
+  // ---- phase 3: fold the slots, one warp per entry, in fold_kernel's order
+  const uint32_t lane = threadIdx.x & 31u, wpb = RED_THREADS / 32;
+  uint32_t mine = 0;
+  for (uint32_t e = blockIdx.x * wpb + (threadIdx.x >> 5); e < MALIO_RED_DOUBLES; e += gridDim.x * wpb) {
+    double sum = 0.0;
+    for (uint32_t bk = lane; bk < gridDim.x; bk += 32) sum += a.block_red[(size_t)bk * MALIO_RED_DOUBLES + e];
 #pragma unroll
-    for (int q = 0; q < RED_KS; ++q) s += s_acc[((size_t)ll * 16 + k) * (RED_TASKS * RED_KS) + tk * RED_KS + q];
-    slot[e] = s;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) { a.d_res[e] = sum; a.h_res[e] = sum; ++mine; }
   }
-  if (threadIdx.x == 0) { slot[MALIO_RED_BLOCKS * 16] = (double)s_cnt_total; slot[MALIO_RED_BLOCKS * 16 + 1] = 0.0; }
+  if (lane == 0 && mine) {
+    __threadfence_system();
+    const uint32_t done = atomicAdd(a.bar + 2, mine) + mine;
+    if (done == a.bar_base[2] + MALIO_RED_DOUBLES) {   // last entry folded: min/max keys, then the flag
+      unsigned long long* hk = reinterpret_cast<unsigned long long*>(a.h_res + MALIO_RED_DOUBLES);
+      hk[0] = a.mmkey[0]; hk[1] = a.mmkey[1]; hk[2] = a.mmkey[2]; hk[3] = a.mmkey[3];
+      __threadfence_system();
+      *reinterpret_cast<volatile uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 8) = a.seq;
+    }
+  }
 }
 
 // second stage: one warp per entry of the reduced system folds the per-block slots in a fixed order
 // (lane-strided partial sums, then a shuffle tree) -> bit-reproducible result, no FP64 atomics
 __global__ void __launch_bounds__(256)
 fold_kernel(const double* __restrict__ block_red, uint32_t n_slots, double* __restrict__ d_res,
-            unsigned long long* __restrict__ next_mmkey, uint32_t* __restrict__ next_cnt) {
+            unsigned long long* __restrict__ next_mmkey, uint32_t* __restrict__ next_cnt, uint32_t* __restrict__ gstats) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {   // arm the other parity's min/max cell for the next pass
+    gstats[2] = 0; gstats[4] = 0;              // and the k-NN fast path's unsettled / ring-2 counters
     next_mmkey[0] = dkey(1000.0); next_mmkey[1] = dkey(-0.0);    // laserMapping.cpp:615-616
     next_mmkey[2] = dkey(9999.0); next_mmkey[3] = dkey(-0.0);    // :646-647
     *next_cnt = 0;
@@ -1106,6 +1620,19 @@ struct DeviceState {
   PassConst last_pc{};
   // stand-alone queries
   float* d_queries = nullptr; uint32_t capQ = 0;
+  // cell-list index over the live snapshot points (k-NN fast path)
+  bool grid_on = false; GridConst grid{}; float grid_h = 0.f;
+  uint32_t *d_cell_start = nullptr, *d_cell_cnt = nullptr, *d_cell_of = nullptr, *d_ctot = nullptr, *d_cbase = nullptr;
+  uint32_t cap_cells = 0, cap_cell_pts = 0;
+  float4* d_cell_pts = nullptr;
+  uint32_t* d_fb_list = nullptr;          // positions the fast path could not settle (-> exact traversal)
+  uint32_t* d_r2_list = nullptr;          // positions that need the 5x5x5 block
+  uint32_t* d_gstats = nullptr;           // [0] occupied cells, [1] live points, [2] fb count, [3] fb count of the last search, [4] ring-2 queries
+  uint32_t* h_gstats = nullptr;            // pinned mirror (8 words, carved out of h_res)
+  // fused pass (single cooperative launch per measurement pass)
+  bool fused = true; int pass_max_blocks = 0;
+  uint32_t* d_bar = nullptr; uint32_t bar_base[3] = {0, 0, 0}; uint32_t seq = 0;
+  double* h_res_dev = nullptr;     // device-side address of the mapped host result buffer
   // multi-GPU
   ncclComm_t comm = nullptr; int rank = 0, world = 1;
 };
@@ -1169,6 +1696,113 @@ int sort_queries(malio_handle* h, DeviceState* D, uint32_t n, const PassConst& p
   return MALIO_OK;
 }
 
+
+// ---- cell-list index: geometry from the snapshot root (its point + both children's boxes bound every live point)
+constexpr uint32_t GRID_MAX_CELLS = 1u << 25;
+bool grid_geometry(const malio_map_node* nodes, uint32_t n, float hcell, GridConst& G) {
+  if (n == 0 || !(hcell > 0.f)) return false;
+  const malio_map_node& r = nodes[0];
+  float lo[3] = {r.x, r.y, r.z}, hi[3] = {r.x, r.y, r.z};
+  auto grow = [&](const float* b) {
+    for (int a = 0; a < 3; ++a) { lo[a] = std::fmin(lo[a], b[2 * a]); hi[a] = std::fmax(hi[a], b[2 * a + 1]); }
+  };
+  if (r.link & MALIO_LINK_HAS_LEFT) grow(r.lbox);
+  if (r.link & MALIO_LINK_HAS_RIGHT) grow(r.rbox);
+  for (int a = 0; a < 3; ++a) if (!std::isfinite(lo[a]) || !std::isfinite(hi[a])) return false;
+  for (int it = 0; it < 64; ++it) {
+    const float inv = 1.0f / hcell;
+    double dims[3];
+    for (int a = 0; a < 3; ++a) dims[a] = std::floor((double)((hi[a] - lo[a]) * inv)) + 1.0;
+    const double cells = (dims[0] + 2 * GRID_PAD) * (dims[1] + 2 * GRID_PAD) * (dims[2] + 2 * GRID_PAD);
+    if (cells + 1 <= (double)GRID_MAX_CELLS && dims[0] < 4000 && dims[1] < 4000 && dims[2] < 4000) {
+      G.ox = lo[0]; G.oy = lo[1]; G.oz = lo[2]; G.inv_h = inv; G.h = hcell;
+      G.nx = (int)dims[0]; G.ny = (int)dims[1]; G.nz = (int)dims[2];
+      G.px = G.nx + 2 * GRID_PAD; G.py = G.ny + 2 * GRID_PAD;
+      G.ncell = (uint32_t)cells;
+      return true;
+    }
+    hcell *= 1.26f;
+  }
+  return false;
+}
+
+// (re)build the index for the snapshot resident in D->d_nodes; leaves {occupied cells, live points} in D->h_gstats
+int grid_build(malio_handle* h, DeviceState* D, const GridConst& G) {
+  cudaStream_t st = D->stream;
+  const uint32_t n = D->n_nodes;
+  const uint32_t ncell_pad = ((G.ncell + 1 + GRID_CHUNK - 1) / GRID_CHUNK) * GRID_CHUNK, nchunk = ncell_pad / GRID_CHUNK;
+  if (ncell_pad > D->cap_cells) {
+    if (int rc = ensure(h, D->d_cell_start, (size_t)ncell_pad)) return rc;
+    if (int rc = ensure(h, D->d_cell_cnt, (size_t)ncell_pad)) return rc;
+    if (!D->d_ctot) { if (int rc = ensure(h, D->d_ctot, 8192)) return rc; if (int rc = ensure(h, D->d_cbase, 8192)) return rc; }
+    D->cap_cells = ncell_pad;
+  }
+  if (D->cap_nodes > D->cap_cell_pts) {
+    if (int rc = ensure(h, D->d_cell_of, (size_t)D->cap_nodes)) return rc;
+    if (int rc = ensure(h, D->d_cell_pts, (size_t)D->cap_nodes)) return rc;
+    D->cap_cell_pts = D->cap_nodes;
+  }
+  CUDA_TRY(cudaMemsetAsync(D->d_cell_cnt, 0, (size_t)ncell_pad * sizeof(uint32_t), st));
+  CUDA_TRY(cudaMemsetAsync(D->d_gstats, 0, 2 * sizeof(uint32_t), st));
+  grid_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(D->d_nodes, n, G, D->d_cell_cnt, D->d_cell_of);
+  grid_scan_local_kernel<<<nchunk, 1024, 0, st>>>(D->d_cell_cnt, D->d_cell_start, D->d_ctot, D->d_gstats);
+  grid_scan_tot_kernel<<<1, 1024, 0, st>>>(D->d_ctot, nchunk, D->d_cbase, D->d_gstats);
+  grid_scan_add_kernel<<<nchunk, 1024, 0, st>>>(D->d_cell_start, D->d_cbase);
+  grid_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(D->d_nodes, n, D->d_cell_of, D->d_cell_start, D->d_cell_cnt, D->d_cell_pts);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(D->h_gstats, D->d_gstats, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  D->ctr.kernel_launches += 5;
+  D->grid = G;
+  return MALIO_OK;
+}
+
+// the k-NN of one search pass: cell-list fast path + exact ikd-Tree-order traversal for what it leaves, or the
+// traversal alone when the index is off
+template <int MODE>
+int run_knn(malio_handle* h, DeviceState* D, uint32_t n, const uint32_t* perm, const PassConst& pc, float max_sqdist) {
+  cudaStream_t st = D->stream;
+  const bool smem_stack = D->depth + KNN_POP_WIDTH <= (uint32_t)KNN_SMEM_DEPTH;
+  const malio_scan_pt* pts = MODE == 0 ? D->d_pts : nullptr;
+  const float* qs = MODE == 0 ? nullptr : D->d_queries;
+  float4* world = MODE == 0 ? D->d_world : nullptr;
+  uint8_t* sel = MODE == 0 ? D->d_sel : nullptr;
+  if (D->grid_on) {
+    // d_gstats: [2] traversal-list length, [4] ring-2 list length (both zeroed by the previous pass / the re-arm)
+    constexpr size_t smem1 = (size_t)GK_CAP * GK_THREADS * sizeof(float4) + (size_t)GK_ROWS1 * GK_THREADS * sizeof(uint2);
+    knn_grid_kernel<MODE, 1><<<(n + GK_THREADS - 1) / GK_THREADS, GK_THREADS, smem1, st>>>(
+        D->d_cell_pts, D->d_cell_start, D->grid, pts, perm, qs, n, pc, max_sqdist, world, D->d_nn_idx, D->d_nn_d2, sel,
+        nullptr, nullptr, D->d_r2_list, D->d_gstats + 4, D->d_fb_list, D->d_gstats + 2);
+    uint32_t r2_blocks = (n + 3) / 4;                       // one warp per listed query, at most ~2 resident waves
+    if (r2_blocks > (uint32_t)D->sm_count * 16) r2_blocks = (uint32_t)D->sm_count * 16;
+    knn_ring2_kernel<MODE><<<r2_blocks, 128, 0, st>>>(
+        D->d_cell_pts, D->d_cell_start, D->grid, pts, perm, qs, n, pc, max_sqdist, D->d_nn_idx, D->d_nn_d2, sel,
+        D->d_r2_list, D->d_gstats + 4, D->d_fb_list, D->d_gstats + 2);
+    D->ctr.kernel_launches += 1;
+    // 8 queries per warp and iteration; at most one resident wave of 64-thread blocks
+    uint32_t fb_blocks = (n + 15) / 16;
+    const uint32_t wave = (uint32_t)D->sm_count * 8;
+    if (fb_blocks > wave) fb_blocks = wave;
+    if (smem_stack)
+      knn_list_kernel<MODE, true><<<fb_blocks, KNN_THREADS, 0, st>>>(D->d_nodes, D->n_nodes, pts, perm, qs, n, pc, max_sqdist,
+                                                                    D->d_fb_list, D->d_gstats + 2, D->d_nn_idx, D->d_nn_d2, sel, D->d_gstats + 3);
+    else
+      knn_list_kernel<MODE, false><<<fb_blocks, KNN_THREADS, 0, st>>>(D->d_nodes, D->n_nodes, pts, perm, qs, n, pc, max_sqdist,
+                                                                     D->d_fb_list, D->d_gstats + 2, D->d_nn_idx, D->d_nn_d2, sel, D->d_gstats + 3);
+    D->ctr.kernel_launches += 2;
+  } else {
+    const int lanes = pick_lanes(n, D->sm_count);
+    if (smem_stack)
+      knn_kernel<MODE, true><<<knn_blocks(n, lanes), KNN_THREADS, 0, st>>>(D->d_nodes, D->n_nodes, pts, perm, qs, n, lanes, pc,
+                                                                          max_sqdist, world, D->d_nn_idx, D->d_nn_d2, sel);
+    else
+      knn_kernel<MODE, false><<<knn_blocks(n, lanes), KNN_THREADS, 0, st>>>(D->d_nodes, D->n_nodes, pts, perm, qs, n, lanes, pc,
+                                                                           max_sqdist, world, D->d_nn_idx, D->d_nn_d2, sel);
+    D->ctr.kernel_launches += 1;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return MALIO_OK;
+}
+
 }  // namespace
 
 // =================================================================== host-facing entry points
@@ -1195,15 +1829,34 @@ int create(malio_handle* h) {
     CUDA_TRY(cudaMemcpy(D->d_mmkey, init, sizeof(init), cudaMemcpyHostToDevice));
   }
   CUDA_TRY(cudaMalloc((void**)&D->d_res, MALIO_RED_DOUBLES * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void**)&D->d_gstats, 8 * sizeof(uint32_t)));
+  CUDA_TRY(cudaMemset(D->d_gstats, 0, 8 * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc((void**)&D->d_hist, SORT_BINS * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc((void**)&D->d_offs, SORT_BINS * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc((void**)&D->d_cursor, SORT_BINS * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc((void**)&D->d_btot, SCAN_BLOCKS * sizeof(uint32_t)));
   CUDA_TRY(cudaMemset(D->d_hist, 0, SORT_BINS * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc((void**)&D->d_rows, (size_t)MALIO_MAX_DOF * 25 * sizeof(double)));
-  D->red_grid = (uint32_t)D->sm_count * 2;   // 81 KB of shared memory per block: 2 blocks per SM are co-resident
+  D->red_grid = (uint32_t)D->sm_count * 4;   // 46 KB of shared memory per block: 4 blocks per SM are co-resident
   CUDA_TRY(cudaMalloc((void**)&D->d_block_red, (size_t)D->red_grid * MALIO_RED_DOUBLES * sizeof(double)));
-  CUDA_TRY(cudaMallocHost((void**)&D->h_res, (MALIO_RED_DOUBLES + 8 + MALIO_MAX_DOF * 25) * sizeof(double)));
+  // pinned + mapped: [0, RED) result | +0..3 min/max keys | +4..7 k-NN list statistics | +8 pass sequence flag | +16.. rows
+  CUDA_TRY(cudaHostAlloc((void**)&D->h_res, (MALIO_RED_DOUBLES + 16 + MALIO_MAX_DOF * 25) * sizeof(double), cudaHostAllocMapped));
+  std::memset(D->h_res, 0, (MALIO_RED_DOUBLES + 16) * sizeof(double));
+  CUDA_TRY(cudaHostGetDevicePointer((void**)&D->h_res_dev, D->h_res, 0));
+  CUDA_TRY(cudaMalloc((void**)&D->d_bar, 4 * sizeof(uint32_t)));
+  CUDA_TRY(cudaMemset(D->d_bar, 0, 4 * sizeof(uint32_t)));
+  CUDA_TRY(cudaFuncSetAttribute(pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RED_SMEM_DOUBLES * (int)sizeof(double)));
+  {
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pass_kernel, RED_THREADS, RED_SMEM_DOUBLES * sizeof(double)));
+    int coop = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, D->device));
+    D->pass_max_blocks = per_sm * D->sm_count;
+    D->fused = coop && per_sm > 0;
+    if (const char* e = getenv("MALIO_FUSED_PASS")) D->fused = D->fused && atoi(e) != 0;
+  }
+  D->h_gstats = reinterpret_cast<uint32_t*>(D->h_res + MALIO_RED_DOUBLES + 4);
+  std::memset(D->h_gstats, 0, 8 * sizeof(uint32_t));
   CUDA_TRY(cudaFuncSetAttribute(reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 RED_SMEM_DOUBLES * (int)sizeof(double)));
   for (int l = 0; l < MALIO_MAX_LIDAR; ++l) { D->tcomp[l] = malio_rigid{{1, 0, 0, 0}, {0, 0, 0}}; }
@@ -1221,7 +1874,8 @@ void destroy(malio_handle* h) {
   void* ptrs[] = {D->d_nodes, D->d_cov, D->d_pts, D->d_perm, D->d_keys16, D->d_hist, D->d_offs, D->d_cursor, D->d_btot, D->d_tmp_ids,
                   D->d_table, D->d_nn_idx, D->d_nn_d2, D->d_sel, D->d_world, D->d_plane, D->d_ucov, D->d_tau, D->d_tau2, D->d_pd2, D->d_rows12, D->d_lid8,
                   D->d_normal_y, D->d_o_ny, D->d_o_idx, D->d_o_d2, D->d_o_sel, D->d_o_world, D->d_block_mm,
-                  D->d_block_cnt, D->d_counters, D->d_mmkey, D->d_block_red, D->d_res, D->d_rows, D->d_queries};
+                  D->d_block_cnt, D->d_counters, D->d_mmkey, D->d_block_red, D->d_res, D->d_rows, D->d_queries,
+                  D->d_cell_start, D->d_cell_cnt, D->d_cell_of, D->d_ctot, D->d_cbase, D->d_cell_pts, D->d_fb_list, D->d_r2_list, D->d_gstats, D->d_bar};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (D->h_res) cudaFreeHost(D->h_res);
   for (auto& e : D->ev) if (e) cudaEventDestroy(e);
@@ -1243,8 +1897,31 @@ int upload_map(malio_handle* h, const malio_map_node* nodes, const float* cov, u
   }
   CUDA_TRY(cudaMemcpyAsync(D->d_nodes, nodes, (size_t)n * sizeof(malio_map_node), cudaMemcpyHostToDevice, D->stream));
   CUDA_TRY(cudaMemcpyAsync(D->d_cov, cov, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, D->stream));
+  D->n_nodes = n; D->depth = depth;
+  // cell-list index for the k-NN fast path.  Cell edge: cfg.knn_cell_size (> 0 fixed, < 0 index off, 0 automatic:
+  // start at 1 m = twice the reference's map voxel, filter_size_map 0.5, and keep 2..9 live points per occupied cell)
+  float hcfg = h->cfg.knn_cell_size;
+  if (const char* e = getenv("MALIO_KNN_CELL")) hcfg = (float)atof(e);
+  D->grid_on = false;
+  if (hcfg >= 0.f && n > 0) {
+    const bool automatic = hcfg == 0.f;
+    float hc = automatic ? (D->grid_h > 0.f ? D->grid_h : 1.0f) : hcfg;
+    for (int attempt = 0; attempt < 6; ++attempt) {
+      GridConst G{};
+      if (!grid_geometry(nodes, n, hc, G)) break;
+      if (int rc = grid_build(h, D, G)) return rc;
+      CUDA_TRY(cudaStreamSynchronize(D->stream));
+      D->grid_on = true;
+      D->grid_h = G.h;
+      if (!automatic || D->h_gstats[0] == 0) break;
+      const double mean = (double)D->h_gstats[1] / (double)D->h_gstats[0];
+      if (mean < 2.0) hc = G.h * 1.5f;
+      else if (mean > 9.0 && G.h > 0.05f) hc = G.h / 1.5f;
+      else break;
+    }
+  }
   CUDA_TRY(cudaStreamSynchronize(D->stream));
-  D->n_nodes = n; D->depth = depth; D->map_ready = true;
+  D->map_ready = true;
   D->ctr.h2d_bytes += (uint64_t)n * (sizeof(malio_map_node) + sizeof(float));
   return MALIO_OK;
 }
@@ -1275,6 +1952,8 @@ static int ensure_point_buffers(malio_handle* h, DeviceState* D, uint32_t n) {
   if ((rc = ensure(h, D->d_o_d2, (size_t)cap * MALIO_K))) return rc;
   if ((rc = ensure(h, D->d_o_sel, cap))) return rc;
   if ((rc = ensure(h, D->d_o_world, (size_t)cap * 3))) return rc;
+  if ((rc = ensure(h, D->d_fb_list, cap))) return rc;
+  if ((rc = ensure(h, D->d_r2_list, cap))) return rc;
   const uint32_t blocks = (cap + PLANE_THREADS - 1) / PLANE_THREADS;
   if ((rc = ensure(h, D->d_block_mm, (size_t)blocks * 4))) return rc;
   if ((rc = ensure(h, D->d_block_cnt, blocks))) return rc;
@@ -1301,6 +1980,7 @@ int upload_scan(malio_handle* h, const malio_scan_pt* pts, uint32_t n, const mal
   CUDA_TRY(cudaMemsetAsync(D->d_sel, 0, D->capN, D->stream));
   CUDA_TRY(cudaMemsetAsync(D->d_normal_y, 0, (size_t)D->capN * sizeof(float), D->stream));
   CUDA_TRY(cudaMemsetAsync(D->d_nn_idx, 0xFF, (size_t)D->capN * MALIO_K * sizeof(uint32_t), D->stream));
+  CUDA_TRY(cudaMemsetAsync(D->d_gstats + 2, 0, 4 * sizeof(uint32_t), D->stream));
   CUDA_TRY(cudaStreamSynchronize(D->stream));
   for (int l = 0; l <= MALIO_MAX_LIDAR; ++l) D->table_off[l] = (l <= L) ? table_off[l] : table_off[L];
   for (int l = 1; l < L; ++l) D->tcomp[l] = tcomp[l - 1];
@@ -1316,6 +1996,7 @@ int rearm_scan(malio_handle* h) {
   CUDA_TRY(cudaMemsetAsync(D->d_sel, 0, D->capN, D->stream));
   CUDA_TRY(cudaMemsetAsync(D->d_normal_y, 0, (size_t)D->capN * sizeof(float), D->stream));
   CUDA_TRY(cudaMemsetAsync(D->d_nn_idx, 0xFF, (size_t)D->capN * MALIO_K * sizeof(uint32_t), D->stream));
+  CUDA_TRY(cudaMemsetAsync(D->d_gstats + 2, 0, 4 * sizeof(uint32_t), D->stream));
   D->perm_valid = false; D->tau_valid = false; D->pass_done = false; D->searched_once = false;
   return MALIO_OK;
 }
@@ -1358,21 +2039,69 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
     if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[5], st_));
     if (redo_knn) {
       knn_now = true;
-      D->ctr.kernel_launches += 1;
-      const int lanes = pick_lanes(N, D->sm_count);
-      if (D->depth + KNN_POP_WIDTH <= (uint32_t)KNN_SMEM_DEPTH)
-        knn_kernel<0, true><<<knn_blocks(N, lanes), KNN_THREADS, 0, st_>>>(
-            D->d_nodes, D->n_nodes, D->d_pts, perm, nullptr, N, lanes, pc, P.knn_max_sqdist, D->d_world, D->d_nn_idx,
-            D->d_nn_d2, D->d_sel);
-      else
-        knn_kernel<0, false><<<knn_blocks(N, lanes), KNN_THREADS, 0, st_>>>(
-            D->d_nodes, D->n_nodes, D->d_pts, perm, nullptr, N, lanes, pc, P.knn_max_sqdist, D->d_world, D->d_nn_idx,
-            D->d_nn_d2, D->d_sel);
+      if (int rc = run_knn<0>(h, D, N, perm, pc, P.knn_max_sqdist)) return rc;
       D->searched_once = true;
       if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[6], st_));
+      if (D->grid_on) CUDA_TRY(cudaMemcpyAsync(D->h_gstats + 2, D->d_gstats + 2, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st_));
     }
   }
   if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[1], st_));
+  unsigned long long* mmkey = D->d_mmkey + 4 * D->parity;
+  unsigned long long* mmkey_next = D->d_mmkey + 4 * (1 - D->parity);
+  uint32_t* cnt_cell = D->d_counters + 4 + D->parity;
+  uint32_t* cnt_next = D->d_counters + 4 + (1 - D->parity);
+  const uint32_t n_tiles = (N + RED_THREADS - 1) / RED_THREADS;
+  // one resident wave, every block the same number of tiles (+-1): no straggler blocks
+  const uint32_t wave = (D->fused && !D->comm && (uint32_t)D->pass_max_blocks < D->red_grid) ? (uint32_t)D->pass_max_blocks : D->red_grid;
+  const uint32_t per_block = n_tiles ? (n_tiles + wave - 1) / wave : 1;
+  const uint32_t grid = n_tiles ? (n_tiles + per_block - 1) / per_block : 1;
+  std::chrono::steady_clock::time_point hp1, hp2;
+  if (D->fused && !D->comm) {
+    // ---- single GPU: the whole pass in one cooperative launch; the result arrives in mapped host memory
+    PassArgs a{};
+    a.pts = D->d_pts; a.perm = perm; a.N = N; a.table = D->d_table; a.nodes = D->d_nodes; a.node_cov = D->d_cov;
+    a.nn_idx = D->d_nn_idx; a.sel = D->d_sel; a.world = D->d_world; a.plane = D->d_plane; a.ucov = D->d_ucov;
+    a.tau2 = D->d_tau2; a.pd2 = D->d_pd2; a.tau = D->d_tau; a.normal_y = D->d_normal_y; a.rows12 = D->d_rows12; a.lid8 = D->d_lid8;
+    a.do_tau = (N > 0 && !D->tau_valid) ? 1 : 0;
+    a.do_fit = (N > 0 && redo_knn) ? 1 : 0;
+    a.mmkey = mmkey; a.mmkey_next = mmkey_next; a.cnt_cell = cnt_cell; a.cnt_next = cnt_next; a.gstats = D->d_gstats;
+    a.bar = D->d_bar;
+    for (int k = 0; k < 3; ++k) a.bar_base[k] = D->bar_base[k];
+    D->bar_base[0] += grid; D->bar_base[1] += grid; D->bar_base[2] += MALIO_RED_DOUBLES;
+    a.n_tiles = n_tiles; a.block_red = D->d_block_red; a.d_res = D->d_res; a.h_res = D->h_res_dev;
+    a.seq = ++D->seq;
+    PassConst pc_arg = pc;
+    ParamConst prm_arg = prm;
+    void* kargs[] = {&a, &pc_arg, &prm_arg};
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)pass_kernel, dim3(grid), dim3(RED_THREADS), kargs,
+                                         RED_SMEM_DOUBLES * sizeof(double), st_));
+    D->tau_valid = D->tau_valid || N > 0;
+    D->ctr.kernel_launches += 1;
+    if (D->timing) { CUDA_TRY(cudaEventRecord(D->ev[2], st_)); CUDA_TRY(cudaEventRecord(D->ev[3], st_)); CUDA_TRY(cudaEventRecord(D->ev[4], st_)); }
+    D->last_parity = D->parity;
+    D->parity = 1 - D->parity;
+    hp1 = std::chrono::steady_clock::now();
+    // the host needs the 3.5 KB system to take the IESKF step: spin on the sequence flag the kernel writes last
+    volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(D->h_res + MALIO_RED_DOUBLES + 8);
+    for (uint64_t spins = 1; *flag != D->seq; ++spins) {
+      __builtin_ia32_pause();
+      if ((spins & 0x3FFF) == 0) {
+        const cudaError_t q = cudaStreamQuery(st_);
+        if (q == cudaErrorNotReady) {
+          if (std::chrono::duration<double>(std::chrono::steady_clock::now() - hp1).count() > 20.0) {
+            h->err = "pass_kernel: no result after 20 s";
+            return MALIO_ERR_CUDA;
+          }
+          continue;
+        }
+        if (q != cudaSuccess) { h->err = std::string("pass_kernel: ") + cudaGetErrorString(q); return MALIO_ERR_CUDA; }
+        if (*flag != D->seq) { h->err = "pass_kernel finished without publishing its result"; return MALIO_ERR_CUDA; }
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (D->timing) CUDA_TRY(cudaEventSynchronize(D->ev[4]));
+    hp2 = std::chrono::steady_clock::now();
+  } else {
   const uint32_t pblocks = N > 0 ? (N + PLANE_THREADS - 1) / PLANE_THREADS : 1;
   if (N > 0 && !D->tau_valid) {   // once per scan
     tau_kernel<<<pblocks, PLANE_THREADS, 0, st_>>>(D->d_pts, perm, N, pc, D->d_table, D->d_tau2);
@@ -1384,23 +2113,15 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
     D->ctr.kernel_launches += 1;
   }
   D->ctr.kernel_launches += 3;     // gate, reduce, fold
-  unsigned long long* mmkey = D->d_mmkey + 4 * D->parity;
-  unsigned long long* mmkey_next = D->d_mmkey + 4 * (1 - D->parity);
-  uint32_t* cnt_cell = D->d_counters + 4 + D->parity;
-  uint32_t* cnt_next = D->d_counters + 4 + (1 - D->parity);
   const uint32_t gblocks = N > 0 ? (N + GATE_THREADS - 1) / GATE_THREADS : 1;
   gate_kernel<<<gblocks, GATE_THREADS, 0, st_>>>(D->d_pts, perm, N, pc, D->d_plane, D->d_ucov, D->d_tau2, D->d_sel,
                                                    D->d_world, D->d_pd2, D->d_tau, D->d_normal_y, D->d_rows12, D->d_lid8, mmkey, cnt_cell);
   if (D->comm)   // keys of {min_u, -max_u, min_tau, -max_tau}: one MIN all-reduce (laserMapping.cpp:615-628, 700-703)
     if (g_nccl.AllReduce(mmkey, mmkey, 4, ncclUint64, ncclMin, D->comm, st_) != ncclSuccess) { h->err = "ncclAllReduce(min) failed"; return MALIO_ERR_NCCL; }
   if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[2], st_));
-  const uint32_t n_tiles = (N + RED_THREADS - 1) / RED_THREADS;
-  // one resident wave, every block the same number of tiles (+-1): no straggler blocks
-  const uint32_t per_block = n_tiles ? (n_tiles + D->red_grid - 1) / D->red_grid : 1;
-  uint32_t grid = n_tiles ? (n_tiles + per_block - 1) / per_block : 1;
   reduce_kernel<<<grid, RED_THREADS, RED_SMEM_DOUBLES * sizeof(double), st_>>>(
       N, prm, pc.ext_en, D->d_sel, D->d_lid8, D->d_rows12, D->d_pd2, D->d_ucov, D->d_tau, mmkey, n_tiles, D->d_block_red);
-  fold_kernel<<<(MALIO_RED_DOUBLES * 32 + 255) / 256, 256, 0, st_>>>(D->d_block_red, grid, D->d_res, mmkey_next, cnt_next);
+  fold_kernel<<<(MALIO_RED_DOUBLES * 32 + 255) / 256, 256, 0, st_>>>(D->d_block_red, grid, D->d_res, mmkey_next, cnt_next, D->d_gstats);
   if (D->comm)   // the reduced system + n_eff: one SUM all-reduce
     if (g_nccl.AllReduce(D->d_res, D->d_res, MALIO_RED_DOUBLES, ncclDouble, ncclSum, D->comm, st_) != ncclSuccess) { h->err = "ncclAllReduce(sum) failed"; return MALIO_ERR_NCCL; }
   if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[3], st_));
@@ -1409,10 +2130,11 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
   D->last_parity = D->parity;
   D->parity = 1 - D->parity;
   if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[4], st_));
-  const auto hp1 = std::chrono::steady_clock::now();
+  hp1 = std::chrono::steady_clock::now();
   CUDA_TRY(cudaStreamSynchronize(st_));
-  const auto hp2 = std::chrono::steady_clock::now();
+  hp2 = std::chrono::steady_clock::now();
   CUDA_TRY(cudaGetLastError());
+  }
   D->pass_done = true;
   D->host_launch_us += std::chrono::duration<double, std::micro>(hp1 - hp0).count();
   D->host_wait_us += std::chrono::duration<double, std::micro>(hp2 - hp1).count();
@@ -1447,6 +2169,7 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
   S.n_points = N; S.n_eff = n_eff; S.searched = redo_knn ? 1 : 0;
   S.u_min = mm[0]; S.u_max = -mm[1]; S.tau_min = mm[2]; S.tau_max = -mm[3];
   float ms = 0.f;
+  if (knn_now && D->grid_on) { D->ctr.knn_fallback_queries += D->h_gstats[3]; D->ctr.knn_ring2_queries += D->h_gstats[5]; }
   if (D->timing) {
   if (N > 0 && sorted_now) { cudaEventElapsedTime(&ms, D->ev[0], D->ev[5]); S.ms_sort = ms; }
   if (knn_now) {
@@ -1496,7 +2219,7 @@ int download_rows(malio_handle* h, double* h_x, double* hvec, uint32_t cap, uint
   rows_kernel<<<1, 256, 0, D->stream>>>(D->N, make_param_const(P), D->last_pc.ext_en, D->d_sel, D->d_lid8, D->d_rows12,
                                           D->d_pd2, D->d_ucov, D->d_tau, D->d_mmkey + 4 * D->last_parity, cap, D->d_rows,
                                           D->d_counters + 3);
-  double* hr = D->h_res + MALIO_RED_DOUBLES + 8;
+  double* hr = D->h_res + MALIO_RED_DOUBLES + 16;
   CUDA_TRY(cudaMemcpyAsync(hr, D->d_rows, (size_t)cap * 25 * sizeof(double), cudaMemcpyDeviceToHost, D->stream));
   uint32_t nr = 0;
   CUDA_TRY(cudaMemcpyAsync(&nr, D->d_counters + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, D->stream));
@@ -1556,26 +2279,23 @@ int knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* idx, float* d2, 
     if (int rc = sort_queries<1>(h, D, nq, pc)) return rc;
     perm = D->d_perm;
   }
+  CUDA_TRY(cudaMemsetAsync(D->d_gstats + 2, 0, 4 * sizeof(uint32_t), D->stream));
   CUDA_TRY(cudaEventRecord(D->ev[0], D->stream));
-  const int lanes = pick_lanes(nq, D->sm_count);
-  if (D->depth + KNN_POP_WIDTH <= (uint32_t)KNN_SMEM_DEPTH)
-    knn_kernel<1, true><<<knn_blocks(nq, lanes), KNN_THREADS, 0, D->stream>>>(
-        D->d_nodes, D->n_nodes, nullptr, perm, D->d_queries, nq, lanes, pc, 0.f, nullptr, D->d_nn_idx, D->d_nn_d2, nullptr);
-  else
-    knn_kernel<1, false><<<knn_blocks(nq, lanes), KNN_THREADS, 0, D->stream>>>(
-        D->d_nodes, D->n_nodes, nullptr, perm, D->d_queries, nq, lanes, pc, 0.f, nullptr, D->d_nn_idx, D->d_nn_d2, nullptr);
+  if (int rc = run_knn<1>(h, D, nq, perm, pc, 0.f)) return rc;
   CUDA_TRY(cudaEventRecord(D->ev[1], D->stream));
   scatter_aux_kernel<<<(nq + 255) / 256, 256, 0, D->stream>>>(perm, nq, nullptr, D->d_nn_idx, D->d_nn_d2, nullptr,
                                                                nullptr, nullptr, idx ? D->d_o_idx : nullptr,
                                                                d2 ? D->d_o_d2 : nullptr, nullptr, nullptr);
   if (idx) CUDA_TRY(cudaMemcpyAsync(idx, D->d_o_idx, (size_t)nq * MALIO_K * sizeof(uint32_t), cudaMemcpyDeviceToHost, D->stream));
   if (d2) CUDA_TRY(cudaMemcpyAsync(d2, D->d_o_d2, (size_t)nq * MALIO_K * sizeof(float), cudaMemcpyDeviceToHost, D->stream));
+  if (D->grid_on) CUDA_TRY(cudaMemcpyAsync(D->h_gstats + 2, D->d_gstats + 2, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, D->stream));
   CUDA_TRY(cudaStreamSynchronize(D->stream));
   CUDA_TRY(cudaGetLastError());
   float ms = 0.f;
   cudaEventElapsedTime(&ms, D->ev[0], D->ev[1]);
   if (ms_out) *ms_out = ms;
-  D->ctr.kernel_launches += 2;   // k-NN + scatter (the sort counts its own)
+  D->ctr.kernel_launches += 1;   // scatter (the sort and the k-NN count their own)
+  if (D->grid_on) { D->ctr.knn_fallback_queries += D->h_gstats[3]; D->ctr.knn_ring2_queries += D->h_gstats[5]; }
   D->ctr.knn_launches += 1; D->ctr.knn_queries += nq; D->ctr.knn_ms += ms;
   D->ctr.h2d_bytes += (uint64_t)nq * 12;
   D->ctr.d2h_bytes += (uint64_t)nq * ((idx ? 20 : 0) + (d2 ? 20 : 0));

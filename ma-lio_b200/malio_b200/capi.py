@@ -50,7 +50,7 @@ class Params(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("params", Params), ("device", C.c_int32), ("sort_queries", C.c_int32),
-                ("max_points", C.c_uint32), ("max_map_nodes", C.c_uint32)]
+                ("max_points", C.c_uint32), ("max_map_nodes", C.c_uint32), ("knn_cell_size", C.c_float)]
 
 
 class PassStats(C.Structure):
@@ -81,7 +81,8 @@ class State(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("knn_launches", C.c_uint64), ("knn_queries", C.c_uint64),
-                ("knn_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("knn_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("knn_fallback_queries", C.c_uint64), ("knn_ring2_queries", C.c_uint64)]
 
 
 class UpdateReport(C.Structure):

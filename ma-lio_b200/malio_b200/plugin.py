@@ -51,13 +51,16 @@ def build_static_snapshot(xyz: np.ndarray, normal_y: np.ndarray | float = 0.001)
 class MeasurementModel:
     """One handle = one GPU.  Mirrors the life cycle of one scan in laserMapping.cpp:935-1082."""
 
-    def __init__(self, n_lidar: int = 3, device: int = 0, sort_queries: bool = True, params: capi.Params | None = None):
+    def __init__(self, n_lidar: int = 3, device: int = 0, sort_queries: bool = True, params: capi.Params | None = None,
+                 knn_cell_size: float = 0.0):
+        """knn_cell_size: edge of the k-NN fast path's cell-list index (0 automatic, < 0 off = ikd-Tree traversal only)."""
         self.lib = capi.load()
         cfg = capi.Config()
         cfg.params = params if params is not None else capi.default_params(n_lidar)
         cfg.params.n_lidar = n_lidar
         cfg.device = device
         cfg.sort_queries = 1 if sort_queries else 0
+        cfg.knn_cell_size = float(knn_cell_size)
         self.n_lidar = n_lidar
         self.n_dof = 17 + 6 * n_lidar
         self.n_cols = 6 * (n_lidar + 1)

@@ -1,0 +1,112 @@
+"""GPU parity of the k-NN fast path (cell-list index over the snapshot, knn_grid_kernel) and its hand-over to the
+exact ikd-Tree-order traversal (knn_list_kernel).  Whatever the cell edge — automatic, tiny, huge, or the index
+switched off — the neighbour lists and float distances must be the reference's, index for index: compared with
+the restated Search (oracle) and, through the golden file, with the real ikd_Tree.cpp."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+import pyoracle as po
+from malio_b200 import capi, plugin, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CELLS = [0.0, -1.0, 0.3, 1.0, 2.5]   # automatic, index off (tree only), small, the default start, large
+
+
+def _search(snap, q, cell, sort=True):
+    m = plugin.MeasurementModel(1, sort_queries=sort, knn_cell_size=cell)
+    m.upload_map(snap)
+    c0 = m.counters()
+    idx, d2, _ = m.Nearest_Search(q)
+    c1 = m.counters()
+    m.close()
+    return idx, d2, int(c1.knn_fallback_queries - c0.knn_fallback_queries), int(c1.knn_ring2_queries - c0.knn_ring2_queries)
+
+
+def test_golden_reference_lists_for_every_cell_size():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ikd_knn_golden.npz"))
+    nodes = g["nodes"].view(capi.MAP_NODE).reshape(-1)
+    snap = plugin.MapSnapshot(nodes, g["node_cov"], g["node_ids"], int(g["max_depth"]))
+    for cell in CELLS:
+        idx, d2, fb, r2 = _search(snap, g["queries"], cell)
+        ok = idx != 0xFFFFFFFF
+        assert np.array_equal(ok.sum(1), g["ref_found"]), cell
+        mapped = np.where(ok, g["node_ids"][np.where(ok, idx, 0)], -1)
+        assert np.array_equal(mapped, g["ref_ids"]), cell
+        assert np.array_equal(d2[ok], g["ref_d2"][ok]), cell
+        if cell < 0:
+            assert fb == 0 and r2 == 0
+
+
+def test_ties_send_queries_to_the_exact_traversal():
+    """Perfect lattice + duplicates: exact float ties at the k-th boundary.  The fast path must notice every one of
+    them and hand the query over; the result is the reference's first-visited-wins list."""
+    rng = np.random.default_rng(11)
+    g = np.arange(-16, 16, dtype=np.float32) * 0.5
+    X, Y, Z = np.meshgrid(g, g, g[:6], indexing="ij")
+    lattice = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1).astype(np.float32)
+    dup = lattice[rng.integers(0, lattice.shape[0], 1000)]
+    xyz = np.concatenate([lattice, dup], axis=0)
+    xyz = xyz[rng.permutation(xyz.shape[0])]
+    snap = plugin.build_static_snapshot(xyz)
+    q = np.concatenate([
+        lattice[rng.integers(0, lattice.shape[0], 2000)] + np.float32(0.25),
+        lattice[rng.integers(0, lattice.shape[0], 2000)],
+        rng.uniform(-8, 8, (2000, 3)).astype(np.float32),
+    ]).astype(np.float32)
+    o_idx, o_d2, _, _ = po.knn_snapshot(snap.nodes, snap.node_cov, q, nthreads=4)
+    for cell in CELLS:
+        idx, d2, fb, _ = _search(snap, q, cell)
+        assert np.array_equal(idx.astype(np.int64), o_idx.astype(np.int64)), cell
+        assert np.array_equal(d2, o_d2), cell
+        if cell >= 0:
+            assert fb >= 4000, (cell, fb)   # every lattice-centre / lattice-point query ties
+
+
+def test_sparse_map_far_queries_and_outside_of_grid():
+    """Neighbourhoods sparser than the cell block (5x5x5 block, then the traversal), queries far outside the map's
+    bounding box, and a map with deleted points (they must never be returned)."""
+    rng = np.random.default_rng(12)
+    xyz = np.concatenate([rng.uniform(-40, 40, (3000, 3)),                 # ~0.006 pts/m^3: 5-NN at ~6 m
+                          rng.uniform(-5, 5, (4000, 3)) + [100, 0, 0]]).astype(np.float32)   # a dense blob
+    snap = plugin.build_static_snapshot(xyz)
+    nodes = snap.nodes.copy()
+    dead = rng.choice(nodes.shape[0], 700, replace=False)
+    nodes["link"][dead] |= capi.LINK_POINT_DELETED
+    snap = plugin.MapSnapshot(nodes, snap.node_cov, snap.node_ids, snap.max_depth)
+    q = np.concatenate([rng.uniform(-45, 45, (3000, 3)), rng.uniform(-6, 6, (3000, 3)) + [100, 0, 0],
+                        rng.uniform(-500, 500, (500, 3)), xyz[dead[:200]]]).astype(np.float32)
+    o_idx, o_d2, _, _ = po.knn_snapshot(nodes, snap.node_cov, q, nthreads=4)
+    assert not np.isin(o_idx, dead).any()
+    seen_fb = seen_r2 = 0
+    for cell in CELLS:
+        idx, d2, fb, r2 = _search(snap, q, cell)
+        assert np.array_equal(idx.astype(np.int64), o_idx.astype(np.int64)), cell
+        assert np.array_equal(d2, o_d2), cell
+        seen_fb += fb; seen_r2 += r2
+    assert seen_fb > 0 and seen_r2 > 0
+
+
+@pytest.mark.parametrize("cell", [-1.0, 0.4, 3.0])
+def test_measurement_pass_identical_with_and_without_index(cell):
+    """A full pass on the churned 3-LiDAR case: neighbour lists, gates and the reduced system with the given cell edge
+    equal the automatic configuration bit for bit (the k-NN result is the only thing the index may influence)."""
+    case = synth.make_case("3L-20k-200k", 20000, 200000, 3, 3, varied_map_cov=True)
+    snap, _ = H.snapshot_for(case, churn=True)
+    ref = H.make_model(case, snap)
+    ok_r, HTH_r, HTh_r, st_r = ref.h_share_model(case.x_prop, True)
+    a_r = ref.aux()
+    m = plugin.MeasurementModel(case.n_lidar, params=case.params, knn_cell_size=cell)
+    m.upload_map(snap)
+    m.upload_scan(case.pts, case.table, case.table_off, case.temporal_comp)
+    ok, HTH, HTh, st = m.h_share_model(case.x_prop, True)
+    a = m.aux()
+    assert ok == ok_r and st.n_eff == st_r.n_eff
+    for k in ("nn_idx", "nn_sqdist", "selected", "world", "normal_y"):
+        assert np.array_equal(a[k], a_r[k]), k
+    assert np.array_equal(HTH, HTH_r) and np.array_equal(HTh, HTh_r)
+    ref.close(); m.close()
