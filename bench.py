@@ -14,7 +14,8 @@ configs[2]).  Synthetic, seeded inputs (malio_b200/synth.py).
           re-armed on the device; sort, k-NN, plane fit, gate, reduction, D2H of the 5 KB system and the host
           35x35 algebra are all inside).
 `e2e`     the same metric through the public C-ABI calls with HOST (pinned) buffers: every step uploads the
-          flattened map snapshot and the scan, runs the update, and reads back the per-point side outputs.
+          flattened map snapshot (compact form: 20 B per node, boxes rebuilt on the device) and the scan, runs the
+          update, and reads back the per-point side outputs.
 L2 is flushed (256 MiB write) between timed steps; each step is bracketed by CUDA events and the per-step
 times are summed (max over ranks).  Only the cpu_baseline / --impl reference legs touch oracle/.
 """
@@ -36,9 +37,8 @@ sys.path.insert(0, os.path.join(ROOT, "ma-lio_b200"))
 METRIC = "scans/sec & ms/IESKF-iter, 100k-pt scan vs 1M-pt map, 1/2/4/8 GPU"
 UNIT = "scans/s"
 WORKLOAD = "C2: 3-LiDAR (Ouster+2xLivox) 100k-pt merged scan vs 1M-pt map snapshot, max_iteration=3"
-NODE_BYTES = 64          # malio_map_node
-VBAR_FALLBACK = 44.6     # mean node visits / query on C2 (oracle restated search; re-measured live when possible)
-NCU_DRAM_BYTES_PER_KNN_LAUNCH = 16.69e6   # dram__bytes_read+write of knn_kernel, profiles/r01_knn_kernel.md
+# dram__bytes_read+write of one knn_grid_kernel launch on C2 (ncu --set full, profiles/r01_knn_grid_kernel.md)
+NCU_DRAM_BYTES_PER_KNN_LAUNCH = 8.56e6
 
 
 def parse():
@@ -208,6 +208,7 @@ def run_ours(args, rank, world):
     t_nodes, h_nodes = pinned(snap.nodes); keep.append(t_nodes)
     t_cov, h_cov = pinned(snap.node_cov); keep.append(t_cov)
     t_pts, h_pts = pinned(np.ascontiguousarray(case.pts[lo:hi])); keep.append(t_pts)
+    t_mp, h_mpts = pinned(plugin.compact_points(snap.nodes)); keep.append(t_mp)
     snap_p = plugin.MapSnapshot(h_nodes, h_cov, snap.node_ids, snap.max_depth)
 
     model = plugin.MeasurementModel(case.n_lidar, device=local_rank, sort_queries=not args.no_sort, params=case.params)
@@ -231,7 +232,7 @@ def run_ours(args, rank, world):
         return model.update_iterated_dyn_share_modified(x, P, case.max_iter), x
 
     def step_e2e():
-        model.upload_map(snap_p)
+        model.upload_map_compact(snap_p, points=h_mpts)
         model.upload_scan(h_pts, case.table, case.table_off, case.temporal_comp)
         x, P = case.x_prop.copy(), case.P_prop.copy()
         rep = model.update_iterated_dyn_share_modified(x, P, case.max_iter)
@@ -296,26 +297,35 @@ def run_ours(args, rank, world):
             dist.destroy_process_group()
         return
 
-    # roofline of the dominant kernel (k-NN): algorithmic bytes per launch / CUDA-event time
+    # roofline of the dominant launch (the k-NN search: cell-list scan + the two list kernels behind it, timed together
+    # with CUDA events on the library's stream): algorithmic bytes per search / event time.
+    #   per query: 16 B scan point + 9 rows x 8 B cell ranges + C x 16 B candidates + 40 B neighbour list + 16 B world
+    #   point + 1 B gate; C = candidates actually scanned (device counter, timing runs only)
     peaks, peak_src = None, "fallback 6650 GB/s (B200_PROFILING.md)"
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         peak = float(peaks["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)"
     except Exception:
         peak = 6650.0
-    vbar = VBAR_FALLBACK
     q_per_launch = (hi - lo)
-    bytes_per_launch = q_per_launch * (16 + vbar * NODE_BYTES + 5 * 4)
+    cand = int(rc1.knn_candidates - rc0.knn_candidates)
     roof = None
     if knn_launches:
+        cbar = cand / float(knn_launches * q_per_launch)
+        bytes_per_launch = q_per_launch * (16 + 9 * 8 + cbar * 16 + 40 + 16 + 1)
         t_launch = knn_ms * 1e-3 / knn_launches
         achieved = bytes_per_launch / t_launch / 1e9
-        roof = {"bound": "hbm", "kernel": "knn_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": "k-NN search: knn_grid_kernel (+ knn_ring2_kernel, knn_list_kernel)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_KNN_LAUNCH if world == 1 else None,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "us_per_launch": t_launch * 1e6,
-                "launches_timed": knn_launches, "peak_source": peak_src,
-                "note": "bytes = Q*(16 + Vbar*64 + 20), Vbar=44.6 node visits/query (oracle traversal); the 64 MB snapshot "
-                        "is L2-resident so DRAM traffic is far below the algorithmic bytes: latency/issue-bound kernel"}
+                "launches_timed": knn_launches, "candidates_per_query": cbar,
+                "fallback_queries_per_search": float(rc1.knn_fallback_queries - rc0.knn_fallback_queries) / knn_launches,
+                "ring2_queries_per_search": float(rc1.knn_ring2_queries - rc0.knn_ring2_queries) / knn_launches,
+                "peak_source": peak_src,
+                "note": "bytes = Q*(16 + 72 + C*16 + 57), C = candidates scanned per query (device counter); the cell-sorted "
+                        "point array (16 MB) and the scan are L2-resident, so DRAM traffic is far below the algorithmic "
+                        "bytes: the kernel is bound by instruction issue of the top-6 insertion and by staging latency"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -340,7 +350,7 @@ def run_ours(args, rank, world):
         "clocks": clocks,
         "e2e": {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e_ms / e_steps, "steps": e_steps,
-                "what": "upload_map + upload_scan (pinned host buffers) + IESKF update + download of normal_y/selected"},
+                "what": "upload_map_compact (20 B/node, boxes + cell index rebuilt on the device) + upload_scan (pinned host buffers) + IESKF update + download of normal_y/selected"},
         "gpu_launches": launches,
         "roofline": roof, "cpu_baseline": cpu,
     }

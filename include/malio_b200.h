@@ -70,6 +70,15 @@ typedef struct malio_map_node {
 #define MALIO_LINK_POINT_DELETED 0x20000000u
 #define MALIO_LINK_INDEX_MASK 0x0FFFFFFFu
 
+/* Compact snapshot record = the first 16 bytes of malio_map_node.  With malio_upload_map_compact() the host ships only
+ * these (plus the map-side weights): 20 bytes per node instead of 68, and the device rebuilds both children's boxes
+ * of every node bottom-up as the tight bounding box of the live (not point_deleted) points below — which is what
+ * KD_TREE::Update maintains in node_range_* (ikd_Tree.cpp:1469-1635). */
+typedef struct malio_map_point {
+  float x, y, z;
+  uint32_t link;      /* as in malio_map_node */
+} malio_map_point;    /* 16 bytes */
+
 /* ---- scan point: feats_down_body entry as h_share_model reads it (laserMapping.cpp:565-570,694) */
 typedef struct malio_scan_pt {
   float x, y, z;        /* point in its own LiDAR frame */
@@ -157,6 +166,12 @@ int malio_comm_init(malio_handle* h, const uint8_t id[MALIO_NCCL_UNIQUE_ID_BYTES
 int malio_upload_map(malio_handle* h, const malio_map_node* nodes, const float* node_cov,
                      uint32_t n_nodes, uint32_t max_depth);
 
+/* Same snapshot in compact form (see malio_map_point): 3.4x less host->device traffic per scan. */
+int malio_upload_map_compact(malio_handle* h, const malio_map_point* pts, const float* node_cov,
+                             uint32_t n_nodes, uint32_t max_depth);
+/* test / debug: read back the device-resident 64-byte node records (boxes included). */
+int malio_download_map_nodes(malio_handle* h, malio_map_node* out, uint32_t capacity);
+
 /* once per scan: this rank's block of the down-sampled merged scan + the pose tables.
  * table holds pose_unc[0], pose_unc[1], ... back to back; pose_unc[l] = table[table_off[l] .. table_off[l+1]).
  * temporal_comp[l-1] is kf.temporal_comp[l-1] (IMU_Processing.hpp:517-519), l = 1..L-1. */
@@ -201,6 +216,7 @@ typedef struct malio_counters {
   uint64_t h2d_bytes, d2h_bytes;
   uint64_t knn_fallback_queries;  /* queries the cell-list fast path handed to the exact ikd-Tree-order traversal */
   uint64_t knn_ring2_queries;     /* queries that needed the 5x5x5 cell block */
+  uint64_t knn_candidates;        /* map points the 3x3x3 scans looked at (summed only while timing is enabled) */
 } malio_counters;
 int malio_get_counters(malio_handle* h, malio_counters* out);
 

@@ -51,6 +51,11 @@ struct PassConst {
   uint32_t table_off[MALIO_MAX_LIDAR + 1];
   int L;
   int ext_en;
+  // rotation matrices (row-major) of the conjugates, filled by the host once per pass: the Jacobian rows are matrix-vector
+  // products with them (9 FP64 instructions each instead of ~33 for a quaternion sandwich; FP64 issue is what bounds the gate)
+  double RsT[9];                       // R(s.rot)^T
+  double ReT[MALIO_MAX_LIDAR][9];      // R(offset_R_l)^T
+  double RcT[MALIO_MAX_LIDAR][9];      // R(temporal_comp_l)^T  (entry 0 unused)
 };
 
 struct ParamConst {
@@ -91,6 +96,16 @@ __device__ __forceinline__ void q_conj_to_R(const double q[4], double R[9]) {
   R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
 }
 
+__device__ __forceinline__ void mat3_mul(const double R[9], const double v[3], double o[3]) {
+  o[0] = fma(R[2], v[2], fma(R[1], v[1], R[0] * v[0]));
+  o[1] = fma(R[5], v[2], fma(R[4], v[1], R[3] * v[0]));
+  o[2] = fma(R[8], v[2], fma(R[7], v[1], R[6] * v[0]));
+}
+__device__ __forceinline__ void cross3_fma(const double a[3], const double b[3], double o[3]) {
+  o[0] = fma(a[1], b[2], -(a[2] * b[1]));
+  o[1] = fma(a[2], b[0], -(a[0] * b[2]));
+  o[2] = fma(a[0], b[1], -(a[1] * b[0]));
+}
 // laserMapping.cpp:569-579: point in its LiDAR frame -> LiDAR-0 body frame b, IMU frame m, world g
 __device__ __forceinline__ void transform_point(const PassConst& pc, float px, float py, float pz, int lid,
                                                 double b[3], double m[3], double g[3]) {
@@ -437,6 +452,66 @@ knn_list_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const malio_
   }
 }
 
+// ------------------------------------------------------------------ snapshot in compact form: boxes rebuilt on the device
+// malio_upload_map_compact ships 16 B per node (point + link).  The 64-byte records the traversal reads (both children's
+// boxes inside the parent) are rebuilt here: a node's box is the tight bounding box of the live points of its subtree
+// = what KD_TREE::Update leaves in node_range_* (ikd_Tree.cpp:1469-1635).  Bottom-up, one thread per node: a thread
+// stores its finished box into its parent's record and the LAST child to arrive (counter) carries the parent upwards.
+constexpr uint32_t TREE_NO_PARENT = 0xFFFFFFFFu;
+__global__ void tree_init_kernel(const float4* __restrict__ mpts, uint32_t n, float4* __restrict__ nodes,
+                                 uint32_t* __restrict__ parent) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 a = mpts[i];
+  nodes[4 * (size_t)i] = a;
+  const uint32_t link = __float_as_uint(a.w);
+  if (link & MALIO_LINK_HAS_LEFT) parent[i + 1] = i;
+  if (link & MALIO_LINK_HAS_RIGHT) parent[link & MALIO_LINK_INDEX_MASK] = i;
+  if (i == 0) parent[0] = TREE_NO_PARENT;
+}
+__global__ void tree_refit_kernel(const float4* __restrict__ mpts, uint32_t n, float4* nodes, const uint32_t* __restrict__ parent,
+                                  uint32_t* __restrict__ arrived) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 a = mpts[i];
+  const uint32_t link = __float_as_uint(a.w);
+  if (link & (MALIO_LINK_HAS_LEFT | MALIO_LINK_HAS_RIGHT)) return;   // leaves start the climb
+  const bool live = !(link & MALIO_LINK_POINT_DELETED);
+  float x0 = live ? a.x : INFINITY, x1 = live ? a.x : -INFINITY, y0 = live ? a.y : INFINITY, y1 = live ? a.y : -INFINITY,
+        z0 = live ? a.z : INFINITY, z1 = live ? a.z : -INFINITY;
+  uint32_t cur = i;
+  for (;;) {
+    const uint32_t par = parent[cur];
+    if (par == TREE_NO_PARENT) break;
+    const float4 pa = mpts[par];
+    const uint32_t plink = __float_as_uint(pa.w);
+    const bool is_left = (plink & MALIO_LINK_HAS_LEFT) && cur == par + 1;
+    float* rec = reinterpret_cast<float*>(nodes + 4 * (size_t)par);
+    float* box = rec + (is_left ? 4 : 10);      // lbox at floats 4..9, rbox at 10..15
+    box[0] = x0; box[1] = x1; box[2] = y0; box[3] = y1; box[4] = z0; box[5] = z1;
+    const uint32_t need = ((plink & MALIO_LINK_HAS_LEFT) ? 1u : 0u) + ((plink & MALIO_LINK_HAS_RIGHT) ? 1u : 0u);
+    __threadfence();
+    if (atomicAdd(arrived + par, 1u) + 1u < need) break;   // the sibling's thread carries the parent
+    __threadfence();
+    if (need == 2) {   // merge the sibling's box, written by another thread: read it from L2
+      const float* sib = rec + (is_left ? 10 : 4);
+      x0 = fminf(x0, __ldcg(sib + 0)); x1 = fmaxf(x1, __ldcg(sib + 1));
+      y0 = fminf(y0, __ldcg(sib + 2)); y1 = fmaxf(y1, __ldcg(sib + 3));
+      z0 = fminf(z0, __ldcg(sib + 4)); z1 = fmaxf(z1, __ldcg(sib + 5));
+    }
+    if (!(plink & MALIO_LINK_POINT_DELETED)) {
+      x0 = fminf(x0, pa.x); x1 = fmaxf(x1, pa.x); y0 = fminf(y0, pa.y); y1 = fmaxf(y1, pa.y);
+      z0 = fminf(z0, pa.z); z1 = fmaxf(z1, pa.z);
+    }
+    cur = par;
+  }
+}
+// full-record upload: the compact mirror (point + link, 16 B stride) the plane fit and the cell-list build read
+__global__ void tree_extract_kernel(const float4* __restrict__ nodes, uint32_t n, float4* __restrict__ mpts) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) mpts[i] = __ldg(nodes + 4 * (size_t)i);
+}
+
 // ------------------------------------------------------------------ K1g: cell-list k-NN, the fast path of K1
 // Nearest_Search's RESULT (the 5 smallest squared distances, ascending) does not depend on how the tree is walked
 // unless distances tie: acceptance is `dist < q.top().dist` (ikd_Tree.cpp:1099), so with pairwise distinct distances
@@ -467,7 +542,7 @@ __global__ void grid_count_kernel(const float4* __restrict__ nodes, uint32_t n, 
                                   uint32_t* __restrict__ cell_of) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float4 a = __ldg(nodes + 4 * (size_t)i);
+  const float4 a = __ldg(nodes + i);   // compact mirror: 16 B stride
   if (__float_as_uint(a.w) & MALIO_LINK_POINT_DELETED) { cell_of[i] = 0xFFFFFFFFu; return; }
   // monotone in each coordinate (subtract, multiply by a positive constant, floor, clamp): what the radius guarantee needs
   int cx = (int)floorf((a.x - G.ox) * G.inv_h), cy = (int)floorf((a.y - G.oy) * G.inv_h), cz = (int)floorf((a.z - G.oz) * G.inv_h);
@@ -540,7 +615,7 @@ __global__ void grid_scatter_kernel(const float4* __restrict__ nodes, uint32_t n
   if (i >= n) return;
   const uint32_t c = cell_of[i];
   if (c == 0xFFFFFFFFu) return;
-  const float4 a = __ldg(nodes + 4 * (size_t)i);
+  const float4 a = __ldg(nodes + i);   // compact mirror: 16 B stride
   const uint32_t slot = start[c] + atomicAdd(cursor + c, 1u);
   cell_pts[slot] = make_float4(a.x, a.y, a.z, __uint_as_float(i));
 }
@@ -593,8 +668,9 @@ knn_grid_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict_
                 float4* __restrict__ world, uint32_t* __restrict__ nn_idx, float* __restrict__ nn_d2,
                 uint8_t* __restrict__ sel, const uint32_t* __restrict__ in_list, const uint32_t* __restrict__ in_count,
                 uint32_t* __restrict__ r2_list, uint32_t* __restrict__ r2_count, uint32_t* __restrict__ fb_list,
-                uint32_t* __restrict__ fb_count) {
+                uint32_t* __restrict__ fb_count, unsigned long long* __restrict__ cand_total) {
   constexpr int ROWS = RING == 1 ? GK_ROWS1 : GK_ROWS2;
+  uint32_t n_cand = 0;   // candidates this thread scanned (statistics for the roofline; only summed when asked for)
   constexpr int HALF = RING == 1 ? 1 : 2;       // the block is (2*HALF+1)^3 cells
   extern __shared__ float4 s_dyn[];
   float4* s_cand = s_dyn;                                              // [GK_CAP][GK_THREADS]
@@ -639,6 +715,7 @@ knn_grid_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict_
           }
         }
         cp_async_wait_all();
+        n_cand += (uint32_t)k;
         // ---- scan them
 #pragma unroll 4
         for (int i = 0; i < k; ++i) {
@@ -664,6 +741,11 @@ knn_grid_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict_
     } else {
       fb_list[atomicAdd(fb_count, 1u)] = p;
     }
+  }
+  if (cand_total) {
+    const uint32_t act = __activemask();
+    const uint32_t tot = __reduce_add_sync(act, n_cand);
+    if ((threadIdx.x & 31u) == (uint32_t)(__ffs(act) - 1)) atomicAdd(cand_total, (unsigned long long)tot);
   }
 }
 
@@ -700,11 +782,25 @@ knn_ring2_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict
     }
     Top6 t;
     t.reset();
-#pragma unroll 1
-    for (int r = 0; r < 25; ++r) {
-      const uint32_t s0 = __shfl_sync(0xffffffffu, rs, r), e0 = __shfl_sync(0xffffffffu, re, r);
-      for (uint32_t j = s0 + lane; j < e0; j += 32) {
-        const float4 c = __ldg(cell_pts + j);
+    // flatten the 25 runs: lane j of every group of 32 candidates finds its run by a 5-step search over the exclusive
+    // prefix of the run lengths (held one per lane), so the whole block costs ceil(total / 32) memory round trips
+    const uint32_t len = re - rs;
+    uint32_t inc = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += v; }
+    const uint32_t excl = inc - len, total = __shfl_sync(0xffffffffu, inc, 31);
+    for (uint32_t base = 0; base < total; base += 32) {
+      const uint32_t j = base + lane;
+      uint32_t r = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const uint32_t cand = r + step;
+        const uint32_t ex = __shfl_sync(0xffffffffu, excl, cand & 31u);
+        if (cand < 32u && ex <= j) r = cand;
+      }
+      const uint32_t ex_r = __shfl_sync(0xffffffffu, excl, r), rs_r = __shfl_sync(0xffffffffu, rs, r);
+      if (j < total) {
+        const float4 c = __ldg(cell_pts + rs_r + (j - ex_r));
         const float dist = (qx - c.x) * (qx - c.x) + (qy - c.y) * (qy - c.y) + (qz - c.z) * (qz - c.z);   // calc_dist
         if (dist < t.d5) t.insert(dist, __float_as_uint(c.w));
       }
@@ -748,7 +844,8 @@ knn_ring2_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict
 // Spatially coherent warps matter (neighbouring queries walk the same upper tree levels: L1 hits, similar visit
 // counts), the exact order does not.  A general radix sort of ~1e5 keys is launch/latency-bound (CUB: 6 kernels,
 // ~57 us here), so this is a hand-written counting sort on a 16-bit cell key:
-//   cell = 2 m; key = LiDAR(2 bits) | z(2 bits) | Morton(x 6 bits, y 6 bits)   (wraps every 128 m / 8 m: only locality matters)
+//   cell = 2 m; key = z(2 bits) | Morton(x 7 bits, y 7 bits)   (wraps every 256 m / 8 m: only locality matters)
+//               or  LiDAR(2 bits) | z(2 bits) | Morton(x 6 bits, y 6 bits) for large scans (see count_kernel)
 //   count_kernel   key per point + histogram (integer atomics)
 //   scan_kernel    exclusive prefix over the 65 536 bins (64 block-local scans + 64 totals)
 //   scatter_kernel slot = offset[key] + atomic cursor  -> tmp (order inside a bin is arrival order ...)
@@ -764,7 +861,7 @@ __device__ __forceinline__ uint32_t spread7(uint32_t v) {   // 7 bits -> every o
 }
 template <int MODE>
 __global__ void count_kernel(const malio_scan_pt* __restrict__ pts, const float* __restrict__ queries, uint32_t N,
-                             PassConst pc, uint16_t* __restrict__ keys, uint32_t* __restrict__ hist) {
+                             PassConst pc, int lid_major, uint16_t* __restrict__ keys, uint32_t* __restrict__ hist) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   float x, y, z;
@@ -779,8 +876,11 @@ __global__ void count_kernel(const malio_scan_pt* __restrict__ pts, const float*
     x = queries[3 * (size_t)i]; y = queries[3 * (size_t)i + 1]; z = queries[3 * (size_t)i + 2];
   }
   const uint32_t ix = (uint32_t)(int)floorf(x * 0.5f), iy = (uint32_t)(int)floorf(y * 0.5f), iz = (uint32_t)(int)floorf(z * 0.5f);
-  // LiDAR id is the major key: the reduction keeps one LiDAR's accumulators in registers while it walks its tiles
-  const uint32_t key = (lid_key << 14) | ((iz & 3u) << 12) | (spread7(iy & 0x3Fu) << 1) | spread7(ix & 0x3Fu);
+  // Small scans (the fused pass keeps all rows of a block in shared memory): pure cell order, best for the k-NN.
+  // Large scans (rows go through global memory tile by tile): LiDAR id as the major key, so that the reduction can keep
+  // one LiDAR's accumulators in registers while it walks its tiles.
+  const uint32_t key = lid_major ? ((lid_key << 14) | ((iz & 3u) << 12) | (spread7(iy & 0x3Fu) << 1) | spread7(ix & 0x3Fu))
+                                 : (((iz & 3u) << 14) | (spread7(iy) << 1) | spread7(ix));
   keys[i] = (uint16_t)key;
   atomicAdd(hist + key, 1u);
 }
@@ -837,7 +937,8 @@ __global__ void scatter_kernel(const uint16_t* __restrict__ keys, uint32_t N, co
 // (bins hold ~10 points, at most a few dozen: a short, fully parallel O(cnt) scan per point)
 __global__ void rank_kernel(const uint16_t* __restrict__ keys, uint32_t N, const uint32_t* __restrict__ offs,
                             const uint32_t* __restrict__ btot, const uint32_t* __restrict__ hist,
-                            const uint32_t* __restrict__ tmp, uint32_t* __restrict__ perm) {
+                            const uint32_t* __restrict__ tmp, uint32_t* __restrict__ perm,
+                            const malio_scan_pt* __restrict__ pts, malio_scan_pt* __restrict__ pts_sorted) {
   __shared__ uint32_t s_base[SCAN_BLOCKS];
   load_bin_base(btot, s_base);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -847,6 +948,7 @@ __global__ void rank_kernel(const uint16_t* __restrict__ keys, uint32_t N, const
   uint32_t rank = 0;
   for (uint32_t j = 0; j < cnt; ++j) rank += (tmp[off + j] < i) ? 1u : 0u;
   perm[off + rank] = i;
+  if (pts_sorted) pts_sorted[off + rank] = pts[i];   // position-ordered copy: the per-pass kernels read it without the perm hop
 }
 
 // ------------------------------------------------------------------ K2: plane fit, gates, point-wise uncertainty
@@ -1047,7 +1149,7 @@ __device__ __forceinline__ void fit_point(const float4* __restrict__ nodes, cons
 #pragma unroll
   for (int j = 0; j < MALIO_K; ++j) {
     const uint32_t idx = nn_idx[(size_t)j * N + p];
-    const float4 a = __ldg(nodes + 4 * (size_t)idx);
+    const float4 a = __ldg(nodes + idx);   // compact mirror of the snapshot: 16 B stride
     A[j][0] = a.x; A[j][1] = a.y; A[j][2] = a.z;
     W[j] = __ldg(node_cov + idx);
   }
@@ -1111,13 +1213,15 @@ tau_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ p
 
 // ---- K2c (every pass): transform, point-to-plane residual, residual gate, min/max of the two weights.
 // d_mmkey layout: dkey of {min_u, -max_u, min_tau, -max_tau}: one (integer) MIN all-reduce serves all four
+struct GateOut { double u, tau; float pd2; int lid; bool selected; };
 // one point of the gate: returns its contribution to the min/max of the two weights in mm
 __device__ __forceinline__ void gate_point(const malio_scan_pt& pt, uint32_t p, const PassConst& pc,
                                            const float4* __restrict__ plane, const double* __restrict__ ucov,
                                            const double2* __restrict__ tau2, uint8_t* __restrict__ sel,
                                            float4* __restrict__ world, float* __restrict__ pd2_out, double* __restrict__ tau,
                                            float* __restrict__ normal_y, double* __restrict__ rows12,
-                                           uint8_t* __restrict__ lid8, MinMax4& mm) {
+                                           uint8_t* __restrict__ lid8, MinMax4& mm, double* __restrict__ srow = nullptr,
+                                           GateOut* __restrict__ go = nullptr) {
   double b[3], m[3], g[3];
   transform_point(pc, pt.x, pt.y, pt.z, pt.lidar, b, m, g);
   const float wx = (float)g[0], wy = (float)g[1], wz = (float)g[2];
@@ -1135,30 +1239,25 @@ __device__ __forceinline__ void gate_point(const malio_scan_pt& pt, uint32_t p, 
       // un-weighted Jacobian row, compact: [ n | A | B | C ]  (laserMapping.cpp:665-693)
       const int lid = pt.lidar;
       const double nvec[3] = {(double)pl.x, (double)pl.y, (double)pl.z};
+      // C0 = R(s.rot)^T n (:676);  A = [m]x C0 (:677);  l = 0: C = C0, B = [b]x R(qE0)^T C (:683-684);
+      // l != 0: C = R(qC_l)^T C0, B = [p]x R(qE_l)^T C (:687-690).  [v]x (R C) = v x (R C): evaluated as matrix-vector
+      // products and cross products with FMAs — equal to the reference's (skew * R) * C to rounding (bar: 1e-9 on the system)
       double C[3], A[3], B[3] = {0.0, 0.0, 0.0};
-      q_rot_conj(pc.rot, nvec, C);                    // :676  s.rot.conjugate() * norm_vec
-      cross3(m, C, A);                                // :677  [point_this]x * C
+      mat3_mul(pc.RsT, nvec, C);
+      cross3_fma(m, C, A);
       double Cc[3] = {0.0, 0.0, 0.0};
       if (pc.ext_en) {
-        double Rq[9], v[3];
-        if (lid == 0) {   // :684  ([b]x R(qE0^T)) C
-          q_conj_to_R(pc.eq[0], Rq);
-          v[0] = b[0]; v[1] = b[1]; v[2] = b[2];
-        } else {          // :687-690
+        double w[3];
+        if (lid == 0) {
+          mat3_mul(pc.ReT[0], C, w);
+          cross3_fma(b, w, B);
+        } else {
           double C2[3];
-          q_rot_conj(pc.cq[lid], C, C2);
+          mat3_mul(pc.RcT[lid], C, C2);
           C[0] = C2[0]; C[1] = C2[1]; C[2] = C2[2];
-          q_conj_to_R(pc.eq[lid], Rq);
-          v[0] = pt.x; v[1] = pt.y; v[2] = pt.z;
-        }
-        // M = skew(v) * Rq, then B = M * C  (same association as the reference's M3D * Quaternion * V3D)
-        const double S[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          double Mi[3];
-#pragma unroll
-          for (int j = 0; j < 3; ++j) Mi[j] = S[3 * i] * Rq[j] + S[3 * i + 1] * Rq[3 + j] + S[3 * i + 2] * Rq[6 + j];
-          B[i] = Mi[0] * C[0] + Mi[1] * C[1] + Mi[2] * C[2];
+          mat3_mul(pc.ReT[lid], C, w);
+          const double v[3] = {(double)pt.x, (double)pt.y, (double)pt.z};
+          cross3_fma(v, w, B);
         }
         Cc[0] = C[0]; Cc[1] = C[1]; Cc[2] = C[2];
       }
@@ -1166,9 +1265,15 @@ __device__ __forceinline__ void gate_point(const malio_scan_pt& pt, uint32_t p, 
       dst[0] = make_double2(nvec[0], nvec[1]); dst[1] = make_double2(nvec[2], A[0]); dst[2] = make_double2(A[1], A[2]);
       dst[3] = make_double2(B[0], B[1]);       dst[4] = make_double2(B[2], Cc[0]);   dst[5] = make_double2(Cc[1], Cc[2]);
       lid8[p] = (uint8_t)lid;
+      if (srow) {   // the fused pass keeps the row on chip across the min/max barrier
+        srow[0] = nvec[0]; srow[1] = nvec[1]; srow[2] = nvec[2]; srow[3] = A[0]; srow[4] = A[1]; srow[5] = A[2];
+        srow[6] = B[0]; srow[7] = B[1]; srow[8] = B[2]; srow[9] = Cc[0]; srow[10] = Cc[1]; srow[11] = Cc[2];
+      }
+      if (go) go->pd2 = pd2;
     }
   }
   const double2 t2 = tau2[p];
+  if (go) { go->selected = selected; go->lid = pt.lidar; go->u = selected ? ucov[p] : 0.0; go->tau = t2.x; }
   if (selected) {
     const double u = ucov[p];
     mm.umin = fmin(mm.umin, u); mm.umax = fmax(mm.umax, u); mm.cnt += 1;
@@ -1405,7 +1510,15 @@ struct PassArgs {
   double* block_red; double* d_res;
   double* h_res;           // mapped host memory: MALIO_RED_DOUBLES result | 4 min/max keys | flag
   uint32_t seq;
+  unsigned long long* dbg; // optional [grid][8] %globaltimer stamps at the phase boundaries (MALIO_PASS_TRACE=1)
 };
+__device__ __forceinline__ void pass_stamp(const PassArgs& a, int k) {
+  if (a.dbg && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.dbg[(size_t)blockIdx.x * 8 + k] = t;
+  }
+}
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -1421,25 +1534,69 @@ __device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t target)
   }
   __syncthreads();
 }
+// FAST: every block owns at most PASS_FAST_TILES tiles and keeps their Jacobian rows in shared memory from the gate to
+// the accumulation (no global round trip, no staging pass); rows stay in their own positions and the workers pick the
+// rows of the LiDAR they are accumulating by a per-row tag, so no prefix sums or compaction barriers are needed.
+// !FAST: any number of tiles per block, rows go through global memory (reduce_block).
+constexpr int PASS_FAST_TILES = 2;
+constexpr int PASS_ROW_STRIDE = 15;        // doubles per staged row: a*J12 (12) | 1/rho^ | z | rho^   (odd: conflict-free)
+constexpr int PASS_FAST_SMEM_DOUBLES = PASS_FAST_TILES * RED_THREADS * PASS_ROW_STRIDE + RED_TASKS * RED_KS * 16;
+static_assert(PASS_FAST_SMEM_DOUBLES <= RED_SMEM_DOUBLES, "the fast path must fit the generic path's shared memory");
+template <bool FAST>
 __global__ void __launch_bounds__(RED_THREADS, 4)
 pass_kernel(PassArgs a, PassConst pc, ParamConst prm) {
   uint32_t t0, t1;
   block_tiles(a.n_tiles, t0, t1);
+  extern __shared__ double smem[];
+  // FAST: rows stay in their own slots; per (tile, LiDAR) the slots that hold a row are listed (compacted) so that the
+  // accumulation loop runs over rows of one LiDAR only, every lane busy
+  __shared__ uint8_t s_list[PASS_FAST_TILES * RED_THREADS];
+  __shared__ uint16_t s_wc[PASS_FAST_TILES][MALIO_MAX_LIDAR][RED_THREADS / 32];   // selected rows per tile, LiDAR, warp
+  GateOut go[PASS_FAST_TILES];
+  uint32_t bal[PASS_FAST_TILES];   // ballot of this thread's LiDAR within its warp (FAST)
+  pass_stamp(a, 0);
   // ---- phase 1: per point, same tile -> block mapping as the accumulation below
   {
     MinMax4 mm{1000.0, 0.0, 9999.0, 0.0, 0u};   // laserMapping.cpp:615-616, 646-647
-    for (uint32_t tile = t0; tile < t1; ++tile) {
-      const uint32_t p = tile * RED_THREADS + threadIdx.x;
-      if (p < a.N) {
-        const malio_scan_pt pt = a.pts[a.perm ? a.perm[p] : p];
-        if (a.do_tau) tau_point(pt, pc, a.table, a.tau2, p);
-        if (a.do_fit && a.sel[p]) fit_point(a.nodes, a.node_cov, a.N, prm, a.nn_idx, a.sel, a.plane, a.ucov, p);
-        gate_point(pt, p, pc, a.plane, a.ucov, a.tau2, a.sel, a.world, a.pd2, a.tau, a.normal_y, a.rows12, a.lid8, mm);
+#pragma unroll
+    for (int k = 0; k < (FAST ? PASS_FAST_TILES : 1); ++k) go[k].selected = false;
+    if (FAST) {
+#pragma unroll
+      for (int k = 0; k < PASS_FAST_TILES; ++k) {
+        const uint32_t tile = t0 + k;
+        const uint32_t p = tile * RED_THREADS + threadIdx.x;
+        if (tile < t1 && p < a.N) {
+          const malio_scan_pt pt = a.pts[a.perm ? a.perm[p] : p];
+          if (a.do_tau) tau_point(pt, pc, a.table, a.tau2, p);
+          if (a.do_fit && a.sel[p]) fit_point(a.nodes, a.node_cov, a.N, prm, a.nn_idx, a.sel, a.plane, a.ucov, p);
+          gate_point(pt, p, pc, a.plane, a.ucov, a.tau2, a.sel, a.world, a.pd2, a.tau, a.normal_y, a.rows12, a.lid8, mm,
+                     smem + (size_t)(k * RED_THREADS + threadIdx.x) * PASS_ROW_STRIDE, &go[k]);
+        }
+        const int l = go[k].selected ? go[k].lid : -1;
+        const uint32_t b0 = __ballot_sync(0xffffffffu, l == 0), b1 = __ballot_sync(0xffffffffu, l == 1),
+                       b2 = __ballot_sync(0xffffffffu, l == 2);
+        bal[k] = l == 0 ? b0 : (l == 1 ? b1 : b2);
+        if ((threadIdx.x & 31) == 0) {
+          s_wc[k][0][threadIdx.x >> 5] = (uint16_t)__popc(b0); s_wc[k][1][threadIdx.x >> 5] = (uint16_t)__popc(b1);
+          s_wc[k][2][threadIdx.x >> 5] = (uint16_t)__popc(b2);
+        }
+      }
+    } else {
+      for (uint32_t tile = t0; tile < t1; ++tile) {
+        const uint32_t p = tile * RED_THREADS + threadIdx.x;
+        if (p < a.N) {
+          const malio_scan_pt pt = a.pts[a.perm ? a.perm[p] : p];
+          if (a.do_tau) tau_point(pt, pc, a.table, a.tau2, p);
+          if (a.do_fit && a.sel[p]) fit_point(a.nodes, a.node_cov, a.N, prm, a.nn_idx, a.sel, a.plane, a.ucov, p);
+          gate_point(pt, p, pc, a.plane, a.ucov, a.tau2, a.sel, a.world, a.pd2, a.tau, a.normal_y, a.rows12, a.lid8, mm);
+        }
       }
     }
     minmax_block_commit<RED_THREADS>(mm, a.mmkey, a.cnt_cell);
   }
+  pass_stamp(a, 1);
   grid_barrier(a.bar + 0, a.bar_base[0] + gridDim.x);
+  pass_stamp(a, 2);
   if (blockIdx.x == 0 && threadIdx.x == 0) {   // arm the other parity's min/max cell for the next pass
     a.mmkey_next[0] = dkey(1000.0); a.mmkey_next[1] = dkey(-0.0);
     a.mmkey_next[2] = dkey(9999.0); a.mmkey_next[3] = dkey(-0.0);
@@ -1447,29 +1604,141 @@ pass_kernel(PassArgs a, PassConst pc, ParamConst prm) {
     a.gstats[2] = 0; a.gstats[4] = 0;
   }
   // ---- phase 2: weights + accumulation into this block's slot
-  reduce_block(a.N, prm, pc.ext_en, a.sel, a.lid8, a.rows12, a.pd2, a.ucov, a.tau, a.mmkey, t0, t1,
-               a.block_red + (size_t)blockIdx.x * MALIO_RED_DOUBLES);
+  double* slot = a.block_red + (size_t)blockIdx.x * MALIO_RED_DOUBLES;
+  if (FAST) {
+    double* s_flush = smem + PASS_FAST_TILES * RED_THREADS * PASS_ROW_STRIDE;
+    const double umin = dkey_inv(a.mmkey[0]), umax = -dkey_inv(a.mmkey[1]), tmin = dkey_inv(a.mmkey[2]), tmax = -dkey_inv(a.mmkey[3]);
+    uint32_t mine = 0;
+    // segment table of the block: seg[k][l] = [beg, end) inside tile k's list (every thread derives it from s_wc)
+    uint32_t seg_beg[PASS_FAST_TILES][MALIO_MAX_LIDAR], seg_end[PASS_FAST_TILES][MALIO_MAX_LIDAR];
+#pragma unroll
+    for (int k = 0; k < PASS_FAST_TILES; ++k) {
+      uint32_t run = 0;
+#pragma unroll
+      for (int l = 0; l < MALIO_MAX_LIDAR; ++l) {
+        seg_beg[k][l] = run;
+#pragma unroll
+        for (int w = 0; w < RED_THREADS / 32; ++w) run += s_wc[k][l][w];
+        seg_end[k][l] = run;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PASS_FAST_TILES; ++k) {
+      if (go[k].selected) {
+        double aw, rho;
+        point_weights(prm, go[k].u, pc.ext_en ? go[k].tau : 0.0, pc.ext_en, umin, umax, tmin, tmax, aw, rho);
+        double* row = smem + (size_t)(k * RED_THREADS + threadIdx.x) * PASS_ROW_STRIDE;
+#pragma unroll
+        for (int c = 0; c < 12; ++c) row[c] = row[c] * aw;                       // laserMapping.cpp:714
+        row[12] = 1.0 / rho;   // HT(:,i) / R_i (esekfom.hpp:627) as a multiply: <= 1 ulp per term
+        row[13] = ((-1) * (double)go[k].pd2) * aw;                               // :707,715
+        row[14] = rho;
+        // compacted position of this row among the tile's rows of its LiDAR
+        const int l = go[k].lid, wid = threadIdx.x >> 5;
+        uint32_t pos = l == 0 ? seg_beg[k][0] : (l == 1 ? seg_beg[k][1] : seg_beg[k][2]);
+        for (int w = 0; w < wid; ++w) pos += s_wc[k][l][w];
+        pos += __popc(bal[k] & ((1u << (threadIdx.x & 31)) - 1u));
+        s_list[k * RED_THREADS + pos] = (uint8_t)threadIdx.x;
+        ++mine;
+      }
+    }
+    __shared__ uint32_t s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    if (mine) atomicAdd(&s_cnt, mine);
+    const int task = threadIdx.x / RED_KS, ks = threadIdx.x % RED_KS;
+    const bool worker = task < RED_TASKS;
+    int gi = 0, gj = 0;
+    if (worker) red_task(task, gi, gj);
+    // thread e < 144 ends up holding entry (task e / 16, element e % 16) of each LiDAR's compact system, e >= 128 wraps
+    // onto threads 0..15 as a second entry: two result registers per LiDAR and thread
+    double res0[MALIO_MAX_LIDAR], res1[MALIO_MAX_LIDAR];
+#pragma unroll
+    for (int ll = 0; ll < MALIO_MAX_LIDAR; ++ll) {
+      res0[ll] = 0.0; res1[ll] = 0.0;
+      if (ll < pc.L) {
+        double acc[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+        if (worker) {
+#pragma unroll
+          for (int k = 0; k < PASS_FAST_TILES; ++k) {
+            for (uint32_t i = seg_beg[k][ll] + ks; i < seg_end[k][ll]; i += RED_KS) {
+              const uint32_t q = k * RED_THREADS + s_list[k * RED_THREADS + i];
+              const double* row = smem + (size_t)q * PASS_ROW_STRIDE;
+              const double ir = row[12];
+              const double a0 = row[4 * gi] * ir, a1 = row[4 * gi + 1] * ir, a2 = row[4 * gi + 2] * ir, a3 = row[4 * gi + 3] * ir;
+              double c0, c1, c2, c3;
+              if (gj < 3) { c0 = row[4 * gj]; c1 = row[4 * gj + 1]; c2 = row[4 * gj + 2]; c3 = row[4 * gj + 3]; }
+              else { const double rho = row[14]; c0 = row[13]; c1 = rho * row[0]; c2 = rho * row[1]; c3 = rho * row[2]; }
+              acc[0] = fma(a0, c0, acc[0]);   acc[1] = fma(a0, c1, acc[1]);   acc[2] = fma(a0, c2, acc[2]);   acc[3] = fma(a0, c3, acc[3]);
+              acc[4] = fma(a1, c0, acc[4]);   acc[5] = fma(a1, c1, acc[5]);   acc[6] = fma(a1, c2, acc[6]);   acc[7] = fma(a1, c3, acc[7]);
+              acc[8] = fma(a2, c0, acc[8]);   acc[9] = fma(a2, c1, acc[9]);   acc[10] = fma(a2, c2, acc[10]); acc[11] = fma(a2, c3, acc[11]);
+              acc[12] = fma(a3, c0, acc[12]); acc[13] = fma(a3, c1, acc[13]); acc[14] = fma(a3, c2, acc[14]); acc[15] = fma(a3, c3, acc[15]);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 16; ++k) s_flush[k * (RED_TASKS * RED_KS) + threadIdx.x] = acc[k];
+        }
+        __syncthreads();
+        {   // fold the RED_KS row-splits in a fixed order
+          const int e0 = threadIdx.x, e1 = threadIdx.x + RED_THREADS;
+          double sum = 0.0;
+#pragma unroll
+          for (int q = 0; q < RED_KS; ++q) sum += s_flush[(e0 % 16) * (RED_TASKS * RED_KS) + (e0 / 16) * RED_KS + q];
+          res0[ll] = sum;
+          if (e1 < RED_TASKS * 16) {
+            sum = 0.0;
+#pragma unroll
+            for (int q = 0; q < RED_KS; ++q) sum += s_flush[(e1 % 16) * (RED_TASKS * RED_KS) + (e1 / 16) * RED_KS + q];
+            res1[ll] = sum;
+          }
+        }
+        __syncthreads();
+      }
+    }
+#pragma unroll
+    for (int ll = 0; ll < MALIO_MAX_LIDAR; ++ll) {
+      slot[ll * RED_TASKS * 16 + threadIdx.x] = res0[ll];
+      if (threadIdx.x + RED_THREADS < RED_TASKS * 16) slot[ll * RED_TASKS * 16 + threadIdx.x + RED_THREADS] = res1[ll];
+    }
+    if (threadIdx.x == 0) { slot[MALIO_RED_BLOCKS * 16] = (double)s_cnt; slot[MALIO_RED_BLOCKS * 16 + 1] = 0.0; }
+  } else {
+    reduce_block(a.N, prm, pc.ext_en, a.sel, a.lid8, a.rows12, a.pd2, a.ucov, a.tau, a.mmkey, t0, t1, slot);
+  }
+  pass_stamp(a, 3);
   grid_barrier(a.bar + 1, a.bar_base[1] + gridDim.x);
+  pass_stamp(a, 4);
   // ---- phase 3: fold the slots, one warp per entry, in fold_kernel's order
   const uint32_t lane = threadIdx.x & 31u, wpb = RED_THREADS / 32;
-  uint32_t mine = 0;
+  uint32_t folded = 0;
   for (uint32_t e = blockIdx.x * wpb + (threadIdx.x >> 5); e < MALIO_RED_DOUBLES; e += gridDim.x * wpb) {
     double sum = 0.0;
     for (uint32_t bk = lane; bk < gridDim.x; bk += 32) sum += a.block_red[(size_t)bk * MALIO_RED_DOUBLES + e];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) { a.d_res[e] = sum; a.h_res[e] = sum; ++mine; }
+    if (lane == 0) a.d_res[e] = sum;
+    ++folded;
   }
-  if (lane == 0 && mine) {
-    __threadfence_system();
-    const uint32_t done = atomicAdd(a.bar + 2, mine) + mine;
-    if (done == a.bar_base[2] + MALIO_RED_DOUBLES) {   // last entry folded: min/max keys, then the flag
-      unsigned long long* hk = reinterpret_cast<unsigned long long*>(a.h_res + MALIO_RED_DOUBLES);
-      hk[0] = a.mmkey[0]; hk[1] = a.mmkey[1]; hk[2] = a.mmkey[2]; hk[3] = a.mmkey[3];
+  if (folded) {   // warp-uniform
+    uint32_t done = 0;
+    if (lane == 0) {
+      __threadfence();
+      done = atomicAdd(a.bar + 2, folded) + folded;
+    }
+    done = __shfl_sync(0xffffffffu, done, 0);
+    if (done == a.bar_base[2] + MALIO_RED_DOUBLES) {
+      // this warp folded the last entry: ship result + min/max keys to the mapped host buffer (posted PCIe writes, one
+      // system-scope fence), then the sequence flag the host is spinning on
+      __threadfence();
+      for (uint32_t e = lane; e < MALIO_RED_DOUBLES; e += 32) a.h_res[e] = __ldcg(a.d_res + e);
+      if (lane < 4) reinterpret_cast<unsigned long long*>(a.h_res + MALIO_RED_DOUBLES)[lane] = a.mmkey[lane];
       __threadfence_system();
-      *reinterpret_cast<volatile uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 8) = a.seq;
+      __syncwarp();
+      if (lane == 0) *reinterpret_cast<volatile uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 8) = a.seq;
     }
   }
+  pass_stamp(a, 5);
 }
 
 // second stage: one warp per entry of the reduced system folds the per-block slots in a fixed order
@@ -1592,9 +1861,12 @@ struct DeviceState {
   double host_launch_us = 0, host_wait_us = 0; uint64_t host_passes = 0;   // MALIO_HOST_PROF=1 prints them at destroy
   // map
   float4* d_nodes = nullptr; float* d_cov = nullptr;
+  float4* d_mpts = nullptr;            // compact mirror: point + link of every node, 16 B stride
+  uint32_t *d_parent = nullptr, *d_arrived = nullptr;   // box rebuild of the compact upload
   uint32_t n_nodes = 0, cap_nodes = 0, depth = 0;
   // scan (caller order) + internal order
   malio_scan_pt* d_pts = nullptr; uint32_t N = 0, capN = 0;
+  malio_scan_pt* d_pts_sorted = nullptr;   // the scan in internal (position) order
   uint32_t* d_perm = nullptr; bool perm_valid = false;
   uint16_t* d_keys16 = nullptr; uint32_t *d_hist = nullptr, *d_offs = nullptr, *d_cursor = nullptr, *d_btot = nullptr, *d_tmp_ids = nullptr;   // counting sort
   double* d_table = nullptr; uint32_t cap_table = 0;
@@ -1627,12 +1899,14 @@ struct DeviceState {
   float4* d_cell_pts = nullptr;
   uint32_t* d_fb_list = nullptr;          // positions the fast path could not settle (-> exact traversal)
   uint32_t* d_r2_list = nullptr;          // positions that need the 5x5x5 block
+  unsigned long long* d_cand = nullptr;   // candidates scanned by knn_grid_kernel since create (summed only while timing is on)
   uint32_t* d_gstats = nullptr;           // [0] occupied cells, [1] live points, [2] fb count, [3] fb count of the last search, [4] ring-2 queries
   uint32_t* h_gstats = nullptr;            // pinned mirror (8 words, carved out of h_res)
   // fused pass (single cooperative launch per measurement pass)
   bool fused = true; int pass_max_blocks = 0;
   uint32_t* d_bar = nullptr; uint32_t bar_base[3] = {0, 0, 0}; uint32_t seq = 0;
   double* h_res_dev = nullptr;     // device-side address of the mapped host result buffer
+  unsigned long long* d_dbg = nullptr; int trace_left = 0;
   // multi-GPU
   ncclComm_t comm = nullptr; int rank = 0, world = 1;
 };
@@ -1655,6 +1929,16 @@ PassConst make_pass_const(const malio_handle* h, const DeviceState* D, const mal
     std::memcpy(pc.ct[l], D->tcomp[l].t, sizeof(pc.ct[l]));
   }
   for (int l = 0; l <= MALIO_MAX_LIDAR; ++l) pc.table_off[l] = D->table_off[l];
+  auto conj_R = [](const double q[4], double R[9]) {   // Eigen's toRotationMatrix of the conjugate, row-major
+    const double w = q[0], x = -q[1], y = -q[2], z = -q[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+    R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+  };
+  conj_R(pc.rot, pc.RsT);
+  for (int l = 0; l < MALIO_MAX_LIDAR; ++l) { conj_R(pc.eq[l], pc.ReT[l]); conj_R(pc.cq[l], pc.RcT[l]); }
   pc.L = h->cfg.params.n_lidar;
   pc.ext_en = h->cfg.params.extrinsic_est_en;
   return pc;
@@ -1687,10 +1971,12 @@ template <int MODE>
 int sort_queries(malio_handle* h, DeviceState* D, uint32_t n, const PassConst& pc) {
   cudaStream_t st = D->stream;
   CUDA_TRY(cudaMemsetAsync(D->d_hist, 0, SORT_BINS * sizeof(uint32_t), st));
-  count_kernel<MODE><<<(n + 255) / 256, 256, 0, st>>>(D->d_pts, D->d_queries, n, pc, D->d_keys16, D->d_hist);
+  const int lid_major = (MODE == 0 && (uint64_t)n > (uint64_t)PASS_FAST_TILES * RED_THREADS * (uint64_t)(D->pass_max_blocks > 0 ? D->pass_max_blocks : 1)) ? 1 : 0;
+  count_kernel<MODE><<<(n + 255) / 256, 256, 0, st>>>(D->d_pts, D->d_queries, n, pc, lid_major, D->d_keys16, D->d_hist);
   scan_kernel<<<SCAN_BLOCKS, SCAN_THREADS, 0, st>>>(D->d_hist, D->d_offs, D->d_cursor, D->d_btot);
   scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(D->d_keys16, n, D->d_offs, D->d_btot, D->d_cursor, D->d_tmp_ids);
-  rank_kernel<<<(n + 255) / 256, 256, 0, st>>>(D->d_keys16, n, D->d_offs, D->d_btot, D->d_hist, D->d_tmp_ids, D->d_perm);
+  rank_kernel<<<(n + 255) / 256, 256, 0, st>>>(D->d_keys16, n, D->d_offs, D->d_btot, D->d_hist, D->d_tmp_ids, D->d_perm,
+                                               MODE == 0 ? D->d_pts : nullptr, MODE == 0 ? D->d_pts_sorted : nullptr);
   CUDA_TRY(cudaGetLastError());
   D->ctr.kernel_launches += 4;
   return MALIO_OK;
@@ -1744,11 +2030,11 @@ int grid_build(malio_handle* h, DeviceState* D, const GridConst& G) {
   }
   CUDA_TRY(cudaMemsetAsync(D->d_cell_cnt, 0, (size_t)ncell_pad * sizeof(uint32_t), st));
   CUDA_TRY(cudaMemsetAsync(D->d_gstats, 0, 2 * sizeof(uint32_t), st));
-  grid_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(D->d_nodes, n, G, D->d_cell_cnt, D->d_cell_of);
+  grid_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(D->d_mpts, n, G, D->d_cell_cnt, D->d_cell_of);
   grid_scan_local_kernel<<<nchunk, 1024, 0, st>>>(D->d_cell_cnt, D->d_cell_start, D->d_ctot, D->d_gstats);
   grid_scan_tot_kernel<<<1, 1024, 0, st>>>(D->d_ctot, nchunk, D->d_cbase, D->d_gstats);
   grid_scan_add_kernel<<<nchunk, 1024, 0, st>>>(D->d_cell_start, D->d_cbase);
-  grid_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(D->d_nodes, n, D->d_cell_of, D->d_cell_start, D->d_cell_cnt, D->d_cell_pts);
+  grid_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(D->d_mpts, n, D->d_cell_of, D->d_cell_start, D->d_cell_cnt, D->d_cell_pts);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(D->h_gstats, D->d_gstats, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   D->ctr.kernel_launches += 5;
@@ -1759,10 +2045,11 @@ int grid_build(malio_handle* h, DeviceState* D, const GridConst& G) {
 // the k-NN of one search pass: cell-list fast path + exact ikd-Tree-order traversal for what it leaves, or the
 // traversal alone when the index is off
 template <int MODE>
-int run_knn(malio_handle* h, DeviceState* D, uint32_t n, const uint32_t* perm, const PassConst& pc, float max_sqdist) {
+int run_knn(malio_handle* h, DeviceState* D, uint32_t n, const malio_scan_pt* pts_in, const uint32_t* perm,
+            const PassConst& pc, float max_sqdist) {
   cudaStream_t st = D->stream;
   const bool smem_stack = D->depth + KNN_POP_WIDTH <= (uint32_t)KNN_SMEM_DEPTH;
-  const malio_scan_pt* pts = MODE == 0 ? D->d_pts : nullptr;
+  const malio_scan_pt* pts = MODE == 0 ? pts_in : nullptr;
   const float* qs = MODE == 0 ? nullptr : D->d_queries;
   float4* world = MODE == 0 ? D->d_world : nullptr;
   uint8_t* sel = MODE == 0 ? D->d_sel : nullptr;
@@ -1771,7 +2058,7 @@ int run_knn(malio_handle* h, DeviceState* D, uint32_t n, const uint32_t* perm, c
     constexpr size_t smem1 = (size_t)GK_CAP * GK_THREADS * sizeof(float4) + (size_t)GK_ROWS1 * GK_THREADS * sizeof(uint2);
     knn_grid_kernel<MODE, 1><<<(n + GK_THREADS - 1) / GK_THREADS, GK_THREADS, smem1, st>>>(
         D->d_cell_pts, D->d_cell_start, D->grid, pts, perm, qs, n, pc, max_sqdist, world, D->d_nn_idx, D->d_nn_d2, sel,
-        nullptr, nullptr, D->d_r2_list, D->d_gstats + 4, D->d_fb_list, D->d_gstats + 2);
+        nullptr, nullptr, D->d_r2_list, D->d_gstats + 4, D->d_fb_list, D->d_gstats + 2, D->timing ? D->d_cand : nullptr);
     uint32_t r2_blocks = (n + 3) / 4;                       // one warp per listed query, at most ~2 resident waves
     if (r2_blocks > (uint32_t)D->sm_count * 16) r2_blocks = (uint32_t)D->sm_count * 16;
     knn_ring2_kernel<MODE><<<r2_blocks, 128, 0, st>>>(
@@ -1829,6 +2116,8 @@ int create(malio_handle* h) {
     CUDA_TRY(cudaMemcpy(D->d_mmkey, init, sizeof(init), cudaMemcpyHostToDevice));
   }
   CUDA_TRY(cudaMalloc((void**)&D->d_res, MALIO_RED_DOUBLES * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void**)&D->d_cand, sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(D->d_cand, 0, sizeof(unsigned long long)));
   CUDA_TRY(cudaMalloc((void**)&D->d_gstats, 8 * sizeof(uint32_t)));
   CUDA_TRY(cudaMemset(D->d_gstats, 0, 8 * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc((void**)&D->d_hist, SORT_BINS * sizeof(uint32_t)));
@@ -1845,10 +2134,13 @@ int create(malio_handle* h) {
   CUDA_TRY(cudaHostGetDevicePointer((void**)&D->h_res_dev, D->h_res, 0));
   CUDA_TRY(cudaMalloc((void**)&D->d_bar, 4 * sizeof(uint32_t)));
   CUDA_TRY(cudaMemset(D->d_bar, 0, 4 * sizeof(uint32_t)));
-  CUDA_TRY(cudaFuncSetAttribute(pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RED_SMEM_DOUBLES * (int)sizeof(double)));
+  CUDA_TRY(cudaFuncSetAttribute(pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RED_SMEM_DOUBLES * (int)sizeof(double)));
+  CUDA_TRY(cudaFuncSetAttribute(pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RED_SMEM_DOUBLES * (int)sizeof(double)));
   {
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pass_kernel, RED_THREADS, RED_SMEM_DOUBLES * sizeof(double)));
+    int per_sm = 0, per_sm2 = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pass_kernel<true>, RED_THREADS, RED_SMEM_DOUBLES * sizeof(double)));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, pass_kernel<false>, RED_THREADS, RED_SMEM_DOUBLES * sizeof(double)));
+    if (per_sm2 < per_sm) per_sm = per_sm2;
     int coop = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, D->device));
     D->pass_max_blocks = per_sm * D->sm_count;
@@ -1871,11 +2163,11 @@ void destroy(malio_handle* h) {
             (unsigned long long)D->host_passes, D->host_launch_us / D->host_passes, D->host_wait_us / D->host_passes);
   cudaSetDevice(D->device);
   if (D->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(D->comm);
-  void* ptrs[] = {D->d_nodes, D->d_cov, D->d_pts, D->d_perm, D->d_keys16, D->d_hist, D->d_offs, D->d_cursor, D->d_btot, D->d_tmp_ids,
+  void* ptrs[] = {D->d_nodes, D->d_cov, D->d_mpts, D->d_parent, D->d_arrived, D->d_pts, D->d_pts_sorted, D->d_perm, D->d_keys16, D->d_hist, D->d_offs, D->d_cursor, D->d_btot, D->d_tmp_ids,
                   D->d_table, D->d_nn_idx, D->d_nn_d2, D->d_sel, D->d_world, D->d_plane, D->d_ucov, D->d_tau, D->d_tau2, D->d_pd2, D->d_rows12, D->d_lid8,
                   D->d_normal_y, D->d_o_ny, D->d_o_idx, D->d_o_d2, D->d_o_sel, D->d_o_world, D->d_block_mm,
                   D->d_block_cnt, D->d_counters, D->d_mmkey, D->d_block_red, D->d_res, D->d_rows, D->d_queries,
-                  D->d_cell_start, D->d_cell_cnt, D->d_cell_of, D->d_ctot, D->d_cbase, D->d_cell_pts, D->d_fb_list, D->d_r2_list, D->d_gstats, D->d_bar};
+                  D->d_cell_start, D->d_cell_cnt, D->d_cell_of, D->d_ctot, D->d_cbase, D->d_cell_pts, D->d_fb_list, D->d_r2_list, D->d_gstats, D->d_bar, D->d_cand};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (D->h_res) cudaFreeHost(D->h_res);
   for (auto& e : D->ev) if (e) cudaEventDestroy(e);
@@ -1884,22 +2176,24 @@ void destroy(malio_handle* h) {
   h->dev = nullptr;
 }
 
-int upload_map(malio_handle* h, const malio_map_node* nodes, const float* cov, uint32_t n, uint32_t depth) {
-  DeviceState* D = (DeviceState*)h->dev;
-  CUDA_TRY(cudaSetDevice(D->device));
-  if (depth > MALIO_MAX_TREE_DEPTH) { h->err = "snapshot deeper than MALIO_MAX_TREE_DEPTH"; return MALIO_ERR_TREE_TOO_DEEP; }
-  if (n > D->cap_nodes) {
-    uint32_t cap = n + n / 8 + 1024;
-    if (cap < h->cfg.max_map_nodes) cap = h->cfg.max_map_nodes;
-    if (int rc = ensure(h, D->d_nodes, (size_t)cap * 4)) return rc;
-    if (int rc = ensure(h, D->d_cov, (size_t)cap)) return rc;
-    D->cap_nodes = cap;
-  }
-  CUDA_TRY(cudaMemcpyAsync(D->d_nodes, nodes, (size_t)n * sizeof(malio_map_node), cudaMemcpyHostToDevice, D->stream));
-  CUDA_TRY(cudaMemcpyAsync(D->d_cov, cov, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, D->stream));
+static int ensure_map_buffers(malio_handle* h, DeviceState* D, uint32_t n) {
+  if (n <= D->cap_nodes) return MALIO_OK;
+  uint32_t cap = n + n / 8 + 1024;
+  if (cap < h->cfg.max_map_nodes) cap = h->cfg.max_map_nodes;
+  if (int rc = ensure(h, D->d_nodes, (size_t)cap * 4)) return rc;
+  if (int rc = ensure(h, D->d_mpts, (size_t)cap)) return rc;
+  if (int rc = ensure(h, D->d_cov, (size_t)cap)) return rc;
+  if (int rc = ensure(h, D->d_parent, (size_t)cap)) return rc;
+  if (int rc = ensure(h, D->d_arrived, (size_t)cap)) return rc;
+  D->cap_nodes = cap;
+  return MALIO_OK;
+}
+
+// after the snapshot is resident (d_nodes, d_mpts, d_cov): cell-list index for the k-NN fast path.
+// Cell edge: cfg.knn_cell_size (> 0 fixed, < 0 index off, 0 automatic: start at 1 m = twice the reference's map voxel,
+// filter_size_map 0.5, and keep 2..9 live points per occupied cell).  root = host copy of node 0 (bounds every live point).
+static int finish_map_upload(malio_handle* h, DeviceState* D, const malio_map_node* root, uint32_t n, uint32_t depth) {
   D->n_nodes = n; D->depth = depth;
-  // cell-list index for the k-NN fast path.  Cell edge: cfg.knn_cell_size (> 0 fixed, < 0 index off, 0 automatic:
-  // start at 1 m = twice the reference's map voxel, filter_size_map 0.5, and keep 2..9 live points per occupied cell)
   float hcfg = h->cfg.knn_cell_size;
   if (const char* e = getenv("MALIO_KNN_CELL")) hcfg = (float)atof(e);
   D->grid_on = false;
@@ -1908,7 +2202,7 @@ int upload_map(malio_handle* h, const malio_map_node* nodes, const float* cov, u
     float hc = automatic ? (D->grid_h > 0.f ? D->grid_h : 1.0f) : hcfg;
     for (int attempt = 0; attempt < 6; ++attempt) {
       GridConst G{};
-      if (!grid_geometry(nodes, n, hc, G)) break;
+      if (!grid_geometry(root, n, hc, G)) break;
       if (int rc = grid_build(h, D, G)) return rc;
       CUDA_TRY(cudaStreamSynchronize(D->stream));
       D->grid_on = true;
@@ -1922,7 +2216,54 @@ int upload_map(malio_handle* h, const malio_map_node* nodes, const float* cov, u
   }
   CUDA_TRY(cudaStreamSynchronize(D->stream));
   D->map_ready = true;
+  return MALIO_OK;
+}
+
+int upload_map(malio_handle* h, const malio_map_node* nodes, const float* cov, uint32_t n, uint32_t depth) {
+  DeviceState* D = (DeviceState*)h->dev;
+  CUDA_TRY(cudaSetDevice(D->device));
+  if (depth > MALIO_MAX_TREE_DEPTH) { h->err = "snapshot deeper than MALIO_MAX_TREE_DEPTH"; return MALIO_ERR_TREE_TOO_DEEP; }
+  if (int rc = ensure_map_buffers(h, D, n)) return rc;
+  CUDA_TRY(cudaMemcpyAsync(D->d_nodes, nodes, (size_t)n * sizeof(malio_map_node), cudaMemcpyHostToDevice, D->stream));
+  CUDA_TRY(cudaMemcpyAsync(D->d_cov, cov, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, D->stream));
+  if (n) {
+    tree_extract_kernel<<<(n + 255) / 256, 256, 0, D->stream>>>(D->d_nodes, n, D->d_mpts);
+    D->ctr.kernel_launches += 1;
+  }
   D->ctr.h2d_bytes += (uint64_t)n * (sizeof(malio_map_node) + sizeof(float));
+  return finish_map_upload(h, D, nodes, n, depth);
+}
+
+int upload_map_compact(malio_handle* h, const malio_map_point* pts, const float* cov, uint32_t n, uint32_t depth) {
+  DeviceState* D = (DeviceState*)h->dev;
+  CUDA_TRY(cudaSetDevice(D->device));
+  if (depth > MALIO_MAX_TREE_DEPTH) { h->err = "snapshot deeper than MALIO_MAX_TREE_DEPTH"; return MALIO_ERR_TREE_TOO_DEEP; }
+  if (int rc = ensure_map_buffers(h, D, n)) return rc;
+  static_assert(sizeof(malio_map_point) == sizeof(float4), "compact record is one float4");
+  CUDA_TRY(cudaMemcpyAsync(D->d_mpts, pts, (size_t)n * sizeof(malio_map_point), cudaMemcpyHostToDevice, D->stream));
+  CUDA_TRY(cudaMemcpyAsync(D->d_cov, cov, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, D->stream));
+  D->ctr.h2d_bytes += (uint64_t)n * (sizeof(malio_map_point) + sizeof(float));
+  malio_map_node root{};
+  if (n) {
+    // rebuild the 64-byte records (children's boxes) on the device, then fetch node 0: its point + its two boxes bound the map
+    CUDA_TRY(cudaMemsetAsync(D->d_arrived, 0, (size_t)n * sizeof(uint32_t), D->stream));
+    tree_init_kernel<<<(n + 255) / 256, 256, 0, D->stream>>>(D->d_mpts, n, D->d_nodes, D->d_parent);
+    tree_refit_kernel<<<(n + 255) / 256, 256, 0, D->stream>>>(D->d_mpts, n, D->d_nodes, D->d_parent, D->d_arrived);
+    CUDA_TRY(cudaGetLastError());
+    D->ctr.kernel_launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(D->h_res + MALIO_RED_DOUBLES + 16, D->d_nodes, sizeof(malio_map_node), cudaMemcpyDeviceToHost, D->stream));
+    CUDA_TRY(cudaStreamSynchronize(D->stream));
+    std::memcpy(&root, D->h_res + MALIO_RED_DOUBLES + 16, sizeof(root));
+  }
+  return finish_map_upload(h, D, &root, n, depth);
+}
+
+int download_map_nodes(malio_handle* h, malio_map_node* out, uint32_t cap) {
+  DeviceState* D = (DeviceState*)h->dev;
+  if (!D->map_ready) { h->err = "download_map_nodes before upload_map"; return MALIO_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(D->device));
+  const uint32_t n = D->n_nodes < cap ? D->n_nodes : cap;
+  CUDA_TRY(cudaMemcpy(out, D->d_nodes, (size_t)n * sizeof(malio_map_node), cudaMemcpyDeviceToHost));
   return MALIO_OK;
 }
 
@@ -1932,6 +2273,7 @@ static int ensure_point_buffers(malio_handle* h, DeviceState* D, uint32_t n) {
   if (cap < h->cfg.max_points) cap = h->cfg.max_points;
   int rc = 0;
   if ((rc = ensure(h, D->d_pts, cap))) return rc;
+  if ((rc = ensure(h, D->d_pts_sorted, cap))) return rc;
   if ((rc = ensure(h, D->d_perm, cap))) return rc;
   if ((rc = ensure(h, D->d_keys16, cap))) return rc;
   if ((rc = ensure(h, D->d_tmp_ids, cap))) return rc;
@@ -2007,7 +2349,12 @@ int set_timing(malio_handle* h, int enable) {
 }
 
 int get_counters(malio_handle* h, malio_counters* out) {
-  *out = ((DeviceState*)h->dev)->ctr;
+  DeviceState* D = (DeviceState*)h->dev;
+  CUDA_TRY(cudaSetDevice(D->device));
+  unsigned long long c = 0;
+  CUDA_TRY(cudaMemcpy(&c, D->d_cand, sizeof(c), cudaMemcpyDeviceToHost));
+  D->ctr.knn_candidates = c;
+  *out = D->ctr;
   return MALIO_OK;
 }
 
@@ -2027,6 +2374,9 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
   const uint32_t* perm = nullptr;
   if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[0], st_));
   bool sorted_now = false, knn_now = false;
+  // the per-pass kernels read the scan in position order: the sorted copy when the scan was sorted, else the upload itself
+  const malio_scan_pt* pts_k = (h->cfg.sort_queries && N > 0) ? D->d_pts_sorted : D->d_pts;
+  const uint32_t* perm_k = nullptr;
   if (N > 0) {
     if (h->cfg.sort_queries) {
       if (!D->perm_valid) {
@@ -2039,7 +2389,7 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
     if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[5], st_));
     if (redo_knn) {
       knn_now = true;
-      if (int rc = run_knn<0>(h, D, N, perm, pc, P.knn_max_sqdist)) return rc;
+      if (int rc = run_knn<0>(h, D, N, pts_k, perm_k, pc, P.knn_max_sqdist)) return rc;
       D->searched_once = true;
       if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[6], st_));
       if (D->grid_on) CUDA_TRY(cudaMemcpyAsync(D->h_gstats + 2, D->d_gstats + 2, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st_));
@@ -2059,7 +2409,7 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
   if (D->fused && !D->comm) {
     // ---- single GPU: the whole pass in one cooperative launch; the result arrives in mapped host memory
     PassArgs a{};
-    a.pts = D->d_pts; a.perm = perm; a.N = N; a.table = D->d_table; a.nodes = D->d_nodes; a.node_cov = D->d_cov;
+    a.pts = pts_k; a.perm = perm_k; a.N = N; a.table = D->d_table; a.nodes = D->d_mpts; a.node_cov = D->d_cov;
     a.nn_idx = D->d_nn_idx; a.sel = D->d_sel; a.world = D->d_world; a.plane = D->d_plane; a.ucov = D->d_ucov;
     a.tau2 = D->d_tau2; a.pd2 = D->d_pd2; a.tau = D->d_tau; a.normal_y = D->d_normal_y; a.rows12 = D->d_rows12; a.lid8 = D->d_lid8;
     a.do_tau = (N > 0 && !D->tau_valid) ? 1 : 0;
@@ -2070,11 +2420,16 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
     D->bar_base[0] += grid; D->bar_base[1] += grid; D->bar_base[2] += MALIO_RED_DOUBLES;
     a.n_tiles = n_tiles; a.block_red = D->d_block_red; a.d_res = D->d_res; a.h_res = D->h_res_dev;
     a.seq = ++D->seq;
+    a.dbg = nullptr;
+    if (getenv("MALIO_PASS_TRACE")) {
+      if (!D->d_dbg) { CUDA_TRY(cudaMalloc((void**)&D->d_dbg, (size_t)4096 * 8 * sizeof(unsigned long long))); D->trace_left = atoi(getenv("MALIO_PASS_TRACE")); }
+      if (D->trace_left > 0 && grid <= 4096) a.dbg = D->d_dbg;
+    }
     PassConst pc_arg = pc;
     ParamConst prm_arg = prm;
     void* kargs[] = {&a, &pc_arg, &prm_arg};
-    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)pass_kernel, dim3(grid), dim3(RED_THREADS), kargs,
-                                         RED_SMEM_DOUBLES * sizeof(double), st_));
+    const void* kfn = per_block <= (uint32_t)PASS_FAST_TILES ? (const void*)pass_kernel<true> : (const void*)pass_kernel<false>;
+    CUDA_TRY(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(RED_THREADS), kargs, RED_SMEM_DOUBLES * sizeof(double), st_));
     D->tau_valid = D->tau_valid || N > 0;
     D->ctr.kernel_launches += 1;
     if (D->timing) { CUDA_TRY(cudaEventRecord(D->ev[2], st_)); CUDA_TRY(cudaEventRecord(D->ev[3], st_)); CUDA_TRY(cudaEventRecord(D->ev[4], st_)); }
@@ -2099,22 +2454,38 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
       }
     }
     std::atomic_thread_fence(std::memory_order_acquire);
+    if (a.dbg) {
+      CUDA_TRY(cudaStreamSynchronize(st_));
+      std::vector<unsigned long long> t((size_t)grid * 8);
+      CUDA_TRY(cudaMemcpy(t.data(), D->d_dbg, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      unsigned long long t00 = ~0ull;
+      for (uint32_t b = 0; b < grid; ++b) if (t[b * 8] < t00) t00 = t[b * 8];
+      const char* nm[6] = {"start", "phase1 done", "barrier1 passed", "phase2 done", "barrier2 passed", "end"};
+      fprintf(stderr, "[malio] pass trace: grid %u fast %d fit %d tau %d (us from first block start: min / mean / max over blocks)\n",
+              grid, per_block <= (uint32_t)PASS_FAST_TILES, a.do_fit, a.do_tau);
+      for (int k = 0; k < 6; ++k) {
+        double mn = 1e30, mx = 0, sm = 0;
+        for (uint32_t b = 0; b < grid; ++b) { const double v = (double)(t[b * 8 + k] - t00) * 1e-3; mn = v < mn ? v : mn; mx = v > mx ? v : mx; sm += v; }
+        fprintf(stderr, "[malio]   %-16s %8.2f %8.2f %8.2f\n", nm[k], mn, sm / grid, mx);
+      }
+      D->trace_left--;
+    }
     if (D->timing) CUDA_TRY(cudaEventSynchronize(D->ev[4]));
     hp2 = std::chrono::steady_clock::now();
   } else {
   const uint32_t pblocks = N > 0 ? (N + PLANE_THREADS - 1) / PLANE_THREADS : 1;
   if (N > 0 && !D->tau_valid) {   // once per scan
-    tau_kernel<<<pblocks, PLANE_THREADS, 0, st_>>>(D->d_pts, perm, N, pc, D->d_table, D->d_tau2);
+    tau_kernel<<<pblocks, PLANE_THREADS, 0, st_>>>(pts_k, perm_k, N, pc, D->d_table, D->d_tau2);
     D->tau_valid = true;
     D->ctr.kernel_launches += 1;
   }
   if (N > 0 && redo_knn) {         // once per search
-    fit_kernel<<<pblocks, PLANE_THREADS, 0, st_>>>(D->d_nodes, D->d_cov, N, prm, D->d_nn_idx, D->d_sel, D->d_plane, D->d_ucov);
+    fit_kernel<<<pblocks, PLANE_THREADS, 0, st_>>>(D->d_mpts, D->d_cov, N, prm, D->d_nn_idx, D->d_sel, D->d_plane, D->d_ucov);
     D->ctr.kernel_launches += 1;
   }
   D->ctr.kernel_launches += 3;     // gate, reduce, fold
   const uint32_t gblocks = N > 0 ? (N + GATE_THREADS - 1) / GATE_THREADS : 1;
-  gate_kernel<<<gblocks, GATE_THREADS, 0, st_>>>(D->d_pts, perm, N, pc, D->d_plane, D->d_ucov, D->d_tau2, D->d_sel,
+  gate_kernel<<<gblocks, GATE_THREADS, 0, st_>>>(pts_k, perm_k, N, pc, D->d_plane, D->d_ucov, D->d_tau2, D->d_sel,
                                                    D->d_world, D->d_pd2, D->d_tau, D->d_normal_y, D->d_rows12, D->d_lid8, mmkey, cnt_cell);
   if (D->comm)   // keys of {min_u, -max_u, min_tau, -max_tau}: one MIN all-reduce (laserMapping.cpp:615-628, 700-703)
     if (g_nccl.AllReduce(mmkey, mmkey, 4, ncclUint64, ncclMin, D->comm, st_) != ncclSuccess) { h->err = "ncclAllReduce(min) failed"; return MALIO_ERR_NCCL; }
@@ -2281,7 +2652,7 @@ int knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* idx, float* d2, 
   }
   CUDA_TRY(cudaMemsetAsync(D->d_gstats + 2, 0, 4 * sizeof(uint32_t), D->stream));
   CUDA_TRY(cudaEventRecord(D->ev[0], D->stream));
-  if (int rc = run_knn<1>(h, D, nq, perm, pc, 0.f)) return rc;
+  if (int rc = run_knn<1>(h, D, nq, nullptr, perm, pc, 0.f)) return rc;
   CUDA_TRY(cudaEventRecord(D->ev[1], D->stream));
   scatter_aux_kernel<<<(nq + 255) / 256, 256, 0, D->stream>>>(perm, nq, nullptr, D->d_nn_idx, D->d_nn_d2, nullptr,
                                                                nullptr, nullptr, idx ? D->d_o_idx : nullptr,

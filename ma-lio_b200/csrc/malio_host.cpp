@@ -372,6 +372,14 @@ int malio_upload_map(malio_handle* h, const malio_map_node* nodes, const float* 
   if (!h || (n_nodes && (!nodes || !node_cov))) return MALIO_ERR_INVALID_ARG;
   return malio_dev::upload_map(h, nodes, node_cov, n_nodes, max_depth);
 }
+int malio_upload_map_compact(malio_handle* h, const malio_map_point* pts, const float* node_cov, uint32_t n_nodes, uint32_t max_depth) {
+  if (!h || (n_nodes && (!pts || !node_cov))) return MALIO_ERR_INVALID_ARG;
+  return malio_dev::upload_map_compact(h, pts, node_cov, n_nodes, max_depth);
+}
+int malio_download_map_nodes(malio_handle* h, malio_map_node* out, uint32_t capacity) {
+  if (!h || !out) return MALIO_ERR_INVALID_ARG;
+  return malio_dev::download_map_nodes(h, out, capacity);
+}
 int malio_upload_scan(malio_handle* h, const malio_scan_pt* pts, uint32_t n_pts, const malio_pose_entry* table,
                       const uint32_t* table_off, const malio_rigid* temporal_comp) {
   if (!h || (n_pts && !pts) || !table || !table_off) return MALIO_ERR_INVALID_ARG;

@@ -25,6 +25,7 @@ LINK_INDEX_MASK = 0x0FFFFFFF
 
 # numpy views of the C structs
 MAP_NODE = np.dtype([("xyz", "<f4", 3), ("link", "<u4"), ("lbox", "<f4", 6), ("rbox", "<f4", 6)])
+MAP_POINT = np.dtype([("xyz", "<f4", 3), ("link", "<u4")])
 SCAN_PT = np.dtype([("xyz", "<f4", 3), ("lidar", "<u2"), ("table_idx", "<u2")])
 POSE_ENTRY = np.dtype([("T", "<f8", (4, 4)), ("cov", "<f8", (6, 6))])
 RIGID = np.dtype([("q", "<f8", 4), ("t", "<f8", 3)])
@@ -82,7 +83,8 @@ class State(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("knn_launches", C.c_uint64), ("knn_queries", C.c_uint64),
                 ("knn_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("knn_fallback_queries", C.c_uint64), ("knn_ring2_queries", C.c_uint64)]
+                ("knn_fallback_queries", C.c_uint64), ("knn_ring2_queries", C.c_uint64),
+                ("knn_candidates", C.c_uint64)]
 
 
 class UpdateReport(C.Structure):
@@ -98,7 +100,7 @@ EXPORTS = [
     "malio_default_params", "malio_create", "malio_destroy", "malio_last_error", "malio_version",
     "malio_get_nccl_unique_id", "malio_comm_init", "malio_upload_map", "malio_upload_scan", "malio_measure",
     "malio_download_rows", "malio_download_aux", "malio_knn", "malio_ieskf_update", "malio_build_static_snapshot",
-    "malio_rearm_scan", "malio_get_counters", "malio_set_timing",
+    "malio_rearm_scan", "malio_get_counters", "malio_set_timing", "malio_upload_map_compact", "malio_download_map_nodes",
 ]
 
 
@@ -128,6 +130,8 @@ def load() -> C.CDLL:
     lib.malio_get_nccl_unique_id.argtypes = [vp]
     lib.malio_comm_init.argtypes = [vp, vp, i32, i32]
     lib.malio_upload_map.argtypes = [vp, vp, vp, u32, u32]
+    lib.malio_upload_map_compact.argtypes = [vp, vp, vp, u32, u32]
+    lib.malio_download_map_nodes.argtypes = [vp, vp, u32]
     lib.malio_upload_scan.argtypes = [vp, vp, u32, vp, vp, vp]
     lib.malio_measure.argtypes = [vp, C.POINTER(PassState), i32, vp, vp, C.POINTER(PassStats)]
     lib.malio_download_rows.argtypes = [vp, vp, vp, u32, C.POINTER(u32)]

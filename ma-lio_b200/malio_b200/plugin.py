@@ -48,6 +48,14 @@ def build_static_snapshot(xyz: np.ndarray, normal_y: np.ndarray | float = 0.001)
     return MapSnapshot(nodes, cov, order.astype(np.int64), int(depth.value))
 
 
+def compact_points(nodes: np.ndarray) -> np.ndarray:
+    """capi.MAP_NODE[M] -> capi.MAP_POINT[M]: the first 16 bytes (point + link) of every record."""
+    out = np.empty(nodes.shape[0], dtype=capi.MAP_POINT)
+    out["xyz"] = nodes["xyz"]
+    out["link"] = nodes["link"]
+    return out
+
+
 class MeasurementModel:
     """One handle = one GPU.  Mirrors the life cycle of one scan in laserMapping.cpp:935-1082."""
 
@@ -105,6 +113,18 @@ class MeasurementModel:
         nodes = np.ascontiguousarray(snap.nodes)
         cov = np.ascontiguousarray(snap.node_cov, dtype=np.float32)
         self._check(self.lib.malio_upload_map(self._h, capi.ptr(nodes), capi.ptr(cov), nodes.shape[0], snap.max_depth))
+
+    def upload_map_compact(self, snap: MapSnapshot, points: np.ndarray | None = None):
+        """Same snapshot, 16 bytes per node (point + link) + the weights: the device rebuilds the children's boxes.
+        `points` may hold the pre-extracted capi.MAP_POINT array (e.g. in pinned memory)."""
+        pts = compact_points(snap.nodes) if points is None else points
+        cov = np.ascontiguousarray(snap.node_cov, dtype=np.float32)
+        self._check(self.lib.malio_upload_map_compact(self._h, capi.ptr(pts), capi.ptr(cov), pts.shape[0], snap.max_depth))
+
+    def download_map_nodes(self, n: int) -> np.ndarray:
+        out = np.zeros(n, dtype=capi.MAP_NODE)
+        self._check(self.lib.malio_download_map_nodes(self._h, capi.ptr(out), n))
+        return out
 
     def upload_scan(self, pts: np.ndarray, table: np.ndarray, table_off: np.ndarray, temporal_comp: np.ndarray | None):
         pts = np.ascontiguousarray(pts)

@@ -110,3 +110,69 @@ def test_measurement_pass_identical_with_and_without_index(cell):
         assert np.array_equal(a[k], a_r[k]), k
     assert np.array_equal(HTH, HTH_r) and np.array_equal(HTh, HTh_r)
     ref.close(); m.close()
+
+
+def _tight_boxes(nodes):
+    """numpy restatement of the box rule: box(node) = bounding box of the live points of its subtree."""
+    n = nodes.shape[0]
+    out = nodes.copy()
+    lo = np.full((n, 3), np.inf, np.float32)
+    hi = np.full((n, 3), -np.inf, np.float32)
+    link = nodes["link"]
+    for i in range(n - 1, -1, -1):   # children have larger indices than their parent (DFS pre-order)
+        if not (link[i] & capi.LINK_POINT_DELETED):
+            lo[i] = np.minimum(lo[i], nodes["xyz"][i]); hi[i] = np.maximum(hi[i], nodes["xyz"][i])
+        for child, key in (((i + 1) if (link[i] & capi.LINK_HAS_LEFT) else -1, "lbox"),
+                           (int(link[i] & capi.LINK_INDEX_MASK) if (link[i] & capi.LINK_HAS_RIGHT) else -1, "rbox")):
+            if child >= 0:
+                out[key][i] = np.stack([lo[child], hi[child]], axis=1).reshape(6)
+                lo[i] = np.minimum(lo[i], lo[child]); hi[i] = np.maximum(hi[i], hi[child])
+    return out
+
+
+def test_compact_upload_rebuilds_the_reference_boxes():
+    """malio_upload_map_compact: 16 B per node go up, the device rebuilds both children's boxes of every node.  On the
+    churned real ikd-Tree (lazy deletes, down-sampling adds) they must equal the node_range_* boxes the flattener copied
+    out of the reference tree, float for float; and searches / passes through the compact upload are identical."""
+    case = synth.make_case("3L-20k-200k", 20000, 200000, 3, 3, varied_map_cov=True)
+    snap, _ = H.snapshot_for(case, churn=True)
+    m = plugin.MeasurementModel(case.n_lidar, params=case.params)
+    m.upload_map_compact(snap)
+    dev = m.download_map_nodes(snap.n_nodes)
+    ref = snap.nodes
+    assert np.array_equal(dev["xyz"], ref["xyz"]) and np.array_equal(dev["link"], ref["link"])
+    has_l = (ref["link"] & capi.LINK_HAS_LEFT) != 0
+    has_r = (ref["link"] & capi.LINK_HAS_RIGHT) != 0
+    assert np.array_equal(dev["lbox"][has_l], ref["lbox"][has_l])
+    assert np.array_equal(dev["rbox"][has_r], ref["rbox"][has_r])
+    m.upload_scan(case.pts, case.table, case.table_off, case.temporal_comp)
+    ok, HTH, HTh, st = m.h_share_model(case.x_prop, True)
+    a = m.aux()
+    full = H.make_model(case, snap)
+    ok_f, HTH_f, HTh_f, st_f = full.h_share_model(case.x_prop, True)
+    a_f = full.aux()
+    for k in ("nn_idx", "nn_sqdist", "selected", "world", "normal_y"):
+        assert np.array_equal(a[k], a_f[k]), k
+    assert np.array_equal(HTH, HTH_f) and np.array_equal(HTh, HTh_f)
+    # the exact traversal on device-built boxes: index off => every query walks the tree
+    t = plugin.MeasurementModel(1, knn_cell_size=-1.0)
+    t.upload_map_compact(snap)
+    q = a["world"][:4000]
+    idx, d2, _ = t.Nearest_Search(q)
+    assert np.array_equal(idx, a["nn_idx"][:4000]) and np.array_equal(d2, a["nn_sqdist"][:4000])
+    # deleted points in a static snapshot (boxes must exclude them)
+    rng = np.random.default_rng(3)
+    s2 = plugin.build_static_snapshot(case.map_xyz[:5000])
+    nodes = s2.nodes.copy()
+    nodes["link"][rng.choice(5000, 300, replace=False)] |= capi.LINK_POINT_DELETED
+    tight = _tight_boxes(nodes)
+    s2 = plugin.MapSnapshot(nodes, s2.node_cov, s2.node_ids, s2.max_depth)
+    t.upload_map_compact(s2)
+    dev2 = t.download_map_nodes(5000)
+    hl = (nodes["link"] & capi.LINK_HAS_LEFT) != 0
+    hr = (nodes["link"] & capi.LINK_HAS_RIGHT) != 0
+    assert np.array_equal(dev2["lbox"][hl], tight["lbox"][hl]) and np.array_equal(dev2["rbox"][hr], tight["rbox"][hr])
+    o_idx, o_d2, _, _ = po.knn_snapshot(tight, s2.node_cov, q[:1000], nthreads=4)
+    idx, d2, _ = t.Nearest_Search(q[:1000])
+    assert np.array_equal(idx.astype(np.int64), o_idx.astype(np.int64)) and np.array_equal(d2, o_d2)
+    m.close(); full.close(); t.close()
