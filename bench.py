@@ -231,12 +231,25 @@ def run_ours(args, rank, world):
         x, P = case.x_prop.copy(), case.P_prop.copy()
         return model.update_iterated_dyn_share_modified(x, P, case.max_iter), x
 
+    # the host side of a real integration knows the map's bounding box (ikd-Tree root node_range_*): node 0's point and
+    # its two children's boxes
+    n0 = snap.nodes[0]
+    boxes = [n0["lbox"] if (n0["link"] & capi.LINK_HAS_LEFT) else None, n0["rbox"] if (n0["link"] & capi.LINK_HAS_RIGHT) else None]
+    blo = np.array(n0["xyz"], np.float32); bhi = blo.copy()
+    for b in boxes:
+        if b is not None:
+            blo = np.minimum(blo, b[0::2]); bhi = np.maximum(bhi, b[1::2])
+    root_box = np.stack([blo, bhi], axis=1).reshape(6).astype(np.float32)
+    t_ny, h_ny = pinned(np.zeros(h_pts.shape[0], np.float32)); keep.append(t_ny)
+    t_sel, h_sel = pinned(np.zeros(h_pts.shape[0], np.uint8)); keep.append(t_sel)
+    aux_out = {"normal_y": h_ny, "selected": h_sel}
+
     def step_e2e():
-        model.upload_map_compact(snap_p, points=h_mpts)
+        model.upload_map_compact(snap_p, points=h_mpts, root_box=root_box)
         model.upload_scan(h_pts, case.table, case.table_off, case.temporal_comp)
         x, P = case.x_prop.copy(), case.P_prop.copy()
         rep = model.update_iterated_dyn_share_modified(x, P, case.max_iter)
-        aux = model.aux(normal_y=True, nn_idx=False, nn_sqdist=False, selected=True, world=False)
+        aux = model.aux(out=aux_out)
         return rep, x, aux
 
     def timed(fn, steps, warmup):

@@ -166,9 +166,11 @@ int malio_comm_init(malio_handle* h, const uint8_t id[MALIO_NCCL_UNIQUE_ID_BYTES
 int malio_upload_map(malio_handle* h, const malio_map_node* nodes, const float* node_cov,
                      uint32_t n_nodes, uint32_t max_depth);
 
-/* Same snapshot in compact form (see malio_map_point): 3.4x less host->device traffic per scan. */
+/* Same snapshot in compact form (see malio_map_point): 3.4x less host->device traffic per scan.
+ * root_box (optional, may be NULL): {x_min,x_max,y_min,y_max,z_min,z_max} bounding every live point — the ikd-Tree
+ * root's node_range_* — saves the read-back of the rebuilt root record. */
 int malio_upload_map_compact(malio_handle* h, const malio_map_point* pts, const float* node_cov,
-                             uint32_t n_nodes, uint32_t max_depth);
+                             uint32_t n_nodes, uint32_t max_depth, const float* root_box);
 /* test / debug: read back the device-resident 64-byte node records (boxes included). */
 int malio_download_map_nodes(malio_handle* h, malio_map_node* out, uint32_t capacity);
 

@@ -2200,14 +2200,18 @@ static int finish_map_upload(malio_handle* h, DeviceState* D, const malio_map_no
   if (hcfg >= 0.f && n > 0) {
     const bool automatic = hcfg == 0.f;
     float hc = automatic ? (D->grid_h > 0.f ? D->grid_h : 1.0f) : hcfg;
-    for (int attempt = 0; attempt < 6; ++attempt) {
+    // A tuned edge from an earlier upload is re-used as is: one build, no host round trip in the middle of the upload;
+    // its occupancy statistics arrive with the final synchronisation and steer the NEXT upload (maps change slowly).
+    const int attempts = (automatic && D->grid_h == 0.f) ? 6 : 1;
+    for (int attempt = 0; attempt < attempts; ++attempt) {
       GridConst G{};
       if (!grid_geometry(root, n, hc, G)) break;
       if (int rc = grid_build(h, D, G)) return rc;
-      CUDA_TRY(cudaStreamSynchronize(D->stream));
       D->grid_on = true;
       D->grid_h = G.h;
-      if (!automatic || D->h_gstats[0] == 0) break;
+      if (attempts == 1) break;
+      CUDA_TRY(cudaStreamSynchronize(D->stream));
+      if (D->h_gstats[0] == 0) break;
       const double mean = (double)D->h_gstats[1] / (double)D->h_gstats[0];
       if (mean < 2.0) hc = G.h * 1.5f;
       else if (mean > 9.0 && G.h > 0.05f) hc = G.h / 1.5f;
@@ -2215,6 +2219,11 @@ static int finish_map_upload(malio_handle* h, DeviceState* D, const malio_map_no
     }
   }
   CUDA_TRY(cudaStreamSynchronize(D->stream));
+  if (D->grid_on && hcfg == 0.f && D->h_gstats[0] != 0) {   // steer the next upload
+    const double mean = (double)D->h_gstats[1] / (double)D->h_gstats[0];
+    if (mean < 2.0) D->grid_h *= 1.5f;
+    else if (mean > 9.0 && D->grid_h > 0.05f) D->grid_h /= 1.5f;
+  }
   D->map_ready = true;
   return MALIO_OK;
 }
@@ -2234,7 +2243,8 @@ int upload_map(malio_handle* h, const malio_map_node* nodes, const float* cov, u
   return finish_map_upload(h, D, nodes, n, depth);
 }
 
-int upload_map_compact(malio_handle* h, const malio_map_point* pts, const float* cov, uint32_t n, uint32_t depth) {
+int upload_map_compact(malio_handle* h, const malio_map_point* pts, const float* cov, uint32_t n, uint32_t depth,
+                       const float* root_box) {
   DeviceState* D = (DeviceState*)h->dev;
   CUDA_TRY(cudaSetDevice(D->device));
   if (depth > MALIO_MAX_TREE_DEPTH) { h->err = "snapshot deeper than MALIO_MAX_TREE_DEPTH"; return MALIO_ERR_TREE_TOO_DEEP; }
@@ -2251,9 +2261,15 @@ int upload_map_compact(malio_handle* h, const malio_map_point* pts, const float*
     tree_refit_kernel<<<(n + 255) / 256, 256, 0, D->stream>>>(D->d_mpts, n, D->d_nodes, D->d_parent, D->d_arrived);
     CUDA_TRY(cudaGetLastError());
     D->ctr.kernel_launches += 2;
-    CUDA_TRY(cudaMemcpyAsync(D->h_res + MALIO_RED_DOUBLES + 16, D->d_nodes, sizeof(malio_map_node), cudaMemcpyDeviceToHost, D->stream));
-    CUDA_TRY(cudaStreamSynchronize(D->stream));
-    std::memcpy(&root, D->h_res + MALIO_RED_DOUBLES + 16, sizeof(root));
+    if (root_box) {   // the caller knows the map's bounding box (the ikd-Tree root's node_range_*): no read-back needed
+      root.x = root_box[0]; root.y = root_box[2]; root.z = root_box[4];
+      root.link = MALIO_LINK_HAS_LEFT;
+      for (int k = 0; k < 6; ++k) root.lbox[k] = root_box[k];
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(D->h_res + MALIO_RED_DOUBLES + 16, D->d_nodes, sizeof(malio_map_node), cudaMemcpyDeviceToHost, D->stream));
+      CUDA_TRY(cudaStreamSynchronize(D->stream));
+      std::memcpy(&root, D->h_res + MALIO_RED_DOUBLES + 16, sizeof(root));
+    }
   }
   return finish_map_upload(h, D, &root, n, depth);
 }

@@ -372,9 +372,10 @@ int malio_upload_map(malio_handle* h, const malio_map_node* nodes, const float* 
   if (!h || (n_nodes && (!nodes || !node_cov))) return MALIO_ERR_INVALID_ARG;
   return malio_dev::upload_map(h, nodes, node_cov, n_nodes, max_depth);
 }
-int malio_upload_map_compact(malio_handle* h, const malio_map_point* pts, const float* node_cov, uint32_t n_nodes, uint32_t max_depth) {
+int malio_upload_map_compact(malio_handle* h, const malio_map_point* pts, const float* node_cov, uint32_t n_nodes, uint32_t max_depth,
+                             const float* root_box) {
   if (!h || (n_nodes && (!pts || !node_cov))) return MALIO_ERR_INVALID_ARG;
-  return malio_dev::upload_map_compact(h, pts, node_cov, n_nodes, max_depth);
+  return malio_dev::upload_map_compact(h, pts, node_cov, n_nodes, max_depth, root_box);
 }
 int malio_download_map_nodes(malio_handle* h, malio_map_node* out, uint32_t capacity) {
   if (!h || !out) return MALIO_ERR_INVALID_ARG;

@@ -29,7 +29,8 @@ namespace malio_dev {
 int create(malio_handle* h);
 void destroy(malio_handle* h);
 int upload_map(malio_handle* h, const malio_map_node* nodes, const float* cov, uint32_t n, uint32_t depth);
-int upload_map_compact(malio_handle* h, const malio_map_point* pts, const float* cov, uint32_t n, uint32_t depth);
+int upload_map_compact(malio_handle* h, const malio_map_point* pts, const float* cov, uint32_t n, uint32_t depth,
+                       const float* root_box);
 int download_map_nodes(malio_handle* h, malio_map_node* out, uint32_t cap);
 int upload_scan(malio_handle* h, const malio_scan_pt* pts, uint32_t n, const malio_pose_entry* table,
                 const uint32_t* table_off, const malio_rigid* tcomp);

@@ -105,7 +105,8 @@ EXPORTS = [
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+    # MALIO_LIB_PATH: another build of the same library (kernel-parameter experiments); the product default is in-tree
+    return os.environ.get("MALIO_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 
 def load() -> C.CDLL:
@@ -130,7 +131,7 @@ def load() -> C.CDLL:
     lib.malio_get_nccl_unique_id.argtypes = [vp]
     lib.malio_comm_init.argtypes = [vp, vp, i32, i32]
     lib.malio_upload_map.argtypes = [vp, vp, vp, u32, u32]
-    lib.malio_upload_map_compact.argtypes = [vp, vp, vp, u32, u32]
+    lib.malio_upload_map_compact.argtypes = [vp, vp, vp, u32, u32, vp]
     lib.malio_download_map_nodes.argtypes = [vp, vp, u32]
     lib.malio_upload_scan.argtypes = [vp, vp, u32, vp, vp, vp]
     lib.malio_measure.argtypes = [vp, C.POINTER(PassState), i32, vp, vp, C.POINTER(PassStats)]

@@ -114,12 +114,15 @@ class MeasurementModel:
         cov = np.ascontiguousarray(snap.node_cov, dtype=np.float32)
         self._check(self.lib.malio_upload_map(self._h, capi.ptr(nodes), capi.ptr(cov), nodes.shape[0], snap.max_depth))
 
-    def upload_map_compact(self, snap: MapSnapshot, points: np.ndarray | None = None):
+    def upload_map_compact(self, snap: MapSnapshot, points: np.ndarray | None = None, root_box: np.ndarray | None = None):
         """Same snapshot, 16 bytes per node (point + link) + the weights: the device rebuilds the children's boxes.
-        `points` may hold the pre-extracted capi.MAP_POINT array (e.g. in pinned memory)."""
+        `points` may hold the pre-extracted capi.MAP_POINT array (e.g. in pinned memory); `root_box` the map's bounding
+        box {x_min,x_max,y_min,y_max,z_min,z_max} when the caller knows it (the ikd-Tree root's node_range_*)."""
         pts = compact_points(snap.nodes) if points is None else points
         cov = np.ascontiguousarray(snap.node_cov, dtype=np.float32)
-        self._check(self.lib.malio_upload_map_compact(self._h, capi.ptr(pts), capi.ptr(cov), pts.shape[0], snap.max_depth))
+        rb = None if root_box is None else np.ascontiguousarray(root_box, dtype=np.float32)
+        self._check(self.lib.malio_upload_map_compact(self._h, capi.ptr(pts), capi.ptr(cov), pts.shape[0], snap.max_depth,
+                                                      capi.ptr(rb)))
 
     def download_map_nodes(self, n: int) -> np.ndarray:
         out = np.zeros(n, dtype=capi.MAP_NODE)
@@ -169,8 +172,15 @@ class MeasurementModel:
         self._check(self.lib.malio_download_rows(self._h, capi.ptr(hx), capi.ptr(hv), cap, C.byref(n)))
         return hx[: n.value], hv[: n.value]
 
-    def aux(self, normal_y=True, nn_idx=True, nn_sqdist=True, selected=True, world=True):
+    def aux(self, normal_y=True, nn_idx=True, nn_sqdist=True, selected=True, world=True, out: dict | None = None):
+        """Side outputs of the last pass in caller order.  `out` may carry pre-allocated (e.g. pinned) arrays under the
+        same keys; missing ones are allocated."""
         n = self.n_points
+        if out is not None:
+            self._check(self.lib.malio_download_aux(self._h, capi.ptr(out.get("normal_y")), capi.ptr(out.get("nn_idx")),
+                                                    capi.ptr(out.get("nn_sqdist")), capi.ptr(out.get("selected")),
+                                                    capi.ptr(out.get("world"))))
+            return out
         o_ny = np.zeros(n, np.float32) if normal_y else None
         o_idx = np.zeros((n, capi.K), np.uint32) if nn_idx else None
         o_d2 = np.zeros((n, capi.K), np.float32) if nn_sqdist else None
