@@ -490,9 +490,10 @@ __global__ void tree_refit_kernel(const float4* __restrict__ mpts, uint32_t n, f
     float* box = rec + (is_left ? 4 : 10);      // lbox at floats 4..9, rbox at 10..15
     box[0] = x0; box[1] = x1; box[2] = y0; box[3] = y1; box[4] = z0; box[5] = z1;
     const uint32_t need = ((plink & MALIO_LINK_HAS_LEFT) ? 1u : 0u) + ((plink & MALIO_LINK_HAS_RIGHT) ? 1u : 0u);
-    __threadfence();
-    if (atomicAdd(arrived + par, 1u) + 1u < need) break;   // the sibling's thread carries the parent
-    __threadfence();
+    // release our box / acquire the sibling's in the one atomic of this level (the climb is a chain of these round trips)
+    uint32_t before;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(before) : "l"(arrived + par) : "memory");
+    if (before + 1u < need) break;   // the sibling's thread carries the parent
     if (need == 2) {   // merge the sibling's box, written by another thread: read it from L2
       const float* sib = rec + (is_left ? 10 : 4);
       x0 = fminf(x0, __ldcg(sib + 0)); x1 = fmaxf(x1, __ldcg(sib + 1));
@@ -570,18 +571,22 @@ __global__ void __launch_bounds__(1024) grid_scan_local_kernel(uint32_t* __restr
   if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = inc;
   if ((threadIdx.x & 31) == 0) s_occ[threadIdx.x >> 5] = occ;
   __syncthreads();
-  uint32_t wbase = 0;
-  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += s_w[w];
-  uint32_t run = wbase + inc - sum;
+  if (threadIdx.x < 32) {   // warp 0: exclusive scan of the 32 warp totals, sum of the occupied-cell counts
+    const uint32_t wt = s_w[threadIdx.x];
+    uint32_t wi = wt, oc = s_occ[threadIdx.x];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (threadIdx.x >= (unsigned)o) wi += t; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) oc += __shfl_xor_sync(0xffffffffu, oc, o);
+    s_w[threadIdx.x] = wi - wt;
+    if (threadIdx.x == 31) ctot[blockIdx.x] = wi;
+    if (threadIdx.x == 0 && oc) atomicAdd(stats, oc);
+  }
+  __syncthreads();
+  uint32_t run = s_w[threadIdx.x >> 5] + inc - sum;
   uint4 o4;
   o4.x = run; run += v.x; o4.y = run; run += v.y; o4.z = run; run += v.z; o4.w = run;
   *reinterpret_cast<uint4*>(start + base) = o4;
-  if (threadIdx.x == 1023) ctot[blockIdx.x] = wbase + inc;
-  if (threadIdx.x == 0) {
-    uint32_t t = 0;
-    for (int w = 0; w < 32; ++w) t += s_occ[w];
-    if (t) atomicAdd(stats, t);
-  }
 }
 __global__ void __launch_bounds__(1024) grid_scan_tot_kernel(const uint32_t* __restrict__ ctot, uint32_t nchunk,
                                                              uint32_t* __restrict__ cbase, uint32_t* __restrict__ stats) {
@@ -1855,6 +1860,8 @@ struct DeviceState {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;            // box rebuild of the compact upload runs beside the scan's first kernels
+  cudaEvent_t ev_h2d = nullptr, ev_refit = nullptr; bool refit_pending = false;
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [5] after sort, [6] after knn kernel
   malio_counters ctr{};
   bool timing = true;   // per-pass CUDA-event timing (malio_set_timing)
@@ -2053,6 +2060,10 @@ int run_knn(malio_handle* h, DeviceState* D, uint32_t n, const malio_scan_pt* pt
   const float* qs = MODE == 0 ? nullptr : D->d_queries;
   float4* world = MODE == 0 ? D->d_world : nullptr;
   uint8_t* sel = MODE == 0 ? D->d_sel : nullptr;
+  auto need_boxes = [&]() -> int {   // the exact traversal reads the 64-byte records: wait for a rebuild still in flight
+    if (D->refit_pending) { CUDA_TRY(cudaStreamWaitEvent(st, D->ev_refit, 0)); D->refit_pending = false; }
+    return MALIO_OK;
+  };
   if (D->grid_on) {
     // d_gstats: [2] traversal-list length, [4] ring-2 list length (both zeroed by the previous pass / the re-arm)
     constexpr size_t smem1 = (size_t)GK_CAP * GK_THREADS * sizeof(float4) + (size_t)GK_ROWS1 * GK_THREADS * sizeof(uint2);
@@ -2069,6 +2080,7 @@ int run_knn(malio_handle* h, DeviceState* D, uint32_t n, const malio_scan_pt* pt
     uint32_t fb_blocks = (n + 15) / 16;
     const uint32_t wave = (uint32_t)D->sm_count * 8;
     if (fb_blocks > wave) fb_blocks = wave;
+    if (int rc = need_boxes()) return rc;
     if (smem_stack)
       knn_list_kernel<MODE, true><<<fb_blocks, KNN_THREADS, 0, st>>>(D->d_nodes, D->n_nodes, pts, perm, qs, n, pc, max_sqdist,
                                                                     D->d_fb_list, D->d_gstats + 2, D->d_nn_idx, D->d_nn_d2, sel, D->d_gstats + 3);
@@ -2077,6 +2089,7 @@ int run_knn(malio_handle* h, DeviceState* D, uint32_t n, const malio_scan_pt* pt
                                                                      D->d_fb_list, D->d_gstats + 2, D->d_nn_idx, D->d_nn_d2, sel, D->d_gstats + 3);
     D->ctr.kernel_launches += 2;
   } else {
+    if (int rc = need_boxes()) return rc;
     const int lanes = pick_lanes(n, D->sm_count);
     if (smem_stack)
       knn_kernel<MODE, true><<<knn_blocks(n, lanes), KNN_THREADS, 0, st>>>(D->d_nodes, D->n_nodes, pts, perm, qs, n, lanes, pc,
@@ -2107,6 +2120,9 @@ int create(malio_handle* h) {
   CUDA_TRY(cudaGetDeviceProperties(&prop, D->device));
   D->sm_count = prop.multiProcessorCount;
   CUDA_TRY(cudaStreamCreateWithFlags(&D->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&D->stream2, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&D->ev_h2d, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&D->ev_refit, cudaEventDisableTiming));
   for (auto& e : D->ev) CUDA_TRY(cudaEventCreate(&e));
   CUDA_TRY(cudaMalloc((void**)&D->d_counters, 8 * sizeof(uint32_t)));
   CUDA_TRY(cudaMemset(D->d_counters, 0, 8 * sizeof(uint32_t)));
@@ -2171,6 +2187,9 @@ void destroy(malio_handle* h) {
   for (void* p : ptrs) if (p) cudaFree(p);
   if (D->h_res) cudaFreeHost(D->h_res);
   for (auto& e : D->ev) if (e) cudaEventDestroy(e);
+  if (D->stream2) { cudaStreamSynchronize(D->stream2); cudaStreamDestroy(D->stream2); }
+  if (D->ev_h2d) cudaEventDestroy(D->ev_h2d);
+  if (D->ev_refit) cudaEventDestroy(D->ev_refit);
   if (D->stream) cudaStreamDestroy(D->stream);
   delete D;
   h->dev = nullptr;
@@ -2232,6 +2251,7 @@ int upload_map(malio_handle* h, const malio_map_node* nodes, const float* cov, u
   DeviceState* D = (DeviceState*)h->dev;
   CUDA_TRY(cudaSetDevice(D->device));
   if (depth > MALIO_MAX_TREE_DEPTH) { h->err = "snapshot deeper than MALIO_MAX_TREE_DEPTH"; return MALIO_ERR_TREE_TOO_DEEP; }
+  if (D->refit_pending) { CUDA_TRY(cudaStreamSynchronize(D->stream2)); D->refit_pending = false; }
   if (int rc = ensure_map_buffers(h, D, n)) return rc;
   CUDA_TRY(cudaMemcpyAsync(D->d_nodes, nodes, (size_t)n * sizeof(malio_map_node), cudaMemcpyHostToDevice, D->stream));
   CUDA_TRY(cudaMemcpyAsync(D->d_cov, cov, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, D->stream));
@@ -2248,26 +2268,34 @@ int upload_map_compact(malio_handle* h, const malio_map_point* pts, const float*
   DeviceState* D = (DeviceState*)h->dev;
   CUDA_TRY(cudaSetDevice(D->device));
   if (depth > MALIO_MAX_TREE_DEPTH) { h->err = "snapshot deeper than MALIO_MAX_TREE_DEPTH"; return MALIO_ERR_TREE_TOO_DEEP; }
+  if (D->refit_pending) { CUDA_TRY(cudaStreamSynchronize(D->stream2)); D->refit_pending = false; }
   if (int rc = ensure_map_buffers(h, D, n)) return rc;
   static_assert(sizeof(malio_map_point) == sizeof(float4), "compact record is one float4");
   CUDA_TRY(cudaMemcpyAsync(D->d_mpts, pts, (size_t)n * sizeof(malio_map_point), cudaMemcpyHostToDevice, D->stream));
+  CUDA_TRY(cudaEventRecord(D->ev_h2d, D->stream));
   CUDA_TRY(cudaMemcpyAsync(D->d_cov, cov, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, D->stream));
   D->ctr.h2d_bytes += (uint64_t)n * (sizeof(malio_map_point) + sizeof(float));
   malio_map_node root{};
   if (n) {
-    // rebuild the 64-byte records (children's boxes) on the device, then fetch node 0: its point + its two boxes bound the map
-    CUDA_TRY(cudaMemsetAsync(D->d_arrived, 0, (size_t)n * sizeof(uint32_t), D->stream));
-    tree_init_kernel<<<(n + 255) / 256, 256, 0, D->stream>>>(D->d_mpts, n, D->d_nodes, D->d_parent);
-    tree_refit_kernel<<<(n + 255) / 256, 256, 0, D->stream>>>(D->d_mpts, n, D->d_nodes, D->d_parent, D->d_arrived);
+    // Rebuild the 64-byte records (children's boxes) on the device.  Only the exact traversal reads them (tie / outlier
+    // queries, index-off mode), so the rebuild runs on a second stream beside the cell-list build and the scan's first
+    // kernels; whoever needs the records waits on ev_refit (run_knn, download_map_nodes).
+    CUDA_TRY(cudaStreamWaitEvent(D->stream2, D->ev_h2d, 0));
+    CUDA_TRY(cudaMemsetAsync(D->d_arrived, 0, (size_t)n * sizeof(uint32_t), D->stream2));
+    tree_init_kernel<<<(n + 255) / 256, 256, 0, D->stream2>>>(D->d_mpts, n, D->d_nodes, D->d_parent);
+    tree_refit_kernel<<<(n + 255) / 256, 256, 0, D->stream2>>>(D->d_mpts, n, D->d_nodes, D->d_parent, D->d_arrived);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(D->ev_refit, D->stream2));
+    D->refit_pending = true;
     D->ctr.kernel_launches += 2;
     if (root_box) {   // the caller knows the map's bounding box (the ikd-Tree root's node_range_*): no read-back needed
       root.x = root_box[0]; root.y = root_box[2]; root.z = root_box[4];
       root.link = MALIO_LINK_HAS_LEFT;
       for (int k = 0; k < 6; ++k) root.lbox[k] = root_box[k];
-    } else {
-      CUDA_TRY(cudaMemcpyAsync(D->h_res + MALIO_RED_DOUBLES + 16, D->d_nodes, sizeof(malio_map_node), cudaMemcpyDeviceToHost, D->stream));
-      CUDA_TRY(cudaStreamSynchronize(D->stream));
+    } else {   // node 0 of the rebuilt records: its point + its two boxes bound the map
+      CUDA_TRY(cudaMemcpyAsync(D->h_res + MALIO_RED_DOUBLES + 16, D->d_nodes, sizeof(malio_map_node), cudaMemcpyDeviceToHost, D->stream2));
+      CUDA_TRY(cudaStreamSynchronize(D->stream2));
+      D->refit_pending = false;
       std::memcpy(&root, D->h_res + MALIO_RED_DOUBLES + 16, sizeof(root));
     }
   }
@@ -2279,6 +2307,7 @@ int download_map_nodes(malio_handle* h, malio_map_node* out, uint32_t cap) {
   if (!D->map_ready) { h->err = "download_map_nodes before upload_map"; return MALIO_ERR_STATE; }
   CUDA_TRY(cudaSetDevice(D->device));
   const uint32_t n = D->n_nodes < cap ? D->n_nodes : cap;
+  if (D->refit_pending) { CUDA_TRY(cudaStreamSynchronize(D->stream2)); D->refit_pending = false; }
   CUDA_TRY(cudaMemcpy(out, D->d_nodes, (size_t)n * sizeof(malio_map_node), cudaMemcpyDeviceToHost));
   return MALIO_OK;
 }
