@@ -263,6 +263,9 @@ def run_ours(args, rank, world):
         for _ in range(steps):
             flush.fill_(1)          # L2 flush, outside the timed bracket
             torch.cuda.synchronize()
+            if world > 1:           # start the ranks together: inside a pass they wait for each other (exchange), so any
+                dist.barrier()      # start skew would be billed to the earlier rank's timed bracket
+                torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             out = fn()

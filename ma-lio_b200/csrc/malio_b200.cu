@@ -1502,6 +1502,48 @@ reduce_kernel(uint32_t N, ParamConst prm, int ext_en, const uint8_t* __restrict_
 // per-pass critical path; arithmetic and summation order are unchanged (bit-identical results).
 // The kernel is launched with cudaLaunchCooperativeKernel (all blocks co-resident), the barriers are plain
 // device-scope counters that only ever grow (the host passes the value they had before the launch).
+// Multi-GPU: the two exchanges of a pass (MIN of the four min/max keys before the weights, SUM of the reduced system at
+// the end) go through per-rank mailboxes in device memory that every peer maps with CUDA IPC and writes over
+// NVLink/NVSwitch from inside pass_kernel — no NCCL call, no extra launch, the cross-GPU latency of a pass is two
+// one-way store + flag hops.  Layout of one rank's mailbox: [parity 2][kind: MIN 64 B | SUM 3584 B][source rank 8].
+constexpr int MAIL_MAX_WORLD = 8;
+constexpr int MAIL_MIN_BYTES = 64;        // u64 keys[4] | u32 count | u32 seq (byte 40)
+constexpr int MAIL_SUM_BYTES = 3584;      // double res[MALIO_RED_DOUBLES] | u32 seq (byte 3480)
+constexpr int MAIL_SUM_SEQ_OFF = 3480;
+static_assert(MALIO_RED_DOUBLES * 8 <= MAIL_SUM_SEQ_OFF, "mailbox slot too small");
+constexpr int MAIL_PARITY_BYTES = MAIL_MAX_WORLD * (MAIL_MIN_BYTES + MAIL_SUM_BYTES);
+constexpr int MAIL_BYTES = 2 * MAIL_PARITY_BYTES;
+struct PeerArgs {
+  unsigned char* mail[MAIL_MAX_WORLD];   // mail[r] = rank r's mailbox as mapped into THIS process (mail[rank] is local)
+  int rank, world;
+};
+__device__ __forceinline__ unsigned char* mail_min_slot(unsigned char* box, uint32_t seq, int src) {
+  return box + (seq & 1u) * MAIL_PARITY_BYTES + src * MAIL_MIN_BYTES;
+}
+__device__ __forceinline__ unsigned char* mail_sum_slot(unsigned char* box, uint32_t seq, int src) {
+  return box + (seq & 1u) * MAIL_PARITY_BYTES + MAIL_MAX_WORLD * MAIL_MIN_BYTES + src * MAIL_SUM_BYTES;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// spin until *p == want; gives up after ~2 s (a peer that never launched) and reports it
+__device__ __forceinline__ bool wait_seq_sys(const uint32_t* p, uint32_t want) {
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (uint32_t it = 0;; ++it) {
+    if (ld_acquire_sys_u32(p) == want) return true;
+    if ((it & 0xFFFu) == 0xFFFu) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 2000000000ull) return false;
+    }
+  }
+}
 struct PassArgs {
   const malio_scan_pt* pts; const uint32_t* perm; uint32_t N;
   const double* table; const float4* nodes; const float* node_cov; const uint32_t* nn_idx;
@@ -1509,7 +1551,8 @@ struct PassArgs {
   double* rows12; uint8_t* lid8;
   int do_tau, do_fit;
   unsigned long long *mmkey, *mmkey_next; uint32_t *cnt_cell, *cnt_next, *gstats;
-  uint32_t* bar;           // [0] barrier 1 arrivals, [1] barrier 2 arrivals, [2] folded entries  (monotone)
+  uint32_t* bar;           // [0] barrier 1 arrivals, [1] barrier 2 arrivals, [2] folded entries  (monotone), [3] release flag of barrier 1 (multi-GPU)
+  PeerArgs peer;
   uint32_t bar_base[3];
   uint32_t n_tiles;
   double* block_red; double* d_res;
@@ -1600,7 +1643,54 @@ pass_kernel(PassArgs a, PassConst pc, ParamConst prm) {
     minmax_block_commit<RED_THREADS>(mm, a.mmkey, a.cnt_cell);
   }
   pass_stamp(a, 1);
-  grid_barrier(a.bar + 0, a.bar_base[0] + gridDim.x);
+  if (a.peer.world <= 1) {
+    grid_barrier(a.bar + 0, a.bar_base[0] + gridDim.x);
+  } else {
+    // barrier 1 fused with the cross-GPU MIN: every block arrives; warp 0 of block 0 waits for the local arrivals, pushes
+    // this GPU's four keys into every peer's mailbox, waits for the peers' keys, writes the global minima into the local
+    // key cell and only then releases the local blocks
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); atomicAdd(a.bar + 0, 1u); }
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+      const int lane = threadIdx.x, me = a.peer.rank, W = a.peer.world;
+      if (lane == 0) while ((int32_t)(ld_acquire_u32(a.bar + 0) - (a.bar_base[0] + gridDim.x)) < 0) { }
+      __syncwarp();
+      unsigned long long k[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) k[c] = __ldcg(a.mmkey + c);
+      bool ok = true;
+      if (lane < W && lane != me) {
+        unsigned char* dst = mail_min_slot(a.peer.mail[lane], a.seq, me);
+        volatile unsigned long long* dk = reinterpret_cast<volatile unsigned long long*>(dst);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dk[c] = k[c];
+        st_release_sys_u32(reinterpret_cast<uint32_t*>(dst + 40), a.seq);
+        const unsigned char* src = mail_min_slot(a.peer.mail[me], a.seq, lane);
+        ok = wait_seq_sys(reinterpret_cast<const uint32_t*>(src + 40), a.seq);
+        const volatile unsigned long long* sk = reinterpret_cast<const volatile unsigned long long*>(src);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) k[c] = sk[c];
+      } else if (lane >= W) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) k[c] = ~0ull;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, k[c], o); k[c] = v < k[c] ? v : k[c]; }
+      }
+      const bool all_ok = __all_sync(0xffffffffu, ok);
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a.mmkey[c] = k[c];
+        if (!all_ok) *reinterpret_cast<volatile uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 9) = 1u;   // peer timeout
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.bar + 3), "r"(a.seq) : "memory");
+      }
+    }
+    if (threadIdx.x == 0) while (ld_acquire_u32(a.bar + 3) != a.seq) { }
+    __syncthreads();
+  }
   pass_stamp(a, 2);
   if (blockIdx.x == 0 && threadIdx.x == 0) {   // arm the other parity's min/max cell for the next pass
     a.mmkey_next[0] = dkey(1000.0); a.mmkey_next[1] = dkey(-0.0);
@@ -1736,7 +1826,31 @@ pass_kernel(PassArgs a, PassConst pc, ParamConst prm) {
       // this warp folded the last entry: ship result + min/max keys to the mapped host buffer (posted PCIe writes, one
       // system-scope fence), then the sequence flag the host is spinning on
       __threadfence();
-      for (uint32_t e = lane; e < MALIO_RED_DOUBLES; e += 32) a.h_res[e] = __ldcg(a.d_res + e);
+      if (a.peer.world > 1) {
+        // cross-GPU SUM: this GPU's folded system goes into slot [me] of every mailbox (its own included), then the
+        // slots of all ranks are added in rank order — the same order on every GPU, so all ranks hold identical bits
+        const int me = a.peer.rank, W = a.peer.world;
+        for (int r = 0; r < W; ++r) {
+          volatile double* dst = reinterpret_cast<volatile double*>(mail_sum_slot(a.peer.mail[r], a.seq, me));
+          for (uint32_t e = lane; e < MALIO_RED_DOUBLES; e += 32) dst[e] = __ldcg(a.d_res + e);
+        }
+        __threadfence_system();
+        __syncwarp();
+        bool ok = true;
+        if ((int)lane < W && (int)lane != me) {
+          st_release_sys_u32(reinterpret_cast<uint32_t*>(mail_sum_slot(a.peer.mail[lane], a.seq, me) + MAIL_SUM_SEQ_OFF), a.seq);
+          ok = wait_seq_sys(reinterpret_cast<const uint32_t*>(mail_sum_slot(a.peer.mail[me], a.seq, (int)lane) + MAIL_SUM_SEQ_OFF), a.seq);
+        }
+        if (!__all_sync(0xffffffffu, ok) && lane == 0) *reinterpret_cast<volatile uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 9) = 1u;
+        for (uint32_t e = lane; e < MALIO_RED_DOUBLES; e += 32) {
+          double sum = 0.0;
+          for (int r = 0; r < W; ++r) sum += reinterpret_cast<const volatile double*>(mail_sum_slot(a.peer.mail[me], a.seq, r))[e];
+          a.d_res[e] = sum;
+          a.h_res[e] = sum;
+        }
+      } else {
+        for (uint32_t e = lane; e < MALIO_RED_DOUBLES; e += 32) a.h_res[e] = __ldcg(a.d_res + e);
+      }
       if (lane < 4) reinterpret_cast<unsigned long long*>(a.h_res + MALIO_RED_DOUBLES)[lane] = a.mmkey[lane];
       __threadfence_system();
       __syncwarp();
@@ -1838,6 +1952,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool load(std::string& err) {
@@ -1848,6 +1963,7 @@ struct NcclApi {
     GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
     CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
     AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
     CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
     GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
     if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "NCCL symbols missing"; return false; }
@@ -1916,6 +2032,7 @@ struct DeviceState {
   unsigned long long* d_dbg = nullptr; int trace_left = 0;
   // multi-GPU
   ncclComm_t comm = nullptr; int rank = 0, world = 1;
+  bool p2p = false; unsigned char* d_mail = nullptr; unsigned char* mail_peer[MAIL_MAX_WORLD] = {nullptr};
 };
 
 template <class T>
@@ -2447,12 +2564,13 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
   uint32_t* cnt_next = D->d_counters + 4 + (1 - D->parity);
   const uint32_t n_tiles = (N + RED_THREADS - 1) / RED_THREADS;
   // one resident wave, every block the same number of tiles (+-1): no straggler blocks
-  const uint32_t wave = (D->fused && !D->comm && (uint32_t)D->pass_max_blocks < D->red_grid) ? (uint32_t)D->pass_max_blocks : D->red_grid;
+  const uint32_t wave = (D->fused && (!D->comm || D->p2p) && (uint32_t)D->pass_max_blocks < D->red_grid) ? (uint32_t)D->pass_max_blocks : D->red_grid;
   const uint32_t per_block = n_tiles ? (n_tiles + wave - 1) / wave : 1;
   const uint32_t grid = n_tiles ? (n_tiles + per_block - 1) / per_block : 1;
   std::chrono::steady_clock::time_point hp1, hp2;
-  if (D->fused && !D->comm) {
-    // ---- single GPU: the whole pass in one cooperative launch; the result arrives in mapped host memory
+  if (D->fused && (!D->comm || D->p2p)) {
+    // ---- the whole pass in one cooperative launch; the result arrives in mapped host memory.  With several GPUs the two
+    // exchanges of the pass happen inside the kernel through the peers' mailboxes (CUDA IPC over NVLink)
     PassArgs a{};
     a.pts = pts_k; a.perm = perm_k; a.N = N; a.table = D->d_table; a.nodes = D->d_mpts; a.node_cov = D->d_cov;
     a.nn_idx = D->d_nn_idx; a.sel = D->d_sel; a.world = D->d_world; a.plane = D->d_plane; a.ucov = D->d_ucov;
@@ -2465,6 +2583,9 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
     D->bar_base[0] += grid; D->bar_base[1] += grid; D->bar_base[2] += MALIO_RED_DOUBLES;
     a.n_tiles = n_tiles; a.block_red = D->d_block_red; a.d_res = D->d_res; a.h_res = D->h_res_dev;
     a.seq = ++D->seq;
+    a.peer.rank = D->rank; a.peer.world = D->p2p ? D->world : 1;
+    for (int r = 0; r < MAIL_MAX_WORLD; ++r) a.peer.mail[r] = D->mail_peer[r];
+    *reinterpret_cast<volatile uint32_t*>(D->h_res + MALIO_RED_DOUBLES + 9) = 0u;
     a.dbg = nullptr;
     if (getenv("MALIO_PASS_TRACE")) {
       if (!D->d_dbg) { CUDA_TRY(cudaMalloc((void**)&D->d_dbg, (size_t)4096 * 8 * sizeof(unsigned long long))); D->trace_left = atoi(getenv("MALIO_PASS_TRACE")); }
@@ -2499,6 +2620,10 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
       }
     }
     std::atomic_thread_fence(std::memory_order_acquire);
+    if (*reinterpret_cast<volatile uint32_t*>(D->h_res + MALIO_RED_DOUBLES + 9) != 0u) {
+      h->err = "pass_kernel: a peer GPU did not answer the in-kernel exchange within 2 s";
+      return MALIO_ERR_NCCL;
+    }
     if (a.dbg) {
       CUDA_TRY(cudaStreamSynchronize(st_));
       std::vector<unsigned long long> t((size_t)grid * 8);
@@ -2741,6 +2866,43 @@ int comm_init(malio_handle* h, const uint8_t* id, int rank, int world) {
     return MALIO_ERR_NCCL;
   }
   D->rank = rank; D->world = world;
+  // ---- peer mailboxes for the in-kernel exchanges (CUDA IPC; NCCL only carries the 64-byte handles).  Falls back to the
+  // NCCL all-reduce path between separate kernels unless EVERY rank succeeded.
+  D->p2p = false;
+  const char* env = getenv("MALIO_P2P");
+  int ok = (world > 1 && world <= MAIL_MAX_WORLD && D->fused && g_nccl.AllGather && !(env && atoi(env) == 0)) ? 1 : 0;
+  cudaIpcMemHandle_t mine{};
+  unsigned char* d_h = nullptr;
+  std::vector<cudaIpcMemHandle_t> all((size_t)world);
+  if (ok) {
+    if (cudaMalloc((void**)&D->d_mail, MAIL_BYTES) != cudaSuccess || cudaMemset(D->d_mail, 0, MAIL_BYTES) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine, D->d_mail) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  }
+  // every rank takes part in the two collectives below whatever its own outcome
+  if (world > 1 && g_nccl.AllGather) {
+    CUDA_TRY(cudaMalloc((void**)&d_h, (size_t)(world + 1) * sizeof(mine) + 2 * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(d_h + (size_t)world * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    if (g_nccl.AllGather(d_h + (size_t)world * sizeof(mine), d_h, sizeof(mine), ncclChar, D->comm, D->stream) != ncclSuccess) ok = 0;
+    CUDA_TRY(cudaStreamSynchronize(D->stream));
+    CUDA_TRY(cudaMemcpy(all.data(), d_h, (size_t)world * sizeof(mine), cudaMemcpyDeviceToHost));
+    if (ok) {
+      for (int r = 0; r < world && ok; ++r) {
+        if (r == rank) { D->mail_peer[r] = D->d_mail; continue; }
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+        D->mail_peer[r] = (unsigned char*)ptr;
+      }
+    }
+    int* d_ok = reinterpret_cast<int*>(d_h + (size_t)(world + 1) * sizeof(mine));
+    CUDA_TRY(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    if (g_nccl.AllReduce(d_ok, d_ok + 1, 1, ncclInt, ncclMin, D->comm, D->stream) != ncclSuccess) ok = 0;
+    CUDA_TRY(cudaStreamSynchronize(D->stream));
+    int all_ok = 0;
+    CUDA_TRY(cudaMemcpy(&all_ok, d_ok + 1, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(d_h);
+    D->p2p = ok && all_ok;
+  }
+  if (getenv("MALIO_HOST_PROF")) fprintf(stderr, "[malio] rank %d/%d: in-kernel peer exchange %s\n", rank, world, D->p2p ? "ON" : "off (NCCL path)");
   return MALIO_OK;
 }
 
