@@ -127,5 +127,50 @@ FlattenResult flatten_ikdtree(const Node* root, malio_map_node* out, uint32_t ca
   return res;
 }
 
+// Compact form for malio_upload_map_compact(): the same DFS, 16 bytes per node (point + link); the children's boxes
+// are not read (the device rebuilds them as the tight boxes of the live points, which is what Update() maintains).
+// root_box_out (6 floats, optional) receives the root's node_range_* = the bounding box of the map.
+template <class Node, class PointFn>
+FlattenResult flatten_ikdtree_compact(const Node* root, malio_map_point* out, uint32_t capacity, PointFn&& on_node,
+                                      float* root_box_out = nullptr) {
+  using detail::EffFlags;
+  FlattenResult res;
+  if (root == nullptr) return res;
+  struct Frame { const Node* node; EffFlags f; uint32_t depth; int64_t parent_slot; };
+  std::vector<Frame> stack;
+  stack.reserve(128);
+  EffFlags rf = detail::stored_flags(root);
+  if (rf.tree_deleted) return res;
+  if (root_box_out) detail::copy_box(root, root_box_out);
+  stack.push_back(Frame{root, rf, 1u, -1});
+  while (!stack.empty()) {
+    Frame fr = stack.back();
+    stack.pop_back();
+    const uint32_t slot = res.n_nodes;
+    if (slot >= capacity || slot > MALIO_LINK_INDEX_MASK) { res.overflow = true; return res; }
+    res.n_nodes++;
+    if (fr.depth > res.max_depth) res.max_depth = fr.depth;
+    if (fr.parent_slot >= 0) out[fr.parent_slot].link |= (slot & MALIO_LINK_INDEX_MASK);
+    const Node* n = fr.node;
+    malio_map_point& o = out[slot];
+    o.x = n->point.x; o.y = n->point.y; o.z = n->point.z;
+    uint32_t link = 0;
+    if (fr.f.point_deleted) link |= MALIO_LINK_POINT_DELETED; else res.n_points++;
+    const Node* l = n->left_son_ptr;
+    const Node* r = n->right_son_ptr;
+    EffFlags lf{}, rfl{};
+    bool has_l = false, has_r = false;
+    if (l != nullptr) { lf = detail::pushed_flags(fr.f, fr.f.need_l, l); has_l = !lf.tree_deleted; }
+    if (r != nullptr) { rfl = detail::pushed_flags(fr.f, fr.f.need_r, r); has_r = !rfl.tree_deleted; }
+    if (has_l) link |= MALIO_LINK_HAS_LEFT;
+    if (has_r) link |= MALIO_LINK_HAS_RIGHT;
+    o.link = link;
+    on_node(n, slot);
+    if (has_r) stack.push_back(Frame{r, rfl, fr.depth + 1, (int64_t)slot});
+    if (has_l) stack.push_back(Frame{l, lf, fr.depth + 1, -1});
+  }
+  return res;
+}
+
 }  // namespace malio
 #endif  // MALIO_FLATTEN_HPP_

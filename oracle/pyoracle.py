@@ -90,6 +90,8 @@ def ref_lib() -> C.CDLL:
         L.ikdref_flatten_points.argtypes = [vp, vp, vp, vp, C.c_int64]
         L.ikdref_snapshot.restype = C.c_int64
         L.ikdref_snapshot.argtypes = [vp, vp, vp, vp, C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.ikdref_snapshot_compact.restype = C.c_int64
+        L.ikdref_snapshot_compact.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(C.c_uint32), vp]
         _ref = L
     return _ref
 
@@ -163,6 +165,17 @@ class RefTree:
         n = self.L.ikdref_snapshot(self.t, ptr(nodes), ptr(cov), ptr(ids), cap, C.byref(depth), C.byref(live))
         assert n >= 0
         return nodes[:n].copy(), cov[:n].copy(), ids[:n].copy(), int(depth.value), int(live.value)
+
+    def snapshot_compact(self):
+        """Flatten through malio::flatten_ikdtree_compact.  Returns (points, node_cov, max_depth, root_box)."""
+        cap = max(self.size(), 1)
+        pts = np.zeros(cap, dtype=capi.MAP_POINT)
+        cov = np.zeros(cap, np.float32)
+        depth = C.c_uint32(0)
+        box = np.zeros(6, np.float32)
+        n = self.L.ikdref_snapshot_compact(self.t, ptr(pts), ptr(cov), cap, C.byref(depth), ptr(box))
+        assert n >= 0
+        return pts[:n].copy(), cov[:n].copy(), int(depth.value), box
 
     def flatten_points(self):
         cap = max(self.size(), 1)

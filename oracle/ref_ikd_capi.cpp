@@ -132,6 +132,16 @@ int64_t ikdref_snapshot(void* t, malio_map_node* nodes, float* node_cov, int32_t
   return res.overflow ? -1 : (int64_t)res.n_nodes;
 }
 
+// the compact flattener (16 B per node + the root's node_range_*) on the real node type
+int64_t ikdref_snapshot_compact(void* t, malio_map_point* pts, float* node_cov, int64_t cap, uint32_t* max_depth, float* root_box) {
+  Tree* tr = (Tree*)t;
+  auto res = malio::flatten_ikdtree_compact(
+      tr->Root_Node, pts, (uint32_t)cap, [&](const Tree::KD_TREE_NODE* n, uint32_t slot) { if (node_cov) node_cov[slot] = n->point.normal_y; },
+      root_box);
+  if (max_depth) *max_depth = res.max_depth;
+  return res.overflow ? -1 : (int64_t)res.n_nodes;
+}
+
 int ikdref_node_bytes() { return (int)sizeof(Tree::KD_TREE_NODE); }
 
 }  // extern "C"

@@ -217,3 +217,40 @@ def test_two_gpu_sharded_update_matches_single_gpu():
                           os.path.join(ROOT, "tests", "mgpu_worker.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MGPU_OK" in out.stdout
+
+
+def test_unfused_kernel_path_matches_fused_pass(monkeypatch):
+    """The separate gate / reduce / fold kernels (the path the NCCL fallback uses) and the fused cooperative pass must
+    agree: identical gates and neighbour lists, reduced system to FP64 rounding, same iterated update."""
+    case = synth.make_case("3L-20k-200k", 20000, 200000, 3, 3, varied_map_cov=True)
+    snap = plugin.build_static_snapshot(case.map_xyz, case.map_normal_y)
+    fused = H.make_model(case, snap)
+    monkeypatch.setenv("MALIO_FUSED_PASS", "0")
+    plain = H.make_model(case, snap)
+    monkeypatch.delenv("MALIO_FUSED_PASS")
+    for conv in (True, False):
+        okf, Hf, hf, sf = fused.h_share_model(case.x_prop, conv)
+        okp, Hp, hp, sp = plain.h_share_model(case.x_prop, conv)
+        assert okf and okp and sf.n_eff == sp.n_eff
+        assert H.rel_err(Hf, Hp) < 1e-11 and H.rel_err(hf, hp) < 1e-11
+        af, ap = fused.aux(), plain.aux()
+        for k in ("nn_idx", "selected", "world", "normal_y"):
+            assert np.array_equal(af[k], ap[k]), k
+    xf, Pf = case.x_prop.copy(), case.P_prop.copy()
+    xp, Pp = case.x_prop.copy(), case.P_prop.copy()
+    fused.rearm_scan(); plain.rearm_scan()
+    rf = fused.update_iterated_dyn_share_modified(xf, Pf, 3)
+    rp = plain.update_iterated_dyn_share_modified(xp, Pp, 3)
+    assert rf.passes == rp.passes and rf.searches == rp.searches
+    assert np.abs(synth.state_to_vec(xf, 3) - synth.state_to_vec(xp, 3)).max() < 1e-9
+    # large scan: more than two tiles per block -> the generic (global-memory rows, LiDAR-major order) variant of the pass
+    big = synth.make_case("3L-180k", 180000, 200000, 3, 3, varied_map_cov=True, map_xyz=case.map_xyz)
+    mb = H.make_model(big, snap)
+    monkeypatch.setenv("MALIO_FUSED_PASS", "0")
+    pb = H.make_model(big, snap)
+    monkeypatch.delenv("MALIO_FUSED_PASS")
+    okf, Hf, hf, sf = mb.h_share_model(big.x_prop, True)
+    okp, Hp, hp, sp = pb.h_share_model(big.x_prop, True)
+    assert okf and okp and sf.n_eff == sp.n_eff and H.rel_err(Hf, Hp) < 1e-11 and H.rel_err(hf, hp) < 1e-11
+    for m in (fused, plain, mb, pb):
+        m.close()

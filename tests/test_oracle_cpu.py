@@ -71,6 +71,36 @@ def test_restated_search_vs_real_tree_after_churn():
     assert np.array_equal(snap.node_cov[ids], r_pts[:, :, 3])
 
 
+@pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref (real ikd_Tree.cpp) only exists in the build container")
+def test_compact_flattener_and_tight_box_rule_on_the_real_tree():
+    """malio::flatten_ikdtree_compact emits exactly the first 16 bytes of every full record, and the boxes the full
+    flattener copies out of the churned reference tree (node_range_*) ARE the tight boxes of the live points below —
+    the rule the device uses to rebuild them after a compact upload (ikd_Tree.cpp:1469-1635)."""
+    case = synth.make_case("t", 2000, 30000, 1, 3, varied_map_cov=True)
+    snap, tree = H.snapshot_for(case, churn=True)
+    pts, cov, depth, root_box = tree.snapshot_compact()
+    nodes = snap.nodes
+    assert pts.shape[0] == nodes.shape[0] and depth == snap.max_depth
+    assert np.array_equal(pts["xyz"], nodes["xyz"]) and np.array_equal(pts["link"], nodes["link"])
+    assert np.array_equal(cov, snap.node_cov)
+    n = nodes.shape[0]
+    link = nodes["link"]
+    lo = np.full((n, 3), np.inf, np.float32)
+    hi = np.full((n, 3), -np.inf, np.float32)
+    for i in range(n - 1, -1, -1):            # children have larger indices than their parent (DFS pre-order)
+        if not (link[i] & capi.LINK_POINT_DELETED):
+            lo[i] = np.minimum(lo[i], nodes["xyz"][i]); hi[i] = np.maximum(hi[i], nodes["xyz"][i])
+        if link[i] & capi.LINK_HAS_LEFT:
+            c = i + 1
+            assert np.array_equal(nodes["lbox"][i], np.stack([lo[c], hi[c]], 1).reshape(6)), i
+            lo[i] = np.minimum(lo[i], lo[c]); hi[i] = np.maximum(hi[i], hi[c])
+        if link[i] & capi.LINK_HAS_RIGHT:
+            c = int(link[i] & capi.LINK_INDEX_MASK)
+            assert np.array_equal(nodes["rbox"][i], np.stack([lo[c], hi[c]], 1).reshape(6)), i
+            lo[i] = np.minimum(lo[i], lo[c]); hi[i] = np.maximum(hi[i], hi[c])
+    assert np.array_equal(root_box, np.stack([lo[0], hi[0]], 1).reshape(6))
+
+
 def test_search_is_exact_knn_bruteforce():
     rng = np.random.default_rng(3)
     xyz = (rng.random((5000, 3)) * [40, 40, 4]).astype(np.float32)
