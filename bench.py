@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
         except Exception:
             self.proc = None
             return
@@ -286,7 +286,6 @@ def run_ours(args, rank, world):
         sampler.start()
     model.set_timing(False)       # no per-pass event records inside the measured loops
     tot_ms, reps, c0, c1, out, (tw0, tw1) = timed(step_resident, args.steps, args.warmup)
-    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     passes = sum(r.passes for r in reps)
     searches = sum(r.searches for r in reps)
     launches = int(c1.kernel_launches - c0.kernel_launches)
@@ -299,7 +298,10 @@ def run_ours(args, rank, world):
     # separate short loop with per-kernel CUDA events on (same steps, L2 flushed): k-NN kernel time for the roofline
     model.set_timing(True)
     r_steps = max(3, min(args.steps, 10))
-    _, r_reps, rc0, rc1, _, _ = timed(step_resident, r_steps, 1)
+    _, r_reps, rc0, rc1, _, (_, tw_end) = timed(step_resident, r_steps, 1)
+    # clocks / throttle reasons sampled (nvidia-smi, 20 ms) from the start of the resident loop to the end of the last
+    # timed loop: all three loops keep the GPU under the same load
+    clocks = sampler.stop(tw0, tw_end) if rank == 0 else None
     knn_launches = int(rc1.knn_launches - rc0.knn_launches)
     knn_ms = float(rc1.knn_ms - rc0.knn_ms)
     dev_ms = float(np.sum([r.ms_device_total for r in r_reps])) * args.steps / r_steps

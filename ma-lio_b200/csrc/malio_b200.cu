@@ -649,6 +649,89 @@ struct Top6 {
   }
 };
 
+// Ring 2 (5x5x5 cells), one WARP per query.  These are the few queries (sparse neighbourhoods) whose 5th neighbour was
+// not proven inside the 3x3x3 block; a single thread would need ~125 candidates x a dependent insertion chain (tens of
+// microseconds of pure latency), so the candidates of one query are spread over the 32 lanes (the 25 runs flattened:
+// lane j of every group of 32 candidates finds its run by a 5-step search over the prefix of the run lengths), every
+// lane keeps its own 6 best, and the warp extracts the 6 overall smallest by six rounds of arg-min over the lane
+// heads.  Equal heads in two lanes are a tie -> exact traversal.  Called by all 32 lanes with the same query.
+template <int MODE>
+__device__ __forceinline__ void ring2_query_warp(const float4* __restrict__ cell_pts, const uint32_t* __restrict__ cell_start,
+                                                 const GridConst& G, float qx, float qy, float qz, uint32_t p, uint32_t N,
+                                                 float max_sqdist, uint32_t* __restrict__ nn_idx, float* __restrict__ nn_d2,
+                                                 uint8_t* __restrict__ sel, uint32_t* __restrict__ fb_list,
+                                                 uint32_t* __restrict__ fb_count) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const float ux = (qx - G.ox) * G.inv_h, uy = (qy - G.oy) * G.inv_h, uz = (qz - G.oz) * G.inv_h;
+  const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
+  const int cx = (int)flx, cy = (int)fly, cz = (int)flz;       // in [-1, n]: ring 1 only lists in-grid queries
+  const float fx = ux - flx, fy = uy - fly, fz = uz - flz;
+  const float fmin = fminf(fminf(fminf(fx, 1.f - fx), fminf(fy, 1.f - fy)), fminf(fz, 1.f - fz));
+  uint32_t rs = 0, re = 0;
+  if (lane < 25) {
+    const uint32_t row = grid_cell_index(G, cx, cy + (int)(lane % 5) - 2, cz + (int)(lane / 5) - 2);
+    rs = __ldg(cell_start + row - 2);
+    re = __ldg(cell_start + row + 3);
+  }
+  Top6 t;
+  t.reset();
+  // flatten the 25 runs: lane j of every group of 32 candidates finds its run by a 5-step search over the exclusive
+  // prefix of the run lengths (held one per lane), so the whole block costs ceil(total / 32) memory round trips
+  const uint32_t len = re - rs;
+  uint32_t inc = len;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += v; }
+  const uint32_t excl = inc - len, total = __shfl_sync(0xffffffffu, inc, 31);
+  for (uint32_t base = 0; base < total; base += 32) {
+    const uint32_t j = base + lane;
+    uint32_t r = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const uint32_t cand = r + step;
+      const uint32_t ex = __shfl_sync(0xffffffffu, excl, cand & 31u);
+      if (cand < 32u && ex <= j) r = cand;
+    }
+    const uint32_t ex_r = __shfl_sync(0xffffffffu, excl, r), rs_r = __shfl_sync(0xffffffffu, rs, r);
+    if (j < total) {
+      const float4 c = __ldg(cell_pts + rs_r + (j - ex_r));
+      const float dist = (qx - c.x) * (qx - c.x) + (qy - c.y) * (qy - c.y) + (qz - c.z) * (qz - c.z);   // calc_dist
+      if (dist < t.d5) t.insert(dist, __float_as_uint(c.w));
+    }
+  }
+  // six rounds: smallest lane head overall, popped from the lane that holds it
+  float od[6];
+  uint32_t oi[6];
+  bool hazard = false;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    float m = t.d0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const uint32_t who = __ballot_sync(0xffffffffu, t.d0 == m && m < INFINITY);
+    if (__popc(who) > 1) hazard = true;
+    const int src = who ? __ffs(who) - 1 : 0;
+    od[k] = m;
+    oi[k] = __shfl_sync(0xffffffffu, t.i0, src);
+    if (who && (int)lane == src) {
+      t.d0 = t.d1; t.d1 = t.d2; t.d2 = t.d3; t.d3 = t.d4; t.d4 = t.d5; t.d5 = INFINITY;
+      t.i0 = t.i1; t.i1 = t.i2; t.i2 = t.i3; t.i3 = t.i4; t.i4 = 0xFFFFFFFFu;
+    }
+  }
+  hazard |= (fabsf(od[1] - od[0]) < 1e-10f) | (fabsf(od[2] - od[1]) < 1e-10f) | (fabsf(od[3] - od[2]) < 1e-10f) |
+            (fabsf(od[4] - od[3]) < 1e-10f) | (fabsf(od[5] - od[4]) < 1e-10f);
+  const float rg = (2.f + fmin - GRID_MARGIN) * G.h;
+  const bool settled = (od[4] < rg * rg) & !hazard;
+  if (lane == 0) {
+    if (settled) {
+#pragma unroll
+      for (int k = 0; k < MALIO_K; ++k) { nn_idx[(size_t)k * N + p] = oi[k]; nn_d2[(size_t)k * N + p] = od[k]; }
+      if (MODE == 0) sel[p] = (od[4] > max_sqdist) ? 0 : 1;   // laserMapping.cpp:587 (five were found)
+    } else {
+      fb_list[atomicAdd(fb_count, 1u)] = p;
+    }
+  }
+}
+
 // Staged scan.  The candidates of one query are 9 (25) short contiguous runs of the cell-sorted point array.  Read
 // run by run with ordinary loads, every run costs a dependent memory round trip (profile: ~90 % of stall samples on the
 // first use of a loaded candidate).  Instead each thread fires cp.async (LDGSTS, 16 B) copies for ALL its candidates into
@@ -680,10 +763,11 @@ knn_grid_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict_
   extern __shared__ float4 s_dyn[];
   float4* s_cand = s_dyn;                                              // [GK_CAP][GK_THREADS]
   uint2* s_rng = reinterpret_cast<uint2*>(s_dyn + GK_CAP * GK_THREADS);   // [ROWS][GK_THREADS]
-  const uint32_t n_items = RING == 1 ? N : *in_count;
-  for (uint32_t item = blockIdx.x * GK_THREADS + threadIdx.x; item < n_items; item += gridDim.x * GK_THREADS) {
-    const uint32_t p = RING == 1 ? item : in_list[item];
-    float qx, qy, qz;
+  // one query per thread (the grid covers N); warps stay whole because the 5x5x5 retry below is warp-cooperative
+  const uint32_t p = blockIdx.x * GK_THREADS + threadIdx.x;
+  bool want_r2 = false;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (p < N) {
     load_query<MODE>(pts, perm, queries, p, pc, qx, qy, qz);
     if (MODE == 0 && RING == 1) world[p] = make_float4(qx, qy, qz, 0.f);
     const float ux = (qx - G.ox) * G.inv_h, uy = (qy - G.oy) * G.inv_h, uz = (qz - G.oz) * G.inv_h;
@@ -741,107 +825,26 @@ knn_grid_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict_
       nn_idx[(size_t)3 * N + p] = t.i3;  nn_d2[(size_t)3 * N + p] = t.d3;
       nn_idx[(size_t)4 * N + p] = t.i4;  nn_d2[(size_t)4 * N + p] = t.d4;
       if (MODE == 0) sel[p] = (t.d4 > max_sqdist) ? 0 : 1;   // laserMapping.cpp:587 (five were found)
-    } else if (RING == 1 && in_grid && !hazard) {
-      r2_list[atomicAdd(r2_count, 1u)] = p;
+    } else if (in_grid && !hazard) {
+      want_r2 = true;                    // 5th neighbour not proven inside the 3x3x3 block
     } else {
       fb_list[atomicAdd(fb_count, 1u)] = p;
     }
+  }
+  // ---- 5x5x5 retry, one query at a time with the whole warp (rare: ~0.1 % of the queries on dense maps)
+  unsigned r2mask = __ballot_sync(0xffffffffu, want_r2);
+  if (r2mask && (threadIdx.x & 31u) == 0) atomicAdd(r2_count, (uint32_t)__popc(r2mask));   // statistics
+  while (r2mask) {
+    const int src = __ffs(r2mask) - 1;
+    r2mask &= r2mask - 1;
+    const float bx = __shfl_sync(0xffffffffu, qx, src), by = __shfl_sync(0xffffffffu, qy, src), bz = __shfl_sync(0xffffffffu, qz, src);
+    const uint32_t bp = __shfl_sync(0xffffffffu, p, src);
+    ring2_query_warp<MODE>(cell_pts, cell_start, G, bx, by, bz, bp, N, max_sqdist, nn_idx, nn_d2, sel, fb_list, fb_count);
   }
   if (cand_total) {
     const uint32_t act = __activemask();
     const uint32_t tot = __reduce_add_sync(act, n_cand);
     if ((threadIdx.x & 31u) == (uint32_t)(__ffs(act) - 1)) atomicAdd(cand_total, (unsigned long long)tot);
-  }
-}
-
-// Ring 2 (5x5x5 cells), one WARP per listed query.  These are the few queries (sparse neighbourhoods) whose 5th
-// neighbour was not proven inside the 3x3x3 block; a single thread would need ~125 candidates x a dependent
-// insertion chain (tens of microseconds of pure latency at the tail of the search), so the candidates of one query
-// are spread over the 32 lanes (coalesced row reads), every lane keeps its own 6 best, and the warp extracts the 6
-// overall smallest by six rounds of arg-min over the lane heads.  Equal heads in two lanes are a tie -> traversal.
-template <int MODE>
-__global__ void __launch_bounds__(128)
-knn_ring2_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict__ cell_start, GridConst G,
-                 const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm,
-                 const float* __restrict__ queries, uint32_t N, PassConst pc, float max_sqdist,
-                 uint32_t* __restrict__ nn_idx, float* __restrict__ nn_d2, uint8_t* __restrict__ sel,
-                 const uint32_t* __restrict__ in_list, const uint32_t* __restrict__ in_count,
-                 uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_count) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t n_items = *in_count;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n_items; item += nwarps) {
-    const uint32_t p = in_list[item];
-    float qx, qy, qz;
-    load_query<MODE>(pts, perm, queries, p, pc, qx, qy, qz);
-    const float ux = (qx - G.ox) * G.inv_h, uy = (qy - G.oy) * G.inv_h, uz = (qz - G.oz) * G.inv_h;
-    const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
-    const int cx = (int)flx, cy = (int)fly, cz = (int)flz;       // in [-1, n]: ring 1 only lists in-grid queries
-    const float fx = ux - flx, fy = uy - fly, fz = uz - flz;
-    const float fmin = fminf(fminf(fminf(fx, 1.f - fx), fminf(fy, 1.f - fy)), fminf(fz, 1.f - fz));
-    uint32_t rs = 0, re = 0;
-    if (lane < 25) {
-      const uint32_t row = grid_cell_index(G, cx, cy + (int)(lane % 5) - 2, cz + (int)(lane / 5) - 2);
-      rs = __ldg(cell_start + row - 2);
-      re = __ldg(cell_start + row + 3);
-    }
-    Top6 t;
-    t.reset();
-    // flatten the 25 runs: lane j of every group of 32 candidates finds its run by a 5-step search over the exclusive
-    // prefix of the run lengths (held one per lane), so the whole block costs ceil(total / 32) memory round trips
-    const uint32_t len = re - rs;
-    uint32_t inc = len;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += v; }
-    const uint32_t excl = inc - len, total = __shfl_sync(0xffffffffu, inc, 31);
-    for (uint32_t base = 0; base < total; base += 32) {
-      const uint32_t j = base + lane;
-      uint32_t r = 0;
-#pragma unroll
-      for (int step = 16; step > 0; step >>= 1) {
-        const uint32_t cand = r + step;
-        const uint32_t ex = __shfl_sync(0xffffffffu, excl, cand & 31u);
-        if (cand < 32u && ex <= j) r = cand;
-      }
-      const uint32_t ex_r = __shfl_sync(0xffffffffu, excl, r), rs_r = __shfl_sync(0xffffffffu, rs, r);
-      if (j < total) {
-        const float4 c = __ldg(cell_pts + rs_r + (j - ex_r));
-        const float dist = (qx - c.x) * (qx - c.x) + (qy - c.y) * (qy - c.y) + (qz - c.z) * (qz - c.z);   // calc_dist
-        if (dist < t.d5) t.insert(dist, __float_as_uint(c.w));
-      }
-    }
-    // six rounds: smallest lane head overall, popped from the lane that holds it
-    float od[6];
-    uint32_t oi[6];
-    bool hazard = false;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      float m = t.d0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      const uint32_t who = __ballot_sync(0xffffffffu, t.d0 == m && m < INFINITY);
-      if (__popc(who) > 1) hazard = true;
-      const int src = who ? __ffs(who) - 1 : 0;
-      od[k] = m;
-      oi[k] = __shfl_sync(0xffffffffu, t.i0, src);
-      if (who && (int)lane == src) {
-        t.d0 = t.d1; t.d1 = t.d2; t.d2 = t.d3; t.d3 = t.d4; t.d4 = t.d5; t.d5 = INFINITY;
-        t.i0 = t.i1; t.i1 = t.i2; t.i2 = t.i3; t.i3 = t.i4; t.i4 = 0xFFFFFFFFu;
-      }
-    }
-    hazard |= (fabsf(od[1] - od[0]) < 1e-10f) | (fabsf(od[2] - od[1]) < 1e-10f) | (fabsf(od[3] - od[2]) < 1e-10f) |
-              (fabsf(od[4] - od[3]) < 1e-10f) | (fabsf(od[5] - od[4]) < 1e-10f);
-    const float rg = (2.f + fmin - GRID_MARGIN) * G.h;
-    const bool settled = (od[4] < rg * rg) & !hazard;
-    if (lane == 0) {
-      if (settled) {
-#pragma unroll
-        for (int k = 0; k < MALIO_K; ++k) { nn_idx[(size_t)k * N + p] = oi[k]; nn_d2[(size_t)k * N + p] = od[k]; }
-        if (MODE == 0) sel[p] = (od[4] > max_sqdist) ? 0 : 1;   // laserMapping.cpp:587 (five were found)
-      } else {
-        fb_list[atomicAdd(fb_count, 1u)] = p;
-      }
-    }
   }
 }
 
@@ -1978,6 +1981,7 @@ struct DeviceState {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;            // box rebuild of the compact upload runs beside the scan's first kernels
   cudaEvent_t ev_h2d = nullptr, ev_refit = nullptr; bool refit_pending = false;
+  cudaEvent_t ev_sorted = nullptr, ev_tau = nullptr;   // point-covariance traces run beside the first search of a scan
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [5] after sort, [6] after knn kernel
   malio_counters ctr{};
   bool timing = true;   // per-pass CUDA-event timing (malio_set_timing)
@@ -2026,7 +2030,7 @@ struct DeviceState {
   uint32_t* d_gstats = nullptr;           // [0] occupied cells, [1] live points, [2] fb count, [3] fb count of the last search, [4] ring-2 queries
   uint32_t* h_gstats = nullptr;            // pinned mirror (8 words, carved out of h_res)
   // fused pass (single cooperative launch per measurement pass)
-  bool fused = true; int pass_max_blocks = 0;
+  bool fused = true; int pass_max_blocks = 0; bool coop_launch = true;
   uint32_t* d_bar = nullptr; uint32_t bar_base[3] = {0, 0, 0}; uint32_t seq = 0;
   double* h_res_dev = nullptr;     // device-side address of the mapped host result buffer
   unsigned long long* d_dbg = nullptr; int trace_left = 0;
@@ -2187,12 +2191,6 @@ int run_knn(malio_handle* h, DeviceState* D, uint32_t n, const malio_scan_pt* pt
     knn_grid_kernel<MODE, 1><<<(n + GK_THREADS - 1) / GK_THREADS, GK_THREADS, smem1, st>>>(
         D->d_cell_pts, D->d_cell_start, D->grid, pts, perm, qs, n, pc, max_sqdist, world, D->d_nn_idx, D->d_nn_d2, sel,
         nullptr, nullptr, D->d_r2_list, D->d_gstats + 4, D->d_fb_list, D->d_gstats + 2, D->timing ? D->d_cand : nullptr);
-    uint32_t r2_blocks = (n + 3) / 4;                       // one warp per listed query, at most ~2 resident waves
-    if (r2_blocks > (uint32_t)D->sm_count * 16) r2_blocks = (uint32_t)D->sm_count * 16;
-    knn_ring2_kernel<MODE><<<r2_blocks, 128, 0, st>>>(
-        D->d_cell_pts, D->d_cell_start, D->grid, pts, perm, qs, n, pc, max_sqdist, D->d_nn_idx, D->d_nn_d2, sel,
-        D->d_r2_list, D->d_gstats + 4, D->d_fb_list, D->d_gstats + 2);
-    D->ctr.kernel_launches += 1;
     // 8 queries per warp and iteration; at most one resident wave of 64-thread blocks
     uint32_t fb_blocks = (n + 15) / 16;
     const uint32_t wave = (uint32_t)D->sm_count * 8;
@@ -2240,6 +2238,8 @@ int create(malio_handle* h) {
   CUDA_TRY(cudaStreamCreateWithFlags(&D->stream2, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&D->ev_h2d, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&D->ev_refit, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&D->ev_sorted, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&D->ev_tau, cudaEventDisableTiming));
   for (auto& e : D->ev) CUDA_TRY(cudaEventCreate(&e));
   CUDA_TRY(cudaMalloc((void**)&D->d_counters, 8 * sizeof(uint32_t)));
   CUDA_TRY(cudaMemset(D->d_counters, 0, 8 * sizeof(uint32_t)));
@@ -2279,6 +2279,7 @@ int create(malio_handle* h) {
     D->pass_max_blocks = per_sm * D->sm_count;
     D->fused = coop && per_sm > 0;
     if (const char* e = getenv("MALIO_FUSED_PASS")) D->fused = D->fused && atoi(e) != 0;
+    if (const char* e = getenv("MALIO_COOP_LAUNCH")) D->coop_launch = atoi(e) != 0;
   }
   D->h_gstats = reinterpret_cast<uint32_t*>(D->h_res + MALIO_RED_DOUBLES + 4);
   std::memset(D->h_gstats, 0, 8 * sizeof(uint32_t));
@@ -2307,6 +2308,8 @@ void destroy(malio_handle* h) {
   if (D->stream2) { cudaStreamSynchronize(D->stream2); cudaStreamDestroy(D->stream2); }
   if (D->ev_h2d) cudaEventDestroy(D->ev_h2d);
   if (D->ev_refit) cudaEventDestroy(D->ev_refit);
+  if (D->ev_sorted) cudaEventDestroy(D->ev_sorted);
+  if (D->ev_tau) cudaEventDestroy(D->ev_tau);
   if (D->stream) cudaStreamDestroy(D->stream);
   delete D;
   h->dev = nullptr;
@@ -2535,7 +2538,7 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
   cudaStream_t st_ = D->stream;
   const uint32_t* perm = nullptr;
   if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[0], st_));
-  bool sorted_now = false, knn_now = false;
+  bool sorted_now = false, knn_now = false, tau_async_outer = false;
   // the per-pass kernels read the scan in position order: the sorted copy when the scan was sorted, else the upload itself
   const malio_scan_pt* pts_k = (h->cfg.sort_queries && N > 0) ? D->d_pts_sorted : D->d_pts;
   const uint32_t* perm_k = nullptr;
@@ -2549,6 +2552,20 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
       perm = D->d_perm;
     }
     if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[5], st_));
+    // once per scan: evalPointUncertainty's trace depends on the point and its table entry only.  On the first pass of
+    // a scan that is a search pass it runs on the second stream beside the k-NN kernels (which leave most of the SMs'
+    // warp slots empty) instead of inside the pass kernel.
+    bool tau_async = false;
+    if (!D->tau_valid && redo_knn && D->fused && !getenv("MALIO_TAU_INLINE")) {
+      CUDA_TRY(cudaEventRecord(D->ev_sorted, st_));
+      CUDA_TRY(cudaStreamWaitEvent(D->stream2, D->ev_sorted, 0));
+      tau_kernel<<<(N + PLANE_THREADS - 1) / PLANE_THREADS, PLANE_THREADS, 0, D->stream2>>>(pts_k, perm_k, N, pc, D->d_table, D->d_tau2);
+      CUDA_TRY(cudaEventRecord(D->ev_tau, D->stream2));
+      D->tau_valid = true;
+      D->ctr.kernel_launches += 1;
+      tau_async = true;
+    }
+    tau_async_outer = tau_async;
     if (redo_knn) {
       knn_now = true;
       if (int rc = run_knn<0>(h, D, N, pts_k, perm_k, pc, P.knn_max_sqdist)) return rc;
@@ -2557,6 +2574,7 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
       if (D->grid_on) CUDA_TRY(cudaMemcpyAsync(D->h_gstats + 2, D->d_gstats + 2, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st_));
     }
   }
+  if (tau_async_outer) CUDA_TRY(cudaStreamWaitEvent(st_, D->ev_tau, 0));
   if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[1], st_));
   unsigned long long* mmkey = D->d_mmkey + 4 * D->parity;
   unsigned long long* mmkey_next = D->d_mmkey + 4 * (1 - D->parity);
@@ -2595,7 +2613,13 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
     ParamConst prm_arg = prm;
     void* kargs[] = {&a, &pc_arg, &prm_arg};
     const void* kfn = per_block <= (uint32_t)PASS_FAST_TILES ? (const void*)pass_kernel<true> : (const void*)pass_kernel<false>;
-    CUDA_TRY(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(RED_THREADS), kargs, RED_SMEM_DOUBLES * sizeof(double), st_));
+    if (D->coop_launch) {
+      CUDA_TRY(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(RED_THREADS), kargs, RED_SMEM_DOUBLES * sizeof(double), st_));
+    } else {
+      // plain launch (MALIO_COOP_LAUNCH=0): the grid never exceeds the co-resident capacity, so the in-kernel barriers are
+      // safe as long as no OTHER grid-synchronising kernel competes for the same GPU at the same time (one handle in flight)
+      CUDA_TRY(cudaLaunchKernel(kfn, dim3(grid), dim3(RED_THREADS), kargs, RED_SMEM_DOUBLES * sizeof(double), st_));
+    }
     D->tau_valid = D->tau_valid || N > 0;
     D->ctr.kernel_launches += 1;
     if (D->timing) { CUDA_TRY(cudaEventRecord(D->ev[2], st_)); CUDA_TRY(cudaEventRecord(D->ev[3], st_)); CUDA_TRY(cudaEventRecord(D->ev[4], st_)); }
