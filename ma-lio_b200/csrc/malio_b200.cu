@@ -745,17 +745,16 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// RING 1: one query per work item p < N (3x3x3 cells); unsettled queries go to the ring-2 list, tie hazards and
-//         out-of-grid queries to the traversal list.
-// RING 2: work items are the ring-2 list (5x5x5 cells); what is still unsettled goes to the traversal list.
+// One query per thread (3x3x3 cells).  Queries whose 5th neighbour is not proven inside the block are retried on the
+// 5x5x5 block by the whole warp (ring2_query_warp) before the kernel ends; tie hazards and out-of-grid queries go to the
+// traversal list.  (RING = 1 is the only instantiation; the constants keep the block geometry in one place.)
 template <int MODE, int RING>
 __global__ void __launch_bounds__(GK_THREADS)
 knn_grid_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict__ cell_start, GridConst G,
                 const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm,
                 const float* __restrict__ queries, uint32_t N, PassConst pc, float max_sqdist,
                 float4* __restrict__ world, uint32_t* __restrict__ nn_idx, float* __restrict__ nn_d2,
-                uint8_t* __restrict__ sel, const uint32_t* __restrict__ in_list, const uint32_t* __restrict__ in_count,
-                uint32_t* __restrict__ r2_list, uint32_t* __restrict__ r2_count, uint32_t* __restrict__ fb_list,
+                uint8_t* __restrict__ sel, uint32_t* __restrict__ r2_count, uint32_t* __restrict__ fb_list,
                 uint32_t* __restrict__ fb_count, unsigned long long* __restrict__ cand_total) {
   constexpr int ROWS = RING == 1 ? GK_ROWS1 : GK_ROWS2;
   uint32_t n_cand = 0;   // candidates this thread scanned (statistics for the roofline; only summed when asked for)
@@ -2025,7 +2024,6 @@ struct DeviceState {
   uint32_t cap_cells = 0, cap_cell_pts = 0;
   float4* d_cell_pts = nullptr;
   uint32_t* d_fb_list = nullptr;          // positions the fast path could not settle (-> exact traversal)
-  uint32_t* d_r2_list = nullptr;          // positions that need the 5x5x5 block
   unsigned long long* d_cand = nullptr;   // candidates scanned by knn_grid_kernel since create (summed only while timing is on)
   uint32_t* d_gstats = nullptr;           // [0] occupied cells, [1] live points, [2] fb count, [3] fb count of the last search, [4] ring-2 queries
   uint32_t* h_gstats = nullptr;            // pinned mirror (8 words, carved out of h_res)
@@ -2190,7 +2188,7 @@ int run_knn(malio_handle* h, DeviceState* D, uint32_t n, const malio_scan_pt* pt
     constexpr size_t smem1 = (size_t)GK_CAP * GK_THREADS * sizeof(float4) + (size_t)GK_ROWS1 * GK_THREADS * sizeof(uint2);
     knn_grid_kernel<MODE, 1><<<(n + GK_THREADS - 1) / GK_THREADS, GK_THREADS, smem1, st>>>(
         D->d_cell_pts, D->d_cell_start, D->grid, pts, perm, qs, n, pc, max_sqdist, world, D->d_nn_idx, D->d_nn_d2, sel,
-        nullptr, nullptr, D->d_r2_list, D->d_gstats + 4, D->d_fb_list, D->d_gstats + 2, D->timing ? D->d_cand : nullptr);
+        D->d_gstats + 4, D->d_fb_list, D->d_gstats + 2, D->timing ? D->d_cand : nullptr);
     // 8 queries per warp and iteration; at most one resident wave of 64-thread blocks
     uint32_t fb_blocks = (n + 15) / 16;
     const uint32_t wave = (uint32_t)D->sm_count * 8;
@@ -2301,7 +2299,7 @@ void destroy(malio_handle* h) {
                   D->d_table, D->d_nn_idx, D->d_nn_d2, D->d_sel, D->d_world, D->d_plane, D->d_ucov, D->d_tau, D->d_tau2, D->d_pd2, D->d_rows12, D->d_lid8,
                   D->d_normal_y, D->d_o_ny, D->d_o_idx, D->d_o_d2, D->d_o_sel, D->d_o_world, D->d_block_mm,
                   D->d_block_cnt, D->d_counters, D->d_mmkey, D->d_block_red, D->d_res, D->d_rows, D->d_queries,
-                  D->d_cell_start, D->d_cell_cnt, D->d_cell_of, D->d_ctot, D->d_cbase, D->d_cell_pts, D->d_fb_list, D->d_r2_list, D->d_gstats, D->d_bar, D->d_cand};
+                  D->d_cell_start, D->d_cell_cnt, D->d_cell_of, D->d_ctot, D->d_cbase, D->d_cell_pts, D->d_fb_list, D->d_gstats, D->d_bar, D->d_cand};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (D->h_res) cudaFreeHost(D->h_res);
   for (auto& e : D->ev) if (e) cudaEventDestroy(e);
@@ -2460,7 +2458,6 @@ static int ensure_point_buffers(malio_handle* h, DeviceState* D, uint32_t n) {
   if ((rc = ensure(h, D->d_o_sel, cap))) return rc;
   if ((rc = ensure(h, D->d_o_world, (size_t)cap * 3))) return rc;
   if ((rc = ensure(h, D->d_fb_list, cap))) return rc;
-  if ((rc = ensure(h, D->d_r2_list, cap))) return rc;
   const uint32_t blocks = (cap + PLANE_THREADS - 1) / PLANE_THREADS;
   if ((rc = ensure(h, D->d_block_mm, (size_t)blocks * 4))) return rc;
   if ((rc = ensure(h, D->d_block_cnt, blocks))) return rc;
