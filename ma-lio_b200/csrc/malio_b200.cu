@@ -1979,7 +1979,9 @@ struct DeviceState {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;            // box rebuild of the compact upload runs beside the scan's first kernels
+  cudaStream_t stream3 = nullptr;            // copy stream for the map-side weights of the compact upload
   cudaEvent_t ev_h2d = nullptr, ev_refit = nullptr; bool refit_pending = false;
+  cudaEvent_t ev_cov = nullptr;
   cudaEvent_t ev_sorted = nullptr, ev_tau = nullptr;   // point-covariance traces run beside the first search of a scan
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [5] after sort, [6] after knn kernel
   malio_counters ctr{};
@@ -2234,8 +2236,10 @@ int create(malio_handle* h) {
   D->sm_count = prop.multiProcessorCount;
   CUDA_TRY(cudaStreamCreateWithFlags(&D->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&D->stream2, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&D->stream3, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&D->ev_h2d, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&D->ev_refit, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&D->ev_cov, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&D->ev_sorted, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&D->ev_tau, cudaEventDisableTiming));
   for (auto& e : D->ev) CUDA_TRY(cudaEventCreate(&e));
@@ -2304,8 +2308,10 @@ void destroy(malio_handle* h) {
   if (D->h_res) cudaFreeHost(D->h_res);
   for (auto& e : D->ev) if (e) cudaEventDestroy(e);
   if (D->stream2) { cudaStreamSynchronize(D->stream2); cudaStreamDestroy(D->stream2); }
+  if (D->stream3) { cudaStreamSynchronize(D->stream3); cudaStreamDestroy(D->stream3); }
   if (D->ev_h2d) cudaEventDestroy(D->ev_h2d);
   if (D->ev_refit) cudaEventDestroy(D->ev_refit);
+  if (D->ev_cov) cudaEventDestroy(D->ev_cov);
   if (D->ev_sorted) cudaEventDestroy(D->ev_sorted);
   if (D->ev_tau) cudaEventDestroy(D->ev_tau);
   if (D->stream) cudaStreamDestroy(D->stream);
@@ -2391,7 +2397,11 @@ int upload_map_compact(malio_handle* h, const malio_map_point* pts, const float*
   static_assert(sizeof(malio_map_point) == sizeof(float4), "compact record is one float4");
   CUDA_TRY(cudaMemcpyAsync(D->d_mpts, pts, (size_t)n * sizeof(malio_map_point), cudaMemcpyHostToDevice, D->stream));
   CUDA_TRY(cudaEventRecord(D->ev_h2d, D->stream));
-  CUDA_TRY(cudaMemcpyAsync(D->d_cov, cov, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, D->stream));
+  // the map-side weights (only the plane fit reads them) follow on a copy stream of their own: their copy overlaps the cell-list
+  // build that starts on the first stream as soon as the points are there
+  CUDA_TRY(cudaStreamWaitEvent(D->stream3, D->ev_h2d, 0));
+  CUDA_TRY(cudaMemcpyAsync(D->d_cov, cov, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, D->stream3));
+  CUDA_TRY(cudaEventRecord(D->ev_cov, D->stream3));
   D->ctr.h2d_bytes += (uint64_t)n * (sizeof(malio_map_point) + sizeof(float));
   malio_map_node root{};
   if (n) {
@@ -2417,7 +2427,9 @@ int upload_map_compact(malio_handle* h, const malio_map_point* pts, const float*
       std::memcpy(&root, D->h_res + MALIO_RED_DOUBLES + 16, sizeof(root));
     }
   }
-  return finish_map_upload(h, D, &root, n, depth);
+  const int rc = finish_map_upload(h, D, &root, n, depth);
+  CUDA_TRY(cudaEventSynchronize(D->ev_cov));   // host buffer consumed; every later launch is issued after this point
+  return rc;
 }
 
 int download_map_nodes(malio_handle* h, malio_map_node* out, uint32_t cap) {
