@@ -1854,6 +1854,8 @@ pass_kernel(PassArgs a, PassConst pc, ParamConst prm) {
         for (uint32_t e = lane; e < MALIO_RED_DOUBLES; e += 32) a.h_res[e] = __ldcg(a.d_res + e);
       }
       if (lane < 4) reinterpret_cast<unsigned long long*>(a.h_res + MALIO_RED_DOUBLES)[lane] = a.mmkey[lane];
+      // k-NN list statistics of the last search as knn_list_kernel published them ([3] traversal list, [5] 5x5x5 retries)
+      if (lane == 4) { uint32_t* hg = reinterpret_cast<uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 4); hg[3] = a.gstats[3]; hg[5] = a.gstats[5]; }
       __threadfence_system();
       __syncwarp();
       if (lane == 0) *reinterpret_cast<volatile uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 8) = a.seq;
@@ -1926,6 +1928,19 @@ __global__ void rows_kernel(uint32_t N, ParamConst prm, int ext_en, const uint8_
   if (threadIdx.x == 0) *n_rows = s_base;
 }
 
+// per-scan state back to "nothing searched yet": point_selected_surf = 0, normal_y = 0, Nearest_Points empty, k-NN list
+// counters 0 — one launch instead of four memsets (this sits at the head of every scan)
+__global__ void reset_scan_kernel(uint32_t cap, uint8_t* __restrict__ sel, float* __restrict__ normal_y,
+                                  uint32_t* __restrict__ nn_idx, uint32_t* __restrict__ gstats) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 4) gstats[2 + i] = 0;
+  if (i < cap) {
+    sel[i] = 0;
+    normal_y[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < MALIO_K; ++j) nn_idx[(size_t)j * cap + i] = 0xFFFFFFFFu;
+  }
+}
 // position space -> caller order
 __global__ void scatter_aux_kernel(const uint32_t* __restrict__ perm, uint32_t N, const float* __restrict__ normal_y,
                                    const uint32_t* __restrict__ nn_idx, const float* __restrict__ nn_d2,
@@ -2493,10 +2508,8 @@ int upload_scan(malio_handle* h, const malio_scan_pt* pts, uint32_t n, const mal
   }
   if (n) CUDA_TRY(cudaMemcpyAsync(D->d_pts, pts, (size_t)n * sizeof(malio_scan_pt), cudaMemcpyHostToDevice, D->stream));
   CUDA_TRY(cudaMemcpyAsync(D->d_table, table, (size_t)n_tab * sizeof(malio_pose_entry), cudaMemcpyHostToDevice, D->stream));
-  CUDA_TRY(cudaMemsetAsync(D->d_sel, 0, D->capN, D->stream));
-  CUDA_TRY(cudaMemsetAsync(D->d_normal_y, 0, (size_t)D->capN * sizeof(float), D->stream));
-  CUDA_TRY(cudaMemsetAsync(D->d_nn_idx, 0xFF, (size_t)D->capN * MALIO_K * sizeof(uint32_t), D->stream));
-  CUDA_TRY(cudaMemsetAsync(D->d_gstats + 2, 0, 4 * sizeof(uint32_t), D->stream));
+  reset_scan_kernel<<<(D->capN + 255) / 256, 256, 0, D->stream>>>(D->capN, D->d_sel, D->d_normal_y, D->d_nn_idx, D->d_gstats);
+  CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(D->stream));
   for (int l = 0; l <= MALIO_MAX_LIDAR; ++l) D->table_off[l] = (l <= L) ? table_off[l] : table_off[L];
   for (int l = 1; l < L; ++l) D->tcomp[l] = tcomp[l - 1];
@@ -2509,10 +2522,8 @@ int rearm_scan(malio_handle* h) {
   DeviceState* D = (DeviceState*)h->dev;
   if (!D->scan_ready) { h->err = "rearm_scan before upload_scan"; return MALIO_ERR_STATE; }
   CUDA_TRY(cudaSetDevice(D->device));
-  CUDA_TRY(cudaMemsetAsync(D->d_sel, 0, D->capN, D->stream));
-  CUDA_TRY(cudaMemsetAsync(D->d_normal_y, 0, (size_t)D->capN * sizeof(float), D->stream));
-  CUDA_TRY(cudaMemsetAsync(D->d_nn_idx, 0xFF, (size_t)D->capN * MALIO_K * sizeof(uint32_t), D->stream));
-  CUDA_TRY(cudaMemsetAsync(D->d_gstats + 2, 0, 4 * sizeof(uint32_t), D->stream));
+  reset_scan_kernel<<<(D->capN + 255) / 256, 256, 0, D->stream>>>(D->capN, D->d_sel, D->d_normal_y, D->d_nn_idx, D->d_gstats);
+  CUDA_TRY(cudaGetLastError());
   D->perm_valid = false; D->tau_valid = false; D->pass_done = false; D->searched_once = false;
   return MALIO_OK;
 }
@@ -2580,7 +2591,9 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
       if (int rc = run_knn<0>(h, D, N, pts_k, perm_k, pc, P.knn_max_sqdist)) return rc;
       D->searched_once = true;
       if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[6], st_));
-      if (D->grid_on) CUDA_TRY(cudaMemcpyAsync(D->h_gstats + 2, D->d_gstats + 2, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st_));
+      // list statistics of this search: the fused pass kernel ships them with its result; the separate-kernel path copies
+      if (D->grid_on && !(D->fused && (!D->comm || D->p2p)))
+        CUDA_TRY(cudaMemcpyAsync(D->h_gstats + 2, D->d_gstats + 2, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st_));
     }
   }
   if (tau_async_outer) CUDA_TRY(cudaStreamWaitEvent(st_, D->ev_tau, 0));
