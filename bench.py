@@ -37,8 +37,9 @@ sys.path.insert(0, os.path.join(ROOT, "ma-lio_b200"))
 METRIC = "scans/sec & ms/IESKF-iter, 100k-pt scan vs 1M-pt map, 1/2/4/8 GPU"
 UNIT = "scans/s"
 WORKLOAD = "C2: 3-LiDAR (Ouster+2xLivox) 100k-pt merged scan vs 1M-pt map snapshot, max_iteration=3"
-# dram__bytes_read+write of one knn_grid_kernel launch on C2 (ncu --set full, profiles/r01_knn_grid_kernel.md)
-NCU_DRAM_BYTES_PER_KNN_LAUNCH = 8.56e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one knn_grid_kernel launch on C2
+# (ncu --set full, profiles/r01_knn_grid_kernel_raw.csv / r01_knn_grid_kernel.md)
+NCU_DRAM_BYTES_PER_KNN_LAUNCH = 8.23e6
 
 
 def parse():
@@ -333,7 +334,7 @@ def run_ours(args, rank, world):
         bytes_per_launch = q_per_launch * (16 + 9 * 8 + cbar * 16 + 40 + 16 + 1)
         t_launch = knn_ms * 1e-3 / knn_launches
         achieved = bytes_per_launch / t_launch / 1e9
-        roof = {"bound": "hbm", "kernel": "k-NN search: knn_grid_kernel (+ knn_ring2_kernel, knn_list_kernel)",
+        roof = {"bound": "hbm", "kernel": "k-NN search: knn_grid_kernel (+ knn_list_kernel)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_KNN_LAUNCH if world == 1 else None,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "us_per_launch": t_launch * 1e6,
