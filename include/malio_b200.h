@@ -208,6 +208,22 @@ int malio_download_rows(malio_handle* h, double* h_x, double* hvec, uint32_t cap
 int malio_download_aux(malio_handle* h, float* normal_y, uint32_t* nn_idx, float* nn_sqdist,
                        uint8_t* selected, float* world);
 
+/* ---- next to the path: map_incremental's per-point decision ------------------------
+ * laserMapping.cpp:398-446, evaluated on the device from what the last pass left there (Nearest_Points of the last
+ * search, normal_y) and the state AFTER the update (pointBodyToWorld, laserMapping.cpp:134-147).  Caller order.
+ *   cls[i] = MALIO_MAP_SKIP   normal_y > cov_threshold (:406)
+ *            MALIO_MAP_ADD    goes to PointToAdd            -> ikdtree.Add_Points(.., true)   (:434, :437, :440)
+ *            MALIO_MAP_ADD_NO_DOWNSAMPLE  PointNoNeedDownsample -> ikdtree.Add_Points(.., false)  (:421-425)
+ *            MALIO_MAP_DROP   a neighbour is closer to the voxel centre (:428-433)
+ *   world : N x 3 feats_down_world for the points that were not skipped (zeros for skipped ones); may be NULL
+ * filter_size_map = filter_size_map_min, ekf_inited = flg_EKF_inited (laserMapping.cpp:989). */
+#define MALIO_MAP_SKIP 0
+#define MALIO_MAP_ADD 1
+#define MALIO_MAP_ADD_NO_DOWNSAMPLE 2
+#define MALIO_MAP_DROP 3
+int malio_map_incremental(malio_handle* h, const malio_pass_state* s, double filter_size_map, int ekf_inited,
+                          uint8_t* cls, float* world);
+
 /* cumulative counters since malio_create: kernels launched by this library, k-NN kernel launches, queries they
  * processed and their summed device time (CUDA events) — what bench.py's roofline is computed from. */
 typedef struct malio_counters {

@@ -1941,6 +1941,65 @@ __global__ void reset_scan_kernel(uint32_t cap, uint8_t* __restrict__ sel, float
     for (int j = 0; j < MALIO_K; ++j) nn_idx[(size_t)j * cap + i] = 0xFFFFFFFFu;
   }
 }
+// ------------------------------------------------------------------ next to the path: map_incremental's decision
+// laserMapping.cpp:398-446 per point, from device-resident data: normal_y and Nearest_Points (indices into the snapshot)
+// of the last pass, the scan point and the state after the update.  pointBodyToWorld (:134-147) has its own operation
+// order (no detour through the LiDAR-0 frame), restated here exactly.  Outputs in caller order.
+__global__ void map_incr_kernel(const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t N,
+                                PassConst pc, const float4* __restrict__ mpts, const uint32_t* __restrict__ nn_idx,
+                                const float* __restrict__ normal_y, double cov_threshold, double fs, int ekf_inited,
+                                uint8_t* __restrict__ cls_out, float* __restrict__ world_out) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  const uint32_t i = perm ? perm[p] : p;
+  uint8_t cls = MALIO_MAP_SKIP;
+  float w[3] = {0.f, 0.f, 0.f};
+  if (!((double)normal_y[p] > cov_threshold)) {                                                 // :406
+    const malio_scan_pt pt = pts[p];
+    const int lid = pt.lidar;
+    const double pb[3] = {(double)pt.x, (double)pt.y, (double)pt.z};
+    double a[3], g[3];
+    q_rot(pc.eq[lid], pb, a);
+    a[0] += pc.et[lid][0]; a[1] += pc.et[lid][1]; a[2] += pc.et[lid][2];
+    if (lid != 0) {                                                                             // :142
+      double b[3];
+      q_rot(pc.cq[lid], a, b);
+      a[0] = b[0] + pc.ct[lid][0]; a[1] = b[1] + pc.ct[lid][1]; a[2] = b[2] + pc.ct[lid][2];
+    }
+    q_rot(pc.rot, a, g);
+    w[0] = (float)(g[0] + pc.pos[0]); w[1] = (float)(g[1] + pc.pos[1]); w[2] = (float)(g[2] + pc.pos[2]);
+    uint32_t id[MALIO_K];
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < MALIO_K; ++j) { id[j] = nn_idx[(size_t)j * N + p]; cnt += id[j] != 0xFFFFFFFFu; }
+    if (cnt > 0 && ekf_inited) {                                                                // :411
+      float mid[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) mid[k] = (float)(floor((double)w[k] / fs) * fs + 0.5 * fs);   // :417-419
+      const float dist = (w[0] - mid[0]) * (w[0] - mid[0]) + (w[1] - mid[1]) * (w[1] - mid[1]) + (w[2] - mid[2]) * (w[2] - mid[2]);
+      const float4 n0 = __ldg(mpts + id[0]);
+      if ((double)fabsf(n0.x - mid[0]) > 0.5 * fs && (double)fabsf(n0.y - mid[1]) > 0.5 * fs && (double)fabsf(n0.z - mid[2]) > 0.5 * fs) {
+        cls = MALIO_MAP_ADD_NO_DOWNSAMPLE;                                                      // :421-425
+      } else {
+        bool need_add = true;
+        if (cnt >= MALIO_K) {                                                                   // :428-429
+#pragma unroll
+          for (int j = 0; j < MALIO_K; ++j) {
+            const float4 q = __ldg(mpts + id[j]);
+            const float dj = (q.x - mid[0]) * (q.x - mid[0]) + (q.y - mid[1]) * (q.y - mid[1]) + (q.z - mid[2]) * (q.z - mid[2]);
+            if (need_add && dj < dist) need_add = false;                                        // :430-434
+          }
+        }
+        cls = need_add ? MALIO_MAP_ADD : MALIO_MAP_DROP;
+      }
+    } else {
+      cls = MALIO_MAP_ADD;                                                                      // :439-440
+    }
+  }
+  cls_out[i] = cls;
+  if (world_out) { world_out[3 * (size_t)i] = w[0]; world_out[3 * (size_t)i + 1] = w[1]; world_out[3 * (size_t)i + 2] = w[2]; }
+}
+
 // position space -> caller order
 __global__ void scatter_aux_kernel(const uint32_t* __restrict__ perm, uint32_t N, const float* __restrict__ normal_y,
                                    const uint32_t* __restrict__ nn_idx, const float* __restrict__ nn_d2,
@@ -2886,6 +2945,27 @@ int knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* idx, float* d2, 
   D->ctr.knn_launches += 1; D->ctr.knn_queries += nq; D->ctr.knn_ms += ms;
   D->ctr.h2d_bytes += (uint64_t)nq * 12;
   D->ctr.d2h_bytes += (uint64_t)nq * ((idx ? 20 : 0) + (d2 ? 20 : 0));
+  return MALIO_OK;
+}
+
+int map_incremental(malio_handle* h, const malio_pass_state* s, double fs, int ekf_inited, uint8_t* cls, float* world) {
+  DeviceState* D = (DeviceState*)h->dev;
+  if (!D->pass_done) { h->err = "map_incremental before measure"; return MALIO_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(D->device));
+  const uint32_t N = D->N;
+  if (N == 0) return MALIO_OK;
+  const bool sorted = h->cfg.sort_queries && D->perm_valid;
+  const PassConst pc = make_pass_const(h, D, s);
+  // d_o_sel / d_o_world: the caller-order staging buffers of download_aux
+  map_incr_kernel<<<(N + 255) / 256, 256, 0, D->stream>>>(sorted ? D->d_pts_sorted : D->d_pts, sorted ? D->d_perm : nullptr, N, pc,
+                                                           D->d_mpts, D->d_nn_idx, D->d_normal_y, h->cfg.params.cov_threshold, fs,
+                                                           ekf_inited, D->d_o_sel, world ? D->d_o_world : nullptr);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(cls, D->d_o_sel, (size_t)N, cudaMemcpyDeviceToHost, D->stream));
+  if (world) CUDA_TRY(cudaMemcpyAsync(world, D->d_o_world, (size_t)N * 3 * sizeof(float), cudaMemcpyDeviceToHost, D->stream));
+  CUDA_TRY(cudaStreamSynchronize(D->stream));
+  D->ctr.kernel_launches += 1;
+  D->ctr.d2h_bytes += (uint64_t)N * (1 + (world ? 12 : 0));
   return MALIO_OK;
 }
 

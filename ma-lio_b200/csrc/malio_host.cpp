@@ -402,6 +402,10 @@ int malio_download_aux(malio_handle* h, float* normal_y, uint32_t* nn_idx, float
   if (!h) return MALIO_ERR_INVALID_ARG;
   return malio_dev::download_aux(h, normal_y, nn_idx, nn_sqdist, selected, world);
 }
+int malio_map_incremental(malio_handle* h, const malio_pass_state* s, double filter_size_map, int ekf_inited, uint8_t* cls, float* world) {
+  if (!h || !s || !cls || !(filter_size_map > 0.0)) return MALIO_ERR_INVALID_ARG;
+  return malio_dev::map_incremental(h, s, filter_size_map, ekf_inited, cls, world);
+}
 int malio_knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* nn_idx, float* nn_sqdist, float* ms_device) {
   if (!h || (nq && !q)) return MALIO_ERR_INVALID_ARG;
   return malio_dev::knn(h, q, nq, nn_idx, nn_sqdist, ms_device);

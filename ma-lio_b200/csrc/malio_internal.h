@@ -39,6 +39,7 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
 int download_rows(malio_handle* h, double* h_x, double* hvec, uint32_t cap, uint32_t* n_rows);
 int download_aux(malio_handle* h, float* normal_y, uint32_t* nn_idx, float* nn_d2, uint8_t* sel, float* world);
 int knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* idx, float* d2, float* ms);
+int map_incremental(malio_handle* h, const malio_pass_state* s, double fs, int ekf_inited, uint8_t* cls, float* world);
 int rearm_scan(malio_handle* h);
 int get_counters(malio_handle* h, malio_counters* out);
 int set_timing(malio_handle* h, int enable);

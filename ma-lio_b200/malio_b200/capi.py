@@ -22,6 +22,7 @@ LINK_HAS_LEFT = 0x80000000
 LINK_HAS_RIGHT = 0x40000000
 LINK_POINT_DELETED = 0x20000000
 LINK_INDEX_MASK = 0x0FFFFFFF
+MAP_SKIP, MAP_ADD, MAP_ADD_NO_DOWNSAMPLE, MAP_DROP = 0, 1, 2, 3
 
 # numpy views of the C structs
 MAP_NODE = np.dtype([("xyz", "<f4", 3), ("link", "<u4"), ("lbox", "<f4", 6), ("rbox", "<f4", 6)])
@@ -100,7 +101,7 @@ EXPORTS = [
     "malio_default_params", "malio_create", "malio_destroy", "malio_last_error", "malio_version",
     "malio_get_nccl_unique_id", "malio_comm_init", "malio_upload_map", "malio_upload_scan", "malio_measure",
     "malio_download_rows", "malio_download_aux", "malio_knn", "malio_ieskf_update", "malio_build_static_snapshot",
-    "malio_rearm_scan", "malio_get_counters", "malio_set_timing", "malio_upload_map_compact", "malio_download_map_nodes",
+    "malio_rearm_scan", "malio_get_counters", "malio_set_timing", "malio_upload_map_compact", "malio_download_map_nodes", "malio_map_incremental",
 ]
 
 
@@ -133,6 +134,7 @@ def load() -> C.CDLL:
     lib.malio_upload_map.argtypes = [vp, vp, vp, u32, u32]
     lib.malio_upload_map_compact.argtypes = [vp, vp, vp, u32, u32, vp]
     lib.malio_download_map_nodes.argtypes = [vp, vp, u32]
+    lib.malio_map_incremental.argtypes = [vp, vp, C.c_double, i32, vp, vp]
     lib.malio_upload_scan.argtypes = [vp, vp, u32, vp, vp, vp]
     lib.malio_measure.argtypes = [vp, C.POINTER(PassState), i32, vp, vp, C.POINTER(PassStats)]
     lib.malio_download_rows.argtypes = [vp, vp, vp, u32, C.POINTER(u32)]

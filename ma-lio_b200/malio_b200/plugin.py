@@ -190,6 +190,17 @@ class MeasurementModel:
                                                 capi.ptr(o_sel), capi.ptr(o_w)))
         return dict(normal_y=o_ny, nn_idx=o_idx, nn_sqdist=o_d2, selected=o_sel, world=o_w)
 
+    def map_incremental(self, s: capi.PassState | capi.State, filter_size_map: float = 0.5, ekf_inited: bool = True,
+                        world: bool = True):
+        """map_incremental's per-point decision (laserMapping.cpp:398-446) with the state after the update.
+        Returns (cls uint8[N] with capi.MAP_* codes, feats_down_world float32[N,3] or None)."""
+        ps = s.pass_state() if isinstance(s, capi.State) else s
+        cls = np.zeros(self.n_points, np.uint8)
+        w = np.zeros((self.n_points, 3), np.float32) if world else None
+        self._check(self.lib.malio_map_incremental(self._h, C.byref(ps), C.c_double(filter_size_map), 1 if ekf_inited else 0,
+                                                   capi.ptr(cls), capi.ptr(w)))
+        return cls, w
+
     def update_iterated_dyn_share_modified(self, x: capi.State, P: np.ndarray, max_iter: int, R: float = 0.001):
         """IESKF update; x and P are updated in place.  Returns the report (status in report.last_status)."""
         assert P.shape == (self.n_dof, self.n_dof) and P.dtype == np.float64 and P.flags["C_CONTIGUOUS"]

@@ -994,6 +994,61 @@ int orc_h_share_model(void* vc, const malio_pass_state* s, int converge, int nth
 }
 
 // esekfom.hpp:622-635 on the dense outputs of the last pass: HTH = (h_x^T / R) h_x ; HTh = (h_x^T / R) h
+// map_incremental's per-point decision (laserMapping.cpp:398-446) with the state after the update
+// (pointBodyToWorld, :134-147).  cls: 0 skipped (:406), 1 PointToAdd, 2 PointNoNeedDownsample, 3 dropped (:431)
+void orc_map_incremental(void* vc, const malio_pass_state* s, double filter_size_map_min, int flg_EKF_inited,
+                         uint8_t* cls, float* world_out) {
+  orc_ctx* c = (orc_ctx*)vc;
+  const malio_params& P = c->prm;
+  const int L = P.n_lidar;
+  const int64_t N = (int64_t)c->pts.size();
+  Q4 qE[MALIO_MAX_LIDAR], qC[MALIO_MAX_LIDAR];
+  double tE[MALIO_MAX_LIDAR][3], tC[MALIO_MAX_LIDAR][3];
+  for (int l = 0; l < L; ++l) { qE[l] = q_from(s->ext[l].q); for (int k = 0; k < 3; ++k) tE[l][k] = s->ext[l].t[k]; }
+  for (int l = 1; l < L; ++l) { qC[l] = q_from(c->tcomp[l - 1].q); for (int k = 0; k < 3; ++k) tC[l][k] = c->tcomp[l - 1].t[k]; }
+  const Q4 srot = q_from(s->rot);
+  for (int64_t i = 0; i < N; ++i) {
+    cls[i] = 0;
+    if (world_out) { world_out[3 * i] = 0.f; world_out[3 * i + 1] = 0.f; world_out[3 * i + 2] = 0.f; }
+    if ((double)c->normal_y[i] > P.cov_threshold) continue;                                   // :406
+    const malio_scan_pt& pb = c->pts[i];
+    const double p_body[3] = {pb.x, pb.y, pb.z};
+    const int lid = pb.lidar;
+    double a[3], g[3];
+    q_rot(qE[lid], p_body, a);
+    for (int k = 0; k < 3; ++k) a[k] += tE[lid][k];
+    if (lid != 0) {                                                                           // :142
+      double b[3];
+      q_rot(qC[lid], a, b);
+      for (int k = 0; k < 3; ++k) a[k] = b[k] + tC[lid][k];
+    }
+    q_rot(srot, a, g);
+    float w[3];
+    for (int k = 0; k < 3; ++k) { g[k] += s->pos[k]; w[k] = (float)g[k]; }
+    if (world_out) { world_out[3 * i] = w[0]; world_out[3 * i + 1] = w[1]; world_out[3 * i + 2] = w[2]; }
+    const int cnt = c->nearest_cnt[i];
+    if (cnt > 0 && flg_EKF_inited) {                                                          // :411
+      const float* near = &c->nearest[(size_t)i * MALIO_K * 4];
+      const double fs = filter_size_map_min;
+      float mid[3];
+      for (int k = 0; k < 3; ++k) mid[k] = (float)(std::floor((double)w[k] / fs) * fs + 0.5 * fs);   // :417-419
+      const float dist = (w[0] - mid[0]) * (w[0] - mid[0]) + (w[1] - mid[1]) * (w[1] - mid[1]) + (w[2] - mid[2]) * (w[2] - mid[2]);
+      if ((double)std::fabs(near[0] - mid[0]) > 0.5 * fs && (double)std::fabs(near[1] - mid[1]) > 0.5 * fs &&
+          (double)std::fabs(near[2] - mid[2]) > 0.5 * fs) { cls[i] = 2; continue; }         // :421-425
+      bool need_add = true;
+      for (int j = 0; j < MALIO_K; ++j) {                                                     // :426-435
+        if (cnt < MALIO_K) break;
+        const float* q = near + 4 * j;
+        const float dj = (q[0] - mid[0]) * (q[0] - mid[0]) + (q[1] - mid[1]) * (q[1] - mid[1]) + (q[2] - mid[2]) * (q[2] - mid[2]);
+        if (dj < dist) { need_add = false; break; }
+      }
+      cls[i] = need_add ? 1 : 3;
+    } else {
+      cls[i] = 1;                                                                             // :439-440
+    }
+  }
+}
+
 void orc_reduce(void* vc, double* HTH, double* HTh) {
   orc_ctx* c = (orc_ctx*)vc;
   const int ncol = 6 * (c->prm.n_lidar + 1);

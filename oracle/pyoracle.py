@@ -59,6 +59,8 @@ def oracle_lib() -> C.CDLL:
         L.orc_get_stats.argtypes = [vp, C.POINTER(capi.PassStats)]
         L.orc_get_dense.argtypes = [vp, vp, vp, vp]
         L.orc_get_aux.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.orc_map_incremental.restype = None
+        L.orc_map_incremental.argtypes = [vp, vp, C.c_double, C.c_int, vp, vp]
         L.orc_get_visits.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.orc_update_iterated.argtypes = [vp, C.POINTER(capi.State), vp, C.c_int, C.c_double, C.c_int, vp, vp, C.POINTER(capi.UpdateReport)]
         _orc = L
@@ -297,6 +299,14 @@ class Oracle:
         cnt = np.zeros(n, np.int32)
         self.L.orc_get_aux(self.c, ptr(ny), ptr(ids), ptr(d2), ptr(sel), ptr(w), ptr(cnt))
         return dict(normal_y=ny, nn_idx=ids, nn_sqdist=d2, selected=sel, world=w, nn_cnt=cnt)
+
+    def map_incremental(self, s, filter_size_map: float = 0.5, ekf_inited: bool = True):
+        """map_incremental's per-point decision (laserMapping.cpp:398-446).  Returns (cls uint8[N], world float32[N,3])."""
+        ps = s.pass_state() if isinstance(s, capi.State) else s
+        cls = np.zeros(self.N, np.uint8)
+        w = np.zeros((self.N, 3), np.float32)
+        self.L.orc_map_incremental(self.c, C.byref(ps), C.c_double(filter_size_map), 1 if ekf_inited else 0, ptr(cls), ptr(w))
+        return cls, w
 
     def visits(self):
         v, s = C.c_int64(0), C.c_int64(0)

@@ -254,3 +254,29 @@ def test_unfused_kernel_path_matches_fused_pass(monkeypatch):
     assert okf and okp and sf.n_eff == sp.n_eff and H.rel_err(Hf, Hp) < 1e-11 and H.rel_err(hf, hp) < 1e-11
     for m in (fused, plain, mb, pb):
         m.close()
+
+
+def test_map_incremental_decision_matches_oracle():
+    """map_incremental's per-point decision (laserMapping.cpp:398-446) evaluated on the device from the
+    data the update left there; classes and feats_down_world must equal the oracle's for the same state, bit for bit
+    (1 and 3 LiDARs, filter initialised or not, two voxel sizes)."""
+    for L, n, m in ((1, 5000, 50000), (3, 20000, 200000)):
+        case = synth.make_case(f"mi{L}", n, m, L, 3, varied_map_cov=True)
+        snap = plugin.build_static_snapshot(case.map_xyz, case.map_normal_y)
+        model = H.make_model(case, snap)
+        orc = H.make_oracle(case, snap)
+        xg, Pg = case.x_prop.copy(), case.P_prop.copy()
+        xo, Po = case.x_prop.copy(), case.P_prop.copy()
+        model.update_iterated_dyn_share_modified(xg, Pg, case.max_iter)
+        orc.update_iterated(xo, Po, case.max_iter, nthreads=4)
+        ag, ao = model.aux(), orc.aux()
+        gi = ag["nn_idx"].astype(np.int64); gi[gi == 0xFFFFFFFF] = -1
+        assert np.array_equal(gi, ao["nn_idx"].astype(np.int64))
+        for fs in (0.5, 0.2):
+            for inited in (True, False):
+                cls_g, w_g = model.map_incremental(xg, fs, inited)
+                cls_o, w_o = orc.map_incremental(xg, fs, inited)
+                assert np.array_equal(cls_g, cls_o), (L, fs, inited, int((cls_g != cls_o).sum()))
+                assert np.array_equal(w_g, w_o)
+        assert len(set(cls_g.tolist())) >= 1
+        model.close()

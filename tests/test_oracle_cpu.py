@@ -374,3 +374,42 @@ def test_product_does_not_link_or_import_the_oracle():
     import subprocess
     out = subprocess.run(["ldd", capi.lib_path()], capture_output=True, text=True).stdout
     assert "oracle" not in out and "ikd_ref" not in out
+
+
+def test_map_incremental_decision_vs_numpy_restatement(small):
+    """the per-point decision of map_incremental (laserMapping.cpp:398-446) — the C++ restatement against
+    an independent numpy one on the same Nearest_Points / normal_y / state."""
+    case, snap = small
+    orc = H.make_oracle(case, snap)
+    x, P = case.x_prop.copy(), case.P_prop.copy()
+    orc.update_iterated(x, P, case.max_iter)
+    fs = 0.5
+    cls, w = orc.map_incremental(x, fs, True)
+    a = orc.aux()
+    xyz = snap.nodes["xyz"]
+    ids = a["nn_idx"]
+    cnt = a["nn_cnt"]
+    keep = ~(a["normal_y"].astype(np.float64) > case.params.cov_threshold)
+    assert np.all(cls[~keep] == capi.MAP_SKIP) and np.all(cls[keep] != capi.MAP_SKIP)
+    mid = (np.floor(w.astype(np.float64) / fs) * fs + 0.5 * fs).astype(np.float32)
+    d = w - mid
+    dist = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    exp = np.full(len(cls), capi.MAP_ADD, np.uint8)
+    for i in np.nonzero(keep)[0]:
+        if cnt[i] == 0:
+            continue
+        n0 = xyz[ids[i, 0]]
+        if np.all(np.abs(n0 - mid[i]).astype(np.float64) > 0.5 * fs):
+            exp[i] = capi.MAP_ADD_NO_DOWNSAMPLE
+            continue
+        if cnt[i] >= 5:
+            q = xyz[ids[i]] - mid[i]
+            dj = (q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1]) + q[:, 2] * q[:, 2]
+            if np.any(dj < dist[i]):
+                exp[i] = capi.MAP_DROP
+    exp[~keep] = capi.MAP_SKIP
+    assert np.array_equal(cls, exp)
+    assert len(set(cls.tolist())) >= 2          # the case exercises more than one branch
+    # before the filter is initialised every kept point is added (:411, :439-440)
+    cls0, _ = orc.map_incremental(x, fs, False)
+    assert np.all(cls0[keep] == capi.MAP_ADD)
