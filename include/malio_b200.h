@@ -224,6 +224,36 @@ int malio_download_aux(malio_handle* h, float* normal_y, uint32_t* nn_idx, float
 int malio_map_incremental(malio_handle* h, const malio_pass_state* s, double filter_size_map, int ekf_inited,
                           uint8_t* cls, float* world);
 
+/* ---- next to the path: the pose-uncertainty table that feeds malio_upload_scan -------------
+ * struct Pose (common_lib.h:57-63) and Barfoot's 4th-order SE(3) covariance compounding
+ * (associate_uct.hpp:29-142), host C++.  Output arguments MAY alias the second input pose exactly as the reference's
+ * call sites do (laserMapping.cpp:1042-1044): the functions touch the fields in the reference's order, so the
+ * aliasing behaviour (adjointMatrix sees the already overwritten T_, associate_uct.hpp:99) is reproduced. */
+typedef struct malio_pose {
+  double q[4];        /* q_, (w,x,y,z) */
+  double t[3];        /* t_ */
+  double T[16];       /* T_, row-major 4x4 */
+  double cov[36];     /* cov_, row-major 6x6 */
+} malio_pose;
+
+/* PoseInitial (common_lib.h:129-142) */
+void malio_pose_initial(malio_pose* pose, const double t[3], const double q[4], const double cov[36]);
+/* compoundPoseWithCov, method 2 (associate_uct.hpp:88-142); also sets pose_cp->cov (:134) */
+void malio_compound_pose_with_cov(const malio_pose* pose_1, const double cov_1[36], const malio_pose* pose_2,
+                                  const double cov_2[36], malio_pose* pose_cp, double cov_cp[36]);
+/* compoundInvPoseWithCov, method 2 (associate_uct.hpp:29-86); does NOT touch pose_cp->cov unless cov_cp points to it */
+void malio_compound_inv_pose_with_cov(const malio_pose* pose_1, const double cov_1[36], const malio_pose* pose_2,
+                                      const double cov_2[36], malio_pose* pose_cp, double cov_cp[36]);
+/* pose_unc of one scan (laserMapping.cpp:1028-1048) in the layout malio_upload_scan takes.
+ *   extrinsic[l]            struct Pose of LiDAR l's extrinsic, l < n_lidar
+ *   temporal_comp[l-1]      kf.temporal_comp[l-1], l = 1..n_lidar-1 (may be NULL when n_lidar == 1)
+ *   lidar_uncertainty[l]    kf.lidar_uncertainty[l][0 .. counts[l]); the LAST entry of each list is dropped (:1035,:1040)
+ * table must hold sum(counts[l] - 1) entries; table_off gets n_lidar + 1 offsets.  Returns the number of entries,
+ * or a negative malio_status. */
+int malio_build_pose_unc(int n_lidar, const malio_pose* extrinsic, const malio_pose* temporal_comp,
+                         const malio_pose* const* lidar_uncertainty, const uint32_t* counts,
+                         malio_pose_entry* table, uint32_t* table_off);
+
 /* cumulative counters since malio_create: kernels launched by this library, k-NN kernel launches, queries they
  * processed and their summed device time (CUDA events) — what bench.py's roofline is computed from. */
 typedef struct malio_counters {

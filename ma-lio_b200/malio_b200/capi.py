@@ -27,6 +27,7 @@ MAP_SKIP, MAP_ADD, MAP_ADD_NO_DOWNSAMPLE, MAP_DROP = 0, 1, 2, 3
 # numpy views of the C structs
 MAP_NODE = np.dtype([("xyz", "<f4", 3), ("link", "<u4"), ("lbox", "<f4", 6), ("rbox", "<f4", 6)])
 MAP_POINT = np.dtype([("xyz", "<f4", 3), ("link", "<u4")])
+POSE = np.dtype([("q", "<f8", 4), ("t", "<f8", 3), ("T", "<f8", (4, 4)), ("cov", "<f8", (6, 6))])   # malio_pose
 SCAN_PT = np.dtype([("xyz", "<f4", 3), ("lidar", "<u2"), ("table_idx", "<u2")])
 POSE_ENTRY = np.dtype([("T", "<f8", (4, 4)), ("cov", "<f8", (6, 6))])
 RIGID = np.dtype([("q", "<f8", 4), ("t", "<f8", 3)])
@@ -102,6 +103,7 @@ EXPORTS = [
     "malio_get_nccl_unique_id", "malio_comm_init", "malio_upload_map", "malio_upload_scan", "malio_measure",
     "malio_download_rows", "malio_download_aux", "malio_knn", "malio_ieskf_update", "malio_build_static_snapshot",
     "malio_rearm_scan", "malio_get_counters", "malio_set_timing", "malio_upload_map_compact", "malio_download_map_nodes", "malio_map_incremental",
+    "malio_pose_initial", "malio_compound_pose_with_cov", "malio_compound_inv_pose_with_cov", "malio_build_pose_unc",
 ]
 
 
@@ -135,6 +137,13 @@ def load() -> C.CDLL:
     lib.malio_upload_map_compact.argtypes = [vp, vp, vp, u32, u32, vp]
     lib.malio_download_map_nodes.argtypes = [vp, vp, u32]
     lib.malio_map_incremental.argtypes = [vp, vp, C.c_double, i32, vp, vp]
+    lib.malio_pose_initial.restype = None
+    lib.malio_pose_initial.argtypes = [vp, vp, vp, vp]
+    lib.malio_compound_pose_with_cov.restype = None
+    lib.malio_compound_pose_with_cov.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.malio_compound_inv_pose_with_cov.restype = None
+    lib.malio_compound_inv_pose_with_cov.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.malio_build_pose_unc.argtypes = [i32, vp, vp, vp, vp, vp, vp]
     lib.malio_upload_scan.argtypes = [vp, vp, u32, vp, vp, vp]
     lib.malio_measure.argtypes = [vp, C.POINTER(PassState), i32, vp, vp, C.POINTER(PassStats)]
     lib.malio_download_rows.argtypes = [vp, vp, vp, u32, C.POINTER(u32)]

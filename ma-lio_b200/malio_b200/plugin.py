@@ -56,6 +56,27 @@ def compact_points(nodes: np.ndarray) -> np.ndarray:
     return out
 
 
+def build_pose_unc(extrinsic: np.ndarray, temporal_comp: np.ndarray | None, lidar_uncertainty: list[np.ndarray]):
+    """pose_unc of one scan (laserMapping.cpp:1028-1048) through the library's host code.  extrinsic: capi.POSE[L],
+    temporal_comp: capi.POSE[L-1] or None, lidar_uncertainty: L arrays of capi.POSE.  Returns (table capi.POSE_ENTRY[],
+    table_off uint32[L+1]) ready for MeasurementModel.upload_scan."""
+    lib = capi.load()
+    L = len(lidar_uncertainty)
+    lists = [np.ascontiguousarray(a, dtype=capi.POSE) for a in lidar_uncertainty]
+    counts = np.array([a.shape[0] for a in lists], np.uint32)
+    ptrs = (C.c_void_p * L)(*[a.ctypes.data for a in lists])
+    n = int(sum(max(int(c) - 1, 0) for c in counts))
+    table = np.zeros(max(n, 1), dtype=capi.POSE_ENTRY)
+    off = np.zeros(L + 1, np.uint32)
+    ext = np.ascontiguousarray(extrinsic, dtype=capi.POSE)
+    tc = None if temporal_comp is None else np.ascontiguousarray(temporal_comp, dtype=capi.POSE)
+    rc = lib.malio_build_pose_unc(L, capi.ptr(ext), capi.ptr(tc), C.cast(ptrs, C.c_void_p), capi.ptr(counts), capi.ptr(table),
+                                  capi.ptr(off))
+    if rc < 0:
+        raise capi.MalioError(-rc, "malio_build_pose_unc")
+    return table[:rc], off
+
+
 class MeasurementModel:
     """One handle = one GPU.  Mirrors the life cycle of one scan in laserMapping.cpp:935-1082."""
 

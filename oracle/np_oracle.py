@@ -251,3 +251,108 @@ def ieskf_update(measure, x, P, max_iter, R=0.001):
             P[:, g:g + 2] = P[:, g:g + 2] @ J2.T
             return x, Lm - K_x[:, :c] @ P[:c, :], dx_log
     return x, P, dx_log
+
+
+# ------------------------------------------------------------------ pose-uncertainty table
+# numpy restatement of MA_LIO/include/associate_uct.hpp:8-142 and the table loop of src/laserMapping.cpp:1028-1048.
+class Pose:
+    """struct Pose (common_lib.h:57-63)."""
+
+    def __init__(self, q, t, cov):
+        self.q = np.asarray(q, np.float64).copy()
+        self.t = np.asarray(t, np.float64).copy()
+        self.cov = np.asarray(cov, np.float64).reshape(6, 6).copy()
+        self.T = np.eye(4)
+        self.set_T()
+
+    def set_T(self):
+        self.T = np.eye(4)
+        self.T[:3, :3] = q_R(self.q)
+        self.T[:3, 3] = self.t
+
+    def copy(self):
+        p = Pose(self.q, self.t, self.cov)
+        p.T = self.T.copy()
+        return p
+
+
+def q_rot(q, v):
+    return q_R(q) @ np.asarray(v, np.float64)
+
+
+def adjoint(T):   # adjointMatrix, associate_uct.hpp:8-15
+    Ad = np.zeros((6, 6))
+    Ad[:3, :3] = T[:3, :3]
+    Ad[:3, 3:] = hat(T[:3, 3]) @ T[:3, :3]
+    Ad[3:, 3:] = T[:3, :3]
+    return Ad
+
+
+def covop1(B):
+    return -np.trace(B) * np.eye(3) + B
+
+
+def covop2(B, C):
+    return covop1(B) @ covop1(C) + covop1(C @ B)
+
+
+def _compound_cov(c1p, c2):   # associate_uct.hpp:52-85 / 107-133
+    c1rr, c1rp, c1pp = c1p[:3, :3], c1p[:3, 3:], c1p[3:, 3:]
+    c2rr, c2rp, c2pp = c2[:3, :3], c2[:3, 3:], c2[3:, 3:]
+    A1 = np.zeros((6, 6)); A2 = np.zeros((6, 6)); B = np.zeros((6, 6))
+    A1[:3, :3] = covop1(c1pp); A1[:3, 3:] = covop1(c1rp + c1rp.T); A1[3:, 3:] = covop1(c1pp)
+    A2[:3, :3] = covop1(c2pp); A2[:3, 3:] = covop1(c2rp + c2rp.T); A2[3:, 3:] = covop1(c2pp)
+    Brr = covop2(c1pp, c2rr) + covop2(c1rp.T, c2rp) + covop2(c1rp, c2rp.T) + covop2(c1rr, c2pp)
+    Brp = covop2(c1pp, c2rp.T) + covop2(c1rp.T, c2pp)
+    Bpp = covop2(c1pp, c2pp)
+    B[:3, :3] = Brr; B[:3, 3:] = Brp; B[3:, :3] = Brp.T; B[3:, 3:] = Bpp
+    return c1p + c2 + (A1 @ c2 + c2 @ A1.T + A2 @ c1p + c1p @ A2.T) / 12 + B / 4
+
+
+def compound_pose_with_cov(p1, cov1, p2, cov2, out):
+    """compoundPoseWithCov, method 2; `out` may be p2 (aliasing as at laserMapping.cpp:1043): fields are touched in the
+    reference's order, so adjointMatrix(pose_2.T_.inverse()) sees the new T_ in that case (associate_uct.hpp:99)."""
+    cov1 = np.asarray(cov1, np.float64).reshape(6, 6).copy()
+    cov2 = np.asarray(cov2, np.float64).reshape(6, 6).copy()
+    q = q_mul(p1.q, p2.q)
+    t = q_rot(p1.q, p2.t) + p1.t
+    out.q = q
+    out.t = t
+    out.set_T()
+    Ad = adjoint(np.linalg.inv(p2.T))
+    c1p = Ad @ cov1 @ Ad.T
+    out.cov = _compound_cov(c1p, cov2)
+    return out.cov
+
+
+def compound_inv_pose_with_cov(p1, cov1, p2, cov2, out):
+    """compoundInvPoseWithCov, method 2 (associate_uct.hpp:29-86); returns cov_cp (the caller decides where it lives)."""
+    cov1 = np.asarray(cov1, np.float64).reshape(6, 6).copy()
+    cov2 = np.asarray(cov2, np.float64).reshape(6, 6).copy()
+    qc = q_conj(p1.q)
+    q = q_mul(qc, p2.q)
+    t = q_rot(qc, p2.t - p1.t)
+    out.q = q
+    out.t = t
+    out.set_T()
+    Ad = adjoint(np.linalg.inv(out.T))
+    c1p = Ad @ cov1 @ Ad.T
+    return _compound_cov(c1p, cov2)
+
+
+def build_pose_unc(extrinsic, temporal_comp, lidar_uncertainty):
+    """laserMapping.cpp:1028-1048.  Returns per-LiDAR lists of Pose."""
+    out = []
+    for num, lst in enumerate(lidar_uncertainty):
+        tab = []
+        for i in range(len(lst) - 1):
+            if num == 0:
+                tab.append(lst[i].copy())
+                continue
+            pp = Pose([1, 0, 0, 0], [0, 0, 0], np.zeros((6, 6)))
+            compound_pose_with_cov(extrinsic[num], extrinsic[num].cov, lst[i], lst[i].cov, pp)
+            compound_pose_with_cov(temporal_comp[num - 1], temporal_comp[num - 1].cov, pp, pp.cov, pp)
+            pp.cov = compound_inv_pose_with_cov(extrinsic[0], extrinsic[0].cov, pp, pp.cov, pp)
+            tab.append(pp.copy())
+        out.append(tab)
+    return out

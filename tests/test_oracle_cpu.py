@@ -413,3 +413,76 @@ def test_map_incremental_decision_vs_numpy_restatement(small):
     # before the filter is initialised every kept point is added (:411, :439-440)
     cls0, _ = orc.map_incremental(x, fs, False)
     assert np.all(cls0[keep] == capi.MAP_ADD)
+
+
+# ------------------------------------------------------------------ pose-uncertainty table (host code)
+def _rand_pose(rng, ang, tr, cov_scale):
+    v = rng.normal(size=3); v *= ang / np.linalg.norm(v)
+    q = npo.so3_exp(v)
+    t = rng.normal(size=3) * tr
+    A = rng.normal(size=(6, 6)) * np.sqrt(cov_scale)
+    return npo.Pose(q, t, A @ A.T)
+
+
+def _to_c(p):
+    a = np.zeros(1, dtype=capi.POSE)
+    a["q"][0] = p.q; a["t"][0] = p.t; a["T"][0] = p.T; a["cov"][0] = p.cov
+    return a
+
+
+def test_pose_compounding_and_table_vs_numpy():
+    """Barfoot's 4th-order SE(3) covariance compounding (associate_uct.hpp:29-142) and the pose_unc table loop
+    (laserMapping.cpp:1028-1048) in the product's host code against the numpy restatement — including the calls whose
+    output aliases the second input (the adjoint then sees the overwritten T_, associate_uct.hpp:99)."""
+    import ctypes as C
+    lib = capi.load()
+    rng = np.random.default_rng(7)
+    p1, p2 = _rand_pose(rng, 0.3, 0.5, 1e-4), _rand_pose(rng, 0.2, 0.3, 1e-5)
+    for fn_c, fn_np, sets_pose_cov in ((lib.malio_compound_pose_with_cov, npo.compound_pose_with_cov, True),
+                                       (lib.malio_compound_inv_pose_with_cov, npo.compound_inv_pose_with_cov, False)):
+        # (a) separate output
+        c1, c2, co = _to_c(p1), _to_c(p2), np.zeros(1, dtype=capi.POSE)
+        cov_out = np.zeros((6, 6))
+        fn_c(capi.ptr(c1), capi.ptr(np.ascontiguousarray(p1.cov)), capi.ptr(c2), capi.ptr(np.ascontiguousarray(p2.cov)),
+             capi.ptr(co), capi.ptr(cov_out))
+        out = npo.Pose([1, 0, 0, 0], [0, 0, 0], np.zeros((6, 6)))
+        ref_cov = fn_np(p1, p1.cov, p2.copy(), p2.cov, out)
+        np.testing.assert_allclose(cov_out, ref_cov, rtol=1e-11, atol=1e-18)
+        np.testing.assert_allclose(co["T"][0], out.T, rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(co["q"][0], out.q, rtol=1e-13, atol=1e-15)
+        assert np.allclose(cov_out, cov_out.T, rtol=1e-12, atol=1e-20) and np.all(np.linalg.eigvalsh(cov_out) > -1e-15)
+        if sets_pose_cov:
+            assert np.array_equal(co["cov"][0], cov_out)
+        # (b) output aliasing the second input, cov_cp = pose_cp.cov (the reference's call pattern)
+        c2b = _to_c(p2)
+        cov_alias = c2b["cov"][0]           # view into the struct: cov_cp IS pose_cp.cov
+        fn_c(capi.ptr(c1), capi.ptr(np.ascontiguousarray(p1.cov)), capi.ptr(c2b), capi.ptr(np.ascontiguousarray(p2.cov)),
+             capi.ptr(c2b), c2b["cov"].ctypes.data_as(C.c_void_p))
+        pa = p2.copy()
+        ref_alias = fn_np(p1, p1.cov, pa, pa.cov.copy(), pa)
+        np.testing.assert_allclose(cov_alias, ref_alias, rtol=1e-11, atol=1e-18)
+        np.testing.assert_allclose(c2b["T"][0], pa.T, rtol=1e-13, atol=1e-15)
+    # first-order sanity: tiny covariances -> cov_cp ~= Ad cov_1 Ad^T + cov_2
+    s1, s2 = _rand_pose(rng, 0.3, 0.5, 1e-12), _rand_pose(rng, 0.2, 0.3, 1e-12)
+    out = npo.Pose([1, 0, 0, 0], [0, 0, 0], np.zeros((6, 6)))
+    cov = npo.compound_pose_with_cov(s1, s1.cov, s2, s2.cov, out)
+    Ad = npo.adjoint(np.linalg.inv(s2.T))
+    np.testing.assert_allclose(cov, Ad @ s1.cov @ Ad.T + s2.cov, rtol=1e-9, atol=1e-24)
+    # ---- the table of one scan, 3 LiDARs
+    ext = [_rand_pose(rng, 0.05 + 0.5 * l, 0.3, 1e-8) for l in range(3)]
+    tcomp = [_rand_pose(rng, 0.01, 0.05, 1e-8) for _ in range(2)]
+    lists = [[_rand_pose(rng, 0.02, 0.02 * (j + 1), 1e-7 * (j + 1)) for j in range(n)] for n in (9, 6, 7)]
+    ref = npo.build_pose_unc(ext, tcomp, lists)
+    table, off = plugin.build_pose_unc(np.concatenate([_to_c(p) for p in ext]), np.concatenate([_to_c(p) for p in tcomp]),
+                                       [np.concatenate([_to_c(p) for p in l]) for l in lists])
+    assert off.tolist() == [0, 8, 13, 19] and table.shape[0] == 19
+    k = 0
+    for l in range(3):
+        for p in ref[l]:
+            np.testing.assert_allclose(table["T"][k], p.T, rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(table["cov"][k], p.cov, rtol=1e-10, atol=1e-20)
+            k += 1
+    # LiDAR 0's entries are copied verbatim (:1034-1036); single-LiDAR tables need no temporal_comp
+    assert np.array_equal(table["cov"][0], lists[0][0].cov) and np.array_equal(table["T"][7], lists[0][7].T)
+    t1, o1 = plugin.build_pose_unc(_to_c(ext[0]), None, [np.concatenate([_to_c(p) for p in lists[0]])])
+    assert o1.tolist() == [0, 8] and np.array_equal(t1["cov"], table["cov"][:8])
