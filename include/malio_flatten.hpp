@@ -172,5 +172,195 @@ FlattenResult flatten_ikdtree_compact(const Node* root, malio_map_point* out, ui
   return res;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Parallel flattening (OpenMP).  The serial DFS above is one dependent pointer chase over ~176-byte nodes: ~50-80 ms for
+// a 1M-node tree on one core — far more than everything the GPU does per scan.  DFS pre-order slots are computable
+// without walking in order once the exported size of every subtree is known (left child = slot + 1, right child =
+// slot + 1 + size(left)), so: (1) walk the top of the tree serially down to subtrees of <= `grain` nodes (KD_TREE_NODE::
+// TreeSize bounds them), (2) count the exported nodes of those subtrees in parallel, (3) size and place the top part,
+// (4) flatten the subtrees in parallel, each into its own slot range.  The result is identical, byte for byte, to the
+// serial functions (tests/test_oracle_cpu.py).  Compile the including translation unit with -fopenmp; without it the
+// pragmas are ignored and the work runs serially.
+namespace detail {
+struct RecFull {
+  using type = malio_map_node;
+  template <class Node>
+  static void boxes(type& o, const Node* l, bool has_l, const Node* r, bool has_r) {
+    for (int k = 0; k < 6; ++k) { o.lbox[k] = 0.0f; o.rbox[k] = 0.0f; }
+    if (has_l) copy_box(l, o.lbox);
+    if (has_r) copy_box(r, o.rbox);
+  }
+};
+struct RecCompact {
+  using type = malio_map_point;
+  template <class Node>
+  static void boxes(type&, const Node*, bool, const Node*, bool) {}
+};
+
+template <class Node>
+inline void child_flags(const Node* n, const EffFlags& f, const Node*& l, const Node*& r, EffFlags& lf, EffFlags& rf, bool& has_l,
+                        bool& has_r) {
+  l = n->left_son_ptr; r = n->right_son_ptr;
+  has_l = false; has_r = false;
+  if (l != nullptr) { lf = pushed_flags(f, f.need_l, l); has_l = !lf.tree_deleted; }
+  if (r != nullptr) { rf = pushed_flags(f, f.need_r, r); has_r = !rf.tree_deleted; }
+}
+
+// exported nodes of the subtree of n (n itself is exported)
+template <class Node>
+inline uint32_t count_exported(const Node* root, const EffFlags& rf) {
+  struct Fr { const Node* n; EffFlags f; };
+  std::vector<Fr> st;
+  st.reserve(64);
+  st.push_back(Fr{root, rf});
+  uint32_t cnt = 0;
+  while (!st.empty()) {
+    Fr fr = st.back();
+    st.pop_back();
+    ++cnt;
+    const Node *l, *r;
+    EffFlags lf{}, rfl{};
+    bool hl, hr;
+    child_flags(fr.n, fr.f, l, r, lf, rfl, hl, hr);
+    if (hr) st.push_back(Fr{r, rfl});
+    if (hl) st.push_back(Fr{l, lf});
+  }
+  return cnt;
+}
+
+// serial pre-order flatten of one subtree into out[base ...] (absolute slots), depth of its root = depth0
+template <class Rec, class Node, class PointFn>
+inline void flatten_subtree(const Node* root, const EffFlags& rf, uint32_t base, uint32_t depth0, typename Rec::type* out,
+                            PointFn& on_node, uint32_t& n_points, uint32_t& max_depth) {
+  struct Fr { const Node* n; EffFlags f; uint32_t depth; int64_t parent_slot; };
+  std::vector<Fr> st;
+  st.reserve(128);
+  st.push_back(Fr{root, rf, depth0, -1});
+  uint32_t slot = base;
+  while (!st.empty()) {
+    Fr fr = st.back();
+    st.pop_back();
+    if (fr.depth > max_depth) max_depth = fr.depth;
+    if (fr.parent_slot >= 0) out[fr.parent_slot].link |= (slot & MALIO_LINK_INDEX_MASK);
+    typename Rec::type& o = out[slot];
+    o.x = fr.n->point.x; o.y = fr.n->point.y; o.z = fr.n->point.z;
+    uint32_t link = 0;
+    if (fr.f.point_deleted) link |= MALIO_LINK_POINT_DELETED; else n_points++;
+    const Node *l, *r;
+    EffFlags lf{}, rfl{};
+    bool hl, hr;
+    child_flags(fr.n, fr.f, l, r, lf, rfl, hl, hr);
+    if (hl) link |= MALIO_LINK_HAS_LEFT;
+    if (hr) link |= MALIO_LINK_HAS_RIGHT;
+    Rec::boxes(o, l, hl, r, hr);
+    o.link = link;
+    on_node(fr.n, slot);
+    if (hr) st.push_back(Fr{r, rfl, fr.depth + 1, (int64_t)slot});
+    if (hl) st.push_back(Fr{l, lf, fr.depth + 1, -1});
+    ++slot;
+  }
+}
+
+template <class Rec, class Node, class PointFn>
+FlattenResult flatten_parallel(const Node* root, typename Rec::type* out, uint32_t capacity, PointFn& on_node, float* root_box_out,
+                               uint32_t grain) {
+  FlattenResult res;
+  if (root == nullptr) return res;
+  const EffFlags rf0 = stored_flags(root);
+  if (rf0.tree_deleted) return res;
+  if (root_box_out) copy_box(root, root_box_out);
+  if (grain < 1024) grain = 1024;
+  // (1) top part: nodes whose TreeSize exceeds the grain, in pre-order; their small children become work items
+  struct Top { const Node* n; EffFlags f; uint32_t depth; int left, right;   // index into tops (>= 0) or -(item + 1), 0 = none
+               uint32_t size, slot; };
+  struct Item { const Node* n; EffFlags f; uint32_t depth; uint32_t size, slot, n_points, max_depth; };
+  std::vector<Top> tops;
+  std::vector<Item> items;
+  if ((uint32_t)root->TreeSize <= grain) {
+    items.push_back(Item{root, rf0, 1u, 0, 0, 0, 0});
+  } else {
+    struct Fr { const Node* n; EffFlags f; uint32_t depth; int parent; bool is_left; };
+    std::vector<Fr> st;
+    st.push_back(Fr{root, rf0, 1u, -1, false});
+    while (!st.empty()) {
+      Fr fr = st.back();
+      st.pop_back();
+      int ref;
+      if ((uint32_t)fr.n->TreeSize <= grain) { items.push_back(Item{fr.n, fr.f, fr.depth, 0, 0, 0, 0}); ref = -(int)items.size(); }
+      else {
+        tops.push_back(Top{fr.n, fr.f, fr.depth, 0, 0, 0, 0});
+        ref = (int)tops.size() - 1;
+        const Node *l, *r;
+        EffFlags lf{}, rfl{};
+        bool hl, hr;
+        child_flags(fr.n, fr.f, l, r, lf, rfl, hl, hr);
+        if (hr) st.push_back(Fr{r, rfl, fr.depth + 1, ref, false});
+        if (hl) st.push_back(Fr{l, lf, fr.depth + 1, ref, true});
+      }
+      if (fr.parent >= 0) {
+        const int enc = ref >= 0 ? ref + 1 : ref;      // tops: index + 1 (> 0), items: -(index + 1) (< 0), 0 = no child
+        if (fr.is_left) tops[fr.parent].left = enc; else tops[fr.parent].right = enc;
+      }
+    }
+  }
+  // (2) exported size of every work item
+  const int64_t n_items = (int64_t)items.size();
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t i = 0; i < n_items; ++i) items[i].size = count_exported(items[i].n, items[i].f);
+  // (3) sizes of the top nodes (children come later in `tops`: reverse order is bottom-up), then slots top-down
+  auto size_of = [&](int enc) -> uint32_t { return enc == 0 ? 0u : (enc > 0 ? tops[enc - 1].size : items[-enc - 1].size); };
+  for (int64_t k = (int64_t)tops.size() - 1; k >= 0; --k) tops[k].size = 1u + size_of(tops[k].left) + size_of(tops[k].right);
+  const uint64_t total = tops.empty() ? (uint64_t)items[0].size : (uint64_t)tops[0].size;
+  if (total > capacity || total > (uint64_t)MALIO_LINK_INDEX_MASK + 1) { res.overflow = true; return res; }
+  auto place = [&](int enc, uint32_t slot) { if (enc > 0) tops[enc - 1].slot = slot; else if (enc < 0) items[-enc - 1].slot = slot; };
+  if (tops.empty()) items[0].slot = 0; else tops[0].slot = 0;
+  for (size_t k = 0; k < tops.size(); ++k) {   // parents precede their children in `tops`
+    place(tops[k].left, tops[k].slot + 1);
+    place(tops[k].right, tops[k].slot + 1 + size_of(tops[k].left));
+  }
+  // top records
+  for (size_t k = 0; k < tops.size(); ++k) {
+    const Top& t = tops[k];
+    typename Rec::type& o = out[t.slot];
+    o.x = t.n->point.x; o.y = t.n->point.y; o.z = t.n->point.z;
+    uint32_t link = 0;
+    if (t.f.point_deleted) link |= MALIO_LINK_POINT_DELETED; else res.n_points++;
+    const Node *l, *r;
+    EffFlags lf{}, rfl{};
+    bool hl, hr;
+    child_flags(t.n, t.f, l, r, lf, rfl, hl, hr);
+    if (hl) link |= MALIO_LINK_HAS_LEFT;
+    if (hr) link |= MALIO_LINK_HAS_RIGHT | ((t.slot + 1 + size_of(t.left)) & MALIO_LINK_INDEX_MASK);
+    Rec::boxes(o, l, hl, r, hr);
+    o.link = link;
+    on_node(t.n, t.slot);
+    if (t.depth > res.max_depth) res.max_depth = t.depth;
+  }
+  // (4) the subtrees, each into its own slot range
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t i = 0; i < n_items; ++i) {
+    uint32_t np = 0, md = 0;
+    flatten_subtree<Rec>(items[i].n, items[i].f, items[i].slot, items[i].depth, out, on_node, np, md);
+    items[i].n_points = np; items[i].max_depth = md;
+  }
+  for (int64_t i = 0; i < n_items; ++i) { res.n_points += items[i].n_points; if (items[i].max_depth > res.max_depth) res.max_depth = items[i].max_depth; }
+  res.n_nodes = (uint32_t)total;
+  return res;
+}
+}  // namespace detail
+
+// Parallel variants: same output as flatten_ikdtree / flatten_ikdtree_compact.  on_node is called concurrently from
+// several threads (each slot exactly once).  grain = largest subtree (by KD_TREE_NODE::TreeSize) flattened by one thread.
+template <class Node, class PointFn>
+FlattenResult flatten_ikdtree_parallel(const Node* root, malio_map_node* out, uint32_t capacity, PointFn&& on_node,
+                                       uint32_t grain = 16384) {
+  return detail::flatten_parallel<detail::RecFull>(root, out, capacity, on_node, nullptr, grain);
+}
+template <class Node, class PointFn>
+FlattenResult flatten_ikdtree_compact_parallel(const Node* root, malio_map_point* out, uint32_t capacity, PointFn&& on_node,
+                                               float* root_box_out = nullptr, uint32_t grain = 16384) {
+  return detail::flatten_parallel<detail::RecCompact>(root, out, capacity, on_node, root_box_out, grain);
+}
+
 }  // namespace malio
 #endif  // MALIO_FLATTEN_HPP_

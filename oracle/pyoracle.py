@@ -94,6 +94,10 @@ def ref_lib() -> C.CDLL:
         L.ikdref_snapshot.argtypes = [vp, vp, vp, vp, C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.ikdref_snapshot_compact.restype = C.c_int64
         L.ikdref_snapshot_compact.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(C.c_uint32), vp]
+        L.ikdref_snapshot_parallel.restype = C.c_int64
+        L.ikdref_snapshot_parallel.argtypes = [vp, vp, vp, vp, C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32]
+        L.ikdref_snapshot_compact_parallel.restype = C.c_int64
+        L.ikdref_snapshot_compact_parallel.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(C.c_uint32), vp, C.c_uint32]
         _ref = L
     return _ref
 
@@ -167,6 +171,29 @@ class RefTree:
         n = self.L.ikdref_snapshot(self.t, ptr(nodes), ptr(cov), ptr(ids), cap, C.byref(depth), C.byref(live))
         assert n >= 0
         return nodes[:n].copy(), cov[:n].copy(), ids[:n].copy(), int(depth.value), int(live.value)
+
+    def snapshot_parallel(self, grain: int = 16384):
+        """malio::flatten_ikdtree_parallel: same return as snapshot()."""
+        cap = max(self.size(), 1)
+        nodes = np.zeros(cap, dtype=capi.MAP_NODE)
+        cov = np.zeros(cap, np.float32)
+        ids = np.zeros(cap, np.int32)
+        depth = C.c_uint32(0)
+        live = C.c_uint32(0)
+        n = self.L.ikdref_snapshot_parallel(self.t, ptr(nodes), ptr(cov), ptr(ids), cap, C.byref(depth), C.byref(live), grain)
+        assert n >= 0
+        return nodes[:n].copy(), cov[:n].copy(), ids[:n].copy(), int(depth.value), int(live.value)
+
+    def snapshot_compact_parallel(self, grain: int = 16384):
+        """malio::flatten_ikdtree_compact_parallel: same return as snapshot_compact()."""
+        cap = max(self.size(), 1)
+        pts = np.zeros(cap, dtype=capi.MAP_POINT)
+        cov = np.zeros(cap, np.float32)
+        depth = C.c_uint32(0)
+        box = np.zeros(6, np.float32)
+        n = self.L.ikdref_snapshot_compact_parallel(self.t, ptr(pts), ptr(cov), cap, C.byref(depth), ptr(box), grain)
+        assert n >= 0
+        return pts[:n].copy(), cov[:n].copy(), int(depth.value), box
 
     def snapshot_compact(self):
         """Flatten through malio::flatten_ikdtree_compact.  Returns (points, node_cov, max_depth, root_box)."""

@@ -142,6 +142,29 @@ int64_t ikdref_snapshot_compact(void* t, malio_map_point* pts, float* node_cov, 
   return res.overflow ? -1 : (int64_t)res.n_nodes;
 }
 
+// the parallel flatteners (same output, OpenMP)
+int64_t ikdref_snapshot_parallel(void* t, malio_map_node* nodes, float* node_cov, int32_t* node_ids, int64_t cap,
+                                 uint32_t* max_depth, uint32_t* n_live_points, uint32_t grain) {
+  Tree* tr = (Tree*)t;
+  auto res = malio::flatten_ikdtree_parallel(
+      tr->Root_Node, nodes, (uint32_t)cap, [&](const Tree::KD_TREE_NODE* n, uint32_t slot) {
+        if (node_cov) node_cov[slot] = n->point.normal_y;
+        if (node_ids) node_ids[slot] = float_to_id(n->point.normal_z);
+      }, grain);
+  if (max_depth) *max_depth = res.max_depth;
+  if (n_live_points) *n_live_points = res.n_points;
+  return res.overflow ? -1 : (int64_t)res.n_nodes;
+}
+int64_t ikdref_snapshot_compact_parallel(void* t, malio_map_point* pts, float* node_cov, int64_t cap, uint32_t* max_depth,
+                                         float* root_box, uint32_t grain) {
+  Tree* tr = (Tree*)t;
+  auto res = malio::flatten_ikdtree_compact_parallel(
+      tr->Root_Node, pts, (uint32_t)cap, [&](const Tree::KD_TREE_NODE* n, uint32_t slot) { if (node_cov) node_cov[slot] = n->point.normal_y; },
+      root_box, grain);
+  if (max_depth) *max_depth = res.max_depth;
+  return res.overflow ? -1 : (int64_t)res.n_nodes;
+}
+
 int ikdref_node_bytes() { return (int)sizeof(Tree::KD_TREE_NODE); }
 
 }  // extern "C"

@@ -101,6 +101,23 @@ def test_compact_flattener_and_tight_box_rule_on_the_real_tree():
     assert np.array_equal(root_box, np.stack([lo[0], hi[0]], 1).reshape(6))
 
 
+@pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref (real ikd_Tree.cpp) only exists in the build container")
+def test_parallel_flatteners_equal_the_serial_ones_on_the_real_tree():
+    """malio::flatten_ikdtree_parallel / _compact_parallel (OpenMP, slots from subtree sizes) must produce the serial
+    flatteners' output byte for byte on the churned reference tree, for grains from 'everything in one item' to 'tops
+    all the way down'."""
+    case = synth.make_case("t", 2000, 60000, 1, 3, varied_map_cov=True)
+    snap, tree = H.snapshot_for(case, churn=True)
+    nodes, cov, ids, depth, live = tree.snapshot()
+    pts, pcov, pdepth, box = tree.snapshot_compact()
+    for grain in (1 << 30, 16384, 4096, 1024):
+        n2, c2, i2, d2, l2 = tree.snapshot_parallel(grain)
+        assert n2.tobytes() == nodes.tobytes() and np.array_equal(c2, cov) and np.array_equal(i2, ids)
+        assert d2 == depth and l2 == live
+        p2, pc2, pd2, b2 = tree.snapshot_compact_parallel(grain)
+        assert p2.tobytes() == pts.tobytes() and np.array_equal(pc2, pcov) and pd2 == pdepth and np.array_equal(b2, box)
+
+
 def test_search_is_exact_knn_bruteforce():
     rng = np.random.default_rng(3)
     xyz = (rng.random((5000, 3)) * [40, 40, 4]).astype(np.float32)
