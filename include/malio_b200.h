@@ -195,7 +195,8 @@ int malio_measure(malio_handle* h, const malio_pass_state* s, int redo_knn,
                   double* HtRinvH, double* HtRinvh, malio_pass_stats* stats);
 
 /* rows of the last pass for the degenerate branch n > N_eff (esekfom.hpp:574-582): up to cap rows of
- * h_x (row-major, c columns) and h, in scan order, already scaled by plane and localization weight. */
+ * h_x (row-major, c columns) and h, in scan order, scaled by the plane weight (laserMapping.cpp:714-715) but NOT yet by
+ * the localization weight: multiply by stats->loc_weight (laserMapping.cpp:758-759), as malio_ieskf_update does. */
 int malio_download_rows(malio_handle* h, double* h_x, double* hvec, uint32_t cap, uint32_t* n_rows);
 
 /* side outputs of the last pass, caller order; any pointer may be NULL.
