@@ -572,7 +572,9 @@ int malio_ieskf_update(malio_handle* h, malio_state* x, double* Pio, int max_ite
   Mat P_prop(n, n);
   std::memcpy(P_prop.a.data(), Pio, sizeof(double) * n * n);
   Mat P = P_prop, Kx(n, c), G(c, c);
-  std::vector<double> g(c), dx(n), dxn(n), Kh(n), step(n);
+  std::vector<double> g(c), dx(n), dxn(n), Kh(n), step(n), KxDx(n);
+  double Ykeep[MALIO_MAX_COLS][MALIO_MAX_DOF];   // Q[:,0:c]^T of the last regular pass (K_x is formed from it only when needed)
+  bool kx_lazy = false;
   bool redo = true;   // dyn_share.converge
   int t = 0, rc_last = MALIO_OK;
   double host_ms = 0.0;
@@ -631,6 +633,8 @@ int malio_ieskf_update(malio_handle* h, malio_state* x, double* Pio, int max_ite
       for (int a = 0; a < n; ++a) for (int q = 0; q < m; ++q) { double s = 0; for (int r = 0; r < m; ++r) s += PHt(a, r) * Si(r, q); K(a, q) = s / R; }
       for (int a = 0; a < n; ++a) { double s = 0; for (int r = 0; r < m; ++r) s += K(a, r) * hv[r]; Kh[a] = s; }
       for (int a = 0; a < n; ++a) for (int b = 0; b < c; ++b) { double s = 0; for (int r = 0; r < m; ++r) s += K(a, r) * H(r, b); Kx(a, b) = s; }
+      for (int a = 0; a < n; ++a) { double s = 0; for (int b = 0; b < c; ++b) s += Kx(a, b) * dxn[b]; KxDx[a] = s; }
+      kx_lazy = false;
     } else {                   // :621-637
       // The reference forms Q = (P^-1 + E^T G E)^-1 with two n x n inversions (E = [I_c 0]) and uses only Q[:, 0:c].
       // By the push-through identity  Q E^T = P E^T (I_c + G P_cc)^-1 : one c x c factorisation instead.
@@ -679,25 +683,25 @@ int malio_ieskf_update(malio_handle* h, malio_state* x, double* Pio, int max_ite
         const double inv = 1.0 / Mt[i][i];
         for (int j = 0; j < n; ++j) Yt[i][j] *= inv;
       }
-      double* Kxd = Kx.a.data();
-      for (int a = 0; a < n; ++a) {
+      // K_h = Q[:,0:c] g (:635).  K_x = Q[:,0:c] G (:637) is only needed as a matrix by the final covariance update;
+      // the state increment needs K_x dx_new = Q[:,0:c] (G dx_new): c*c + n*c products instead of n*c*c per pass.
+      double Gdx[CM];
+      for (int k = 0; k < c; ++k) {
+        const double* gr = Gd + (size_t)k * c;
         double s = 0.0;
-        double* kr = Kxd + (size_t)a * c;
-        for (int b = 0; b < c; ++b) kr[b] = 0.0;
-        for (int k = 0; k < c; ++k) {
-          const double y = Yt[k][a];
-          s += y * g[k];                                             // K_h = Q[:,0:c] g            (:635)
-          const double* gr = Gd + (size_t)k * c;
-          for (int b = 0; b < c; ++b) kr[b] += y * gr[b];            // K_x = Q[:,0:c] G            (:637)
-        }
-        Kh[a] = s;
+        for (int b = 0; b < c; ++b) s += gr[b] * dxn[b];
+        Gdx[k] = s;
       }
+      for (int a = 0; a < n; ++a) {
+        double s = 0.0, u = 0.0;
+        for (int k = 0; k < c; ++k) { const double y = Yt[k][a]; s += y * g[k]; u += y * Gdx[k]; }
+        Kh[a] = s;
+        KxDx[a] = u;
+      }
+      kx_lazy = true;
+      std::memcpy(Ykeep, Yt, sizeof(Yt));
     }
-    for (int a = 0; a < n; ++a) {          // dx_ = K_h + (K_x - I) dx_new, :642
-      double s = Kh[a] - dxn[a];
-      for (int b = 0; b < c; ++b) s += Kx(a, b) * dxn[b];
-      step[a] = s;
-    }
+    for (int a = 0; a < n; ++a) step[a] = Kh[a] + KxDx[a] - dxn[a];   // dx_ = K_h + (K_x - I) dx_new, :642
     std::memcpy(rp.dx_last, step.data(), sizeof(double) * n);
     boxplus(ly, *x, step.data());          // :646
     redo = true;                           // :649-657
@@ -705,6 +709,19 @@ int malio_ieskf_update(malio_handle* h, malio_state* x, double* Pio, int max_ite
     if (redo) t++;
     if (!t && it == max_iter - 2) redo = true;   // :660-663
     if (t > 1 || it == max_iter - 1) {     // final covariance, :665-718
+      if (kx_lazy) {                       // K_x = Q[:,0:c] G (:637), once
+        const double* Gd = G.a.data();
+        double* Kxd = Kx.a.data();
+        for (int a = 0; a < n; ++a) {
+          double* kr = Kxd + (size_t)a * c;
+          for (int b = 0; b < c; ++b) kr[b] = 0.0;
+          for (int k = 0; k < c; ++k) {
+            const double y = Ykeep[k][a];
+            const double* gr = Gd + (size_t)k * c;
+            for (int b = 0; b < c; ++b) kr[b] += y * gr[b];
+          }
+        }
+      }
       Mat Lm = P;
       for (int s = 0; s <= ly.L; ++s) {
         const int idx = ly.so3[s];
