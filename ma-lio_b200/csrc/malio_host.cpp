@@ -573,7 +573,9 @@ int malio_ieskf_update(malio_handle* h, malio_state* x, double* Pio, int max_ite
   std::memcpy(P_prop.a.data(), Pio, sizeof(double) * n * n);
   Mat P = P_prop, Kx(n, c), G(c, c);
   std::vector<double> g(c), dx(n), dxn(n), Kh(n), step(n), KxDx(n);
-  double Ykeep[MALIO_MAX_COLS][MALIO_MAX_DOF];   // Q[:,0:c]^T of the last regular pass (K_x is formed from it only when needed)
+  double LU[MALIO_MAX_COLS][MALIO_MAX_COLS];     // factors of Mt = (I + G P_cc)^T of the last regular pass, and its row interchanges
+  int piv[MALIO_MAX_COLS];
+  double Ykeep[MALIO_MAX_COLS][MALIO_MAX_DOF];   // Q[:,0:c]^T, solved for only by the pass that updates the covariance
   bool kx_lazy = false;
   bool redo = true;   // dyn_share.converge
   int t = 0, rc_last = MALIO_OK;
@@ -643,8 +645,12 @@ int malio_ieskf_update(malio_handle* h, malio_state* x, double* Pio, int max_ite
       // the GPU idle: every microsecond here is a microsecond of scan latency).
       //   Mt = (I + G P_cc)^T  (row a, col b) = delta_ab + sum_k G(b,k) P(a,k)   [P is symmetric after the
       //   congruence projections above];  solve Mt * Yt = (P[:,0:c])^T  =>  Y = Yt^T = Q[:, 0:c]
-      constexpr int CM = MALIO_MAX_COLS, NM = MALIO_MAX_DOF;
-      double Mt[CM][CM], Yt[CM][NM];
+      // Per pass only two vectors of Q[:,0:c] are needed: K_h = Q[:,0:c] g and K_x dx_new = Q[:,0:c] (G dx_new), i.e.
+      //   S z = rhs  with S = I + G P_cc,   then  P[:,0:c] z.
+      // So Mt = S^T is LU-factorised once (partial pivoting, factors kept), the two right-hand sides go through the
+      // TRANSPOSED triangular solves (S = U^T L^T Pm), and the full n x c block Q[:,0:c] — 35 right-hand sides — is
+      // only solved for in the pass that updates the covariance (below), from the same factors.
+      constexpr int CM = MALIO_MAX_COLS;
       const double* Gd = G.a.data();
       const double* Pd = P.a.data();
       for (int a = 0; a < c; ++a)
@@ -653,53 +659,53 @@ int malio_ieskf_update(malio_handle* h, malio_state* x, double* Pio, int max_ite
           const double* pr = Pd + (size_t)a * n;
           double s = 0.0;
           for (int k = 0; k < c; ++k) s += gr[k] * pr[k];
-          Mt[a][b] = s + ((a == b) ? 1.0 : 0.0);
+          LU[a][b] = s + ((a == b) ? 1.0 : 0.0);
         }
-      for (int a = 0; a < c; ++a) for (int j = 0; j < n; ++j) Yt[a][j] = Pd[(size_t)a * n + j];   // P(j,a) = P(a,j)
-      // LU with partial pivoting on Mt, the row operations applied to Yt as they happen
-      for (int k = 0; k < c; ++k) {
+      for (int k = 0; k < c; ++k) {          // Pm Mt = L U, L unit lower (multipliers stored below the diagonal)
         int p = k;
-        double best = std::fabs(Mt[k][k]);
-        for (int i = k + 1; i < c; ++i) if (std::fabs(Mt[i][k]) > best) { best = std::fabs(Mt[i][k]); p = i; }
+        double best = std::fabs(LU[k][k]);
+        for (int i = k + 1; i < c; ++i) if (std::fabs(LU[i][k]) > best) { best = std::fabs(LU[i][k]); p = i; }
         if (best == 0.0) { h->err = "singular information matrix"; if (rep) *rep = rp; return MALIO_ERR_INVALID_ARG; }
-        if (p != k) {
-          for (int j = 0; j < c; ++j) std::swap(Mt[k][j], Mt[p][j]);
-          for (int j = 0; j < n; ++j) std::swap(Yt[k][j], Yt[p][j]);
-        }
-        const double inv = 1.0 / Mt[k][k];
+        piv[k] = p;
+        if (p != k) for (int j = 0; j < c; ++j) std::swap(LU[k][j], LU[p][j]);
+        const double inv = 1.0 / LU[k][k];
         for (int i = k + 1; i < c; ++i) {
-          const double f = Mt[i][k] * inv;
+          const double f = LU[i][k] * inv;
+          LU[i][k] = f;
           if (f == 0.0) continue;
-          for (int j = k + 1; j < c; ++j) Mt[i][j] -= f * Mt[k][j];
-          for (int j = 0; j < n; ++j) Yt[i][j] -= f * Yt[k][j];
+          for (int j = k + 1; j < c; ++j) LU[i][j] -= f * LU[k][j];
         }
       }
-      for (int i = c - 1; i >= 0; --i) {
-        for (int k = i + 1; k < c; ++k) {
-          const double f = Mt[i][k];
-          if (f == 0.0) continue;
-          for (int j = 0; j < n; ++j) Yt[i][j] -= f * Yt[k][j];
-        }
-        const double inv = 1.0 / Mt[i][i];
-        for (int j = 0; j < n; ++j) Yt[i][j] *= inv;
-      }
-      // K_h = Q[:,0:c] g (:635).  K_x = Q[:,0:c] G (:637) is only needed as a matrix by the final covariance update;
-      // the state increment needs K_x dx_new = Q[:,0:c] (G dx_new): c*c + n*c products instead of n*c*c per pass.
-      double Gdx[CM];
+      // S z = rhs:  Mt = Pm^T L U  =>  S = Mt^T = U^T L^T Pm  =>  U^T w = rhs (forward), L^T v = w (backward), z = Pm^T v
+      double z1[CM], z2[CM];
       for (int k = 0; k < c; ++k) {
+        z1[k] = g[k];
         const double* gr = Gd + (size_t)k * c;
-        double s = 0.0;
-        for (int b = 0; b < c; ++b) s += gr[b] * dxn[b];
-        Gdx[k] = s;
+        double sdx = 0.0;
+        for (int b = 0; b < c; ++b) sdx += gr[b] * dxn[b];
+        z2[k] = sdx;                         // G dx_new
       }
-      for (int a = 0; a < n; ++a) {
+      for (int i = 0; i < c; ++i) {          // U^T w = rhs
+        double s1 = z1[i], s2 = z2[i];
+        for (int k = 0; k < i; ++k) { s1 -= LU[k][i] * z1[k]; s2 -= LU[k][i] * z2[k]; }
+        const double inv = 1.0 / LU[i][i];
+        z1[i] = s1 * inv; z2[i] = s2 * inv;
+      }
+      for (int i = c - 1; i >= 0; --i) {     // L^T v = w  (unit diagonal)
+        double s1 = z1[i], s2 = z2[i];
+        for (int k = i + 1; k < c; ++k) { s1 -= LU[k][i] * z1[k]; s2 -= LU[k][i] * z2[k]; }
+        z1[i] = s1; z2[i] = s2;
+      }
+      for (int k = c - 1; k >= 0; --k)       // z = Pm^T v: undo the row interchanges in reverse order
+        if (piv[k] != k) { std::swap(z1[k], z1[piv[k]]); std::swap(z2[k], z2[piv[k]]); }
+      for (int a = 0; a < n; ++a) {          // K_h = P[:,0:c] z1 (:635), K_x dx_new = P[:,0:c] z2 (:637,:642)
+        const double* pr = Pd + (size_t)a * n;
         double s = 0.0, u = 0.0;
-        for (int k = 0; k < c; ++k) { const double y = Yt[k][a]; s += y * g[k]; u += y * Gdx[k]; }
+        for (int k = 0; k < c; ++k) { s += pr[k] * z1[k]; u += pr[k] * z2[k]; }
         Kh[a] = s;
         KxDx[a] = u;
       }
       kx_lazy = true;
-      std::memcpy(Ykeep, Yt, sizeof(Yt));
     }
     for (int a = 0; a < n; ++a) step[a] = Kh[a] + KxDx[a] - dxn[a];   // dx_ = K_h + (K_x - I) dx_new, :642
     std::memcpy(rp.dx_last, step.data(), sizeof(double) * n);
@@ -709,8 +715,28 @@ int malio_ieskf_update(malio_handle* h, malio_state* x, double* Pio, int max_ite
     if (redo) t++;
     if (!t && it == max_iter - 2) redo = true;   // :660-663
     if (t > 1 || it == max_iter - 1) {     // final covariance, :665-718
-      if (kx_lazy) {                       // K_x = Q[:,0:c] G (:637), once
+      if (kx_lazy) {                       // Q[:,0:c]^T = Mt^-1 P[:,0:c]^T from the stored factors, then K_x = Q[:,0:c] G (:637)
         const double* Gd = G.a.data();
+        const double* Pd = P.a.data();
+        for (int a = 0; a < c; ++a) for (int j = 0; j < n; ++j) Ykeep[a][j] = Pd[(size_t)a * n + j];   // P(j,a) = P(a,j)
+        for (int k = 0; k < c; ++k)          // Pm: all row interchanges first (the stored multipliers were swapped with their rows)
+          if (piv[k] != k) for (int j = 0; j < n; ++j) std::swap(Ykeep[k][j], Ykeep[piv[k]][j]);
+        for (int k = 0; k < c; ++k) {        // L^-1 (forward, unit diagonal)
+          for (int i = k + 1; i < c; ++i) {
+            const double f = LU[i][k];
+            if (f == 0.0) continue;
+            for (int j = 0; j < n; ++j) Ykeep[i][j] -= f * Ykeep[k][j];
+          }
+        }
+        for (int i = c - 1; i >= 0; --i) {   // U^-1 (backward)
+          for (int k = i + 1; k < c; ++k) {
+            const double f = LU[i][k];
+            if (f == 0.0) continue;
+            for (int j = 0; j < n; ++j) Ykeep[i][j] -= f * Ykeep[k][j];
+          }
+          const double inv = 1.0 / LU[i][i];
+          for (int j = 0; j < n; ++j) Ykeep[i][j] *= inv;
+        }
         double* Kxd = Kx.a.data();
         for (int a = 0; a < n; ++a) {
           double* kr = Kxd + (size_t)a * c;
