@@ -1,27 +1,35 @@
 #!/usr/bin/env python
 """bench.py — scans/sec & ms/IESKF-iter of the MA-LIO measurement hot path (BASELINE.json metric).
 
-  python bench.py --gpus N --steps K --warmup W            # CUDA path (this repo)
+  python bench.py --gpus N --steps K --warmup W            # CUDA path (this repo), config C2 (the metric's config)
   python bench.py --impl reference --gpus N ...            # the reference's own CPU path on the host cores
-  torchrun ... bench.py --gpus N ...                       # N > 1: one rank per GPU, NCCL
+  python bench.py --config C4|C5 ...                       # the other BASELINE configs (not the driver's bench line)
+  torchrun ... bench.py --gpus N ...                       # N > 1: one rank per GPU
 
-A *step* is one scan: the full iterated update (esekfom.hpp:495-721; max_iteration 3 => up to 4 measurement
-passes, k-NN on the first pass and after a converged step) of the 3-LiDAR 100k-point merged scan against the
-1M-point map snapshot (BASELINE configs[1], "C2"; with --gpus N > 1 the same scan point-sharded over N ranks:
-configs[2]).  Synthetic, seeded inputs (malio_b200/synth.py).
+A *step* is one scan: the full iterated update (esekfom.hpp:495-721; max_iteration 3 => up to 4 measurement passes,
+k-NN on the first pass and after a converged step) of the 3-LiDAR 100k-point merged scan against the 1M-point map
+(BASELINE configs[1], "C2"; with --gpus N > 1 the same scan point-sharded over N ranks: configs[2]).  Synthetic, seeded
+inputs (malio_b200/synth.py).  The map is a LIVE reference ikd-Tree (the real ikd_Tree.cpp, oracle/_ref: Build + the
+scripted churn of SURVEY.md §8d — 2 % Add_Points with down-sampling, a no-down-sampling batch, one Delete_Point_Boxes —
+so lazy flags and rebuilt subtrees exist); where oracle/_ref is not built the product's static builder stands in and the
+line says so.  The tree is INPUT here, exactly what a MA-LIO checkout holds on its host; nothing under oracle/ computes
+any part of the measured result.
 
 `value`   scans/sec with every input already resident in HBM when the timed region starts (the per-scan state is
-          re-armed on the device; sort, k-NN, plane fit, gate, reduction, D2H of the 5 KB system and the host
-          35x35 algebra are all inside).
-`e2e`     the same metric through the public C-ABI calls with HOST (pinned) buffers: every step uploads the
-          flattened map snapshot (compact form: 20 B per node, boxes rebuilt on the device) and the scan, runs the
-          update, and reads back the per-point side outputs.
-L2 is flushed (256 MiB write) between timed steps; each step is bracketed by CUDA events and the per-step
-times are summed (max over ranks).  Only the cpu_baseline / --impl reference legs touch oracle/.
+          re-armed on the device; sort, k-NN, plane fit, gate, reduction, D2H of the 3.5 KB system and the host 35x35
+          algebra are all inside).
+`e2e`     the same metric from HOST data through the public C-ABI, what a MA-LIO checkout would see per scan:
+          flatten of the live ikd-Tree (include/malio_flatten.hpp, OpenMP on the host threads; `flatten_ms`) -> compact
+          snapshot upload (20 B per node, boxes + cell index rebuilt on the device) -> scan upload -> iterated update ->
+          download of the per-point side outputs.  `e2e.snapshot_only` repeats it with the flatten left out (the round-1
+          definition) for comparison.
+L2 is flushed (256 MiB write) between timed steps; each step is bracketed by CUDA events and the per-step times are
+summed (max over ranks).  Only the cpu_baseline / --impl reference legs time anything under oracle/.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -36,10 +44,14 @@ sys.path.insert(0, os.path.join(ROOT, "ma-lio_b200"))
 
 METRIC = "scans/sec & ms/IESKF-iter, 100k-pt scan vs 1M-pt map, 1/2/4/8 GPU"
 UNIT = "scans/s"
-WORKLOAD = "C2: 3-LiDAR (Ouster+2xLivox) 100k-pt merged scan vs 1M-pt map snapshot, max_iteration=3"
-# dram__bytes_read.sum + dram__bytes_write.sum of one knn_grid_kernel launch on C2
-# (ncu --set full, profiles/r01_knn_grid_kernel_raw.csv / r01_knn_grid_kernel.md)
-NCU_DRAM_BYTES_PER_KNN_LAUNCH = 8.23e6
+WORKLOADS = {
+    "C2": "C2: 3-LiDAR (Ouster+2xLivox) 100k-pt merged scan vs 1M-pt map (live ikd-Tree, churned), max_iteration=3",
+    "C4": "C4: dense urban 300k-pt merged scan vs 5M-pt map, max_iteration=5",
+    "C5": "C5: k-NN microbench, 1M queries vs 10M-pt tree, k=5",
+}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (profiles/), C2 only
+NCU_DRAM_BYTES = {"knn": 8.23e6, "pass": None}
+REF_CPU_BUDGET_S = 150.0   # bound of the CPU arms' total run time (both thread counts together)
 
 
 def parse():
@@ -48,8 +60,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2", choices=["C2", "C4", "C5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sort", action="store_true")
+    ap.add_argument("--static-map", action="store_true", help="static balanced snapshot instead of the live ikd-Tree")
     return ap.parse_args()
 
 
@@ -100,13 +114,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------ reference / CPU arm
 class c_stdout_to_stderr:
     """The reference ikd-Tree printf()s thread start/stop notices on stdout; keep fd 1 clean for the JSON line."""
 
     def __enter__(self):
-        import ctypes
-        self.libc = ctypes.CDLL(None)
+        self.libc = C.CDLL(None)
         sys.stdout.flush()
         self.saved = os.dup(1)
         os.dup2(2, 1)
@@ -125,18 +137,49 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
-def cpu_reference_run(case, steps: int, warmup: int, threads: int):
+def load_case(config: str):
+    from malio_b200 import synth
+    return synth.case_C4() if config == "C4" else synth.case_C2()
+
+
+# ------------------------------------------------------------------ the map as the host holds it
+CHURN_NOTE = "Build + 2% Add_Points(downsample) + 0.5% Add_Points(no downsample) + one 12x12x6 m Delete_Point_Boxes"
+
+
+def live_tree(case, seed=7):
+    """The reference's KD_TREE (oracle/_ref = the real ikd_Tree.cpp) holding the case's map after the scripted churn of
+    SURVEY.md §8d.  Returns a pyoracle.RefTree or None when oracle/_ref was not built."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as po
+    if not po.ref_available():
+        return None
+    tree = po.RefTree(box_length=0.5)
+    tree.build(case.map_xyz, case.map_normal_y)
+    rng = np.random.default_rng(seed)
+    M = case.map_xyz.shape[0]
+    k = max(M // 50, 10)
+    add = case.map_xyz[rng.integers(0, M, k)] + rng.normal(0, 0.3, (k, 3)).astype(np.float32)
+    tree.add_points(add, np.full(k, 0.001, np.float32), downsample=True)
+    add2 = case.map_xyz[rng.integers(0, M, k // 4)] + rng.normal(0, 0.2, (k // 4, 3)).astype(np.float32)
+    tree.add_points(add2, np.full(k // 4, 0.001, np.float32), downsample=False)
+    c = case.map_xyz[rng.integers(0, M)]
+    tree.delete_boxes([[c[0] - 6, c[1] - 6, c[2] - 3, c[0] + 6, c[1] + 6, c[2] + 3]])
+    tree.wait_rebuild()
+    return tree
+
+
+# ------------------------------------------------------------------ reference / CPU arm
+def cpu_reference_run(case, tree, steps: int, warmup: int, threads: int):
     """The reference's CPU path: real ikd_Tree.cpp (oracle/_ref) for the k-NN when it was compiled here, else the
-    restated search; restated h_share_model + update_iterated_dyn_share_modified (oracle/).  Returns
-    (scans_per_s, ms_per_pass, kind, passes_per_scan)."""
+    restated search; restated h_share_model + update_iterated_dyn_share_modified (oracle/), with esekfom.hpp:622-635
+    evaluated the optimised way (orc_reduce_fast).  Returns a dict."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle as po
     orc = po.Oracle(case.params)
-    if po.ref_available():
-        tree = po.RefTree(box_length=0.5)
-        tree.build(case.map_xyz, case.map_normal_y)
+    orc.set_fast_reduce(True)
+    if tree is not None:
         orc.set_knn_ref(tree)
-        kind = "reference"
+        kind = "reference-knn+port"
     else:
         from malio_b200 import plugin
         snap = plugin.build_static_snapshot(case.map_xyz, case.map_normal_y)
@@ -146,40 +189,193 @@ def cpu_reference_run(case, steps: int, warmup: int, threads: int):
     for i in range(warmup + steps):
         orc.set_scan(case.pts, case.table, case.table_off, case.temporal_comp)
         x, P = case.x_prop.copy(), case.P_prop.copy()
+        if i == warmup:
+            orc.reset_times()
         t0 = time.perf_counter()
         rc, _, _, rep = orc.update_iterated(x, P, case.max_iter, nthreads=threads)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
             passes += rep.passes
+    tK, tB, tA, npass = orc.times()
     tot = float(np.sum(times))
     orc.close()
-    if kind == "reference":
-        tree.close()
-    return steps / tot, 1e3 * tot / max(passes, 1), kind, passes / max(steps, 1)
+    npass = max(npass, 1)
+    return {"scans_per_s": steps / tot, "ms_per_pass": 1e3 * tot / max(passes, 1), "kind": kind, "threads": threads,
+            "passes_per_scan": passes / max(steps, 1), "steps": steps, "warmup": warmup,
+            "split_ms_per_pass": {"K_nearest_search": 1e3 * tK / npass, "B_h_share_model_rest": 1e3 * tB / npass,
+                                  "A_ieskf_rest": 1e3 * tA / npass}}
+
+
+def cpu_arms(case, tree, steps, warmup):
+    """Both thread counts the survey asks for: 3 (what the reference ships, CMakeLists.txt:23-25) and all host threads.
+    Steps are honoured up to a wall-clock budget (a full C2 scan is 0.2-0.7 s of CPU)."""
+    th_all = host_threads()
+    runs = []
+    budget = REF_CPU_BUDGET_S / 2
+    for th in ([3, th_all] if th_all > 3 else [th_all]):
+        probe = cpu_reference_run(case, tree, 1, 1, th)       # also the first warm-up
+        est = 1.0 / probe["scans_per_s"]
+        k = int(max(1, min(steps, budget / est - warmup)))
+        w = int(max(0, min(warmup - 1, budget / est - k)))
+        runs.append(cpu_reference_run(case, tree, k, w, th))
+        runs[-1]["warmup"] = w + 2
+    best = max(runs, key=lambda r: r["scans_per_s"])
+    return best, runs
+
+
+def cpu_baseline_obj(best, runs, what):
+    return {"value": best["scans_per_s"], "unit": UNIT, "cores": best["threads"], "kind": best["kind"],
+            "ms_per_ieskf_iter": best["ms_per_pass"], "split_ms_per_pass": best["split_ms_per_pass"],
+            "by_threads": {str(r["threads"]): {"value": r["scans_per_s"], "ms_per_ieskf_iter": r["ms_per_pass"],
+                                               "split_ms_per_pass": r["split_ms_per_pass"], "steps": r["steps"]} for r in runs},
+            "sample": what,
+            "notes": "K = KD_TREE::Nearest_Search of the real ikd_Tree.cpp (g++ -O3); B/A = line-by-line port (no Eigen in the "
+                     "image) with the O(N) algebra of esekfom.hpp:622-635 blocked, AVX-dispatched and threaded (more generous than "
+                     "the reference's baseline-x86-64 Eigen build); value = the faster of 3 threads (reference default) / all threads"}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    from malio_b200 import synth
-    case = synth.case_C2()
-    threads = host_threads()
-    steps = max(1, min(args.steps, 5))    # each step is one full scan on the CPU (~0.3-1 s with all cores): bounded
-    warm = min(args.warmup, 1)
+    if args.config == "C5":
+        return run_reference_c5(args)
+    case = load_case(args.config)
     with c_stdout_to_stderr():
-        sps, ms_pass, kind, ppscan = cpu_reference_run(case, steps, warm, threads)
+        tree = None if args.static_map else live_tree(case)
+        best, runs = cpu_arms(case, tree, args.steps, args.warmup)
+        if tree is not None:
+            tree.close()
+    sps = best["scans_per_s"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": 1e3 / sps, "ms_per_ieskf_iter": ms_pass, "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": best["steps"],
+        "warmup": best["warmup"], "ms_per_step": 1e3 / sps, "ms_per_ieskf_iter": best["ms_per_pass"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64/f32", "data": "synthetic (seeded, malio_b200/synth.py)",
-        "config": {"workload": WORKLOAD, "passes_per_scan": ppscan, "host_threads": threads},
-        "cpu_baseline": {"value": sps, "unit": UNIT, "cores": threads, "kind": kind,
-                         "sample": f"{steps} full C2 scans (100k pts vs 1M-pt ikd-Tree), all host threads in the point loop"},
+        "config": {"workload": WORKLOADS[args.config], "passes_per_scan": best["passes_per_scan"], "host_threads": host_threads(),
+                   "steps_requested": args.steps, "warmup_requested": args.warmup,
+                   "map": ("live reference ikd-Tree: " + CHURN_NOTE) if tree is not None else "static snapshot (restated search)"},
+        "cpu_baseline": cpu_baseline_obj(best, runs, f"{best['steps']} full {args.config} scans per thread count (steps bounded by a "
+                                                         f"{REF_CPU_BUDGET_S:.0f} s CPU budget)"),
         "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ C5: k-NN microbench
+def c5_cpu(xyz, q, sample=200_000):
+    """Reference KD_TREE::Nearest_Search (real ikd_Tree.cpp) on a bounded sample of the queries, 3 threads and all."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as po
+    if not po.ref_available():
+        return None
+    tree = po.RefTree(box_length=0.5)
+    tree.build(xyz)
+    out = {}
+    th_all = host_threads()
+    for th in ([3, th_all] if th_all > 3 else [th_all]):
+        tree.knn(q[:20000], nthreads=th)
+        t0 = time.perf_counter()
+        tree.knn(q[:sample], nthreads=th)
+        out[str(th)] = sample / (time.perf_counter() - t0)
+    tree.close()
+    best = max(out, key=lambda k: out[k])
+    return {"value": out[best], "unit": "queries/s", "cores": int(best), "kind": "reference", "by_threads": out,
+            "sample": f"{sample} of the 1M queries against the full 10M-point reference ikd-Tree (Build), after a 20k warm-up"}
+
+
+def run_reference_c5(args):
+    from malio_b200 import synth
+    xyz, q = synth.knn_microbench()
+    with c_stdout_to_stderr():
+        cpu = c5_cpu(xyz, q)
+    line = {"impl": "reference", "metric": "k-NN queries/s, 1M queries vs 10M-pt tree, k=5", "value": cpu["value"] if cpu else None,
+            "unit": "queries/s", "n_gpus": args.gpus, "steps": 1, "warmup": 1, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded)", "config": {"workload": WORKLOADS["C5"]},
+            "cpu_baseline": cpu, "e2e": {"value": cpu["value"] if cpu else None, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_ours_c5(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    from malio_b200 import plugin, synth
+    from malio_b200 import dist as mdist
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    xyz, q_all = synth.knn_microbench()
+    lo, hi = mdist.shard_bounds(q_all.shape[0], rank, world)      # queries shard by block, tree replicated: no collective
+    q = np.ascontiguousarray(q_all[lo:hi])
+    snap = plugin.build_static_snapshot(xyz)
+    m = plugin.MeasurementModel(1, device=local_rank, sort_queries=not args.no_sort)
+    m.upload_map(snap)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        m.Nearest_Search(q)
+    steps = max(3, min(args.steps, 10))
+    c0 = m.counters()
+    dev_ms, e2e_ms = [], []
+    tw0 = time.time()
+    for _ in range(steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        idx, d2, ms = m.Nearest_Search(q)      # host queries -> host lists (H2D 12 B, D2H 40 B per query inside)
+        e1.record(); torch.cuda.synchronize()
+        dev_ms.append(ms); e2e_ms.append(e0.elapsed_time(e1))
+    tw1 = time.time()
+    c1 = m.counters()
+    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
+    t = torch.tensor([float(np.sum(dev_ms)), float(np.sum(e2e_ms))], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        m.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    Q = q_all.shape[0]
+    dev_s, e2e_s = t[0].item() * 1e-3 / steps, t[1].item() * 1e-3 / steps
+    peak, peak_src = 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    cand = float(c1.knn_candidates - c0.knn_candidates) / float((c1.knn_queries - c0.knn_queries) or 1)
+    bytes_per_launch = (hi - lo) * (12 + 9 * 8 + cand * 16 + 40)
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        with c_stdout_to_stderr():
+            cpu = c5_cpu(xyz, q_all)
+    line = {"metric": "k-NN queries/s, 1M queries vs 10M-pt tree, k=5", "value": Q / dev_s, "unit": "queries/s", "n_gpus": world,
+            "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_s * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded, malio_b200/synth.py knn_microbench)",
+            "config": {"workload": WORKLOADS["C5"], "l2": "flushed between timed steps (256 MiB write); the 160 MB cell-sorted point array exceeds L2",
+                       "queries_per_rank": hi - lo, "parallelism": f"query-block x{world}, replicated tree, no collective"},
+            "clocks": clocks,
+            "e2e": {"value": Q / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": (hi - lo) * 12, "d2h_bytes_per_step": (hi - lo) * 40,
+                    "ms_per_step": e2e_s * 1e3, "what": "malio_knn: host queries -> sort -> search -> caller-order lists on the host"},
+            "gpu_launches": int(c1.kernel_launches - c0.kernel_launches),
+            "roofline": {"bound": "hbm", "kernel": "knn_grid_kernel (+ knn_list_kernel)", "achieved": bytes_per_launch / dev_s / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": bytes_per_launch / dev_s / 1e9 / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": bytes_per_launch, "us_per_launch": dev_s * 1e6, "candidates_per_query": cand,
+                         "fallback_queries_per_search": float(c1.knn_fallback_queries - c0.knn_fallback_queries) / steps,
+                         "ring2_queries_per_search": float(c1.knn_ring2_queries - c0.knn_ring2_queries) / steps, "peak_source": peak_src,
+                         "note": "bytes = Q*(12 + 72 + C*16 + 40); device time = CUDA events around the search kernels (malio_knn ms_device)"},
+            "cpu_baseline": cpu}
+    print(json.dumps(line))
+    m.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------ CUDA arm
@@ -187,39 +383,50 @@ def run_ours(args, rank, world):
     import torch
     import torch.distributed as dist
     from malio_b200 import capi, plugin, synth
+    from malio_b200 import dist as mdist
 
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
-    case = synth.case_C2()
+    case = load_case(args.config)
     N_total = case.pts.shape[0]
     # contiguous block of the merged scan per rank; map, tables and state are replicated
-    from malio_b200 import dist as mdist
     lo, hi = mdist.shard_bounds(N_total, rank, world)
-    snap = plugin.build_static_snapshot(case.map_xyz, case.map_normal_y)
 
     def pinned(a):
-        t = torch.empty(a.nbytes, dtype=torch.uint8).pin_memory()
-        v = t.numpy().view(a.dtype).reshape(a.shape)
+        t = torch.empty(max(a.nbytes, 1), dtype=torch.uint8).pin_memory()
+        v = t.numpy()[: a.nbytes].view(a.dtype).reshape(a.shape)
         v[...] = a
         return t, v
 
     keep = []
-    t_nodes, h_nodes = pinned(snap.nodes); keep.append(t_nodes)
-    t_cov, h_cov = pinned(snap.node_cov); keep.append(t_cov)
+    tree = None
+    with c_stdout_to_stderr():
+        if not args.static_map:
+            tree = live_tree(case)
+    if tree is not None:
+        nodes, cov, ids, depth, live = tree.snapshot()
+        snap = plugin.MapSnapshot(nodes, cov, ids, depth)
+        map_desc = "live reference ikd-Tree: " + CHURN_NOTE
+    else:
+        snap = plugin.build_static_snapshot(case.map_xyz, case.map_normal_y)
+        map_desc = "static balanced snapshot (oracle/_ref not built)"
+    M_nodes = snap.n_nodes
+    cap_nodes = M_nodes + M_nodes // 8 + 1024
     t_pts, h_pts = pinned(np.ascontiguousarray(case.pts[lo:hi])); keep.append(t_pts)
-    t_mp, h_mpts = pinned(plugin.compact_points(snap.nodes)); keep.append(t_mp)
-    snap_p = plugin.MapSnapshot(h_nodes, h_cov, snap.node_ids, snap.max_depth)
+    t_mp, h_mpts = pinned(np.zeros(cap_nodes, dtype=capi.MAP_POINT)); keep.append(t_mp)
+    t_cv, h_cov = pinned(np.zeros(cap_nodes, dtype=np.float32)); keep.append(t_cv)
+    h_mpts[:M_nodes] = plugin.compact_points(snap.nodes)
+    h_cov[:M_nodes] = snap.node_cov
 
     model = plugin.MeasurementModel(case.n_lidar, device=local_rank, sort_queries=not args.no_sort, params=case.params)
     if world > 1:
         mdist.init_comm(model, rank, world, device=torch.device("cuda", local_rank))
-    model.upload_map(snap_p)
+    model.upload_map(snap)
     model.upload_scan(h_pts, case.table, case.table_off, case.temporal_comp)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    n_dof = case.n_dof
 
     def barrier():
         torch.cuda.synchronize()
@@ -232,32 +439,55 @@ def run_ours(args, rank, world):
         x, P = case.x_prop.copy(), case.P_prop.copy()
         return model.update_iterated_dyn_share_modified(x, P, case.max_iter), x
 
-    # the host side of a real integration knows the map's bounding box (ikd-Tree root node_range_*): node 0's point and
-    # its two children's boxes
+    # root box of the map = the ikd-Tree root's node_range_* (node 0's point + its two children's boxes)
     n0 = snap.nodes[0]
-    boxes = [n0["lbox"] if (n0["link"] & capi.LINK_HAS_LEFT) else None, n0["rbox"] if (n0["link"] & capi.LINK_HAS_RIGHT) else None]
     blo = np.array(n0["xyz"], np.float32); bhi = blo.copy()
-    for b in boxes:
-        if b is not None:
+    for b, bit in ((n0["lbox"], capi.LINK_HAS_LEFT), (n0["rbox"], capi.LINK_HAS_RIGHT)):
+        if n0["link"] & bit:
             blo = np.minimum(blo, b[0::2]); bhi = np.maximum(bhi, b[1::2])
     root_box = np.stack([blo, bhi], axis=1).reshape(6).astype(np.float32)
     t_ny, h_ny = pinned(np.zeros(h_pts.shape[0], np.float32)); keep.append(t_ny)
     t_sel, h_sel = pinned(np.zeros(h_pts.shape[0], np.uint8)); keep.append(t_sel)
     aux_out = {"normal_y": h_ny, "selected": h_sel}
+    flat = {"s": 0.0, "n": 0}
+    if tree is not None:
+        import pyoracle as po
+        reflib = po.ref_lib()
+        f_depth = C.c_uint32(0)
+        f_box = np.zeros(6, np.float32)
 
-    def step_e2e():
-        model.upload_map_compact(snap_p, points=h_mpts, root_box=root_box)
+    def step_e2e_snapshot_only():
+        sp = plugin.MapSnapshot(None, h_cov[:M_nodes], None, snap.max_depth)
+        model.upload_map_compact(sp, points=h_mpts[:M_nodes], root_box=root_box)
         model.upload_scan(h_pts, case.table, case.table_off, case.temporal_comp)
         x, P = case.x_prop.copy(), case.P_prop.copy()
         rep = model.update_iterated_dyn_share_modified(x, P, case.max_iter)
-        aux = model.aux(out=aux_out)
-        return rep, x, aux
+        model.aux(out=aux_out)
+        return rep, x
+
+    def step_e2e():
+        if tree is None:
+            return step_e2e_snapshot_only()
+        # what a MA-LIO checkout does per scan: flatten the live tree (product header malio_flatten.hpp instantiated on
+        # the real KD_TREE_NODE; OpenMP over the host threads) straight into pinned memory, then upload
+        t0 = time.perf_counter()
+        n = reflib.ikdref_snapshot_compact_parallel(tree.t, capi.ptr(h_mpts), capi.ptr(h_cov), cap_nodes, C.byref(f_depth),
+                                                    capi.ptr(f_box), 16384)
+        flat["s"] += time.perf_counter() - t0; flat["n"] += 1
+        sp = plugin.MapSnapshot(None, h_cov[:n], None, int(f_depth.value))
+        model.upload_map_compact(sp, points=h_mpts[:n], root_box=f_box)
+        model.upload_scan(h_pts, case.table, case.table_off, case.temporal_comp)
+        x, P = case.x_prop.copy(), case.P_prop.copy()
+        rep = model.update_iterated_dyn_share_modified(x, P, case.max_iter)
+        model.aux(out=aux_out)
+        return rep, x
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
             flush.fill_(1)
         barrier()
+        flat["s"], flat["n"] = 0.0, 0
         ms, reps = [], []
         c0 = model.counters()
         t_wall0 = time.time()
@@ -287,6 +517,7 @@ def run_ours(args, rank, world):
         sampler.start()
     model.set_timing(False)       # no per-pass event records inside the measured loops
     tot_ms, reps, c0, c1, out, (tw0, tw1) = timed(step_resident, args.steps, args.warmup)
+    x_res = out[1]
     passes = sum(r.passes for r in reps)
     searches = sum(r.searches for r in reps)
     launches = int(c1.kernel_launches - c0.kernel_launches)
@@ -295,20 +526,44 @@ def run_ours(args, rank, world):
 
     e_steps = max(3, min(args.steps, 10))
     e_ms, e_reps, ec0, ec1, e_out, _ = timed(step_e2e, e_steps, min(args.warmup, 3))
+    flatten_ms = 1e3 * flat["s"] / max(flat["n"], 1) if tree is not None else None
+    h2d = int(ec1.h2d_bytes - ec0.h2d_bytes) // e_steps
+    d2h = int(ec1.d2h_bytes - ec0.d2h_bytes) // e_steps
+    s_ms, _, _, _, _, _ = timed(step_e2e_snapshot_only, e_steps, 1)
 
-    # separate short loop with per-kernel CUDA events on (same steps, L2 flushed): k-NN kernel time for the roofline
+    # separate short loop with per-kernel CUDA events on (same steps, L2 flushed): kernel times for the rooflines
     model.set_timing(True)
     r_steps = max(3, min(args.steps, 10))
     _, r_reps, rc0, rc1, _, (_, tw_end) = timed(step_resident, r_steps, 1)
-    # clocks / throttle reasons sampled (nvidia-smi, 20 ms) from the start of the resident loop to the end of the last
-    # timed loop: all three loops keep the GPU under the same load
     clocks = sampler.stop(tw0, tw_end) if rank == 0 else None
     knn_launches = int(rc1.knn_launches - rc0.knn_launches)
     knn_ms = float(rc1.knn_ms - rc0.knn_ms)
+    pass_launches = int(rc1.pass_launches - rc0.pass_launches)
+    pass_fit = int(rc1.pass_fit_launches - rc0.pass_fit_launches)
+    pass_ms = float(rc1.pass_ms - rc0.pass_ms)
     dev_ms = float(np.sum([r.ms_device_total for r in r_reps])) * args.steps / r_steps
     e_value = e_steps / (e_ms * 1e-3)
-    h2d = int(ec1.h2d_bytes - ec0.h2d_bytes) // e_steps
-    d2h = int(ec1.d2h_bytes - ec0.d2h_bytes) // e_steps
+
+    # ---- N > 1: the sharded result must equal a single-GPU run of the whole scan (outside every timed region)
+    parity_n = None
+    if world > 1:
+        vec = synth.state_to_vec(x_res, case.n_lidar)
+        tv = torch.from_numpy(vec.copy()).cuda()
+        tv0 = tv.clone()
+        dist.broadcast(tv0, 0)
+        same = torch.tensor([1.0 if torch.equal(tv, tv0) else 0.0], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            single = plugin.MeasurementModel(case.n_lidar, device=local_rank, sort_queries=not args.no_sort, params=case.params)
+            single.upload_map(snap)
+            single.upload_scan(np.ascontiguousarray(case.pts), case.table, case.table_off, case.temporal_comp)
+            x1, P1 = case.x_prop.copy(), case.P_prop.copy()
+            rep1 = single.update_iterated_dyn_share_modified(x1, P1, case.max_iter)
+            d = float(np.abs(synth.state_to_vec(x1, case.n_lidar) - vec).max())
+            ok = bool(same.item() == 1.0) and d < 1e-9 and rep1.passes == reps[-1].passes and rep1.n_eff_last == reps[-1].n_eff_last
+            parity_n = {"status": "ok" if ok else "FAILED", "ranks_bit_identical": bool(same.item() == 1.0), "state_max_abs_diff_vs_1gpu": d,
+                        "passes": [int(rep1.passes), int(reps[-1].passes)], "n_eff_last": [int(rep1.n_eff_last), int(reps[-1].n_eff_last)]}
+            single.close()
 
     if rank != 0:
         model.close()
@@ -316,44 +571,55 @@ def run_ours(args, rank, world):
             dist.destroy_process_group()
         return
 
-    # roofline of the dominant launch (the k-NN search: cell-list scan + the two list kernels behind it, timed together
-    # with CUDA events on the library's stream): algorithmic bytes per search / event time.
-    #   per query: 16 B scan point + 9 rows x 8 B cell ranges + C x 16 B candidates + 40 B neighbour list + 16 B world
-    #   point + 1 B gate; C = candidates actually scanned (device counter, timing runs only)
-    peaks, peak_src = None, "fallback 6650 GB/s (B200_PROFILING.md)"
+    peak, peak_src = 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
     try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        peak = float(peaks["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)"
     except Exception:
-        peak = 6650.0
+        pass
     q_per_launch = (hi - lo)
     cand = int(rc1.knn_candidates - rc0.knn_candidates)
-    roof = None
+    roofs = []
     if knn_launches:
         cbar = cand / float(knn_launches * q_per_launch)
         bytes_per_launch = q_per_launch * (16 + 9 * 8 + cbar * 16 + 40 + 16 + 1)
         t_launch = knn_ms * 1e-3 / knn_launches
         achieved = bytes_per_launch / t_launch / 1e9
-        roof = {"bound": "hbm", "kernel": "k-NN search: knn_grid_kernel (+ knn_list_kernel)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_KNN_LAUNCH if world == 1 else None,
-                "algorithmic_bytes_per_launch": bytes_per_launch, "us_per_launch": t_launch * 1e6,
-                "launches_timed": knn_launches, "candidates_per_query": cbar,
-                "fallback_queries_per_search": float(rc1.knn_fallback_queries - rc0.knn_fallback_queries) / knn_launches,
-                "ring2_queries_per_search": float(rc1.knn_ring2_queries - rc0.knn_ring2_queries) / knn_launches,
-                "peak_source": peak_src,
-                "note": "bytes = Q*(16 + 72 + C*16 + 57), C = candidates scanned per query (device counter); the cell-sorted "
-                        "point array (16 MB) and the scan are L2-resident, so DRAM traffic is far below the algorithmic "
-                        "bytes: the kernel is bound by instruction issue of the top-6 insertion and by staging latency"}
+        roofs.append({"bound": "hbm", "kernel": "k-NN search: knn_grid_kernel (+ knn_list_kernel)",
+                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                      "traffic": NCU_DRAM_BYTES["knn"] if (world == 1 and args.config == "C2") else None,
+                      "algorithmic_bytes_per_launch": bytes_per_launch, "us_per_launch": t_launch * 1e6,
+                      "us_per_step": knn_ms * 1e3 / r_steps, "launches_timed": knn_launches, "candidates_per_query": cbar,
+                      "fallback_queries_per_search": float(rc1.knn_fallback_queries - rc0.knn_fallback_queries) / knn_launches,
+                      "ring2_queries_per_search": float(rc1.knn_ring2_queries - rc0.knn_ring2_queries) / knn_launches,
+                      "peak_source": peak_src,
+                      "note": "bytes = Q*(16 + 72 + C*16 + 57), C = candidates scanned per query (device counter); the cell-sorted point "
+                              "array and the scan are L2-resident at C2, so DRAM traffic is far below the algorithmic bytes"})
+    if pass_launches:
+        # per point and pass: in 16 (scan point) + 16 (plane) + 8 (plane cov) + 16 (traces) + 1 (selected);
+        # out 16 (world) + 4 (residual) + 8 (trace) + 4 (normal_y) + 96 (Jacobian row kept for the degenerate branch) + 1 + 1;
+        # a search pass adds the plane fit: 20 (neighbour ids) + 5 x 20 (neighbour points + weights) + 24 (plane, plane cov)
+        fit_frac = pass_fit / float(pass_launches)
+        bytes_pt = 57 + 130 + fit_frac * 144
+        bytes_per_launch = q_per_launch * bytes_pt + 434 * 8 * 2
+        t_launch = pass_ms * 1e-3 / pass_launches
+        achieved = bytes_per_launch / t_launch / 1e9
+        roofs.append({"bound": "hbm", "kernel": "pass_kernel (plane fit on search passes + gate + Jacobian rows + H^T R^-1 [H|h] + fold)",
+                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES["pass"],
+                      "algorithmic_bytes_per_launch": bytes_per_launch, "us_per_launch": t_launch * 1e6,
+                      "us_per_step": pass_ms * 1e3 / r_steps, "launches_timed": pass_launches, "search_pass_fraction": fit_frac,
+                      "peak_source": peak_src,
+                      "note": "bytes/point = 57 in + 130 out (+144 on search passes); everything is L2-resident at C2: the kernel is "
+                              "bound by FP64 dependent-chain latency and two grid barriers, not by HBM (see profiles/)"})
+    roofs.sort(key=lambda r: -r["us_per_step"])
+    roof = roofs[0] if roofs else None
+    roof2 = roofs[1] if len(roofs) > 1 else None
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
-            th = host_threads()
             with c_stdout_to_stderr():
-                sps, ms_pass, kind, _ = cpu_reference_run(case, 2, 1, th)
-            cpu = {"value": sps, "unit": UNIT, "cores": th, "kind": kind, "ms_per_ieskf_iter": ms_pass,
-                   "sample": "2 full C2 scans after 1 warm-up (100k pts vs 1M-pt ikd-Tree), all host threads"}
+                best, runs = cpu_arms(case, tree, 3, 1)
+            cpu = cpu_baseline_obj(best, runs, f"3 full {args.config} scans after warm-up per thread count, same live ikd-Tree as the GPU arm")
         except Exception as e:   # the checker is optional for the product line
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
 
@@ -361,20 +627,28 @@ def run_ours(args, rank, world):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": tot_ms / args.steps, "ms_per_ieskf_iter": tot_ms / max(passes, 1), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64 (Jacobian, reduction, filter) / f32 (k-NN, plane fit)",
-        "data": "synthetic (seeded, malio_b200/synth.py), random-free weights n/a",
-        "config": {"workload": WORKLOAD, "parallelism": f"point-block x{world}", "passes_per_scan": passes / args.steps,
+        "data": "synthetic (seeded, malio_b200/synth.py)",
+        "config": {"workload": WORKLOADS[args.config], "parallelism": f"point-block x{world}", "passes_per_scan": passes / args.steps,
                    "knn_passes_per_scan": searches / args.steps, "l2": "flushed between timed steps (256 MiB write)",
-                   "sort_queries": not args.no_sort, "points_per_rank": hi - lo, "map_nodes": snap.n_nodes},
+                   "sort_queries": not args.no_sort, "points_per_rank": hi - lo, "map_nodes": M_nodes, "map": map_desc},
         "device_ms_per_step": dev_ms / args.steps, "host_solve_ms_per_step": host_ms / args.steps,
         "clocks": clocks,
         "e2e": {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e_ms / e_steps, "steps": e_steps,
-                "what": "upload_map_compact (20 B/node, boxes + cell index rebuilt on the device) + upload_scan (pinned host buffers) + IESKF update + download of normal_y/selected"},
+                "ms_per_step": e_ms / e_steps, "steps": e_steps, "flatten_ms": flatten_ms, "flatten_host_threads": host_threads(),
+                "snapshot_only": {"value": e_steps / (s_ms * 1e-3), "ms_per_step": s_ms / e_steps,
+                                  "what": "the same step without the host flatten (pre-flattened pinned arrays)"},
+                "what": "flatten of the live ikd-Tree (host, OpenMP) + upload_map_compact (20 B/node, boxes + cell index rebuilt on the "
+                        "device) + upload_scan (pinned host buffers) + IESKF update + download of normal_y/selected"},
         "gpu_launches": launches,
-        "roofline": roof, "cpu_baseline": cpu,
+        "roofline": roof, "roofline_secondary": roof2, "cpu_baseline": cpu,
     }
+    if parity_n is not None:
+        line["parity_n"] = parity_n
     print(json.dumps(line))
     model.close()
+    if tree is not None:
+        with c_stdout_to_stderr():
+            tree.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -389,7 +663,10 @@ def main():
     if world != args.gpus and world == 1 and args.gpus > 1:
         print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun --nproc-per-node {args.gpus}"}))
         sys.exit(2)
-    run_ours(args, rank, world)
+    if args.config == "C5":
+        run_ours_c5(args, rank, world)
+    else:
+        run_ours(args, rank, world)
 
 
 if __name__ == "__main__":

@@ -195,7 +195,8 @@ int malio_measure(malio_handle* h, const malio_pass_state* s, int redo_knn,
                   double* HtRinvH, double* HtRinvh, malio_pass_stats* stats);
 
 /* rows of the last pass for the degenerate branch n > N_eff (esekfom.hpp:574-582): up to cap rows of
- * h_x (row-major, c columns) and h, in scan order, scaled by the plane weight (laserMapping.cpp:714-715) but NOT yet by
+ * h_x (row-major, c columns) and h, in the library's internal (cell-sorted) point order — with a communicator attached the
+ * rows of all ranks, concatenated in rank order — scaled by the plane weight (laserMapping.cpp:714-715) but NOT yet by
  * the localization weight: multiply by stats->loc_weight (laserMapping.cpp:758-759), as malio_ieskf_update does. */
 int malio_download_rows(malio_handle* h, double* h_x, double* hvec, uint32_t cap, uint32_t* n_rows);
 
@@ -266,6 +267,10 @@ typedef struct malio_counters {
   uint64_t knn_fallback_queries;  /* queries the cell-list fast path handed to the exact ikd-Tree-order traversal */
   uint64_t knn_ring2_queries;     /* queries that needed the 5x5x5 cell block */
   uint64_t knn_candidates;        /* map points the 3x3x3 scans looked at (summed only while timing is enabled) */
+  uint64_t pass_launches;         /* measurement passes timed (fused pass kernel, or gate+reduce+fold on the NCCL path) */
+  uint64_t pass_points;           /* scan points those passes processed */
+  uint64_t pass_fit_launches;     /* ... of which ran the plane fit (search passes) */
+  double pass_ms;                 /* their summed device time (CUDA events; only while timing is enabled) */
 } malio_counters;
 int malio_get_counters(malio_handle* h, malio_counters* out);
 

@@ -126,6 +126,11 @@ __device__ __forceinline__ void transform_point(const PassConst& pc, float px, f
   g[0] += pc.pos[0]; g[1] += pc.pos[1]; g[2] += pc.pos[2];
 }
 
+// Device-side fault word (bit 0: a traversal stack overflowed, i.e. the snapshot is deeper than the max_depth the caller
+// declared at upload).  Kernels only ever set bits; measure() / knn() read it back with their results and fail loudly.
+__device__ uint32_t g_fault_word = 0;
+constexpr uint32_t FAULT_STACK_OVERFLOW = 1u;
+
 // ------------------------------------------------------------------ K1: k-NN over the flattened ikd-Tree snapshot
 // calc_box_dist (ikd_Tree.cpp:1702-1720).  For lo <= hi at most one of `p < lo`, `p > hi` fires per axis and
 // (p-lo)^2 == (lo-p)^2 exactly, so  t = max(lo-p, p-hi, 0);  m += t*t  (in x,y,z order, adding an exact 0 when
@@ -239,7 +244,10 @@ __device__ __noinline__ void knn_exact_query(const float4* __restrict__ nodes, f
     const bool left_first = dl <= dr;
     const uint32_t n_near = left_first ? li : ri, n_far = left_first ? ri : li;
     const float d_near = left_first ? dl : dr, d_far = left_first ? dr : dl;
-    if (d_far < top) { st_n[sp] = n_far; st_d[sp] = d_far; sp++; }
+    if (d_far < top) {
+      if (sp < MALIO_MAX_TREE_DEPTH) { st_n[sp] = n_far; st_d[sp] = d_far; sp++; }
+      else atomicOr(&g_fault_word, FAULT_STACK_OVERFLOW);
+    }
     if (d_near < top) { cur = n_near; continue; }
     go = false;
     while (sp > 0) {
@@ -328,7 +336,11 @@ __device__ __forceinline__ void knn_tree_lane(const float4* __restrict__ nodes, 
       const uint32_t n_near = left_first ? li : ri, n_far = left_first ? ri : li;
       const float d_near = left_first ? dl : dr, d_far = left_first ? dr : dl;
       // d4 == +inf while fewer than k are held, so `d < d4` also covers `q.size() < k` for present children
-      if (d_far < d4) { ST(sp) = make_uint2(n_far, __float_as_uint(d_far)); sp++; }
+      if (d_far < d4) {
+        constexpr int LIMIT = SMEM_STACK ? KNN_SMEM_DEPTH : MALIO_MAX_TREE_DEPTH + KNN_POP_WIDTH;
+        if (sp < LIMIT) { ST(sp) = make_uint2(n_far, __float_as_uint(d_far)); sp++; }
+        else atomicOr(&g_fault_word, FAULT_STACK_OVERFLOW);   // deeper than declared: the result is not trusted, the call fails
+      }
       if (d_near < d4) { cur = n_near; }
       else {
         // unwind: the reference re-tests one pending far child per returning recursion level; here the top
@@ -1509,6 +1521,7 @@ reduce_kernel(uint32_t N, ParamConst prm, int ext_en, const uint8_t* __restrict_
 // NVLink/NVSwitch from inside pass_kernel — no NCCL call, no extra launch, the cross-GPU latency of a pass is two
 // one-way store + flag hops.  Layout of one rank's mailbox: [parity 2][kind: MIN 64 B | SUM 3584 B][source rank 8].
 constexpr int MAIL_MAX_WORLD = 8;
+constexpr int ROWS_DOUBLES = MALIO_MAX_DOF * 25 + 8;   // rows of the degenerate branch (25 doubles each) | row count | padding
 constexpr int MAIL_MIN_BYTES = 64;        // u64 keys[4] | u32 count | u32 seq (byte 40)
 constexpr int MAIL_SUM_BYTES = 3584;      // double res[MALIO_RED_DOUBLES] | u32 seq (byte 3480)
 constexpr int MAIL_SUM_SEQ_OFF = 3480;
@@ -1575,12 +1588,22 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
   return v;
 }
 // all threads of all blocks call this; returns when `expected` arrivals have been counted
-__device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t target) {
+// Gives up after ~2 s (a block of the grid that never became resident: only possible when the launch was not cooperative
+// and another kernel holds the SMs) and raises the fault word of the mapped result buffer, which measure() reports.
+__device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t target, uint32_t* fault) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(counter, 1u);
-    while ((int32_t)(ld_acquire_u32(counter) - target) < 0) { }
+    unsigned long long t0 = 0;
+    for (uint32_t it = 0; (int32_t)(ld_acquire_u32(counter) - target) < 0; ++it) {
+      if ((it & 0x3FFFu) == 0x3FFFu) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t0 == 0) t0 = t1;
+        else if (t1 - t0 > 2000000000ull) { *reinterpret_cast<volatile uint32_t*>(fault) = 2u; break; }
+      }
+    }
   }
   __syncthreads();
 }
@@ -1646,7 +1669,7 @@ pass_kernel(PassArgs a, PassConst pc, ParamConst prm) {
   }
   pass_stamp(a, 1);
   if (a.peer.world <= 1) {
-    grid_barrier(a.bar + 0, a.bar_base[0] + gridDim.x);
+    grid_barrier(a.bar + 0, a.bar_base[0] + gridDim.x, reinterpret_cast<uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 9));
   } else {
     // barrier 1 fused with the cross-GPU MIN: every block arrives; warp 0 of block 0 waits for the local arrivals, pushes
     // this GPU's four keys into every peer's mailbox, waits for the peers' keys, writes the global minima into the local
@@ -1804,7 +1827,7 @@ pass_kernel(PassArgs a, PassConst pc, ParamConst prm) {
     reduce_block(a.N, prm, pc.ext_en, a.sel, a.lid8, a.rows12, a.pd2, a.ucov, a.tau, a.mmkey, t0, t1, slot);
   }
   pass_stamp(a, 3);
-  grid_barrier(a.bar + 1, a.bar_base[1] + gridDim.x);
+  grid_barrier(a.bar + 1, a.bar_base[1] + gridDim.x, reinterpret_cast<uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 9));
   pass_stamp(a, 4);
   // ---- phase 3: fold the slots, one warp per entry, in fold_kernel's order
   const uint32_t lane = threadIdx.x & 31u, wpb = RED_THREADS / 32;
@@ -1855,7 +1878,7 @@ pass_kernel(PassArgs a, PassConst pc, ParamConst prm) {
       }
       if (lane < 4) reinterpret_cast<unsigned long long*>(a.h_res + MALIO_RED_DOUBLES)[lane] = a.mmkey[lane];
       // k-NN list statistics of the last search as knn_list_kernel published them ([3] traversal list, [5] 5x5x5 retries)
-      if (lane == 4) { uint32_t* hg = reinterpret_cast<uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 4); hg[3] = a.gstats[3]; hg[5] = a.gstats[5]; }
+      if (lane == 4) { uint32_t* hg = reinterpret_cast<uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 4); hg[3] = a.gstats[3]; hg[5] = a.gstats[5]; hg[6] = g_fault_word; }
       __threadfence_system();
       __syncwarp();
       if (lane == 0) *reinterpret_cast<volatile uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 8) = a.seq;
@@ -1925,7 +1948,10 @@ __global__ void rows_kernel(uint32_t N, ParamConst prm, int ext_en, const uint8_
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *n_rows = s_base;
+  if (threadIdx.x == 0) {
+    *n_rows = s_base;
+    rows[(size_t)MALIO_MAX_DOF * 25] = (double)(s_base < cap ? s_base : cap);   // count travels with the rows (multi-rank gather)
+  }
 }
 
 // per-scan state back to "nothing searched yet": point_selected_surf = 0, normal_y = 0, Nearest_Points empty, k-NN list
@@ -2105,6 +2131,7 @@ struct DeviceState {
   uint32_t* h_gstats = nullptr;            // pinned mirror (8 words, carved out of h_res)
   // fused pass (single cooperative launch per measurement pass)
   bool fused = true; int pass_max_blocks = 0; bool coop_launch = true;
+  bool tau_inline = false; int trace_passes = 0; float env_knn_cell = -1.f; bool env_knn_cell_set = false; bool host_prof = false;   // environment switches, read once in create()
   uint32_t* d_bar = nullptr; uint32_t bar_base[3] = {0, 0, 0}; uint32_t seq = 0;
   double* h_res_dev = nullptr;     // device-side address of the mapped host result buffer
   unsigned long long* d_dbg = nullptr; int trace_left = 0;
@@ -2334,7 +2361,7 @@ int create(malio_handle* h) {
   CUDA_TRY(cudaMalloc((void**)&D->d_cursor, SORT_BINS * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc((void**)&D->d_btot, SCAN_BLOCKS * sizeof(uint32_t)));
   CUDA_TRY(cudaMemset(D->d_hist, 0, SORT_BINS * sizeof(uint32_t)));
-  CUDA_TRY(cudaMalloc((void**)&D->d_rows, (size_t)MALIO_MAX_DOF * 25 * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void**)&D->d_rows, (size_t)ROWS_DOUBLES * (1 + MAIL_MAX_WORLD) * sizeof(double)));   // own rows | gathered rows of all ranks
   D->red_grid = (uint32_t)D->sm_count * 4;   // 46 KB of shared memory per block: 4 blocks per SM are co-resident
   CUDA_TRY(cudaMalloc((void**)&D->d_block_red, (size_t)D->red_grid * MALIO_RED_DOUBLES * sizeof(double)));
   // pinned + mapped: [0, RED) result | +0..3 min/max keys | +4..7 k-NN list statistics | +8 pass sequence flag | +16.. rows
@@ -2356,6 +2383,10 @@ int create(malio_handle* h) {
     D->fused = coop && per_sm > 0;
     if (const char* e = getenv("MALIO_FUSED_PASS")) D->fused = D->fused && atoi(e) != 0;
     if (const char* e = getenv("MALIO_COOP_LAUNCH")) D->coop_launch = atoi(e) != 0;
+    D->tau_inline = getenv("MALIO_TAU_INLINE") != nullptr;
+    if (const char* e = getenv("MALIO_PASS_TRACE")) D->trace_passes = atoi(e);
+    if (const char* e = getenv("MALIO_KNN_CELL")) { D->env_knn_cell = (float)atof(e); D->env_knn_cell_set = true; }
+    D->host_prof = getenv("MALIO_HOST_PROF") != nullptr;
   }
   D->h_gstats = reinterpret_cast<uint32_t*>(D->h_res + MALIO_RED_DOUBLES + 4);
   std::memset(D->h_gstats, 0, 8 * sizeof(uint32_t));
@@ -2368,7 +2399,7 @@ int create(malio_handle* h) {
 void destroy(malio_handle* h) {
   DeviceState* D = (DeviceState*)h->dev;
   if (!D) return;
-  if (getenv("MALIO_HOST_PROF") && D->host_passes)
+  if (D->host_prof && D->host_passes)
     fprintf(stderr, "[malio] passes %llu: host launch %.1f us/pass, host wait-for-device %.1f us/pass\n",
             (unsigned long long)D->host_passes, D->host_launch_us / D->host_passes, D->host_wait_us / D->host_passes);
   cudaSetDevice(D->device);
@@ -2411,8 +2442,13 @@ static int ensure_map_buffers(malio_handle* h, DeviceState* D, uint32_t n) {
 // filter_size_map 0.5, and keep 2..9 live points per occupied cell).  root = host copy of node 0 (bounds every live point).
 static int finish_map_upload(malio_handle* h, DeviceState* D, const malio_map_node* root, uint32_t n, uint32_t depth) {
   D->n_nodes = n; D->depth = depth;
+  {
+    const uint32_t zero = 0;
+    CUDA_TRY(cudaMemcpyToSymbolAsync(g_fault_word, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, D->stream));
+    D->h_gstats[6] = 0;
+  }
   float hcfg = h->cfg.knn_cell_size;
-  if (const char* e = getenv("MALIO_KNN_CELL")) hcfg = (float)atof(e);
+  if (D->env_knn_cell_set) hcfg = D->env_knn_cell;
   D->grid_on = false;
   if (hcfg >= 0.f && n > 0) {
     const bool automatic = hcfg == 0.f;
@@ -2559,6 +2595,11 @@ int upload_scan(malio_handle* h, const malio_scan_pt* pts, uint32_t n, const mal
   const int L = h->cfg.params.n_lidar;
   for (int l = 0; l < L; ++l)
     if (table_off[l + 1] < table_off[l] + 2) { h->err = "pose table of each LiDAR needs >= 2 entries"; return MALIO_ERR_INVALID_ARG; }
+  {   // pt.lidar indexes per-LiDAR tables on the device: reject ids outside [0, L) here (one vectorisable sweep)
+    uint32_t bad = 0;
+    for (uint32_t i = 0; i < n; ++i) bad |= (uint32_t)(pts[i].lidar >= (uint16_t)L);
+    if (bad) { h->err = "scan point with lidar id >= n_lidar"; return MALIO_ERR_INVALID_ARG; }
+  }
   if (int rc = ensure_point_buffers(h, D, n > 0 ? n : 1)) return rc;
   const uint32_t n_tab = table_off[L];
   if (n_tab > D->cap_table) {
@@ -2635,7 +2676,7 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
     // a scan that is a search pass it runs on the second stream beside the k-NN kernels (which leave most of the SMs'
     // warp slots empty) instead of inside the pass kernel.
     bool tau_async = false;
-    if (!D->tau_valid && redo_knn && D->fused && !getenv("MALIO_TAU_INLINE")) {
+    if (!D->tau_valid && redo_knn && D->fused && !D->tau_inline) {
       CUDA_TRY(cudaEventRecord(D->ev_sorted, st_));
       CUDA_TRY(cudaStreamWaitEvent(D->stream2, D->ev_sorted, 0));
       tau_kernel<<<(N + PLANE_THREADS - 1) / PLANE_THREADS, PLANE_THREADS, 0, D->stream2>>>(pts_k, perm_k, N, pc, D->d_table, D->d_tau2);
@@ -2651,8 +2692,10 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
       D->searched_once = true;
       if (D->timing) CUDA_TRY(cudaEventRecord(D->ev[6], st_));
       // list statistics of this search: the fused pass kernel ships them with its result; the separate-kernel path copies
-      if (D->grid_on && !(D->fused && (!D->comm || D->p2p)))
-        CUDA_TRY(cudaMemcpyAsync(D->h_gstats + 2, D->d_gstats + 2, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st_));
+      if (!(D->fused && (!D->comm || D->p2p))) {
+        if (D->grid_on) CUDA_TRY(cudaMemcpyAsync(D->h_gstats + 2, D->d_gstats + 2, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st_));
+        CUDA_TRY(cudaMemcpyFromSymbolAsync(D->h_gstats + 6, g_fault_word, sizeof(uint32_t), 0, cudaMemcpyDeviceToHost, st_));
+      }
     }
   }
   if (tau_async_outer) CUDA_TRY(cudaStreamWaitEvent(st_, D->ev_tau, 0));
@@ -2686,8 +2729,8 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
     for (int r = 0; r < MAIL_MAX_WORLD; ++r) a.peer.mail[r] = D->mail_peer[r];
     *reinterpret_cast<volatile uint32_t*>(D->h_res + MALIO_RED_DOUBLES + 9) = 0u;
     a.dbg = nullptr;
-    if (getenv("MALIO_PASS_TRACE")) {
-      if (!D->d_dbg) { CUDA_TRY(cudaMalloc((void**)&D->d_dbg, (size_t)4096 * 8 * sizeof(unsigned long long))); D->trace_left = atoi(getenv("MALIO_PASS_TRACE")); }
+    if (D->trace_passes > 0) {
+      if (!D->d_dbg) { CUDA_TRY(cudaMalloc((void**)&D->d_dbg, (size_t)4096 * 8 * sizeof(unsigned long long))); D->trace_left = D->trace_passes; }
       if (D->trace_left > 0 && grid <= 4096) a.dbg = D->d_dbg;
     }
     PassConst pc_arg = pc;
@@ -2725,7 +2768,8 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
       }
     }
     std::atomic_thread_fence(std::memory_order_acquire);
-    if (*reinterpret_cast<volatile uint32_t*>(D->h_res + MALIO_RED_DOUBLES + 9) != 0u) {
+    if (const uint32_t fault = *reinterpret_cast<volatile uint32_t*>(D->h_res + MALIO_RED_DOUBLES + 9)) {
+      if (fault == 2u) { h->err = "pass_kernel: a grid barrier did not complete within 2 s (blocks not co-resident)"; return MALIO_ERR_CUDA; }
       h->err = "pass_kernel: a peer GPU did not answer the in-kernel exchange within 2 s";
       return MALIO_ERR_NCCL;
     }
@@ -2782,6 +2826,10 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
   CUDA_TRY(cudaGetLastError());
   }
   D->pass_done = true;
+  if (D->h_gstats[6] & FAULT_STACK_OVERFLOW) {
+    h->err = "k-NN traversal stack overflow: the snapshot is deeper than the max_depth declared at upload";
+    return MALIO_ERR_TREE_TOO_DEEP;
+  }
   D->host_launch_us += std::chrono::duration<double, std::micro>(hp1 - hp0).count();
   D->host_wait_us += std::chrono::duration<double, std::micro>(hp2 - hp1).count();
   D->host_passes += 1;
@@ -2826,6 +2874,8 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
   cudaEventElapsedTime(&ms, D->ev[1], D->ev[2]); S.ms_plane = ms;
   cudaEventElapsedTime(&ms, D->ev[2], D->ev[3]); S.ms_reduce = ms;
   cudaEventElapsedTime(&ms, D->ev[0], D->ev[4]); S.ms_total = ms;
+  cudaEventElapsedTime(&ms, D->ev[1], D->ev[4]);
+  D->ctr.pass_launches += 1; D->ctr.pass_points += N; D->ctr.pass_ms += ms; D->ctr.pass_fit_launches += redo_knn ? 1 : 0;
   }
   if (n_eff < 1) {
     S.valid = 0;
@@ -2861,16 +2911,33 @@ int download_rows(malio_handle* h, double* h_x, double* hvec, uint32_t cap, uint
   const malio_params& P = h->cfg.params;
   const int L = P.n_lidar, c = 6 * (L + 1);
   if (cap > MALIO_MAX_DOF) cap = MALIO_MAX_DOF;
-  const uint32_t* perm = (h->cfg.sort_queries && D->perm_valid) ? D->d_perm : nullptr;
   rows_kernel<<<1, 256, 0, D->stream>>>(D->N, make_param_const(P), D->last_pc.ext_en, D->d_sel, D->d_lid8, D->d_rows12,
                                           D->d_pd2, D->d_ucov, D->d_tau, D->d_mmkey + 4 * D->last_parity, cap, D->d_rows,
                                           D->d_counters + 3);
   double* hr = D->h_res + MALIO_RED_DOUBLES + 16;
-  CUDA_TRY(cudaMemcpyAsync(hr, D->d_rows, (size_t)cap * 25 * sizeof(double), cudaMemcpyDeviceToHost, D->stream));
   uint32_t nr = 0;
-  CUDA_TRY(cudaMemcpyAsync(&nr, D->d_counters + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, D->stream));
-  CUDA_TRY(cudaStreamSynchronize(D->stream));
-  if (nr > cap) nr = cap;
+  std::vector<double> gathered;
+  if (D->comm && D->world > 1) {
+    // stats->n_eff is summed over the ranks, the rows are not: gather every rank's (at most cap) rows and concatenate them in
+    // rank order, so that every rank forms the same H and takes the same step (esekfom.hpp:574-582 needs all N_eff rows)
+    if (!g_nccl.AllGather) { h->err = "ncclAllGather unavailable: cannot gather the rows of the degenerate branch"; return MALIO_ERR_NCCL; }
+    double* d_all = D->d_rows + ROWS_DOUBLES;
+    if (g_nccl.AllGather(D->d_rows, d_all, ROWS_DOUBLES, ncclDouble, D->comm, D->stream) != ncclSuccess) { h->err = "ncclAllGather(rows) failed"; return MALIO_ERR_NCCL; }
+    gathered.resize((size_t)ROWS_DOUBLES * D->world);
+    CUDA_TRY(cudaMemcpyAsync(gathered.data(), d_all, gathered.size() * sizeof(double), cudaMemcpyDeviceToHost, D->stream));
+    CUDA_TRY(cudaStreamSynchronize(D->stream));
+    D->ctr.kernel_launches += 1;
+    for (int r = 0; r < D->world && nr < cap; ++r) {
+      const double* src = gathered.data() + (size_t)r * ROWS_DOUBLES;
+      const uint32_t cnt = (uint32_t)(src[(size_t)MALIO_MAX_DOF * 25] + 0.5);
+      for (uint32_t k = 0; k < cnt && nr < cap; ++k, ++nr) std::memcpy(hr + (size_t)nr * 25, src + (size_t)k * 25, 25 * sizeof(double));
+    }
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(hr, D->d_rows, (size_t)cap * 25 * sizeof(double), cudaMemcpyDeviceToHost, D->stream));
+    CUDA_TRY(cudaMemcpyAsync(&nr, D->d_counters + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, D->stream));
+    CUDA_TRY(cudaStreamSynchronize(D->stream));
+    if (nr > cap) nr = cap;
+  }
   int map[MALIO_MAX_COLS];
   for (int k = 0; k < 6; ++k) map[k] = k;
   for (int l = 0; l < L; ++l)
@@ -2935,8 +3002,13 @@ int knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* idx, float* d2, 
   if (idx) CUDA_TRY(cudaMemcpyAsync(idx, D->d_o_idx, (size_t)nq * MALIO_K * sizeof(uint32_t), cudaMemcpyDeviceToHost, D->stream));
   if (d2) CUDA_TRY(cudaMemcpyAsync(d2, D->d_o_d2, (size_t)nq * MALIO_K * sizeof(float), cudaMemcpyDeviceToHost, D->stream));
   if (D->grid_on) CUDA_TRY(cudaMemcpyAsync(D->h_gstats + 2, D->d_gstats + 2, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, D->stream));
+  CUDA_TRY(cudaMemcpyFromSymbolAsync(D->h_gstats + 6, g_fault_word, sizeof(uint32_t), 0, cudaMemcpyDeviceToHost, D->stream));
   CUDA_TRY(cudaStreamSynchronize(D->stream));
   CUDA_TRY(cudaGetLastError());
+  if (D->h_gstats[6] & FAULT_STACK_OVERFLOW) {
+    h->err = "k-NN traversal stack overflow: the snapshot is deeper than the max_depth declared at upload";
+    return MALIO_ERR_TREE_TOO_DEEP;
+  }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, D->ev[0], D->ev[1]);
   if (ms_out) *ms_out = ms;
@@ -3028,7 +3100,7 @@ int comm_init(malio_handle* h, const uint8_t* id, int rank, int world) {
     cudaFree(d_h);
     D->p2p = ok && all_ok;
   }
-  if (getenv("MALIO_HOST_PROF")) fprintf(stderr, "[malio] rank %d/%d: in-kernel peer exchange %s\n", rank, world, D->p2p ? "ON" : "off (NCCL path)");
+  if (D->host_prof) fprintf(stderr, "[malio] rank %d/%d: in-kernel peer exchange %s\n", rank, world, D->p2p ? "ON" : "off (NCCL path)");
   return MALIO_OK;
 }
 

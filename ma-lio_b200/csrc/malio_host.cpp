@@ -622,6 +622,11 @@ int malio_ieskf_update(malio_handle* h, malio_state* x, double* Pio, int max_ite
       uint32_t nr = 0;
       const int rc2 = malio_dev::download_rows(h, rows.data(), hv.data(), (uint32_t)m, &nr);
       if (rc2 != MALIO_OK) { if (rep) *rep = rp; return rc2; }
+      if ((int)nr != m) {   // a partial H would make the ranks step to different states: fail instead
+        h->err = "degenerate branch: rows returned != N_eff";
+        if (rep) *rep = rp;
+        return MALIO_ERR_STATE;
+      }
       Mat H(m, n);
       for (int r = 0; r < m; ++r) {
         for (int k = 0; k < c; ++k) H(r, k) = rows[(size_t)r * c + k] * st.loc_weight;

@@ -86,7 +86,8 @@ class Counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("knn_launches", C.c_uint64), ("knn_queries", C.c_uint64),
                 ("knn_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("knn_fallback_queries", C.c_uint64), ("knn_ring2_queries", C.c_uint64),
-                ("knn_candidates", C.c_uint64)]
+                ("knn_candidates", C.c_uint64), ("pass_launches", C.c_uint64), ("pass_points", C.c_uint64),
+                ("pass_fit_launches", C.c_uint64), ("pass_ms", C.c_double)]
 
 
 class UpdateReport(C.Structure):
@@ -172,6 +173,24 @@ class MalioError(RuntimeError):
 
 
 def default_params(n_lidar: int) -> Params:
+    """The reference defaults (City.yaml / mapping_city.launch) — the same values malio_default_params() fills in; kept in
+    Python as well so that input generators (synth.py) work without mapping the CUDA library (bench.py --impl reference).
+    tests/test_oracle_cpu.py checks the two agree."""
+    p = Params()
+    p.n_lidar = n_lidar
+    p.extrinsic_est_en = 1
+    p.plane_th = 0.4
+    p.knn_max_sqdist = 5.0
+    p.cov_threshold = 0.5
+    p.point_cov_max, p.point_cov_min = 0.00125, 0.00075
+    p.plane_cov_max, p.plane_cov_min = 1.0, 0.8
+    p.localize_cov_max, p.localize_cov_min = 2.0, 0.3
+    p.localize_thresh_max, p.localize_thresh_min = 0.7, 0.2
+    p.range_min, p.range_max = 0.0, 1.0
+    return p
+
+
+def default_params_from_library(n_lidar: int) -> Params:
     p = Params()
     load().malio_default_params(C.byref(p), n_lidar)
     return p

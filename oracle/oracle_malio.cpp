@@ -698,6 +698,13 @@ struct orc_ctx {
   bool mm_override = false;
   double ov_umin = 0, ov_umax = 0, ov_tmin = 0, ov_tmax = 0;
   double raw_min_cov = 9999, raw_max_cov = 0;   // local min/max trace of the selected points of the last pass
+  // timing split for bench.py's CPU arms (seconds, accumulated since orc_reset_times):
+  //   t_K  wall share of Nearest_Search inside S1 (per-thread search time summed / threads)
+  //   t_B  rest of h_share_model (S1 without the search, S2-S6)
+  //   t_A  update_iterated_dyn_share_modified outside h_share_model (esekfom.hpp:521-718)
+  double t_K = 0, t_B = 0, t_A = 0;
+  int time_passes = 0;
+  bool fast_reduce = false;   // timing arms only: esekfom.hpp:622-635 evaluated by orc_reduce_fast (blocked, vectorised, threaded)
 };
 
 extern "C" {
@@ -776,8 +783,7 @@ void orc_S2_Mx(const double vec[3], const double delta[2], double res[6]) { S2_M
 
 // ------------------------------------------------------------------ B: h_share_model (laserMapping.cpp:552-760)
 // converge = ekfom_data.converge on entry.  Returns 1 if valid, 0 if "No Effective Points".
-int orc_h_share_model(void* vc, const malio_pass_state* s, int converge, int nthreads) {
-  orc_ctx* c = (orc_ctx*)vc;
+static int h_share_model_impl(orc_ctx* c, const malio_pass_state* s, int converge, int nthreads, double* knn_wall_s) {
   const malio_params& P = c->prm;
   const int L = P.n_lidar;
   const int64_t N = (int64_t)c->pts.size();
@@ -795,9 +801,11 @@ int orc_h_share_model(void* vc, const malio_pass_state* s, int converge, int nth
   std::vector<float> normvec((size_t)N * 4, 0.f);
   if (nthreads < 1) nthreads = 1;
   int64_t visits = 0;
+  const double t_enter = omp_get_wtime();
+  double knn_thread_s = 0.0;   // per-thread time inside Nearest_Search, summed over threads
 
   // ---- S1 (:559-612)
-#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 256) reduction(+ : visits)
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 256) reduction(+ : visits, knn_thread_s)
   for (int64_t i = 0; i < N; ++i) {
     const malio_scan_pt& pb = c->pts[i];
     double p_body[3] = {pb.x, pb.y, pb.z};
@@ -822,8 +830,10 @@ int orc_h_share_model(void* vc, const malio_pass_state* s, int converge, int nth
       float d2[MALIO_K];
       int32_t ids[MALIO_K];
       int found;
+      const double tk0 = omp_get_wtime();
       if (c->hook) found = c->hook(c->hook_ctx, pw, MALIO_K, near, d2, ids);
       else found = knn_snapshot(c->nodes, c->node_cov, c->n_nodes, pw, MALIO_K, near, d2, ids, &visits);
+      knn_thread_s += omp_get_wtime() - tk0;
       c->nearest_cnt[i] = found;
       for (int k = 0; k < MALIO_K; ++k) { c->nearest_ids[(size_t)i * MALIO_K + k] = ids[k]; c->nearest_d2[(size_t)i * MALIO_K + k] = d2[k]; }
       c->selected[i] = found < MALIO_K ? 0 : (d2[MALIO_K - 1] > P.knn_max_sqdist ? 0 : 1);
@@ -845,6 +855,8 @@ int orc_h_share_model(void* vc, const malio_pass_state* s, int converge, int nth
     }
   }
   if (converge) { c->visits += visits; c->searches += N; }
+  *knn_wall_s = knn_thread_s / (double)nthreads;
+  (void)t_enter;
 
   // ---- S2 (:614-632) compaction + min/max unit cov
   int effct = 0;
@@ -993,6 +1005,25 @@ int orc_h_share_model(void* vc, const malio_pass_state* s, int converge, int nth
   return 1;
 }
 
+int orc_h_share_model(void* vc, const malio_pass_state* s, int converge, int nthreads) {
+  orc_ctx* c = (orc_ctx*)vc;
+  const double t0 = omp_get_wtime();
+  double knn_s = 0.0;
+  const int rc = h_share_model_impl(c, s, converge, nthreads < 1 ? 1 : nthreads, &knn_s);
+  const double dt = omp_get_wtime() - t0;
+  c->t_K += knn_s;
+  c->t_B += dt - knn_s;
+  c->time_passes += 1;
+  return rc;
+}
+void orc_reset_times(void* vc) { orc_ctx* c = (orc_ctx*)vc; c->t_K = c->t_B = c->t_A = 0; c->time_passes = 0; }
+void orc_get_times(void* vc, double out[3], int* passes) {
+  orc_ctx* c = (orc_ctx*)vc;
+  out[0] = c->t_K; out[1] = c->t_B; out[2] = c->t_A;
+  if (passes) *passes = c->time_passes;
+}
+void orc_set_fast_reduce(void* vc, int enable) { ((orc_ctx*)vc)->fast_reduce = enable != 0; }
+
 // esekfom.hpp:622-635 on the dense outputs of the last pass: HTH = (h_x^T / R) h_x ; HTh = (h_x^T / R) h
 // map_incremental's per-point decision (laserMapping.cpp:398-446) with the state after the update
 // (pointBodyToWorld, :134-147).  cls: 0 skipped (:406), 1 PointToAdd, 2 PointNoNeedDownsample, 3 dropped (:431)
@@ -1067,6 +1098,64 @@ void orc_reduce(void* vc, double* HTH, double* HTh) {
     double s = 0;
     for (int i = 0; i < c->n_eff; ++i) s += HT[(size_t)a * c->n_eff + i] * c->h[i];
     HTh[a] = s;
+  }
+}
+
+// Timing arms only (bench.py cpu_baseline / --impl reference): the same esekfom.hpp:622-635 quantities, evaluated the way
+// an optimised build of the reference evaluates them — Eigen's `HT * h_x_` GEMM (:629) and `P_inv.block * HT * dyn_share.h`
+// (:635, which Eigen evaluates left to right: an n x c x N product before the N-vector) — i.e. blocked, vectorised
+// (run-time dispatch to AVX2 / AVX-512 clones: MORE generous than the reference's baseline x86-64 build) and spread over
+// `nthreads` OpenMP threads with per-thread accumulators.  Summation order differs from orc_reduce, so the parity tests
+// never use it.  Kh (n) may be NULL; Pinv_blk is P_inv[:, 0:ncol] TRANSPOSED ([k][q]) with leading dimension ldp.
+__attribute__((target_clones("avx512f", "avx2", "default"), optimize("O3")))
+static void reduce_rows_fast(const double* hx, const double* h, const double* R, int ncol, int64_t i0, int64_t i1,
+                             double* HTH, double* HTh, const double* Pinv_blk, int ldp, int n, double* Kh) {
+  double s[MALIO_MAX_COLS], kq[MALIO_MAX_DOF];
+  for (int64_t i = i0; i < i1; ++i) {
+    double r = R[i];
+    if (r < 0.0001) r = 0.001;
+    const double* row = hx + (size_t)i * ncol;
+    for (int k = 0; k < ncol; ++k) s[k] = row[k] / r;
+    for (int a = 0; a < ncol; ++a) {
+      double* out = HTH + (size_t)a * ncol;
+      const double sa = s[a];
+      for (int b = 0; b < ncol; ++b) out[b] += sa * row[b];
+    }
+    const double hi = h[i];
+    for (int a = 0; a < ncol; ++a) HTh[a] += s[a] * hi;
+    if (Kh) {   // column i of P_inv.block * HT (Pinv_blk is passed TRANSPOSED: [k][q], unit stride over q), times h_i
+      for (int q = 0; q < n; ++q) kq[q] = 0.0;
+      for (int k = 0; k < ncol; ++k) {
+        const double* pr = Pinv_blk + (size_t)k * ldp;
+        const double sk = s[k];
+        for (int q = 0; q < n; ++q) kq[q] += pr[q] * sk;
+      }
+      for (int q = 0; q < n; ++q) Kh[q] += kq[q] * hi;
+    }
+  }
+}
+void orc_reduce_fast(void* vc, double* HTH, double* HTh, const double* Pinv_blk, int ldp, int n, double* Kh, int nthreads) {
+  orc_ctx* c = (orc_ctx*)vc;
+  const int ncol = 6 * (c->prm.n_lidar + 1);
+  if (nthreads < 1) nthreads = 1;
+  std::vector<double> part((size_t)nthreads * (ncol * ncol + ncol + MALIO_MAX_DOF), 0.0);
+  const int64_t N = c->n_eff;
+#pragma omp parallel num_threads(nthreads)
+  {
+    const int t = omp_get_thread_num(), T = omp_get_num_threads();
+    double* base = part.data() + (size_t)t * (ncol * ncol + ncol + MALIO_MAX_DOF);
+    const int64_t i0 = N * t / T, i1 = N * (t + 1) / T;
+    reduce_rows_fast(c->h_x.data(), c->h.data(), c->R.data(), ncol, i0, i1, base, base + ncol * ncol, Pinv_blk, ldp, n,
+                     Kh ? base + ncol * ncol + ncol : nullptr);
+  }
+  std::fill(HTH, HTH + ncol * ncol, 0.0);
+  std::fill(HTh, HTh + ncol, 0.0);
+  if (Kh) std::fill(Kh, Kh + n, 0.0);
+  for (int t = 0; t < nthreads; ++t) {
+    const double* base = part.data() + (size_t)t * (ncol * ncol + ncol + MALIO_MAX_DOF);
+    for (int k = 0; k < ncol * ncol; ++k) HTH[k] += base[k];
+    for (int k = 0; k < ncol; ++k) HTh[k] += base[ncol * ncol + k];
+    if (Kh) for (int k = 0; k < n; ++k) Kh[k] += base[ncol * ncol + ncol + k];
   }
 }
 
@@ -1158,6 +1247,7 @@ int orc_update_iterated(void* vc, malio_state* x_, double* P_, int maximum_iter,
   };
 
   std::vector<double> P(P_, P_ + (size_t)n * n);
+  double t_seg = omp_get_wtime();   // t_A: everything of this function outside h_share_model
   for (int i = -1; i < maximum_iter; i++) {
     valid = true;
     malio_pass_state ps;
@@ -1165,7 +1255,9 @@ int orc_update_iterated(void* vc, malio_state* x_, double* P_, int maximum_iter,
     std::memcpy(ps.pos, x_->pos, sizeof(ps.pos));
     std::memcpy(ps.ext, x_->ext, sizeof(ps.ext));
     const bool searched = converge;
+    c->t_A += omp_get_wtime() - t_seg;
     valid = orc_h_share_model(c, &ps, converge ? 1 : 0, nthreads) != 0;   // :512
+    t_seg = omp_get_wtime();
     passes++;
     if (searched) searches++;
     if (pass_flags) pass_flags[i + 1] = (valid ? 1 : 0) | (searched ? 2 : 0);
@@ -1220,9 +1312,15 @@ int orc_update_iterated(void* vc, malio_state* x_, double* P_, int maximum_iter,
     } else {   // :621-637
       std::vector<double> P_temp((size_t)n * n), P_inv((size_t)n * n), HTH((size_t)ncol * ncol), HTh(ncol);
       inverse_lu(P.data(), n, P_temp.data());
-      orc_reduce(c, HTH.data(), HTh.data());
+      if (c->fast_reduce) orc_reduce_fast(c, HTH.data(), HTh.data(), nullptr, 0, n, nullptr, nthreads);   // :629 (timing arms)
+      else orc_reduce(c, HTH.data(), HTh.data());
       for (int a = 0; a < ncol; ++a) for (int b = 0; b < ncol; ++b) P_temp[(size_t)a * n + b] += HTH[(size_t)a * ncol + b];
       inverse_lu(P_temp.data(), n, P_inv.data());
+      if (c->fast_reduce) {   // :635 in the reference's evaluation order: (P_inv.block * HT) * h, a second pass over the rows
+        std::vector<double> HTH2((size_t)ncol * ncol), HTh2(ncol), PT((size_t)ncol * n);
+        for (int a = 0; a < n; ++a) for (int k = 0; k < ncol; ++k) PT[(size_t)k * n + a] = P_inv[(size_t)a * n + k];
+        orc_reduce_fast(c, HTH2.data(), HTh2.data(), PT.data(), n, n, K_h.data(), nthreads);
+      } else
       for (int a = 0; a < n; ++a) { double s = 0; for (int k = 0; k < ncol; ++k) s += P_inv[(size_t)a * n + k] * HTh[k]; K_h[a] = s; }
       std::fill(K_x.begin(), K_x.end(), 0.0);
       for (int a = 0; a < n; ++a) for (int b = 0; b < ncol; ++b) { double s = 0; for (int k = 0; k < ncol; ++k) s += P_inv[(size_t)a * n + k] * HTH[(size_t)k * ncol + b]; K_x[(size_t)a * n + b] = s; }
@@ -1288,11 +1386,13 @@ int orc_update_iterated(void* vc, malio_state* x_, double* P_, int maximum_iter,
           P_[(size_t)a * n + b] = L_[(size_t)a * n + b] - s;
         }
       if (rep) { rep->passes = passes; rep->searches = searches; rep->converged_count = t; rep->last_status = 0; }
+      c->t_A += omp_get_wtime() - t_seg;
       return 0;
     }
   }
   // fell out of the loop (last pass invalid): the reference leaves P_ = P_propagated (or the last :530 value)
   std::memcpy(P_, P.data(), (size_t)n * n * 8);
+  c->t_A += omp_get_wtime() - t_seg;
   if (rep) { rep->passes = passes; rep->searches = searches; rep->converged_count = t; rep->last_status = MALIO_ERR_NO_EFFECTIVE_POINTS; }
   return 1;
 }

@@ -62,6 +62,9 @@ def oracle_lib() -> C.CDLL:
         L.orc_map_incremental.restype = None
         L.orc_map_incremental.argtypes = [vp, vp, C.c_double, C.c_int, vp, vp]
         L.orc_get_visits.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.orc_reset_times.argtypes = [vp]
+        L.orc_get_times.argtypes = [vp, vp, C.POINTER(C.c_int)]
+        L.orc_set_fast_reduce.argtypes = [vp, C.c_int]
         L.orc_update_iterated.argtypes = [vp, C.POINTER(capi.State), vp, C.c_int, C.c_double, C.c_int, vp, vp, C.POINTER(capi.UpdateReport)]
         _orc = L
     return _orc
@@ -339,6 +342,20 @@ class Oracle:
         v, s = C.c_int64(0), C.c_int64(0)
         self.L.orc_get_visits(self.c, C.byref(v), C.byref(s))
         return int(v.value), int(s.value)
+
+    def set_fast_reduce(self, enable: bool):
+        """Timing arms only: esekfom.hpp:622-635 through the blocked / vectorised / threaded evaluation (orc_reduce_fast)."""
+        self.L.orc_set_fast_reduce(self.c, 1 if enable else 0)
+
+    def reset_times(self):
+        self.L.orc_reset_times(self.c)
+
+    def times(self):
+        """(seconds in K = Nearest_Search, B = rest of h_share_model, A = rest of the update, passes) since reset_times()."""
+        out = np.zeros(3)
+        n = C.c_int(0)
+        self.L.orc_get_times(self.c, ptr(out), C.byref(n))
+        return float(out[0]), float(out[1]), float(out[2]), int(n.value)
 
     def update_iterated(self, x: capi.State, P: np.ndarray, max_iter: int, R=0.001, nthreads=1):
         n = self.n_dof

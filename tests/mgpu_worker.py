@@ -45,6 +45,27 @@ if rank == 0:
     assert rep1.passes == rep.passes and rep1.searches == rep.searches
     assert np.abs(synth.state_to_vec(x1, 3) - vec).max() < 1e-9
     print("MGPU_OK n_eff", st.n_eff, "passes", rep.passes)
+
+# degenerate branch (esekfom.hpp:574-582, N_eff < n = 35): every rank must build H from the rows of ALL ranks
+few = np.ascontiguousarray(case.pts[:: max(case.pts.shape[0] // 26, 1)][:26])
+flo, fhi = mdist.shard_bounds(few.shape[0], rank, world)
+m.upload_scan(few[flo:fhi], case.table, case.table_off, case.temporal_comp)
+xd, Pd = case.x_prop.copy(), case.P_prop.copy()
+repd = m.update_iterated_dyn_share_modified(xd, Pd, 3)
+vd = synth.state_to_vec(xd, 3)
+td = torch.from_numpy(np.concatenate([vd, Pd.ravel()])).cuda()
+td0 = td.clone()
+dist.broadcast(td0, 0)
+assert torch.equal(td, td0), "ranks disagree in the degenerate branch"
+if rank == 0:
+    assert 0 < repd.n_eff_last < 35, repd.n_eff_last
+    s.upload_scan(few, case.table, case.table_off, case.temporal_comp)
+    x2, P2 = case.x_prop.copy(), case.P_prop.copy()
+    rep2 = s.update_iterated_dyn_share_modified(x2, P2, 3)
+    assert rep2.n_eff_last == repd.n_eff_last and rep2.passes == repd.passes
+    assert np.abs(synth.state_to_vec(x2, 3) - vd).max() < 1e-9
+    assert np.abs(P2 - Pd).max() / np.abs(P2).max() < 1e-9
+    print("MGPU_DEGENERATE_OK n_eff", repd.n_eff_last)
 dist.barrier()
 m.close()
 dist.destroy_process_group()

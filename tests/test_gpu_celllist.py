@@ -176,3 +176,25 @@ def test_compact_upload_rebuilds_the_reference_boxes():
     idx, d2, _ = t.Nearest_Search(q[:1000])
     assert np.array_equal(idx.astype(np.int64), o_idx.astype(np.int64)) and np.array_equal(d2, o_d2)
     m.close(); full.close(); t.close()
+
+
+@pytest.mark.parametrize("offset", [1.0e5, 1.0e6])
+def test_map_far_from_the_origin_float32_quantisation(offset):
+    """Maps at large absolute coordinates (UTM-like 1e5..1e6 m): float32 spacing there is 0.008..0.06 m, so coordinates —
+    and with them squared distances — collapse onto a coarse lattice and exact ties become common.  Correctness must
+    hold by construction (ties go to the exact ikd-order traversal); the fallback fraction is what it costs, recorded
+    in the test output (pytest -s) and in DESIGN.md."""
+    rng = np.random.default_rng(31)
+    base = rng.uniform(-30, 30, (60000, 3)).astype(np.float64)
+    base[:, 2] = rng.uniform(0, 6, 60000)
+    xyz = (base + np.array([offset, -0.7 * offset, 50.0])).astype(np.float32)
+    snap = plugin.build_static_snapshot(xyz)
+    q = (xyz[rng.integers(0, xyz.shape[0], 20000)].astype(np.float64) + rng.normal(0, 0.3, (20000, 3))).astype(np.float32)
+    o_idx, o_d2, _, _ = po.knn_snapshot(snap.nodes, snap.node_cov, q, nthreads=8)
+    for cell in (0.0, -1.0, 1.0):
+        idx, d2, fb, r2 = _search(snap, q, cell)
+        assert np.array_equal(idx.astype(np.int64), o_idx.astype(np.int64)), (offset, cell)
+        assert np.array_equal(d2, o_d2), (offset, cell)
+        if cell >= 0:
+            print(f"[far-from-origin] offset {offset:.0e} cell {cell}: {fb} of {q.shape[0]} queries ({100.0 * fb / q.shape[0]:.2f} %) took "
+                  f"the exact traversal, {r2} the 5x5x5 block")

@@ -216,7 +216,7 @@ def test_two_gpu_sharded_update_matches_single_gpu():
                           "--master-addr", "127.0.0.1", "--master-port", "29611",
                           os.path.join(ROOT, "tests", "mgpu_worker.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert "MGPU_OK" in out.stdout
+    assert "MGPU_OK" in out.stdout and "MGPU_DEGENERATE_OK" in out.stdout
 
 
 def test_unfused_kernel_path_matches_fused_pass(monkeypatch):

@@ -503,3 +503,37 @@ def test_pose_compounding_and_table_vs_numpy():
     assert np.array_equal(table["cov"][0], lists[0][0].cov) and np.array_equal(table["T"][7], lists[0][7].T)
     t1, o1 = plugin.build_pose_unc(_to_c(ext[0]), None, [np.concatenate([_to_c(p) for p in lists[0]])])
     assert o1.tolist() == [0, 8] and np.array_equal(t1["cov"], table["cov"][:8])
+
+
+def test_python_default_params_equal_the_library_defaults():
+    """capi.default_params is restated in Python (so that bench.py --impl reference never maps the CUDA library): it must
+    stay equal to malio_default_params()."""
+    import ctypes as C
+    for L in (1, 2, 3):
+        a, b = capi.default_params(L), capi.default_params_from_library(L)
+        assert bytes(C.string_at(C.byref(a), C.sizeof(a))) == bytes(C.string_at(C.byref(b), C.sizeof(b)))
+
+
+def test_reference_arm_does_not_map_the_cuda_library_and_reports_the_split():
+    """bench.py --impl reference: the CPU arm must not load libmalio_b200.so, must honour --steps and must report the
+    K / B / A split at 3 threads and at all host threads (tiny stand-in workload: the arm itself is what is tested)."""
+    import json, subprocess, sys, textwrap
+    code = textwrap.dedent(f"""
+        import sys, json
+        sys.path.insert(0, {ROOT!r}); sys.argv = ['bench.py']
+        import bench
+        from malio_b200 import synth
+        case = synth.make_case('mini', 3000, 30000, 3, 3)
+        with bench.c_stdout_to_stderr():
+            tree = bench.live_tree(case)
+            best, runs = bench.cpu_arms(case, tree, 2, 1)
+            if tree is not None: tree.close()
+        mapped = [l for l in open('/proc/self/maps') if 'libmalio_b200' in l]
+        print(json.dumps(dict(best=best, n_runs=len(runs), mapped=len(mapped))))
+    """)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["mapped"] == 0
+    assert r["best"]["steps"] == 2 and set(r["best"]["split_ms_per_pass"]) == {"K_nearest_search", "B_h_share_model_rest", "A_ieskf_rest"}
+    assert r["n_runs"] >= 1
