@@ -256,6 +256,86 @@ int malio_build_pose_unc(int n_lidar, const malio_pose* extrinsic, const malio_p
                          const malio_pose* const* lidar_uncertainty, const uint32_t* counts,
                          malio_pose_entry* table, uint32_t* table_off);
 
+/* ---- next to the path: per-raw-point B-spline undistortion ------------------------------------
+ * ImuProcess::UndistortPcl's point loop (IMU_Processing.hpp:468-508) for ONE LiDAR: per raw point the spline pose
+ * BsplineSE3::get_pose (BsplineSE3.cpp:84-118: 3 x exp_se3(b * log_se3(.)), quat_ops.h:190-243), the motion compensation
+ * into the LiDAR's scan-end frame (:492) and the walk of the IMU-covariance list that yields the point's uncertainty-table
+ * index (:476-486, written to `intensity` :496).  On the device the log_se3 of every control-point pair is taken once,
+ * each point evaluates three exp_se3, and the sequential one-pop-per-point walk is computed as a min-plus prefix scan.
+ * Points arrive in buffer order (ascending time); like the reference the loop runs from the last point down to the
+ * SECOND one — point 0 is never touched.  Where get_pose fails the point keeps its coordinates and `intensity`. */
+typedef struct malio_raw_pt {
+  float x, y, z;
+  float curvature;      /* time offset from the scan start in ms (preprocess.cpp:91,139,200) */
+} malio_raw_pt;
+
+typedef struct malio_undistort_args {
+  double beg_time;            /* meas.lidar_beg_time[lid_num - num - 1] (:474) */
+  malio_rigid extrinsic;      /* extrinsic_quat[num], extrinsic_trans[num] */
+  malio_rigid lt_imu_frame;   /* lt_imu_frame_quat[num], lt_imu_frame_trans[num]: IMU pose at this LiDAR's scan end */
+  const double* ctrl_t;       /* spline control points: timestamps ascending (BsplineSE3::control_points keys) */
+  const double* ctrl_T;       /* ... and their 4x4 poses, row-major, n_ctrl x 16 */
+  uint32_t n_ctrl;            /* <= MALIO_MAX_CTRL */
+  const double* imu_cov_t;    /* imu_cov[k].first.first, ascending */
+  uint32_t n_cov;             /* <= MALIO_MAX_COV */
+  int32_t cov_pointer;        /* its value when the point loop starts (:455-466) */
+} malio_undistort_args;
+#define MALIO_MAX_CTRL 512
+#define MALIO_MAX_COV 512
+#define MALIO_IDX_UNTOUCHED INT32_MIN
+
+/* lidar = slot (0..L-1) whose device-resident result malio_voxel_grid(.., NULL input) picks up.  Host outputs (any may be
+ * NULL): xyz n x 3 float; idx n (the value the reference writes to `intensity`, MALIO_IDX_UNTOUCHED where it writes nothing);
+ * ok n (spline_flag); pop_point[k] = index of the point at which the k-th table entry is pushed (:487-494), n_pops their
+ * number (the host builds those <= n_cov entries with malio_bspline_get_pose + malio_compound_*); pose n x 7 (q wxyz, p). */
+int malio_undistort(malio_handle* h, int lidar, const malio_raw_pt* pts, uint32_t n, const malio_undistort_args* a,
+                    float* xyz, int32_t* idx, uint8_t* ok, int32_t* pop_point, uint32_t* n_pops, double* pose);
+
+/* BsplineSE3::get_pose on the host (lt_imu_frame poses, the <= n_cov table-entry poses).  q = (w,x,y,z).  1 on success. */
+int malio_bspline_get_pose(const double* ctrl_t, const double* ctrl_T, uint32_t n_ctrl, double timestamp, double q[4], double p[3]);
+
+/* ---- next to the path (second half): pcl::VoxelGrid down-sampling (laserMapping.cpp:968-983) --------
+ * PCL's filter with setLeafSize(leaf, leaf, leaf) and default settings restated on the device: voxel index
+ * floor(x / leaf) relative to the cloud's minimum, one output point per occupied voxel in ascending voxel index, every
+ * field the centroid of the voxel's points (float sums taken in ascending input index).  What the hot path reads of the
+ * result is x, y, z and the averaged `intensity` (the table index, moved to normal_x at :975).
+ * in == NULL: take the device-resident output of the last malio_undistort(h, lidar, ...) (x, y, z, intensity = idx,
+ * curvature; points the undistortion left untouched keep intensity 0).  in != NULL: n x 5 floats
+ * {x, y, z, intensity, curvature} from the host.  Outputs (may be NULL): out n_out x 5 floats, same layout; *n_out.
+ * The down-sampled cloud also stays on the device as LiDAR `lidar`'s part of the next scan (malio_upload_scan_device). */
+int malio_voxel_grid(malio_handle* h, int lidar, const float* in, uint32_t n, float leaf, float* out, uint32_t out_cap,
+                     uint32_t* n_out);
+
+/* Merge the device-resident down-sampled clouds of LiDARs 0..L-1 (feats_down_body = sum of feats_down_vec[num],
+ * laserMapping.cpp:983; lidar id -> `intensity`, int(averaged intensity) -> table_idx) into the scan of the handle without
+ * a host bounce; then as malio_upload_scan.  n_total (optional) receives the merged size. */
+int malio_upload_scan_device(malio_handle* h, const malio_pose_entry* table, const uint32_t* table_off,
+                             const malio_rigid* temporal_comp, uint32_t* n_total);
+
+/* ---- next to the path: City dataset .bin scans without ROS -------------------------------------
+ * One file = one scan of packed records as the reference's file player reads them (file_player/src/ROSThread.cpp:776-795
+ * Livox, :952-967 Ouster), followed by the per-sensor conversion of MA_LIO/src/preprocess.cpp to the time-stamped raw
+ * cloud (x, y, z, curvature = time offset in ms) that UndistortPcl / malio_undistort consume.  Host code. */
+typedef struct malio_livox_pt {   /* livox_ros_driver::CustomPoint fields the player fills */
+  float x, y, z;
+  uint8_t reflectivity, tag, line, pad;
+  uint32_t offset_time;           /* only 2 bytes per record are stored in the file (ROSThread.cpp:789) */
+} malio_livox_pt;
+typedef struct malio_ouster_pt {  /* OusterPointXYZIRT */
+  float x, y, z, intensity;
+  uint16_t ring, pad;
+  uint32_t t;
+} malio_ouster_pt;
+/* out may be NULL to count.  eof_quirk != 0 appends the zero record the player's `while(!file.eof())` loop produces. */
+int malio_read_livox_bin(const char* path, malio_livox_pt* out, uint32_t cap, uint32_t* n_out, int eof_quirk);
+int malio_read_ouster_bin(const char* path, malio_ouster_pt* out, uint32_t cap, uint32_t* n_out, int eof_quirk);
+/* Preprocess::avia_handler (preprocess.cpp:59-110): n_scans = N_SCANS[lidar], point_filter_num, blind as in the YAML */
+int malio_preprocess_livox(const malio_livox_pt* pts, uint32_t n, int n_scans, int point_filter_num, double blind, malio_raw_pt* out,
+                           float* intensity, uint32_t cap, uint32_t* n_out);
+/* Preprocess::oust64_handler (preprocess.cpp:112-152) */
+int malio_preprocess_ouster(const malio_ouster_pt* pts, uint32_t n, int point_filter_num, double blind, float time_unit_scale,
+                            malio_raw_pt* out, float* intensity, uint32_t cap, uint32_t* n_out);
+
 /* cumulative counters since malio_create: kernels launched by this library, k-NN kernel launches, queries they
  * processed and their summed device time (CUDA events) — what bench.py's roofline is computed from. */
 typedef struct malio_counters {

@@ -406,6 +406,26 @@ int malio_map_incremental(malio_handle* h, const malio_pass_state* s, double fil
   if (!h || !s || !cls || !(filter_size_map > 0.0)) return MALIO_ERR_INVALID_ARG;
   return malio_dev::map_incremental(h, s, filter_size_map, ekf_inited, cls, world);
 }
+// ---------------------------------------------------------------- N2 / N3 wrappers (malio_preproc.cu)
+int malio_undistort(malio_handle* h, int lidar, const malio_raw_pt* pts, uint32_t n, const malio_undistort_args* a, float* xyz,
+                    int32_t* idx, uint8_t* ok, int32_t* pop_point, uint32_t* n_pops, double* pose) {
+  if (!h || !a || (n && !pts) || !a->ctrl_t || !a->ctrl_T || (a->n_cov && !a->imu_cov_t)) return MALIO_ERR_INVALID_ARG;
+  // the walk of IMU_Processing.hpp:476-486 assumes the cloud sorted by time (sort at :232): checked, not assumed
+  for (uint32_t i = 1; i < n; ++i)
+    if (pts[i].curvature < pts[i - 1].curvature) { h->err = "malio_undistort: points must be sorted by curvature (IMU_Processing.hpp:232)"; return MALIO_ERR_INVALID_ARG; }
+  return malio_pre::undistort(h, lidar, pts, n, a, xyz, idx, ok, pop_point, n_pops, pose);
+}
+int malio_voxel_grid(malio_handle* h, int lidar, const float* in, uint32_t n, float leaf, float* out, uint32_t out_cap, uint32_t* n_out) {
+  if (!h) return MALIO_ERR_INVALID_ARG;
+  return malio_pre::voxel_grid(h, lidar, in, n, leaf, out, out_cap, n_out);
+}
+int malio_upload_scan_device(malio_handle* h, const malio_pose_entry* table, const uint32_t* table_off, const malio_rigid* temporal_comp,
+                             uint32_t* n_total) {
+  if (!h || !table || !table_off) return MALIO_ERR_INVALID_ARG;
+  if (h->cfg.params.n_lidar > 1 && !temporal_comp) { h->err = "temporal_comp required for L > 1"; return MALIO_ERR_INVALID_ARG; }
+  return malio_pre::upload_scan_device(h, table, table_off, temporal_comp, n_total);
+}
+
 // ---------------------------------------------------------------- pose-uncertainty table (associate_uct.hpp:8-142)
 namespace {
 struct M6 { double a[6][6]; };

@@ -22,6 +22,8 @@ struct malio_handle {
   malio_config cfg{};
   std::string err;
   void* dev = nullptr;   // DeviceState*, owned by the CUDA TU
+  void* pre = nullptr;   // PreState*, owned by malio_preproc.cu (undistortion / voxel grid buffers)
+  void* mapst = nullptr; // MapOpsState*, owned by malio_mapops.cu (device-resident map replay)
 };
 
 // CUDA TU entry points used by the C-ABI wrappers
@@ -41,11 +43,22 @@ int download_aux(malio_handle* h, float* normal_y, uint32_t* nn_idx, float* nn_d
 int knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* idx, float* d2, float* ms);
 int map_incremental(malio_handle* h, const malio_pass_state* s, double fs, int ekf_inited, uint8_t* cls, float* world);
 int rearm_scan(malio_handle* h);
+int reserve_scan(malio_handle* h, uint32_t n);
 int get_counters(malio_handle* h, malio_counters* out);
 int set_timing(malio_handle* h, int enable);
 int comm_init(malio_handle* h, const uint8_t* id, int rank, int world);
 int get_unique_id(uint8_t* id);
 }  // namespace malio_dev
+
+// malio_preproc.cu
+namespace malio_pre {
+void destroy(malio_handle* h);
+int undistort(malio_handle* h, int lidar, const malio_raw_pt* pts, uint32_t n, const malio_undistort_args* a, float* xyz,
+              int32_t* idx, uint8_t* ok, int32_t* pop_point, uint32_t* n_pops, double* pose);
+int voxel_grid(malio_handle* h, int lidar, const float* in, uint32_t n, float leaf, float* out, uint32_t out_cap, uint32_t* n_out);
+int upload_scan_device(malio_handle* h, const malio_pose_entry* table, const uint32_t* table_off, const malio_rigid* tcomp,
+                       uint32_t* n_total);
+}  // namespace malio_pre
 
 // host math shared by measure() (localization weight) and the IESKF
 namespace malio_host {

@@ -31,11 +31,21 @@ POSE = np.dtype([("q", "<f8", 4), ("t", "<f8", 3), ("T", "<f8", (4, 4)), ("cov",
 SCAN_PT = np.dtype([("xyz", "<f4", 3), ("lidar", "<u2"), ("table_idx", "<u2")])
 POSE_ENTRY = np.dtype([("T", "<f8", (4, 4)), ("cov", "<f8", (6, 6))])
 RIGID = np.dtype([("q", "<f8", 4), ("t", "<f8", 3)])
+LIVOX_PT = np.dtype([("xyz", "<f4", 3), ("reflectivity", "u1"), ("tag", "u1"), ("line", "u1"), ("pad", "u1"), ("offset_time", "<u4")])
+OUSTER_PT = np.dtype([("xyz", "<f4", 3), ("intensity", "<f4"), ("ring", "<u2"), ("pad", "<u2"), ("t", "<u4")])
+RAW_PT = np.dtype([("xyz", "<f4", 3), ("curvature", "<f4")])   # malio_raw_pt
+IDX_UNTOUCHED = -(1 << 31)
 assert MAP_NODE.itemsize == 64 and SCAN_PT.itemsize == 16 and POSE_ENTRY.itemsize == 416 and RIGID.itemsize == 56
 
 
 class Rigid(C.Structure):
     _fields_ = [("q", C.c_double * 4), ("t", C.c_double * 3)]
+
+
+class UndistortArgs(C.Structure):
+    _fields_ = [("beg_time", C.c_double), ("extrinsic", Rigid), ("lt_imu_frame", Rigid), ("ctrl_t", C.c_void_p),
+                ("ctrl_T", C.c_void_p), ("n_ctrl", C.c_uint32), ("imu_cov_t", C.c_void_p), ("n_cov", C.c_uint32),
+                ("cov_pointer", C.c_int32)]
 
 
 class PassState(C.Structure):
@@ -104,6 +114,8 @@ EXPORTS = [
     "malio_get_nccl_unique_id", "malio_comm_init", "malio_upload_map", "malio_upload_scan", "malio_measure",
     "malio_download_rows", "malio_download_aux", "malio_knn", "malio_ieskf_update", "malio_build_static_snapshot",
     "malio_rearm_scan", "malio_get_counters", "malio_set_timing", "malio_upload_map_compact", "malio_download_map_nodes", "malio_map_incremental",
+    "malio_read_livox_bin", "malio_read_ouster_bin", "malio_preprocess_livox", "malio_preprocess_ouster",
+    "malio_undistort", "malio_bspline_get_pose", "malio_voxel_grid", "malio_upload_scan_device",
     "malio_pose_initial", "malio_compound_pose_with_cov", "malio_compound_inv_pose_with_cov", "malio_build_pose_unc",
 ]
 
@@ -146,6 +158,14 @@ def load() -> C.CDLL:
     lib.malio_compound_inv_pose_with_cov.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.malio_build_pose_unc.argtypes = [i32, vp, vp, vp, vp, vp, vp]
     lib.malio_upload_scan.argtypes = [vp, vp, u32, vp, vp, vp]
+    lib.malio_read_livox_bin.argtypes = [C.c_char_p, vp, u32, C.POINTER(u32), i32]
+    lib.malio_read_ouster_bin.argtypes = [C.c_char_p, vp, u32, C.POINTER(u32), i32]
+    lib.malio_preprocess_livox.argtypes = [vp, u32, i32, i32, C.c_double, vp, vp, u32, C.POINTER(u32)]
+    lib.malio_preprocess_ouster.argtypes = [vp, u32, i32, C.c_double, C.c_float, vp, vp, u32, C.POINTER(u32)]
+    lib.malio_undistort.argtypes = [vp, i32, vp, u32, C.POINTER(UndistortArgs), vp, vp, vp, vp, C.POINTER(u32), vp]
+    lib.malio_bspline_get_pose.argtypes = [vp, vp, u32, C.c_double, vp, vp]
+    lib.malio_voxel_grid.argtypes = [vp, i32, vp, u32, C.c_float, vp, u32, C.POINTER(u32)]
+    lib.malio_upload_scan_device.argtypes = [vp, vp, vp, vp, C.POINTER(u32)]
     lib.malio_measure.argtypes = [vp, C.POINTER(PassState), i32, vp, vp, C.POINTER(PassStats)]
     lib.malio_download_rows.argtypes = [vp, vp, vp, u32, C.POINTER(u32)]
     lib.malio_download_aux.argtypes = [vp, vp, vp, vp, vp, vp]

@@ -77,6 +77,15 @@ def build_pose_unc(extrinsic: np.ndarray, temporal_comp: np.ndarray | None, lida
     return table[:rc], off
 
 
+def bspline_get_pose(ctrl_t: np.ndarray, ctrl_T: np.ndarray, timestamp: float):
+    """BsplineSE3::get_pose (BsplineSE3.cpp:84-118) through the library's host code.  Returns (ok, q wxyz, p)."""
+    ct = np.ascontiguousarray(ctrl_t, np.float64)
+    cT = np.ascontiguousarray(ctrl_T, np.float64).reshape(-1, 16)
+    q, p = np.zeros(4), np.zeros(3)
+    ok = capi.load().malio_bspline_get_pose(capi.ptr(ct), capi.ptr(cT), ct.shape[0], float(timestamp), capi.ptr(q), capi.ptr(p))
+    return bool(ok), q, p
+
+
 class MeasurementModel:
     """One handle = one GPU.  Mirrors the life cycle of one scan in laserMapping.cpp:935-1082."""
 
@@ -160,6 +169,51 @@ class MeasurementModel:
         self._check(self.lib.malio_upload_scan(self._h, capi.ptr(pts), pts.shape[0], capi.ptr(table),
                                                capi.ptr(table_off), capi.ptr(tc)))
         self.n_points = int(pts.shape[0])
+
+    # ---- the two stages before the path
+    def undistort(self, lidar: int, pts: np.ndarray, beg_time: float, extrinsic, lt_imu_frame, ctrl_t, ctrl_T, imu_cov_t,
+                  cov_pointer: int, want_pose: bool = False):
+        """UndistortPcl's per-point loop for one LiDAR (IMU_Processing.hpp:468-508).  pts: capi.RAW_PT[n] sorted by
+        curvature; extrinsic / lt_imu_frame: (q wxyz, t).  Returns dict(xyz, idx, ok, pop_point, pose?)."""
+        pts = np.ascontiguousarray(pts)
+        assert pts.dtype == capi.RAW_PT
+        n = pts.shape[0]
+        ct = np.ascontiguousarray(ctrl_t, np.float64)
+        cT = np.ascontiguousarray(ctrl_T, np.float64).reshape(-1, 16)
+        cv = np.ascontiguousarray(imu_cov_t, np.float64)
+        a = capi.UndistortArgs()
+        a.beg_time = float(beg_time)
+        a.extrinsic.q[:] = list(map(float, extrinsic[0])); a.extrinsic.t[:] = list(map(float, extrinsic[1]))
+        a.lt_imu_frame.q[:] = list(map(float, lt_imu_frame[0])); a.lt_imu_frame.t[:] = list(map(float, lt_imu_frame[1]))
+        a.ctrl_t = ct.ctypes.data; a.ctrl_T = cT.ctypes.data; a.n_ctrl = ct.shape[0]
+        a.imu_cov_t = cv.ctypes.data if cv.shape[0] else None; a.n_cov = cv.shape[0]; a.cov_pointer = int(cov_pointer)
+        xyz = np.zeros((n, 3), np.float32); idx = np.zeros(n, np.int32); ok = np.zeros(n, np.uint8)
+        pop = np.full(max(cv.shape[0], 1), -1, np.int32); npop = C.c_uint32(0)
+        pose = np.zeros((n, 7)) if want_pose else None
+        self._check(self.lib.malio_undistort(self._h, lidar, capi.ptr(pts), n, C.byref(a), capi.ptr(xyz), capi.ptr(idx), capi.ptr(ok),
+                                             capi.ptr(pop), C.byref(npop), capi.ptr(pose)))
+        return dict(xyz=xyz, idx=idx, ok=ok, pop_point=pop[: npop.value], pose=pose)
+
+    def voxel_grid(self, lidar: int, pts5: np.ndarray | None, leaf: float):
+        """pcl::VoxelGrid (laserMapping.cpp:968-983) on the device.  pts5: float32[n,5] {x,y,z,intensity,curvature}, or None to
+        take the device-resident output of the last undistort() of this LiDAR slot.  Returns float32[m,5]."""
+        n = 0 if pts5 is None else int(pts5.shape[0])
+        inp = None if pts5 is None else np.ascontiguousarray(pts5, np.float32)
+        m = C.c_uint32(0)
+        self._check(self.lib.malio_voxel_grid(self._h, lidar, capi.ptr(inp), n, C.c_float(leaf), None, 0, C.byref(m)))
+        out = np.zeros((m.value, 5), np.float32)
+        if m.value:   # second call only fetches (the result is device-resident); kept simple: recompute with the output buffer
+            self._check(self.lib.malio_voxel_grid(self._h, lidar, capi.ptr(inp), n, C.c_float(leaf), capi.ptr(out), m.value, C.byref(m)))
+        return out
+
+    def upload_scan_device(self, table: np.ndarray, table_off: np.ndarray, temporal_comp: np.ndarray | None) -> int:
+        """Merge the device-resident down-sampled clouds of all LiDAR slots into the scan (no host bounce)."""
+        table = np.ascontiguousarray(table); table_off = np.ascontiguousarray(table_off, dtype=np.uint32)
+        tc = None if temporal_comp is None else np.ascontiguousarray(temporal_comp)
+        n = C.c_uint32(0)
+        self._check(self.lib.malio_upload_scan_device(self._h, capi.ptr(table), capi.ptr(table_off), capi.ptr(tc), C.byref(n)))
+        self.n_points = int(n.value)
+        return self.n_points
 
     def rearm_scan(self):
         """Reset the per-scan state of the scan already resident on the device (no host copy)."""

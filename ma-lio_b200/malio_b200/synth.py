@@ -323,3 +323,49 @@ def knn_microbench(M: int = 10_000_000, Q: int = 1_000_000, seed_map: int = 42, 
     rq = np.random.default_rng(seed_q)
     q = xyz[rq.integers(0, M, Q)] + rq.normal(0, 0.1, size=(Q, 3)).astype(np.float32)
     return xyz, np.ascontiguousarray(q.astype(np.float32))
+
+
+# ------------------------------------------------------------------ N2: raw scan + spline for the undistortion
+def _se3(q, t):
+    T = np.eye(4)
+    T[:3, :3] = q_to_R(q)
+    T[:3, 3] = t
+    return T
+
+
+def undistort_case(n: int = 60000, lidar: int = 0, seed: int = 51, scan_ms: float = 100.0, imu_hz: float = 200.0,
+                   sorted_times: bool = True):
+    """One LiDAR's raw scan for UndistortPcl's point loop: n points with time offsets (`curvature`, ms) over one scan, a
+    cubic-spline control-point set at the reference's fixed 10 ms spacing (BsplineSE3.cpp:34) covering the scan with two
+    control points of margin on both sides (a smooth vehicle motion: ~8 m/s, ~0.6 rad/s), the IMU-covariance time list at
+    imu_hz, and cov_pointer as IMU_Processing.hpp:455-466 leaves it.  Returns a dict of plain arrays."""
+    rng = np.random.default_rng(seed)
+    t0 = 1000.0 + 0.0137          # lidar_beg_time
+    end_time = t0 + scan_ms * 1e-3
+    ctrl_t = t0 - 0.031 + 0.01 * np.arange(int(scan_ms / 10) + 8)
+    axis = rand_unit(rng)
+    w = axis * 0.6
+    v = np.array([8.0, 0.5, -0.1])
+    acc = rng.normal(0, 1.0, 3)
+    ctrl_T = np.zeros((ctrl_t.shape[0], 4, 4))
+    for k, tk in enumerate(ctrl_t):
+        dt = tk - t0
+        q = q_mul(q_exp([0.1, -0.05, 0.7]), q_exp(w * dt + 0.5 * rng.normal(0, 0.01, 3) * dt * dt))
+        ctrl_T[k] = _se3(q, np.array([3.0, -2.0, 1.5]) + v * dt + 0.5 * acc * dt * dt)
+    pts = np.zeros(n, dtype=capi.RAW_PT)
+    rad = rng.uniform(1.0, 80.0, n)
+    az = rng.uniform(-np.pi, np.pi, n)
+    el = rng.uniform(-0.4, 0.4, n)
+    pts["xyz"] = np.stack([rad * np.cos(el) * np.cos(az), rad * np.cos(el) * np.sin(az), rad * np.sin(el)], axis=1).astype(np.float32)
+    curv = rng.uniform(0.0, scan_ms, n).astype(np.float32)
+    pts["curvature"] = np.sort(curv) if sorted_times else curv
+    # imu_cov: forward-propagation stamps from before the scan start to past its end (IMU_Processing.hpp:327-360)
+    cov_t = t0 - 0.004 + np.arange(int((scan_ms * 1e-3 + 0.02) * imu_hz)) / imu_hz
+    cp = cov_t.shape[0] - 1
+    while cov_t[cp] > end_time:   # :455-466
+        cp -= 1
+    cp += 1
+    cp = min(cp, cov_t.shape[0] - 1)
+    ext = (q_normalize(EXTRINSICS[lidar][0]), np.array(EXTRINSICS[lidar][1]))
+    return dict(pts=pts, beg_time=t0, end_time=end_time, ctrl_t=ctrl_t, ctrl_T=ctrl_T.reshape(-1, 16), imu_cov_t=cov_t,
+                cov_pointer=int(cp), extrinsic=ext)

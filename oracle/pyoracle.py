@@ -65,6 +65,15 @@ def oracle_lib() -> C.CDLL:
         L.orc_reset_times.argtypes = [vp]
         L.orc_get_times.argtypes = [vp, vp, C.POINTER(C.c_int)]
         L.orc_set_fast_reduce.argtypes = [vp, C.c_int]
+        L.orc_bspline_get_pose.argtypes = [vp, vp, C.c_int, C.c_double, vp, vp]
+        L.orc_log_se3.argtypes = [vp, vp]
+        L.orc_exp_se3.argtypes = [vp, vp]
+        L.orc_quat_from_R.argtypes = [vp, vp]
+        L.orc_undistort.restype = None
+        L.orc_undistort.argtypes = [vp, C.c_int64, C.c_double, vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, vp,
+                                    C.POINTER(C.c_int32), vp]
+        L.orc_voxel_grid.restype = C.c_int64
+        L.orc_voxel_grid.argtypes = [vp, C.c_int64, C.c_float, vp, C.c_int64, vp]
         L.orc_update_iterated.argtypes = [vp, C.POINTER(capi.State), vp, C.c_int, C.c_double, C.c_int, vp, vp, C.POINTER(capi.UpdateReport)]
         _orc = L
     return _orc
@@ -364,3 +373,43 @@ class Oracle:
         rep = capi.UpdateReport()
         rc = self.L.orc_update_iterated(self.c, C.byref(x), ptr(P), max_iter, R, nthreads, ptr(dx_log), ptr(flags), C.byref(rep))
         return rc, dx_log, flags, rep
+
+
+# ------------------------------------------------------------------ N2 / N3 restatements (oracle_undistort.cpp)
+def bspline_get_pose(ctrl_t, ctrl_T, timestamp):
+    L = oracle_lib()
+    ct = np.ascontiguousarray(ctrl_t, np.float64)
+    cT = np.ascontiguousarray(ctrl_T, np.float64).reshape(-1, 16)
+    q, p = np.zeros(4), np.zeros(3)
+    ok = L.orc_bspline_get_pose(ptr(ct), ptr(cT), ct.shape[0], float(timestamp), ptr(q), ptr(p))
+    return bool(ok), q, p
+
+
+def undistort(pts, beg_time, extrinsic, lt_imu_frame, ctrl_t, ctrl_T, imu_cov_t, cov_pointer, want_pose=False):
+    """The per-point loop of UndistortPcl for one LiDAR (IMU_Processing.hpp:468-508), sequential, as the reference runs it."""
+    L = oracle_lib()
+    pts = np.ascontiguousarray(pts)
+    n = pts.shape[0]
+    raw = np.ascontiguousarray(pts.view(np.float32).reshape(n, 4))
+    ct = np.ascontiguousarray(ctrl_t, np.float64)
+    cT = np.ascontiguousarray(ctrl_T, np.float64).reshape(-1, 16)
+    cv = np.ascontiguousarray(imu_cov_t, np.float64)
+    eq, et = np.ascontiguousarray(extrinsic[0], np.float64), np.ascontiguousarray(extrinsic[1], np.float64)
+    lq, lt = np.ascontiguousarray(lt_imu_frame[0], np.float64), np.ascontiguousarray(lt_imu_frame[1], np.float64)
+    xyz = np.zeros((n, 3), np.float32); idx = np.zeros(n, np.int32); ok = np.zeros(n, np.uint8)
+    pop = np.full(max(cv.shape[0], 1), -1, np.int32); npop = C.c_int32(0)
+    pose = np.zeros((n, 7)) if want_pose else None
+    L.orc_undistort(ptr(raw), n, float(beg_time), ptr(eq), ptr(et), ptr(lq), ptr(lt), ptr(ct), ptr(cT), ct.shape[0], ptr(cv),
+                    cv.shape[0], int(cov_pointer), ptr(xyz), ptr(idx), ptr(ok), ptr(pop), C.byref(npop), ptr(pose))
+    return dict(xyz=xyz, idx=idx, ok=ok, pop_point=pop[: min(npop.value, cv.shape[0])], n_pops=npop.value, pose=pose)
+
+
+def voxel_grid(pts8, leaf):
+    """pcl::VoxelGrid restated (all 8 float fields of PointXYZINormal averaged).  Returns (out[m,8], voxel_of[n])."""
+    L = oracle_lib()
+    p = np.ascontiguousarray(pts8, np.float32)
+    n = p.shape[0]
+    out = np.zeros((max(n, 1), 8), np.float32)
+    vo = np.zeros(max(n, 1), np.int32)
+    m = L.orc_voxel_grid(ptr(p), n, C.c_float(leaf), ptr(out), n, ptr(vo))
+    return out[:m].copy(), vo[:n].copy()
