@@ -33,11 +33,19 @@ int download_aux(malio_handle*, float*, uint32_t*, float*, uint8_t*, float*) { r
 int knn(malio_handle*, const float*, uint32_t, uint32_t*, float*, float*) { return MALIO_ERR_STATE; }
 int map_incremental(malio_handle*, const malio_pass_state*, double, int, uint8_t*, float*) { return MALIO_ERR_STATE; }
 int rearm_scan(malio_handle*) { return MALIO_OK; }
+int reserve_scan(malio_handle*, uint32_t) { return MALIO_OK; }
 int get_counters(malio_handle*, malio_counters* out) { std::memset(out, 0, sizeof(*out)); return MALIO_OK; }
 int set_timing(malio_handle*, int) { return MALIO_OK; }
 int comm_init(malio_handle*, const uint8_t*, int, int) { return MALIO_ERR_NCCL; }
 int get_unique_id(uint8_t*) { return MALIO_ERR_NCCL; }
 }  // namespace malio_dev
+
+namespace malio_pre {
+void destroy(malio_handle*) {}
+int undistort(malio_handle*, int, const malio_raw_pt*, uint32_t, const malio_undistort_args*, float*, int32_t*, uint8_t*, int32_t*, uint32_t*, double*) { return MALIO_ERR_STATE; }
+int voxel_grid(malio_handle*, int, const float*, uint32_t, float, float*, uint32_t, uint32_t*) { return MALIO_ERR_STATE; }
+int upload_scan_device(malio_handle*, const malio_pose_entry*, const uint32_t*, const malio_rigid*, uint32_t*) { return MALIO_ERR_STATE; }
+}  // namespace malio_pre
 
 namespace malio_host {
 // sym3_singular_values lives in malio_host.cpp (declared in malio_internal.h); nothing to add here
