@@ -456,13 +456,24 @@ def run_ours(args, rank, world):
         f_depth = C.c_uint32(0)
         f_box = np.zeros(6, np.float32)
 
+    stages = {}
+
+    def lap(name, t0):
+        stages[name] = stages.get(name, 0.0) + (time.perf_counter() - t0)
+        return time.perf_counter()
+
     def step_e2e_snapshot_only():
+        t0 = time.perf_counter()
         sp = plugin.MapSnapshot(None, h_cov[:M_nodes], None, snap.max_depth)
         model.upload_map_compact(sp, points=h_mpts[:M_nodes], root_box=root_box)
+        t0 = lap("upload_map_compact", t0)
         model.upload_scan(h_pts, case.table, case.table_off, case.temporal_comp)
+        t0 = lap("upload_scan", t0)
         x, P = case.x_prop.copy(), case.P_prop.copy()
         rep = model.update_iterated_dyn_share_modified(x, P, case.max_iter)
+        t0 = lap("update", t0)
         model.aux(out=aux_out)
+        lap("aux", t0)
         return rep, x
 
     def step_e2e():
@@ -529,7 +540,9 @@ def run_ours(args, rank, world):
     flatten_ms = 1e3 * flat["s"] / max(flat["n"], 1) if tree is not None else None
     h2d = int(ec1.h2d_bytes - ec0.h2d_bytes) // e_steps
     d2h = int(ec1.d2h_bytes - ec0.d2h_bytes) // e_steps
-    s_ms, _, _, _, _, _ = timed(step_e2e_snapshot_only, e_steps, 1)
+    step_e2e_snapshot_only(); stages.clear()
+    s_ms, _, _, _, _, _ = timed(step_e2e_snapshot_only, e_steps, 0)
+    stage_ms = {k: 1e3 * v / e_steps for k, v in stages.items()}
 
     # separate short loop with per-kernel CUDA events on (same steps, L2 flushed): kernel times for the rooflines
     model.set_timing(True)
@@ -635,7 +648,7 @@ def run_ours(args, rank, world):
         "clocks": clocks,
         "e2e": {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e_ms / e_steps, "steps": e_steps, "flatten_ms": flatten_ms, "flatten_host_threads": host_threads(),
-                "snapshot_only": {"value": e_steps / (s_ms * 1e-3), "ms_per_step": s_ms / e_steps,
+                "snapshot_only": {"value": e_steps / (s_ms * 1e-3), "ms_per_step": s_ms / e_steps, "host_wall_ms_per_stage": stage_ms,
                                   "what": "the same step without the host flatten (pre-flattened pinned arrays)"},
                 "what": "flatten of the live ikd-Tree (host, OpenMP) + upload_map_compact (20 B/node, boxes + cell index rebuilt on the "
                         "device) + upload_scan (pinned host buffers) + IESKF update + download of normal_y/selected"},

@@ -336,6 +336,32 @@ int malio_preprocess_livox(const malio_livox_pt* pts, uint32_t n, int n_scans, i
 int malio_preprocess_ouster(const malio_ouster_pt* pts, uint32_t n, int point_filter_num, double blind, float time_unit_scale,
                             malio_raw_pt* out, float* intensity, uint32_t cap, uint32_t* n_out);
 
+/* ---- next to the path: the map as a device-resident point set, kept in step by deltas -------------
+ * Instead of flattening the live ikd-Tree and re-uploading ~20 B per node every scan, the device keeps the map's live
+ * points in slots {x, y, z, normal_y, id} and receives what the reference's map-maintenance calls change
+ * (include/malio_mapsync.hpp has the host side and the reasoning):
+ *   malio_map_build          <- KD_TREE::Build(points)                         ikd_Tree.cpp:370-424  (laserMapping.cpp:1007)
+ *   malio_map_delete_boxes   <- KD_TREE::Delete_Point_Boxes(boxes)             :648-676              (laserMapping.cpp:223)
+ *   malio_map_add_points     <- KD_TREE::Add_Points(points, false)             :478-584              (laserMapping.cpp:444)
+ *   malio_map_sync_voxels    <- KD_TREE::Add_Points(points, true) followed by malio::collect_voxel_sync on the tree: the
+ *                               content of every touched voxel box replaces the device's                (laserMapping.cpp:443)
+ * Boxes are half-open, min <= p < max per axis, exactly Search_by_range's / Delete_by_range's test (:1270,:807).
+ * The cell-list index is rebuilt on the device (~70 us at 1M points) by the next malio_measure / malio_knn / malio_map_commit;
+ * dead slots are compacted away when they exceed half of the slots.  In this mode the search never walks a tree: every
+ * neighbour list and every distance is the reference's, except for exact distance ties, which the reference breaks by
+ * traversal order — those queries are counted (malio_counters.knn_tie_queries) and broken by slot index.
+ * nn_idx of malio_download_aux / malio_knn are SLOT indices in this mode; malio_map_download gives slot -> id.
+ * A later malio_upload_map* call switches the handle back to snapshot mode. */
+int malio_map_build(malio_handle* h, const float* xyz, const float* normal_y, const int32_t* ids /* may be NULL: 0..n-1 */, uint32_t n);
+int malio_map_add_points(malio_handle* h, const float* xyz, const float* normal_y, const int32_t* ids /* may be NULL */, uint32_t n);
+int malio_map_delete_boxes(malio_handle* h, const float* boxes /* nb x {min3, max3} */, uint32_t nb, uint32_t* n_deleted);
+int malio_map_sync_voxels(malio_handle* h, const float* boxes, uint32_t nb, const float* xyz, const float* normal_y,
+                          const int32_t* ids, uint32_t n_points, uint32_t* n_deleted);
+int malio_map_commit(malio_handle* h);
+int malio_map_info(malio_handle* h, uint32_t* n_live, uint32_t* n_slots);
+/* live points in slot order (test / debug): any of xyz (n x 3), normal_y, ids, slots may be NULL */
+int malio_map_download(malio_handle* h, float* xyz, float* normal_y, int32_t* ids, uint32_t* slots, uint32_t cap, uint32_t* n);
+
 /* cumulative counters since malio_create: kernels launched by this library, k-NN kernel launches, queries they
  * processed and their summed device time (CUDA events) — what bench.py's roofline is computed from. */
 typedef struct malio_counters {
@@ -351,6 +377,10 @@ typedef struct malio_counters {
   uint64_t pass_points;           /* scan points those passes processed */
   uint64_t pass_fit_launches;     /* ... of which ran the plane fit (search passes) */
   double pass_ms;                 /* their summed device time (CUDA events; only while timing is enabled) */
+  uint64_t knn_tie_queries;       /* device-resident map mode: queries with two of the six best distances within PointType_CMP's
+                                     1e-10 window, broken by slot index instead of the reference's traversal order (exempted ties) */
+  uint64_t map_slots, map_live;   /* device-resident map: slots in use / live points after the last commit */
+  uint64_t map_compactions;
 } malio_counters;
 int malio_get_counters(malio_handle* h, malio_counters* out);
 

@@ -1,0 +1,85 @@
+// malio_mapsync.hpp — host side of the device-resident map: keeping the GPU's copy of the map's
+// POINT SET in step with the live ikd-Tree by deltas instead of flattening and re-uploading the tree every scan.
+//
+// north_star keeps "ikd-Tree incremental insert/delete on CPU".  The device does not need the tree's topology for the
+// search (the k-NN fast path works on a cell list of the live points), only the set of live points.  What the
+// reference's map-maintenance calls do to that set:
+//   KD_TREE::Delete_Point_Boxes (ikd_Tree.cpp:648-676, Delete_by_range :785-857)   every live point with
+//        min <= p < max (per axis) dies                      -> mirrored by malio_map_delete_boxes with the same boxes
+//   KD_TREE::Add_Points(.., false) (:478-584, Add_by_point :982-1042)              every point is inserted
+//                                                            -> mirrored by malio_map_add_points
+//   KD_TREE::Add_Points(.., true)                                                   per new point: the live points of its
+//        voxel box are searched (Search_by_range, :1257-1296), a down-sample winner is chosen, the box is emptied and the
+//        winner re-inserted (:493-533).  WHICH stored point wins depends on the order Search_by_range visits them whenever
+//        covariances are equal (the rule at :512-523 is not a total order) — i.e. on the tree's topology, which even depends
+//        on the timing of the background re-build thread.  It therefore cannot be replayed without the tree; the host
+//        tree stays the authority and the device is RE-SYNCHRONISED per touched voxel: after the reference's own
+//        Add_Points call, collect_voxel_sync() asks the tree (public KD_TREE::Box_Search) for the content of every
+//        distinct voxel the new points fall into and malio_map_sync_voxels() replaces the device's content of those
+//        voxels with it.  Exact whatever the topology; host cost = one Box_Search per touched voxel (the reference's
+//        Add_Points itself does one per new point), H2D = the points of the touched voxels.
+//
+// Works on any tree type with the reference's interface (KD_TREE<PointType>: Box_Search(const BoxPointType&, PointVector&),
+// PointType with x, y, z, normal_y).  Nothing here is copied from the reference.
+#ifndef MALIO_MAPSYNC_HPP_
+#define MALIO_MAPSYNC_HPP_
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <unordered_set>
+#include <vector>
+
+namespace malio {
+
+struct VoxelSync {
+  std::vector<float> boxes;        // nb x {min_x, min_y, min_z, max_x, max_y, max_z}   (half-open: min <= p < max)
+  std::vector<uint32_t> counts;    // nb: live points of each box after the Add_Points call
+  std::vector<float> xyz;          // sum(counts) x 3
+  std::vector<float> normal_y;     // sum(counts)
+  std::vector<int32_t> ids;        // sum(counts), filled when an id accessor is given
+  uint32_t outside_own_box = 0;    // new points not inside the voxel box computed from them (float rounding for a
+                                   // downsample_size that is not a power of two): those voxels cannot be re-synchronised
+                                   // by box and the caller should fall back to a full snapshot for this scan
+};
+
+// Voxel box of a point exactly as KD_TREE::Add_Points computes it (ikd_Tree.cpp:493-498): float arithmetic.
+inline void voxel_box_of(float x, float y, float z, float ds, float box[6]) {
+  box[0] = std::floor(x / ds) * ds; box[3] = box[0] + ds;
+  box[1] = std::floor(y / ds) * ds; box[4] = box[1] + ds;
+  box[2] = std::floor(z / ds) * ds; box[5] = box[2] + ds;
+}
+
+// Call AFTER tree.Add_Points(added, true).  BoxT = the tree's BoxPointType (vertex_min[3], vertex_max[3]).
+template <class Tree, class BoxT, class PointVector, class IdFn>
+void collect_voxel_sync(Tree& tree, const PointVector& added, float downsample_size, VoxelSync& out, IdFn id_of) {
+  out = VoxelSync{};
+  struct Key { int32_t a, b, c; bool operator==(const Key& o) const { return a == o.a && b == o.b && c == o.c; } };
+  struct KeyHash { size_t operator()(const Key& k) const { return (size_t)k.a * 73856093u ^ (size_t)k.b * 19349663u ^ (size_t)k.c * 83492791u; } };
+  std::unordered_set<Key, KeyHash> seen;
+  seen.reserve(added.size() * 2 + 16);
+  PointVector storage;
+  for (size_t i = 0; i < added.size(); ++i) {
+    float box[6];
+    voxel_box_of(added[i].x, added[i].y, added[i].z, downsample_size, box);
+    if (!(box[0] <= added[i].x && box[3] > added[i].x && box[1] <= added[i].y && box[4] > added[i].y && box[2] <= added[i].z && box[5] > added[i].z))
+      out.outside_own_box++;
+    const Key k{(int32_t)std::floor(added[i].x / downsample_size), (int32_t)std::floor(added[i].y / downsample_size),
+                (int32_t)std::floor(added[i].z / downsample_size)};
+    if (!seen.insert(k).second) continue;
+    BoxT b;
+    for (int a = 0; a < 3; ++a) { b.vertex_min[a] = box[a]; b.vertex_max[a] = box[3 + a]; }
+    tree.Box_Search(b, storage);
+    out.boxes.insert(out.boxes.end(), box, box + 6);
+    out.counts.push_back((uint32_t)storage.size());
+    for (const auto& p : storage) {
+      out.xyz.push_back(p.x); out.xyz.push_back(p.y); out.xyz.push_back(p.z);
+      out.normal_y.push_back(p.normal_y);
+      out.ids.push_back(id_of(p));
+    }
+  }
+}
+
+}  // namespace malio
+
+#endif  // MALIO_MAPSYNC_HPP_

@@ -502,9 +502,6 @@ __global__ void tree_extract_kernel(const float4* __restrict__ nodes, uint32_t n
 // is tried (r = (2 + min frac) h), and what is still unsettled — ties, very sparse neighbourhoods, queries outside
 // the grid — goes to knn_list_kernel, i.e. through the exact ikd-Tree-order traversal above.
 
-__device__ __forceinline__ uint32_t grid_cell_index(const GridConst& G, int cx, int cy, int cz) {
-  return (uint32_t)(((cz + GRID_PAD) * G.py + (cy + GRID_PAD)) * G.px + (cx + GRID_PAD));
-}
 
 __global__ void grid_count_kernel(const float4* __restrict__ nodes, uint32_t n, GridConst G, uint32_t* __restrict__ cnt,
                                   uint32_t* __restrict__ cell_of) {
@@ -811,6 +808,149 @@ knn_grid_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict_
     const uint32_t act = __activemask();
     const uint32_t tot = __reduce_add_sync(act, n_cand);
     if ((threadIdx.x & 31u) == (uint32_t)(__ffs(act) - 1)) atomicAdd(cand_total, (unsigned long long)tot);
+  }
+}
+
+// ------------------------------------------------------------------ K1r: tree-free exact search (device-resident map mode)
+// When the map lives on the device as a point set kept in step with the host's ikd-Tree by deltas (malio_mapops.cu), there
+// is no flattened tree to walk.  The queries the 3x3x3 / 5x5x5 scans leave open — sparse neighbourhoods, queries outside the
+// grid, tie hazards — are settled by one warp per query scanning cell blocks of growing half-width r: the block contains
+// every point closer than (r + min frac - margin) h, so the list is final once the 5th distance is below that radius, or once
+// the block covers the whole grid.  Same float distance expression as everywhere (calc_dist).  Ties (two of the six best
+// within PointType_CMP's 1e-10 window) cannot be resolved the reference's way without its traversal order: they are broken
+// by the smaller slot index, deterministically, and COUNTED (malio_counters.knn_tie_queries) — the documented exemption of
+// SURVEY.md §7 ("ties at the k-th boundary resolve by first visited wins ... the harness must detect and exempt exact ties").
+struct Top6T {
+  float d0, d1, d2, d3, d4, d5;
+  uint32_t i0, i1, i2, i3, i4, i5;
+  __device__ __forceinline__ void reset() {
+    d0 = d1 = d2 = d3 = d4 = d5 = INFINITY;
+    i0 = i1 = i2 = i3 = i4 = i5 = 0xFFFFFFFFu;
+  }
+  static __device__ __forceinline__ bool lt(float da, uint32_t ia, float db, uint32_t ib) { return da < db || (da == db && ia < ib); }
+  __device__ __forceinline__ void insert(float dist, uint32_t idx) {   // precondition: lt(dist, idx, d5, i5)
+    const bool c0 = lt(dist, idx, d0, i0), c1 = lt(dist, idx, d1, i1), c2 = lt(dist, idx, d2, i2), c3 = lt(dist, idx, d3, i3), c4 = lt(dist, idx, d4, i4);
+    d5 = c4 ? d4 : dist;               i5 = c4 ? i4 : idx;
+    d4 = c4 ? (c3 ? d3 : dist) : d4;   i4 = c4 ? (c3 ? i3 : idx) : i4;
+    d3 = c3 ? (c2 ? d2 : dist) : d3;   i3 = c3 ? (c2 ? i2 : idx) : i3;
+    d2 = c2 ? (c1 ? d1 : dist) : d2;   i2 = c2 ? (c1 ? i1 : idx) : i2;
+    d1 = c1 ? (c0 ? d0 : dist) : d1;   i1 = c1 ? (c0 ? i0 : idx) : i1;
+    d0 = c0 ? dist : d0;               i0 = c0 ? idx : i0;
+  }
+  __device__ __forceinline__ void pop() {
+    d0 = d1; d1 = d2; d2 = d3; d3 = d4; d4 = d5; d5 = INFINITY;
+    i0 = i1; i1 = i2; i2 = i3; i3 = i4; i4 = i5; i5 = 0xFFFFFFFFu;
+  }
+};
+template <int MODE>
+__device__ __forceinline__ void ring_search_warp(const float4* __restrict__ cell_pts, const uint32_t* __restrict__ cell_start,
+                                                 const GridConst& G, float qx, float qy, float qz, uint32_t p, uint32_t N,
+                                                 float max_sqdist, uint32_t* __restrict__ nn_idx, float* __restrict__ nn_d2,
+                                                 uint8_t* __restrict__ sel, uint32_t* __restrict__ tie_count) {
+  const uint32_t lane = threadIdx.x & 31u;
+  float od[6];
+  uint32_t oi[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { od[k] = INFINITY; oi[k] = 0xFFFFFFFFu; }
+  const bool finite = isfinite(qx) && isfinite(qy) && isfinite(qz);
+  if (finite) {
+    const float lim = 1.0e9f;
+    const float ux = fminf(fmaxf((qx - G.ox) * G.inv_h, -lim), lim), uy = fminf(fmaxf((qy - G.oy) * G.inv_h, -lim), lim),
+                uz = fminf(fmaxf((qz - G.oz) * G.inv_h, -lim), lim);
+    const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
+    const long long cx = (long long)flx, cy = (long long)fly, cz = (long long)flz;
+    const float fx = ux - flx, fy = uy - fly, fz = uz - flz;
+    const float fmin = fminf(fminf(fminf(fx, 1.f - fx), fminf(fy, 1.f - fy)), fminf(fz, 1.f - fz));
+    // rounding of (q - o) * inv_h grows with its magnitude: ~2^-22 relative
+    const float margin = GRID_MARGIN + 4.0e-7f * fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz));
+    auto outside = [](long long c, int n) -> long long { return c < 0 ? -c : (c > (long long)n - 1 ? c - ((long long)n - 1) : 0); };
+    long long r = outside(cx, G.nx);
+    r = r > outside(cy, G.ny) ? r : outside(cy, G.ny);
+    r = r > outside(cz, G.nz) ? r : outside(cz, G.nz);
+    if (r < 3) r = 3;
+    for (;;) {
+      const int x0 = (int)(cx - r > 0 ? cx - r : 0), x1 = (int)(cx + r < G.nx - 1 ? cx + r : G.nx - 1);
+      const int y0 = (int)(cy - r > 0 ? cy - r : 0), y1 = (int)(cy + r < G.ny - 1 ? cy + r : G.ny - 1);
+      const int z0 = (int)(cz - r > 0 ? cz - r : 0), z1 = (int)(cz + r < G.nz - 1 ? cz + r : G.nz - 1);
+      const bool covers_all = (cx - r <= 0) && (cx + r >= G.nx - 1) && (cy - r <= 0) && (cy + r >= G.ny - 1) && (cz - r <= 0) && (cz + r >= G.nz - 1);
+      Top6T t;
+      t.reset();
+      if (x0 <= x1 && y0 <= y1 && z0 <= z1) {
+        const uint32_t ycnt = (uint32_t)(y1 - y0 + 1), nrows = ycnt * (uint32_t)(z1 - z0 + 1);
+        for (uint32_t rowbase = 0; rowbase < nrows; rowbase += 32) {
+          const uint32_t row = rowbase + lane;
+          uint32_t rs = 0, re = 0;
+          if (row < nrows) {
+            const int y = y0 + (int)(row % ycnt), z = z0 + (int)(row / ycnt);
+            rs = __ldg(cell_start + grid_cell_index(G, x0, y, z));
+            re = __ldg(cell_start + grid_cell_index(G, x1, y, z) + 1);
+          }
+          const uint32_t len = re - rs;
+          uint32_t inc = len;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += v; }
+          const uint32_t excl = inc - len, total = __shfl_sync(0xffffffffu, inc, 31);
+          for (uint32_t base = 0; base < total; base += 32) {
+            const uint32_t j = base + lane;
+            uint32_t rr = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+              const uint32_t cand = rr + step;
+              const uint32_t ex = __shfl_sync(0xffffffffu, excl, cand & 31u);
+              if (cand < 32u && ex <= j) rr = cand;
+            }
+            const uint32_t ex_r = __shfl_sync(0xffffffffu, excl, rr), rs_r = __shfl_sync(0xffffffffu, rs, rr);
+            if (j < total) {
+              const float4 c = __ldg(cell_pts + rs_r + (j - ex_r));
+              const float dist = (qx - c.x) * (qx - c.x) + (qy - c.y) * (qy - c.y) + (qz - c.z) * (qz - c.z);   // calc_dist
+              const uint32_t idx = __float_as_uint(c.w);
+              if (Top6T::lt(dist, idx, t.d5, t.i5)) t.insert(dist, idx);
+            }
+          }
+        }
+      }
+      // six rounds of (distance, slot) arg-min over the lane heads
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        float m = t.d0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        uint32_t mi = (t.d0 == m) ? t.i0 : 0xFFFFFFFFu;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mi = min(mi, __shfl_xor_sync(0xffffffffu, mi, o));
+        od[k] = m; oi[k] = (m < INFINITY) ? mi : 0xFFFFFFFFu;
+        if (m < INFINITY && t.d0 == m && t.i0 == mi) t.pop();
+      }
+      const float rg = ((float)r + fmin - margin) * G.h;
+      if (covers_all || od[4] < rg * rg) break;
+      r = r + (r >> 1) + 1;
+    }
+  }
+  if (lane == 0) {
+    const bool tie = (od[1] < INFINITY && fabsf(od[1] - od[0]) < 1e-10f) | (od[2] < INFINITY && fabsf(od[2] - od[1]) < 1e-10f) |
+                     (od[3] < INFINITY && fabsf(od[3] - od[2]) < 1e-10f) | (od[4] < INFINITY && fabsf(od[4] - od[3]) < 1e-10f) |
+                     (od[5] < INFINITY && fabsf(od[5] - od[4]) < 1e-10f);
+    if (tie) atomicAdd(tie_count, 1u);
+#pragma unroll
+    for (int k = 0; k < MALIO_K; ++k) { nn_idx[(size_t)k * N + p] = oi[k]; nn_d2[(size_t)k * N + p] = od[k]; }
+    if (MODE == 0) sel[p] = (oi[4] == 0xFFFFFFFFu) ? 0 : (od[4] > max_sqdist ? 0 : 1);   // laserMapping.cpp:587
+  }
+}
+template <int MODE>
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_ring_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict__ cell_start, GridConst G,
+                const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm, const float* __restrict__ queries,
+                uint32_t N, PassConst pc, float max_sqdist, const uint32_t* __restrict__ plist, const uint32_t* __restrict__ pcount,
+                uint32_t* __restrict__ nn_idx, float* __restrict__ nn_d2, uint8_t* __restrict__ sel, uint32_t* __restrict__ count_out,
+                uint32_t* __restrict__ tie_count) {
+  const uint32_t count = *pcount;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { count_out[0] = count; count_out[2] = count_out[1]; }
+  const uint32_t warp = (blockIdx.x * KNN_THREADS + threadIdx.x) >> 5, nwarps = (gridDim.x * KNN_THREADS) >> 5;
+  for (uint32_t k = warp; k < count; k += nwarps) {
+    const uint32_t p = plist[k];
+    float qx, qy, qz;
+    load_query<MODE>(pts, perm, queries, p, pc, qx, qy, qz);
+    ring_search_warp<MODE>(cell_pts, cell_start, G, qx, qy, qz, p, N, max_sqdist, nn_idx, nn_d2, sel, tie_count);
   }
 }
 
@@ -1825,7 +1965,7 @@ pass_kernel(PassArgs a, PassConst pc, ParamConst prm) {
       }
       if (lane < 4) reinterpret_cast<unsigned long long*>(a.h_res + MALIO_RED_DOUBLES)[lane] = a.mmkey[lane];
       // k-NN list statistics of the last search as knn_list_kernel published them ([3] traversal list, [5] 5x5x5 retries)
-      if (lane == 4) { uint32_t* hg = reinterpret_cast<uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 4); hg[3] = a.gstats[3]; hg[5] = a.gstats[5]; hg[6] = g_fault_word; }
+      if (lane == 4) { uint32_t* hg = reinterpret_cast<uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 4); hg[3] = a.gstats[3]; hg[5] = a.gstats[5]; hg[6] = g_fault_word; hg[7] = a.gstats[7]; }
       __threadfence_system();
       __syncwarp();
       if (lane == 0) *reinterpret_cast<volatile uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 8) = a.seq;
@@ -2170,6 +2310,14 @@ int run_knn(malio_handle* h, DeviceState* D, uint32_t n, const malio_scan_pt* pt
     uint32_t fb_blocks = (n + 15) / 16;
     const uint32_t wave = (uint32_t)D->sm_count * 8;
     if (fb_blocks > wave) fb_blocks = wave;
+    if (D->tree_free) {   // device-resident map: no tree to walk, the open queries are settled on the cell list itself
+      knn_ring_kernel<MODE><<<fb_blocks, KNN_THREADS, 0, st>>>(D->d_cell_pts, D->d_cell_start, D->grid, pts, perm, qs, n, pc, max_sqdist,
+                                                             D->d_fb_list, D->d_gstats + 2, D->d_nn_idx, D->d_nn_d2, sel, D->d_gstats + 3,
+                                                             D->d_gstats + 7);
+      D->ctr.kernel_launches += 2;
+      CUDA_TRY(cudaGetLastError());
+      return MALIO_OK;
+    }
     if (int rc = need_boxes()) return rc;
     if (smem_stack)
       knn_list_kernel<MODE, true><<<fb_blocks, KNN_THREADS, 0, st>>>(D->d_nodes, D->n_nodes, pts, perm, qs, n, pc, max_sqdist,
@@ -2179,6 +2327,7 @@ int run_knn(malio_handle* h, DeviceState* D, uint32_t n, const malio_scan_pt* pt
                                                                      D->d_fb_list, D->d_gstats + 2, D->d_nn_idx, D->d_nn_d2, sel, D->d_gstats + 3);
     D->ctr.kernel_launches += 2;
   } else {
+    if (D->tree_free) { h->err = "device-resident map: the cell-list index is required (map extent too large for it?)"; return MALIO_ERR_STATE; }
     if (int rc = need_boxes()) return rc;
     const int lanes = pick_lanes(n, D->sm_count);
     if (smem_stack)
@@ -2274,6 +2423,8 @@ void destroy(malio_handle* h) {
   DeviceState* D = (DeviceState*)h->dev;
   if (!D) return;
   malio_pre::destroy(h);
+  malio_map::destroy(h);
+  if (D->d_ids) cudaFree(D->d_ids);
   if (D->host_prof && D->host_passes)
     fprintf(stderr, "[malio] passes %llu: host launch %.1f us/pass, host wait-for-device %.1f us/pass\n",
             (unsigned long long)D->host_passes, D->host_launch_us / D->host_passes, D->host_wait_us / D->host_passes);
@@ -2300,7 +2451,7 @@ void destroy(malio_handle* h) {
 }
 
 static int ensure_map_buffers(malio_handle* h, DeviceState* D, uint32_t n) {
-  if (n <= D->cap_nodes) return MALIO_OK;
+  if (n <= D->cap_nodes && D->d_nodes) return MALIO_OK;   // (slot mode grows d_mpts / d_cov only: no tree records there)
   uint32_t cap = n + n / 8 + 1024;
   if (cap < h->cfg.max_map_nodes) cap = h->cfg.max_map_nodes;
   if (int rc = ensure(h, D->d_nodes, (size_t)cap * 4)) return rc;
@@ -2362,6 +2513,7 @@ int upload_map(malio_handle* h, const malio_map_node* nodes, const float* cov, u
   if (depth > MALIO_MAX_TREE_DEPTH) { h->err = "snapshot deeper than MALIO_MAX_TREE_DEPTH"; return MALIO_ERR_TREE_TOO_DEEP; }
   if (D->refit_pending) { CUDA_TRY(cudaStreamSynchronize(D->stream2)); D->refit_pending = false; }
   if (int rc = ensure_map_buffers(h, D, n)) return rc;
+  D->tree_free = false;
   CUDA_TRY(cudaMemcpyAsync(D->d_nodes, nodes, (size_t)n * sizeof(malio_map_node), cudaMemcpyHostToDevice, D->stream));
   CUDA_TRY(cudaMemcpyAsync(D->d_cov, cov, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, D->stream));
   if (n) {
@@ -2379,6 +2531,7 @@ int upload_map_compact(malio_handle* h, const malio_map_point* pts, const float*
   if (depth > MALIO_MAX_TREE_DEPTH) { h->err = "snapshot deeper than MALIO_MAX_TREE_DEPTH"; return MALIO_ERR_TREE_TOO_DEEP; }
   if (D->refit_pending) { CUDA_TRY(cudaStreamSynchronize(D->stream2)); D->refit_pending = false; }
   if (int rc = ensure_map_buffers(h, D, n)) return rc;
+  D->tree_free = false;
   static_assert(sizeof(malio_map_point) == sizeof(float4), "compact record is one float4");
   CUDA_TRY(cudaMemcpyAsync(D->d_mpts, pts, (size_t)n * sizeof(malio_map_point), cudaMemcpyHostToDevice, D->stream));
   CUDA_TRY(cudaEventRecord(D->ev_h2d, D->stream));
@@ -2417,9 +2570,54 @@ int upload_map_compact(malio_handle* h, const malio_map_point* pts, const float*
   return rc;
 }
 
+// ---- device-resident map (malio_mapops.cu): slot storage and the index over it
+// grow d_mpts / d_cov / d_ids to hold n slots, keeping the first `keep` of them
+int grow_slots(malio_handle* h, uint32_t n, uint32_t keep) {
+  DeviceState* D = (DeviceState*)h->dev;
+  CUDA_TRY(cudaSetDevice(D->device));
+  if (n <= D->cap_slots && D->d_ids) return MALIO_OK;
+  uint32_t cap = n + n / 2 + 4096;
+  if (cap < h->cfg.max_map_nodes) cap = h->cfg.max_map_nodes;
+  float4* nm = nullptr; float* nc = nullptr; int32_t* ni = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&nm, (size_t)cap * sizeof(float4)));
+  CUDA_TRY(cudaMalloc((void**)&nc, (size_t)cap * sizeof(float)));
+  CUDA_TRY(cudaMalloc((void**)&ni, (size_t)cap * sizeof(int32_t)));
+  CUDA_TRY(cudaStreamSynchronize(D->stream));
+  if (keep && D->tree_free) {
+    CUDA_TRY(cudaMemcpy(nm, D->d_mpts, (size_t)keep * sizeof(float4), cudaMemcpyDeviceToDevice));
+    CUDA_TRY(cudaMemcpy(nc, D->d_cov, (size_t)keep * sizeof(float), cudaMemcpyDeviceToDevice));
+    if (D->d_ids) CUDA_TRY(cudaMemcpy(ni, D->d_ids, (size_t)keep * sizeof(int32_t), cudaMemcpyDeviceToDevice));
+  }
+  if (D->d_mpts) cudaFree(D->d_mpts);
+  if (D->d_cov) cudaFree(D->d_cov);
+  if (D->d_ids) cudaFree(D->d_ids);
+  // the tree records belong to the snapshot mode; they are re-created by the next malio_upload_map* call
+  if (D->d_nodes) { cudaFree(D->d_nodes); D->d_nodes = nullptr; }
+  if (D->d_parent) { cudaFree(D->d_parent); D->d_parent = nullptr; }
+  if (D->d_arrived) { cudaFree(D->d_arrived); D->d_arrived = nullptr; }
+  D->d_mpts = nm; D->d_cov = nc; D->d_ids = ni;
+  D->cap_slots = cap;
+  D->cap_nodes = cap;      // sizes the cell-list arrays (grid_build)
+  return MALIO_OK;
+}
+// (re)build the cell-list index over the n_slots slots; box = {x_min,x_max,y_min,y_max,z_min,z_max} of the live points
+int index_from_slots(malio_handle* h, uint32_t n_slots, const float box[6]) {
+  DeviceState* D = (DeviceState*)h->dev;
+  CUDA_TRY(cudaSetDevice(D->device));
+  if (D->refit_pending) { CUDA_TRY(cudaStreamSynchronize(D->stream2)); D->refit_pending = false; }
+  D->tree_free = true;
+  malio_map_node root{};
+  root.x = box[0]; root.y = box[2]; root.z = box[4];
+  root.link = MALIO_LINK_HAS_LEFT;
+  for (int k = 0; k < 6; ++k) root.lbox[k] = box[k];
+  const int rc = finish_map_upload(h, D, &root, n_slots, 0);
+  if (rc == MALIO_OK && n_slots > 0 && !D->grid_on) { h->err = "device-resident map: extent too large for the cell-list index"; return MALIO_ERR_CAPACITY; }
+  return rc;
+}
+
 int download_map_nodes(malio_handle* h, malio_map_node* out, uint32_t cap) {
   DeviceState* D = (DeviceState*)h->dev;
-  if (!D->map_ready) { h->err = "download_map_nodes before upload_map"; return MALIO_ERR_STATE; }
+  if (!D->map_ready || D->tree_free) { h->err = "download_map_nodes needs a snapshot uploaded with malio_upload_map*"; return MALIO_ERR_STATE; }
   CUDA_TRY(cudaSetDevice(D->device));
   const uint32_t n = D->n_nodes < cap ? D->n_nodes : cap;
   if (D->refit_pending) { CUDA_TRY(cudaStreamSynchronize(D->stream2)); D->refit_pending = false; }
@@ -2528,6 +2726,7 @@ int get_counters(malio_handle* h, malio_counters* out) {
   unsigned long long c = 0;
   CUDA_TRY(cudaMemcpy(&c, D->d_cand, sizeof(c), cudaMemcpyDeviceToHost));
   D->ctr.knn_candidates = c;
+  D->ctr.knn_tie_queries = D->h_gstats[7];
   *out = D->ctr;
   return MALIO_OK;
 }
@@ -2535,6 +2734,7 @@ int get_counters(malio_handle* h, malio_counters* out) {
 int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* HtRinvH, double* HtRinvh,
             malio_pass_stats* st) {
   DeviceState* D = (DeviceState*)h->dev;
+  if (h->mapst) { if (int rc = malio_map::commit(h)) return rc; }   // device-resident map: pending deltas -> index
   if (!D->map_ready || !D->scan_ready) { h->err = "measure before upload_map/upload_scan"; return MALIO_ERR_STATE; }
   CUDA_TRY(cudaSetDevice(D->device));
   const malio_params& P = h->cfg.params;
@@ -2584,6 +2784,7 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
       if (!(D->fused && (!D->comm || D->p2p))) {
         if (D->grid_on) CUDA_TRY(cudaMemcpyAsync(D->h_gstats + 2, D->d_gstats + 2, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st_));
         CUDA_TRY(cudaMemcpyFromSymbolAsync(D->h_gstats + 6, g_fault_word, sizeof(uint32_t), 0, cudaMemcpyDeviceToHost, st_));
+        CUDA_TRY(cudaMemcpyAsync(D->h_gstats + 7, D->d_gstats + 7, sizeof(uint32_t), cudaMemcpyDeviceToHost, st_));
       }
     }
   }
@@ -2864,6 +3065,7 @@ int download_aux(malio_handle* h, float* normal_y, uint32_t* nn_idx, float* nn_d
 
 int knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* idx, float* d2, float* ms_out) {
   DeviceState* D = (DeviceState*)h->dev;
+  if (h->mapst) { if (int rc = malio_map::commit(h)) return rc; }
   if (!D->map_ready) { h->err = "knn before upload_map"; return MALIO_ERR_STATE; }
   CUDA_TRY(cudaSetDevice(D->device));
   if (nq == 0) return MALIO_OK;
@@ -2892,6 +3094,7 @@ int knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* idx, float* d2, 
   if (d2) CUDA_TRY(cudaMemcpyAsync(d2, D->d_o_d2, (size_t)nq * MALIO_K * sizeof(float), cudaMemcpyDeviceToHost, D->stream));
   if (D->grid_on) CUDA_TRY(cudaMemcpyAsync(D->h_gstats + 2, D->d_gstats + 2, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, D->stream));
   CUDA_TRY(cudaMemcpyFromSymbolAsync(D->h_gstats + 6, g_fault_word, sizeof(uint32_t), 0, cudaMemcpyDeviceToHost, D->stream));
+  CUDA_TRY(cudaMemcpyAsync(D->h_gstats + 7, D->d_gstats + 7, sizeof(uint32_t), cudaMemcpyDeviceToHost, D->stream));
   CUDA_TRY(cudaStreamSynchronize(D->stream));
   CUDA_TRY(cudaGetLastError());
   if (D->h_gstats[6] & FAULT_STACK_OVERFLOW) {

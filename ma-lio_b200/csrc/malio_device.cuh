@@ -62,6 +62,9 @@ struct GridConst {
 constexpr int GRID_PAD = 3;          // empty border cells: queries up to one cell outside the box still take the fast path
 constexpr int GRID_CHUNK = 4096;          // cells per scan block (1024 threads x 4)
 constexpr float GRID_MARGIN = 0.005f;     // in cells: >> rounding of (x - o) * inv_h (< 1e-3 cells for < 4096 cells/axis)
+__host__ __device__ __forceinline__ uint32_t grid_cell_index(const GridConst& G, int cx, int cy, int cz) {
+  return (uint32_t)(((cz + GRID_PAD) * G.py + (cy + GRID_PAD)) * G.px + (cx + GRID_PAD));
+}
 
 constexpr int MAIL_MAX_WORLD = 8;
 constexpr int ROWS_DOUBLES = MALIO_MAX_DOF * 25 + 8;   // rows of the degenerate branch (25 doubles each) | row count | padding
@@ -89,6 +92,9 @@ struct DeviceState {
   float4* d_mpts = nullptr;            // compact mirror: point + link of every node, 16 B stride
   uint32_t *d_parent = nullptr, *d_arrived = nullptr;   // box rebuild of the compact upload
   uint32_t n_nodes = 0, cap_nodes = 0, depth = 0;
+  // device-resident map mode (malio_mapops.cu): d_mpts / d_cov / d_ids are slots of a point set (link word = deleted bit only),
+  // there are no 64-byte tree records and the search never walks a tree
+  bool tree_free = false; int32_t* d_ids = nullptr; uint32_t cap_slots = 0;
   // scan (caller order) + internal order
   malio_scan_pt* d_pts = nullptr; uint32_t N = 0, capN = 0;
   malio_scan_pt* d_pts_sorted = nullptr;   // the scan in internal (position) order

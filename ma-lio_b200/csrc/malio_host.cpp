@@ -406,6 +406,30 @@ int malio_map_incremental(malio_handle* h, const malio_pass_state* s, double fil
   if (!h || !s || !cls || !(filter_size_map > 0.0)) return MALIO_ERR_INVALID_ARG;
   return malio_dev::map_incremental(h, s, filter_size_map, ekf_inited, cls, world);
 }
+// ---------------------------------------------------------------- N1 wrappers (malio_mapops.cu)
+int malio_map_build(malio_handle* h, const float* xyz, const float* normal_y, const int32_t* ids, uint32_t n) {
+  if (!h || (n && (!xyz || !normal_y))) return MALIO_ERR_INVALID_ARG;
+  return malio_map::build(h, xyz, normal_y, ids, n);
+}
+int malio_map_add_points(malio_handle* h, const float* xyz, const float* normal_y, const int32_t* ids, uint32_t n) {
+  if (!h || (n && (!xyz || !normal_y))) return MALIO_ERR_INVALID_ARG;
+  return malio_map::add_points(h, xyz, normal_y, ids, n);
+}
+int malio_map_delete_boxes(malio_handle* h, const float* boxes, uint32_t nb, uint32_t* n_deleted) {
+  if (!h || (nb && !boxes)) return MALIO_ERR_INVALID_ARG;
+  return malio_map::delete_boxes(h, boxes, nb, n_deleted);
+}
+int malio_map_sync_voxels(malio_handle* h, const float* boxes, uint32_t nb, const float* xyz, const float* normal_y, const int32_t* ids,
+                          uint32_t n_points, uint32_t* n_deleted) {
+  if (!h || (nb && !boxes) || (n_points && (!xyz || !normal_y))) return MALIO_ERR_INVALID_ARG;
+  return malio_map::sync_voxels(h, boxes, nb, xyz, normal_y, ids, n_points, n_deleted);
+}
+int malio_map_commit(malio_handle* h) { return h ? malio_map::commit(h) : MALIO_ERR_INVALID_ARG; }
+int malio_map_info(malio_handle* h, uint32_t* n_live, uint32_t* n_slots) { return h ? malio_map::info(h, n_live, n_slots) : MALIO_ERR_INVALID_ARG; }
+int malio_map_download(malio_handle* h, float* xyz, float* normal_y, int32_t* ids, uint32_t* slots, uint32_t cap, uint32_t* n) {
+  return h ? malio_map::download(h, xyz, normal_y, ids, slots, cap, n) : MALIO_ERR_INVALID_ARG;
+}
+
 // ---------------------------------------------------------------- N2 / N3 wrappers (malio_preproc.cu)
 int malio_undistort(malio_handle* h, int lidar, const malio_raw_pt* pts, uint32_t n, const malio_undistort_args* a, float* xyz,
                     int32_t* idx, uint8_t* ok, int32_t* pop_point, uint32_t* n_pops, double* pose) {

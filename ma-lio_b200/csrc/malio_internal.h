@@ -44,11 +44,26 @@ int knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* idx, float* d2, 
 int map_incremental(malio_handle* h, const malio_pass_state* s, double fs, int ekf_inited, uint8_t* cls, float* world);
 int rearm_scan(malio_handle* h);
 int reserve_scan(malio_handle* h, uint32_t n);
+int grow_slots(malio_handle* h, uint32_t n, uint32_t keep);
+int index_from_slots(malio_handle* h, uint32_t n_slots, const float box[6]);
 int get_counters(malio_handle* h, malio_counters* out);
 int set_timing(malio_handle* h, int enable);
 int comm_init(malio_handle* h, const uint8_t* id, int rank, int world);
 int get_unique_id(uint8_t* id);
 }  // namespace malio_dev
+
+// malio_mapops.cu — the device-resident map
+namespace malio_map {
+void destroy(malio_handle* h);
+int commit(malio_handle* h);   // pending deltas -> compaction (when worth it) + cell-list index; no-op when clean
+int build(malio_handle* h, const float* xyz, const float* normal_y, const int32_t* ids, uint32_t n);
+int add_points(malio_handle* h, const float* xyz, const float* normal_y, const int32_t* ids, uint32_t n);
+int delete_boxes(malio_handle* h, const float* boxes, uint32_t nb, uint32_t* n_deleted);
+int sync_voxels(malio_handle* h, const float* boxes, uint32_t nb, const float* xyz, const float* normal_y, const int32_t* ids, uint32_t m,
+                uint32_t* n_deleted);
+int info(malio_handle* h, uint32_t* n_live, uint32_t* n_slots);
+int download(malio_handle* h, float* xyz, float* normal_y, int32_t* ids, uint32_t* slots, uint32_t cap, uint32_t* n);
+}  // namespace malio_map
 
 // malio_preproc.cu
 namespace malio_pre {

@@ -97,7 +97,8 @@ class Counters(C.Structure):
                 ("knn_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("knn_fallback_queries", C.c_uint64), ("knn_ring2_queries", C.c_uint64),
                 ("knn_candidates", C.c_uint64), ("pass_launches", C.c_uint64), ("pass_points", C.c_uint64),
-                ("pass_fit_launches", C.c_uint64), ("pass_ms", C.c_double)]
+                ("pass_fit_launches", C.c_uint64), ("pass_ms", C.c_double), ("knn_tie_queries", C.c_uint64),
+                ("map_slots", C.c_uint64), ("map_live", C.c_uint64), ("map_compactions", C.c_uint64)]
 
 
 class UpdateReport(C.Structure):
@@ -114,7 +115,8 @@ EXPORTS = [
     "malio_get_nccl_unique_id", "malio_comm_init", "malio_upload_map", "malio_upload_scan", "malio_measure",
     "malio_download_rows", "malio_download_aux", "malio_knn", "malio_ieskf_update", "malio_build_static_snapshot",
     "malio_rearm_scan", "malio_get_counters", "malio_set_timing", "malio_upload_map_compact", "malio_download_map_nodes", "malio_map_incremental",
-    "malio_read_livox_bin", "malio_read_ouster_bin", "malio_preprocess_livox", "malio_preprocess_ouster",
+    "malio_map_build", "malio_map_add_points", "malio_map_delete_boxes", "malio_map_sync_voxels", "malio_map_commit", "malio_map_info",
+    "malio_map_download", "malio_read_livox_bin", "malio_read_ouster_bin", "malio_preprocess_livox", "malio_preprocess_ouster",
     "malio_undistort", "malio_bspline_get_pose", "malio_voxel_grid", "malio_upload_scan_device",
     "malio_pose_initial", "malio_compound_pose_with_cov", "malio_compound_inv_pose_with_cov", "malio_build_pose_unc",
 ]
@@ -158,6 +160,13 @@ def load() -> C.CDLL:
     lib.malio_compound_inv_pose_with_cov.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.malio_build_pose_unc.argtypes = [i32, vp, vp, vp, vp, vp, vp]
     lib.malio_upload_scan.argtypes = [vp, vp, u32, vp, vp, vp]
+    lib.malio_map_build.argtypes = [vp, vp, vp, vp, u32]
+    lib.malio_map_add_points.argtypes = [vp, vp, vp, vp, u32]
+    lib.malio_map_delete_boxes.argtypes = [vp, vp, u32, C.POINTER(u32)]
+    lib.malio_map_sync_voxels.argtypes = [vp, vp, u32, vp, vp, vp, u32, C.POINTER(u32)]
+    lib.malio_map_commit.argtypes = [vp]
+    lib.malio_map_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
+    lib.malio_map_download.argtypes = [vp, vp, vp, vp, vp, u32, C.POINTER(u32)]
     lib.malio_read_livox_bin.argtypes = [C.c_char_p, vp, u32, C.POINTER(u32), i32]
     lib.malio_read_ouster_bin.argtypes = [C.c_char_p, vp, u32, C.POINTER(u32), i32]
     lib.malio_preprocess_livox.argtypes = [vp, u32, i32, i32, C.c_double, vp, vp, u32, C.POINTER(u32)]

@@ -170,6 +170,58 @@ class MeasurementModel:
                                                capi.ptr(table_off), capi.ptr(tc)))
         self.n_points = int(pts.shape[0])
 
+    # ---- the map as a device-resident point set kept in step by deltas (include/malio_mapsync.hpp)
+    @staticmethod
+    def _f32(a, cols=None):
+        a = np.ascontiguousarray(a, np.float32)
+        return a if cols is None else a.reshape(-1, cols)
+
+    def map_build(self, xyz, normal_y, ids=None):
+        """KD_TREE::Build: the device-resident map starts as these points (handle switches to device-map mode)."""
+        xyz = self._f32(xyz, 3); ny = self._f32(normal_y)
+        i = None if ids is None else np.ascontiguousarray(ids, np.int32)
+        self._check(self.lib.malio_map_build(self._h, capi.ptr(xyz), capi.ptr(ny), capi.ptr(i), xyz.shape[0]))
+
+    def map_add_points(self, xyz, normal_y, ids=None):
+        """Mirror of KD_TREE::Add_Points(points, false)."""
+        xyz = self._f32(xyz, 3); ny = self._f32(normal_y)
+        i = None if ids is None else np.ascontiguousarray(ids, np.int32)
+        self._check(self.lib.malio_map_add_points(self._h, capi.ptr(xyz), capi.ptr(ny), capi.ptr(i), xyz.shape[0]))
+
+    def map_delete_boxes(self, boxes) -> int:
+        """Mirror of KD_TREE::Delete_Point_Boxes; boxes: nb x {min3, max3}, half-open.  Returns the points deleted."""
+        b = self._f32(boxes, 6)
+        n = C.c_uint32(0)
+        self._check(self.lib.malio_map_delete_boxes(self._h, capi.ptr(b), b.shape[0], C.byref(n)))
+        return int(n.value)
+
+    def map_sync_voxels(self, sync: dict) -> int:
+        """After the host tree's Add_Points(points, true): replace the content of every touched voxel box by what
+        malio::collect_voxel_sync read back from the tree (dict with boxes, xyz, normal_y, ids)."""
+        b = self._f32(sync["boxes"], 6); xyz = self._f32(sync["xyz"], 3); ny = self._f32(sync["normal_y"])
+        i = None if sync.get("ids") is None else np.ascontiguousarray(sync["ids"], np.int32)
+        n = C.c_uint32(0)
+        self._check(self.lib.malio_map_sync_voxels(self._h, capi.ptr(b) if b.shape[0] else None, b.shape[0],
+                                                   capi.ptr(xyz) if xyz.shape[0] else None, capi.ptr(ny) if xyz.shape[0] else None,
+                                                   capi.ptr(i) if (i is not None and xyz.shape[0]) else None, xyz.shape[0], C.byref(n)))
+        return int(n.value)
+
+    def map_commit(self):
+        self._check(self.lib.malio_map_commit(self._h))
+
+    def map_info(self):
+        a, b = C.c_uint32(0), C.c_uint32(0)
+        self._check(self.lib.malio_map_info(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def map_download(self):
+        """Live points of the device-resident map in slot order: dict(xyz, normal_y, ids, slots)."""
+        live, _ = self.map_info()
+        xyz = np.zeros((live, 3), np.float32); ny = np.zeros(live, np.float32); ids = np.zeros(live, np.int32); sl = np.zeros(live, np.uint32)
+        n = C.c_uint32(0)
+        self._check(self.lib.malio_map_download(self._h, capi.ptr(xyz), capi.ptr(ny), capi.ptr(ids), capi.ptr(sl), live, C.byref(n)))
+        return dict(xyz=xyz, normal_y=ny, ids=ids, slots=sl)
+
     # ---- the two stages before the path (SURVEY.md §8f N2, N3)
     def undistort(self, lidar: int, pts: np.ndarray, beg_time: float, extrinsic, lt_imu_frame, ctrl_t, ctrl_T, imu_cov_t,
                   cov_pointer: int, want_pose: bool = False):

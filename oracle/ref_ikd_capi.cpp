@@ -17,6 +17,7 @@
 #undef private
 
 #include "malio_flatten.hpp"
+#include "malio_mapsync.hpp"
 
 using Tree = KD_TREE<pcl::PointXYZINormal>;
 using PV = Tree::PointVector;
@@ -163,6 +164,26 @@ int64_t ikdref_snapshot_compact_parallel(void* t, malio_map_point* pts, float* n
       root_box, grain);
   if (max_depth) *max_depth = res.max_depth;
   return res.overflow ? -1 : (int64_t)res.n_nodes;
+}
+
+// Add_Points(.., true) followed by the product's collect_voxel_sync (include/malio_mapsync.hpp) on the real tree.
+// Returns tmp_counter of Add_Points; the sync record is copied into caller arrays (capacities given), sizes in out_n[3] =
+// {n_boxes, n_points, outside_own_box}.
+static malio::VoxelSync g_sync;
+int ikdref_add_points_synced(void* t, const float* xyz, const float* normal_y, const int32_t* ids, int64_t n, float ds, int64_t* out_n) {
+  Tree* tr = (Tree*)t;
+  PV v = make_points(xyz, normal_y, ids, n);
+  const int c = tr->Add_Points(v, true);
+  malio::collect_voxel_sync<Tree, BoxPointType>(*tr, v, ds, g_sync, [](const pcl::PointXYZINormal& p) { return float_to_id(p.normal_z); });
+  out_n[0] = (int64_t)g_sync.counts.size(); out_n[1] = (int64_t)g_sync.normal_y.size(); out_n[2] = g_sync.outside_own_box;
+  return c;
+}
+void ikdref_fetch_sync(float* boxes, uint32_t* counts, float* pxyz, float* pny, int32_t* pids) {
+  if (boxes && !g_sync.boxes.empty()) std::memcpy(boxes, g_sync.boxes.data(), g_sync.boxes.size() * 4);
+  if (counts && !g_sync.counts.empty()) std::memcpy(counts, g_sync.counts.data(), g_sync.counts.size() * 4);
+  if (pxyz && !g_sync.xyz.empty()) std::memcpy(pxyz, g_sync.xyz.data(), g_sync.xyz.size() * 4);
+  if (pny && !g_sync.normal_y.empty()) std::memcpy(pny, g_sync.normal_y.data(), g_sync.normal_y.size() * 4);
+  if (pids && !g_sync.ids.empty()) std::memcpy(pids, g_sync.ids.data(), g_sync.ids.size() * 4);
 }
 
 int ikdref_node_bytes() { return (int)sizeof(Tree::KD_TREE_NODE); }

@@ -40,6 +40,17 @@ int comm_init(malio_handle*, const uint8_t*, int, int) { return MALIO_ERR_NCCL; 
 int get_unique_id(uint8_t*) { return MALIO_ERR_NCCL; }
 }  // namespace malio_dev
 
+namespace malio_map {
+void destroy(malio_handle*) {}
+int commit(malio_handle*) { return MALIO_OK; }
+int build(malio_handle*, const float*, const float*, const int32_t*, uint32_t) { return MALIO_ERR_STATE; }
+int add_points(malio_handle*, const float*, const float*, const int32_t*, uint32_t) { return MALIO_ERR_STATE; }
+int delete_boxes(malio_handle*, const float*, uint32_t, uint32_t*) { return MALIO_ERR_STATE; }
+int sync_voxels(malio_handle*, const float*, uint32_t, const float*, const float*, const int32_t*, uint32_t, uint32_t*) { return MALIO_ERR_STATE; }
+int info(malio_handle*, uint32_t*, uint32_t*) { return MALIO_ERR_STATE; }
+int download(malio_handle*, float*, float*, int32_t*, uint32_t*, uint32_t, uint32_t*) { return MALIO_ERR_STATE; }
+}  // namespace malio_map
+
 namespace malio_pre {
 void destroy(malio_handle*) {}
 int undistort(malio_handle*, int, const malio_raw_pt*, uint32_t, const malio_undistort_args*, float*, int32_t*, uint8_t*, int32_t*, uint32_t*, double*) { return MALIO_ERR_STATE; }
