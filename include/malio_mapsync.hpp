@@ -51,14 +51,18 @@ inline void voxel_box_of(float x, float y, float z, float ds, float box[6]) {
 }
 
 // Call AFTER tree.Add_Points(added, true).  BoxT = the tree's BoxPointType (vertex_min[3], vertex_max[3]).
+// threads > 1 runs the Box_Search calls of the distinct voxels concurrently (OpenMP).  Search_by_range only WRITES to the
+// tree through Push_Down, and only on nodes with a pending lazy flag; the Add_Points call that precedes this one walked
+// exactly these boxes (Search_by_range, Delete_by_range, Add_by_point all push the flags down on their way), so the
+// read-back finds none pending and is read-only in practice — the same situation as the reference's own multi-threaded
+// Nearest_Search (laserMapping.cpp:559-563).  Callers that prefer not to rely on that keep threads = 1.
 template <class Tree, class BoxT, class PointVector, class IdFn>
-void collect_voxel_sync(Tree& tree, const PointVector& added, float downsample_size, VoxelSync& out, IdFn id_of) {
+void collect_voxel_sync(Tree& tree, const PointVector& added, float downsample_size, VoxelSync& out, IdFn id_of, int threads = 1) {
   out = VoxelSync{};
   struct Key { int32_t a, b, c; bool operator==(const Key& o) const { return a == o.a && b == o.b && c == o.c; } };
   struct KeyHash { size_t operator()(const Key& k) const { return (size_t)k.a * 73856093u ^ (size_t)k.b * 19349663u ^ (size_t)k.c * 83492791u; } };
   std::unordered_set<Key, KeyHash> seen;
   seen.reserve(added.size() * 2 + 16);
-  PointVector storage;
   for (size_t i = 0; i < added.size(); ++i) {
     float box[6];
     voxel_box_of(added[i].x, added[i].y, added[i].z, downsample_size, box);
@@ -67,17 +71,28 @@ void collect_voxel_sync(Tree& tree, const PointVector& added, float downsample_s
     const Key k{(int32_t)std::floor(added[i].x / downsample_size), (int32_t)std::floor(added[i].y / downsample_size),
                 (int32_t)std::floor(added[i].z / downsample_size)};
     if (!seen.insert(k).second) continue;
-    BoxT b;
-    for (int a = 0; a < 3; ++a) { b.vertex_min[a] = box[a]; b.vertex_max[a] = box[3 + a]; }
-    tree.Box_Search(b, storage);
     out.boxes.insert(out.boxes.end(), box, box + 6);
-    out.counts.push_back((uint32_t)storage.size());
-    for (const auto& p : storage) {
+  }
+  const int64_t nb = (int64_t)(out.boxes.size() / 6);
+  out.counts.assign((size_t)nb, 0u);
+  std::vector<PointVector> found((size_t)nb);
+  if (threads < 1) threads = 1;
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 16) if (threads > 1)
+  for (int64_t k = 0; k < nb; ++k) {
+    BoxT b;
+    for (int a = 0; a < 3; ++a) { b.vertex_min[a] = out.boxes[6 * (size_t)k + a]; b.vertex_max[a] = out.boxes[6 * (size_t)k + 3 + a]; }
+    tree.Box_Search(b, found[(size_t)k]);
+    out.counts[(size_t)k] = (uint32_t)found[(size_t)k].size();
+  }
+  size_t total = 0;
+  for (int64_t k = 0; k < nb; ++k) total += out.counts[(size_t)k];
+  out.xyz.reserve(total * 3); out.normal_y.reserve(total); out.ids.reserve(total);
+  for (int64_t k = 0; k < nb; ++k)
+    for (const auto& p : found[(size_t)k]) {
       out.xyz.push_back(p.x); out.xyz.push_back(p.y); out.xyz.push_back(p.z);
       out.normal_y.push_back(p.normal_y);
       out.ids.push_back(id_of(p));
     }
-  }
 }
 
 }  // namespace malio

@@ -110,7 +110,9 @@ def ref_lib() -> C.CDLL:
         L.ikdref_snapshot_parallel.argtypes = [vp, vp, vp, vp, C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32]
         L.ikdref_snapshot_compact_parallel.restype = C.c_int64
         L.ikdref_snapshot_compact_parallel.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(C.c_uint32), vp, C.c_uint32]
-        L.ikdref_add_points_synced.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, vp]
+        L.ikdref_add_points_synced.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, vp, C.c_int]
+        L.ikdref_collect_sync.restype = None
+        L.ikdref_collect_sync.argtypes = [vp, vp, C.c_int64, C.c_float, vp, C.c_int]
         L.ikdref_fetch_sync.restype = None
         L.ikdref_fetch_sync.argtypes = [vp, vp, vp, vp, vp]
         _ref = L
@@ -152,7 +154,7 @@ class RefTree:
         self.n_ids = max(self.n_ids, int(ids.max()) + 1 if len(ids) else 0)
         return self.L.ikdref_add_points(self.t, ptr(xyz), ptr(ny), ptr(ids), xyz.shape[0], 1 if downsample else 0)
 
-    def add_points_synced(self, xyz, normal_y=None, ids=None, downsample_size=0.5):
+    def add_points_synced(self, xyz, normal_y=None, ids=None, downsample_size=0.5, threads=1):
         """Add_Points(.., true) + the product's collect_voxel_sync on this tree (include/malio_mapsync.hpp).  Returns
         (tmp_counter, dict(boxes[nb,6], counts[nb], xyz[m,3], normal_y[m], ids[m], outside_own_box))."""
         xyz = np.ascontiguousarray(xyz, np.float32)
@@ -162,13 +164,27 @@ class RefTree:
         ids = np.ascontiguousarray(ids, np.int32)
         self.n_ids = max(self.n_ids, int(ids.max()) + 1 if len(ids) else 0)
         sz = np.zeros(3, np.int64)
-        c = self.L.ikdref_add_points_synced(self.t, ptr(xyz), ptr(ny), ptr(ids), xyz.shape[0], C.c_float(downsample_size), ptr(sz))
+        c = self.L.ikdref_add_points_synced(self.t, ptr(xyz), ptr(ny), ptr(ids), xyz.shape[0], C.c_float(downsample_size), ptr(sz), int(threads))
         nb, m = int(sz[0]), int(sz[1])
         boxes = np.zeros((nb, 6), np.float32); counts = np.zeros(nb, np.uint32)
         pxyz = np.zeros((m, 3), np.float32); pny = np.zeros(m, np.float32); pids = np.zeros(m, np.int32)
         self.L.ikdref_fetch_sync(ptr(boxes) if nb else None, ptr(counts) if nb else None, ptr(pxyz) if m else None,
                                  ptr(pny) if m else None, ptr(pids) if m else None)
         return c, dict(boxes=boxes, counts=counts, xyz=pxyz, normal_y=pny, ids=pids, outside_own_box=int(sz[2]))
+
+    def collect_sync(self, xyz, downsample_size=0.5, out=None, threads=1):
+        """malio::collect_voxel_sync alone (the caller already ran add_points(xyz, .., downsample=True)).  `out`: optional dict of
+        pre-allocated arrays (boxes, counts, xyz, normal_y, ids) large enough to receive the record (e.g. pinned memory)."""
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        sz = np.zeros(3, np.int64)
+        self.L.ikdref_collect_sync(self.t, ptr(xyz), xyz.shape[0], C.c_float(downsample_size), ptr(sz), int(threads))
+        nb, m = int(sz[0]), int(sz[1])
+        if out is None:
+            out = dict(boxes=np.zeros((max(nb, 1), 6), np.float32), counts=np.zeros(max(nb, 1), np.uint32), xyz=np.zeros((max(m, 1), 3), np.float32),
+                       normal_y=np.zeros(max(m, 1), np.float32), ids=np.zeros(max(m, 1), np.int32))
+        self.L.ikdref_fetch_sync(ptr(out["boxes"]), ptr(out["counts"]), ptr(out["xyz"]), ptr(out["normal_y"]), ptr(out["ids"]))
+        return dict(boxes=out["boxes"][:nb], counts=out["counts"][:nb], xyz=out["xyz"][:m], normal_y=out["normal_y"][:m], ids=out["ids"][:m],
+                    outside_own_box=int(sz[2]))
 
     def delete_boxes(self, boxes) -> int:
         b = np.ascontiguousarray(boxes, np.float32).reshape(-1, 6)

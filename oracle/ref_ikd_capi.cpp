@@ -170,13 +170,20 @@ int64_t ikdref_snapshot_compact_parallel(void* t, malio_map_point* pts, float* n
 // Returns tmp_counter of Add_Points; the sync record is copied into caller arrays (capacities given), sizes in out_n[3] =
 // {n_boxes, n_points, outside_own_box}.
 static malio::VoxelSync g_sync;
-int ikdref_add_points_synced(void* t, const float* xyz, const float* normal_y, const int32_t* ids, int64_t n, float ds, int64_t* out_n) {
+int ikdref_add_points_synced(void* t, const float* xyz, const float* normal_y, const int32_t* ids, int64_t n, float ds, int64_t* out_n, int threads) {
   Tree* tr = (Tree*)t;
   PV v = make_points(xyz, normal_y, ids, n);
   const int c = tr->Add_Points(v, true);
-  malio::collect_voxel_sync<Tree, BoxPointType>(*tr, v, ds, g_sync, [](const pcl::PointXYZINormal& p) { return float_to_id(p.normal_z); });
+  malio::collect_voxel_sync<Tree, BoxPointType>(*tr, v, ds, g_sync, [](const pcl::PointXYZINormal& p) { return float_to_id(p.normal_z); }, threads);
   out_n[0] = (int64_t)g_sync.counts.size(); out_n[1] = (int64_t)g_sync.normal_y.size(); out_n[2] = g_sync.outside_own_box;
   return c;
+}
+// collect only (after the caller ran Add_Points(.., true) with these points): what the product adds per scan on the host
+void ikdref_collect_sync(void* t, const float* xyz, int64_t n, float ds, int64_t* out_n, int threads) {
+  Tree* tr = (Tree*)t;
+  PV v = make_points(xyz, nullptr, nullptr, n);
+  malio::collect_voxel_sync<Tree, BoxPointType>(*tr, v, ds, g_sync, [](const pcl::PointXYZINormal& p) { return float_to_id(p.normal_z); }, threads);
+  out_n[0] = (int64_t)g_sync.counts.size(); out_n[1] = (int64_t)g_sync.normal_y.size(); out_n[2] = g_sync.outside_own_box;
 }
 void ikdref_fetch_sync(float* boxes, uint32_t* counts, float* pxyz, float* pny, int32_t* pids) {
   if (boxes && !g_sync.boxes.empty()) std::memcpy(boxes, g_sync.boxes.data(), g_sync.boxes.size() * 4);

@@ -42,7 +42,8 @@ def same_set(tree, mirror):
 
 
 @pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref (the real ikd_Tree.cpp) was not built")
-def test_delta_protocol_keeps_a_flat_mirror_equal_to_the_real_tree():
+@pytest.mark.parametrize("threads", [1, 8])
+def test_delta_protocol_keeps_a_flat_mirror_equal_to_the_real_tree(threads):
     tree = po.RefTree(box_length=0.5)
     mir = nm.MirrorMap()
     synced_pts = 0
@@ -53,7 +54,7 @@ def test_delta_protocol_keeps_a_flat_mirror_equal_to_the_real_tree():
         _, a, ny, ids, b, ny2, ids2, boxes = ev
         if boxes is not None:
             assert tree.delete_boxes(boxes) == mir.delete_boxes(boxes)
-        cnt, sync = tree.add_points_synced(a, ny, ids, 0.5)
+        cnt, sync = tree.add_points_synced(a, ny, ids, 0.5, threads=threads)
         assert sync["outside_own_box"] == 0 and cnt > 0
         assert len(np.unique(sync["boxes"], axis=0)) == len(sync["boxes"])       # distinct voxels
         mir.sync_voxels(sync)
