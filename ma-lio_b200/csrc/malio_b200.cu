@@ -396,7 +396,9 @@ knn_list_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const malio_
                 const uint32_t* __restrict__ perm, const float* __restrict__ queries, uint32_t N, PassConst pc,
                 float max_sqdist, const uint32_t* __restrict__ plist, const uint32_t* __restrict__ pcount,
                 uint32_t* __restrict__ nn_idx, float* __restrict__ nn_d2, uint8_t* __restrict__ sel,
-                uint32_t* __restrict__ count_out) {
+                uint32_t* __restrict__ count_out, const ScanCtl* __restrict__ ctl) {
+  if (ctl && !(ctl->active && ctl->redo)) return;
+  const PassConst& pcr = ctl ? ctl->pc : pc;
   const uint32_t count = *pcount;
   if (blockIdx.x == 0 && threadIdx.x == 0) { count_out[0] = count; count_out[2] = count_out[1]; }   // [1] = ring-2 counter
   const uint32_t lane = threadIdx.x & 31u;
@@ -406,7 +408,7 @@ knn_list_kernel(const float4* __restrict__ nodes, uint32_t n_nodes, const malio_
     const bool valid = (lane < lanes) && (base + lane < count);
     const uint32_t p = valid ? plist[base + lane] : 0u;
     float qx = 0.f, qy = 0.f, qz = 0.f;
-    if (valid) load_query<MODE>(pts, perm, queries, p, pc, qx, qy, qz);
+    if (valid) load_query<MODE>(pts, perm, queries, p, pcr, qx, qy, qz);
     uint32_t oi[MALIO_K];
     float od[MALIO_K];
     int found = 0;
@@ -719,7 +721,10 @@ knn_grid_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict_
                 const float* __restrict__ queries, uint32_t N, PassConst pc, float max_sqdist,
                 float4* __restrict__ world, uint32_t* __restrict__ nn_idx, float* __restrict__ nn_d2,
                 uint8_t* __restrict__ sel, uint32_t* __restrict__ r2_count, uint32_t* __restrict__ fb_list,
-                uint32_t* __restrict__ fb_count, unsigned long long* __restrict__ cand_total) {
+                uint32_t* __restrict__ fb_count, unsigned long long* __restrict__ cand_total, const ScanCtl* __restrict__ ctl) {
+  // device-side iterated update: this launch was enqueued before it was known whether the pass repeats the search
+  if (ctl && !(ctl->active && ctl->redo)) return;
+  const PassConst& pcr = ctl ? ctl->pc : pc;
   constexpr int ROWS = RING == 1 ? GK_ROWS1 : GK_ROWS2;
   uint32_t n_cand = 0;   // candidates this thread scanned (statistics for the roofline; only summed when asked for)
   constexpr int HALF = RING == 1 ? 1 : 2;       // the block is (2*HALF+1)^3 cells
@@ -731,7 +736,7 @@ knn_grid_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict_
   bool want_r2 = false;
   float qx = 0.f, qy = 0.f, qz = 0.f;
   if (p < N) {
-    load_query<MODE>(pts, perm, queries, p, pc, qx, qy, qz);
+    load_query<MODE>(pts, perm, queries, p, pcr, qx, qy, qz);
     if (MODE == 0 && RING == 1) world[p] = make_float4(qx, qy, qz, 0.f);
     const float ux = (qx - G.ox) * G.inv_h, uy = (qy - G.oy) * G.inv_h, uz = (qz - G.oz) * G.inv_h;
     const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
@@ -942,14 +947,16 @@ knn_ring_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict_
                 const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm, const float* __restrict__ queries,
                 uint32_t N, PassConst pc, float max_sqdist, const uint32_t* __restrict__ plist, const uint32_t* __restrict__ pcount,
                 uint32_t* __restrict__ nn_idx, float* __restrict__ nn_d2, uint8_t* __restrict__ sel, uint32_t* __restrict__ count_out,
-                uint32_t* __restrict__ tie_count) {
+                uint32_t* __restrict__ tie_count, const ScanCtl* __restrict__ ctl) {
+  if (ctl && !(ctl->active && ctl->redo)) return;
+  const PassConst& pcr = ctl ? ctl->pc : pc;
   const uint32_t count = *pcount;
   if (blockIdx.x == 0 && threadIdx.x == 0) { count_out[0] = count; count_out[2] = count_out[1]; }
   const uint32_t warp = (blockIdx.x * KNN_THREADS + threadIdx.x) >> 5, nwarps = (gridDim.x * KNN_THREADS) >> 5;
   for (uint32_t k = warp; k < count; k += nwarps) {
     const uint32_t p = plist[k];
     float qx, qy, qz;
-    load_query<MODE>(pts, perm, queries, p, pc, qx, qy, qz);
+    load_query<MODE>(pts, perm, queries, p, pcr, qx, qy, qz);
     ring_search_warp<MODE>(cell_pts, cell_start, G, qx, qy, qz, p, N, max_sqdist, nn_idx, nn_d2, sel, tie_count);
   }
 }
@@ -1660,6 +1667,8 @@ struct PassArgs {
   double* block_red; double* d_res;
   double* h_res;           // mapped host memory: MALIO_RED_DOUBLES result | 4 min/max keys | flag
   uint32_t seq;
+  // device-side iterated update: non-null -> run / repeat-the-plane-fit / parity / sequence number come from the control block
+  const ScanCtl* ctl; unsigned long long* mmkey_base; uint32_t* cnt_base;
   unsigned long long* dbg; // optional [grid][8] %globaltimer stamps at the phase boundaries (MALIO_PASS_TRACE=1)
 };
 __device__ __forceinline__ void pass_stamp(const PassArgs& a, int k) {
@@ -1704,7 +1713,26 @@ constexpr int PASS_FAST_SMEM_DOUBLES = PASS_FAST_TILES * RED_THREADS * PASS_ROW_
 static_assert(PASS_FAST_SMEM_DOUBLES <= RED_SMEM_DOUBLES, "the fast path must fit the generic path's shared memory");
 template <bool FAST>
 __global__ void __launch_bounds__(RED_THREADS, 4)
-pass_kernel(PassArgs a, PassConst pc, ParamConst prm) {
+pass_kernel(PassArgs a_in, PassConst pc_in, ParamConst prm) {
+  if (a_in.ctl && !a_in.ctl->active) return;
+  // the per-pass quantities: launch arguments, or (device-side update) the control block the solve kernel maintains
+  struct Eff {
+    int do_tau, do_fit; unsigned long long *mmkey, *mmkey_next; uint32_t *cnt_cell, *cnt_next; uint32_t bar_base[3]; uint32_t seq;
+  } ef;
+  if (a_in.ctl) {
+    const int par = a_in.ctl->parity;
+    ef.do_tau = 0; ef.do_fit = a_in.ctl->redo;
+    ef.mmkey = a_in.mmkey_base + 4 * par; ef.mmkey_next = a_in.mmkey_base + 4 * (1 - par);
+    ef.cnt_cell = a_in.cnt_base + par; ef.cnt_next = a_in.cnt_base + (1 - par);
+    ef.bar_base[0] = ef.bar_base[1] = ef.bar_base[2] = 0u;   // the solve kernel zeroes the counters after every pass
+    ef.seq = a_in.ctl->seq;
+  } else {
+    ef.do_tau = a_in.do_tau; ef.do_fit = a_in.do_fit; ef.mmkey = a_in.mmkey; ef.mmkey_next = a_in.mmkey_next; ef.cnt_cell = a_in.cnt_cell;
+    ef.cnt_next = a_in.cnt_next; ef.bar_base[0] = a_in.bar_base[0]; ef.bar_base[1] = a_in.bar_base[1]; ef.bar_base[2] = a_in.bar_base[2];
+    ef.seq = a_in.seq;
+  }
+  const PassConst& pc = a_in.ctl ? a_in.ctl->pc : pc_in;
+  const PassArgs& a = a_in;
   uint32_t t0, t1;
   block_tiles(a.n_tiles, t0, t1);
   extern __shared__ double smem[];
@@ -1727,8 +1755,8 @@ pass_kernel(PassArgs a, PassConst pc, ParamConst prm) {
         const uint32_t p = tile * RED_THREADS + threadIdx.x;
         if (tile < t1 && p < a.N) {
           const malio_scan_pt pt = a.pts[a.perm ? a.perm[p] : p];
-          if (a.do_tau) tau_point(pt, pc, a.table, a.tau2, p);
-          if (a.do_fit && a.sel[p]) fit_point(a.nodes, a.node_cov, a.N, prm, a.nn_idx, a.sel, a.plane, a.ucov, p);
+          if (ef.do_tau) tau_point(pt, pc, a.table, a.tau2, p);
+          if (ef.do_fit && a.sel[p]) fit_point(a.nodes, a.node_cov, a.N, prm, a.nn_idx, a.sel, a.plane, a.ucov, p);
           gate_point(pt, p, pc, a.plane, a.ucov, a.tau2, a.sel, a.world, a.pd2, a.tau, a.normal_y, a.rows12, a.lid8, mm,
                      smem + (size_t)(k * RED_THREADS + threadIdx.x) * PASS_ROW_STRIDE, &go[k]);
         }
@@ -1746,17 +1774,17 @@ pass_kernel(PassArgs a, PassConst pc, ParamConst prm) {
         const uint32_t p = tile * RED_THREADS + threadIdx.x;
         if (p < a.N) {
           const malio_scan_pt pt = a.pts[a.perm ? a.perm[p] : p];
-          if (a.do_tau) tau_point(pt, pc, a.table, a.tau2, p);
-          if (a.do_fit && a.sel[p]) fit_point(a.nodes, a.node_cov, a.N, prm, a.nn_idx, a.sel, a.plane, a.ucov, p);
+          if (ef.do_tau) tau_point(pt, pc, a.table, a.tau2, p);
+          if (ef.do_fit && a.sel[p]) fit_point(a.nodes, a.node_cov, a.N, prm, a.nn_idx, a.sel, a.plane, a.ucov, p);
           gate_point(pt, p, pc, a.plane, a.ucov, a.tau2, a.sel, a.world, a.pd2, a.tau, a.normal_y, a.rows12, a.lid8, mm);
         }
       }
     }
-    minmax_block_commit<RED_THREADS>(mm, a.mmkey, a.cnt_cell);
+    minmax_block_commit<RED_THREADS>(mm, ef.mmkey, ef.cnt_cell);
   }
   pass_stamp(a, 1);
   if (a.peer.world <= 1) {
-    grid_barrier(a.bar + 0, a.bar_base[0] + gridDim.x, reinterpret_cast<uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 9));
+    grid_barrier(a.bar + 0, ef.bar_base[0] + gridDim.x, reinterpret_cast<uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 9));
   } else {
     // barrier 1 fused with the cross-GPU MIN: every block arrives; warp 0 of block 0 waits for the local arrivals, pushes
     // this GPU's four keys into every peer's mailbox, waits for the peers' keys, writes the global minima into the local
@@ -1765,20 +1793,20 @@ pass_kernel(PassArgs a, PassConst pc, ParamConst prm) {
     if (threadIdx.x == 0) { __threadfence(); atomicAdd(a.bar + 0, 1u); }
     if (blockIdx.x == 0 && threadIdx.x < 32) {
       const int lane = threadIdx.x, me = a.peer.rank, W = a.peer.world;
-      if (lane == 0) while ((int32_t)(ld_acquire_u32(a.bar + 0) - (a.bar_base[0] + gridDim.x)) < 0) { }
+      if (lane == 0) while ((int32_t)(ld_acquire_u32(a.bar + 0) - (ef.bar_base[0] + gridDim.x)) < 0) { }
       __syncwarp();
       unsigned long long k[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) k[c] = __ldcg(a.mmkey + c);
+      for (int c = 0; c < 4; ++c) k[c] = __ldcg(ef.mmkey + c);
       bool ok = true;
       if (lane < W && lane != me) {
-        unsigned char* dst = mail_min_slot(a.peer.mail[lane], a.seq, me);
+        unsigned char* dst = mail_min_slot(a.peer.mail[lane], ef.seq, me);
         volatile unsigned long long* dk = reinterpret_cast<volatile unsigned long long*>(dst);
 #pragma unroll
         for (int c = 0; c < 4; ++c) dk[c] = k[c];
-        st_release_sys_u32(reinterpret_cast<uint32_t*>(dst + 40), a.seq);
-        const unsigned char* src = mail_min_slot(a.peer.mail[me], a.seq, lane);
-        ok = wait_seq_sys(reinterpret_cast<const uint32_t*>(src + 40), a.seq);
+        st_release_sys_u32(reinterpret_cast<uint32_t*>(dst + 40), ef.seq);
+        const unsigned char* src = mail_min_slot(a.peer.mail[me], ef.seq, lane);
+        ok = wait_seq_sys(reinterpret_cast<const uint32_t*>(src + 40), ef.seq);
         const volatile unsigned long long* sk = reinterpret_cast<const volatile unsigned long long*>(src);
 #pragma unroll
         for (int c = 0; c < 4; ++c) k[c] = sk[c];
@@ -1794,27 +1822,27 @@ pass_kernel(PassArgs a, PassConst pc, ParamConst prm) {
       const bool all_ok = __all_sync(0xffffffffu, ok);
       if (lane == 0) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) a.mmkey[c] = k[c];
+        for (int c = 0; c < 4; ++c) ef.mmkey[c] = k[c];
         if (!all_ok) *reinterpret_cast<volatile uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 9) = 1u;   // peer timeout
         __threadfence();
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.bar + 3), "r"(a.seq) : "memory");
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.bar + 3), "r"(ef.seq) : "memory");
       }
     }
-    if (threadIdx.x == 0) while (ld_acquire_u32(a.bar + 3) != a.seq) { }
+    if (threadIdx.x == 0) while (ld_acquire_u32(a.bar + 3) != ef.seq) { }
     __syncthreads();
   }
   pass_stamp(a, 2);
   if (blockIdx.x == 0 && threadIdx.x == 0) {   // arm the other parity's min/max cell for the next pass
-    a.mmkey_next[0] = dkey(1000.0); a.mmkey_next[1] = dkey(-0.0);
-    a.mmkey_next[2] = dkey(9999.0); a.mmkey_next[3] = dkey(-0.0);
-    *a.cnt_next = 0;
+    ef.mmkey_next[0] = dkey(1000.0); ef.mmkey_next[1] = dkey(-0.0);
+    ef.mmkey_next[2] = dkey(9999.0); ef.mmkey_next[3] = dkey(-0.0);
+    *ef.cnt_next = 0;
     a.gstats[2] = 0; a.gstats[4] = 0;
   }
   // ---- phase 2: weights + accumulation into this block's slot
   double* slot = a.block_red + (size_t)blockIdx.x * MALIO_RED_DOUBLES;
   if (FAST) {
     double* s_flush = smem + PASS_FAST_TILES * RED_THREADS * PASS_ROW_STRIDE;
-    const double umin = dkey_inv(a.mmkey[0]), umax = -dkey_inv(a.mmkey[1]), tmin = dkey_inv(a.mmkey[2]), tmax = -dkey_inv(a.mmkey[3]);
+    const double umin = dkey_inv(ef.mmkey[0]), umax = -dkey_inv(ef.mmkey[1]), tmin = dkey_inv(ef.mmkey[2]), tmax = -dkey_inv(ef.mmkey[3]);
     uint32_t mine = 0;
     // segment table of the block: seg[k][l] = [beg, end) inside tile k's list (every thread derives it from s_wc)
     uint32_t seg_beg[PASS_FAST_TILES][MALIO_MAX_LIDAR], seg_end[PASS_FAST_TILES][MALIO_MAX_LIDAR];
@@ -1911,10 +1939,10 @@ pass_kernel(PassArgs a, PassConst pc, ParamConst prm) {
     }
     if (threadIdx.x == 0) { slot[MALIO_RED_BLOCKS * 16] = (double)s_cnt; slot[MALIO_RED_BLOCKS * 16 + 1] = 0.0; }
   } else {
-    reduce_block(a.N, prm, pc.ext_en, a.sel, a.lid8, a.rows12, a.pd2, a.ucov, a.tau, a.mmkey, t0, t1, slot);
+    reduce_block(a.N, prm, pc.ext_en, a.sel, a.lid8, a.rows12, a.pd2, a.ucov, a.tau, ef.mmkey, t0, t1, slot);
   }
   pass_stamp(a, 3);
-  grid_barrier(a.bar + 1, a.bar_base[1] + gridDim.x, reinterpret_cast<uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 9));
+  grid_barrier(a.bar + 1, ef.bar_base[1] + gridDim.x, reinterpret_cast<uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 9));
   pass_stamp(a, 4);
   // ---- phase 3: fold the slots, one warp per entry, in fold_kernel's order
   const uint32_t lane = threadIdx.x & 31u, wpb = RED_THREADS / 32;
@@ -1934,7 +1962,7 @@ pass_kernel(PassArgs a, PassConst pc, ParamConst prm) {
       done = atomicAdd(a.bar + 2, folded) + folded;
     }
     done = __shfl_sync(0xffffffffu, done, 0);
-    if (done == a.bar_base[2] + MALIO_RED_DOUBLES) {
+    if (done == ef.bar_base[2] + MALIO_RED_DOUBLES) {
       // this warp folded the last entry: ship result + min/max keys to the mapped host buffer (posted PCIe writes, one
       // system-scope fence), then the sequence flag the host is spinning on
       __threadfence();
@@ -1943,32 +1971,32 @@ pass_kernel(PassArgs a, PassConst pc, ParamConst prm) {
         // slots of all ranks are added in rank order — the same order on every GPU, so all ranks hold identical bits
         const int me = a.peer.rank, W = a.peer.world;
         for (int r = 0; r < W; ++r) {
-          volatile double* dst = reinterpret_cast<volatile double*>(mail_sum_slot(a.peer.mail[r], a.seq, me));
+          volatile double* dst = reinterpret_cast<volatile double*>(mail_sum_slot(a.peer.mail[r], ef.seq, me));
           for (uint32_t e = lane; e < MALIO_RED_DOUBLES; e += 32) dst[e] = __ldcg(a.d_res + e);
         }
         __threadfence_system();
         __syncwarp();
         bool ok = true;
         if ((int)lane < W && (int)lane != me) {
-          st_release_sys_u32(reinterpret_cast<uint32_t*>(mail_sum_slot(a.peer.mail[lane], a.seq, me) + MAIL_SUM_SEQ_OFF), a.seq);
-          ok = wait_seq_sys(reinterpret_cast<const uint32_t*>(mail_sum_slot(a.peer.mail[me], a.seq, (int)lane) + MAIL_SUM_SEQ_OFF), a.seq);
+          st_release_sys_u32(reinterpret_cast<uint32_t*>(mail_sum_slot(a.peer.mail[lane], ef.seq, me) + MAIL_SUM_SEQ_OFF), ef.seq);
+          ok = wait_seq_sys(reinterpret_cast<const uint32_t*>(mail_sum_slot(a.peer.mail[me], ef.seq, (int)lane) + MAIL_SUM_SEQ_OFF), ef.seq);
         }
         if (!__all_sync(0xffffffffu, ok) && lane == 0) *reinterpret_cast<volatile uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 9) = 1u;
         for (uint32_t e = lane; e < MALIO_RED_DOUBLES; e += 32) {
           double sum = 0.0;
-          for (int r = 0; r < W; ++r) sum += reinterpret_cast<const volatile double*>(mail_sum_slot(a.peer.mail[me], a.seq, r))[e];
+          for (int r = 0; r < W; ++r) sum += reinterpret_cast<const volatile double*>(mail_sum_slot(a.peer.mail[me], ef.seq, r))[e];
           a.d_res[e] = sum;
           a.h_res[e] = sum;
         }
       } else {
         for (uint32_t e = lane; e < MALIO_RED_DOUBLES; e += 32) a.h_res[e] = __ldcg(a.d_res + e);
       }
-      if (lane < 4) reinterpret_cast<unsigned long long*>(a.h_res + MALIO_RED_DOUBLES)[lane] = a.mmkey[lane];
+      if (lane < 4) reinterpret_cast<unsigned long long*>(a.h_res + MALIO_RED_DOUBLES)[lane] = ef.mmkey[lane];
       // k-NN list statistics of the last search as knn_list_kernel published them ([3] traversal list, [5] 5x5x5 retries)
       if (lane == 4) { uint32_t* hg = reinterpret_cast<uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 4); hg[3] = a.gstats[3]; hg[5] = a.gstats[5]; hg[6] = g_fault_word; hg[7] = a.gstats[7]; }
       __threadfence_system();
       __syncwarp();
-      if (lane == 0) *reinterpret_cast<volatile uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 8) = a.seq;
+      if (lane == 0) *reinterpret_cast<volatile uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 8) = ef.seq;
     }
   }
   pass_stamp(a, 5);
@@ -2289,7 +2317,7 @@ int grid_build(malio_handle* h, DeviceState* D, const GridConst& G) {
 // traversal alone when the index is off
 template <int MODE>
 int run_knn(malio_handle* h, DeviceState* D, uint32_t n, const malio_scan_pt* pts_in, const uint32_t* perm,
-            const PassConst& pc, float max_sqdist) {
+            const PassConst& pc, float max_sqdist, const ScanCtl* ctl = nullptr) {
   cudaStream_t st = D->stream;
   const bool smem_stack = D->depth + KNN_POP_WIDTH <= (uint32_t)KNN_SMEM_DEPTH;
   const malio_scan_pt* pts = MODE == 0 ? pts_in : nullptr;
@@ -2305,7 +2333,7 @@ int run_knn(malio_handle* h, DeviceState* D, uint32_t n, const malio_scan_pt* pt
     constexpr size_t smem1 = (size_t)GK_CAP * GK_THREADS * sizeof(float4) + (size_t)GK_ROWS1 * GK_THREADS * sizeof(uint2);
     knn_grid_kernel<MODE, 1><<<(n + GK_THREADS - 1) / GK_THREADS, GK_THREADS, smem1, st>>>(
         D->d_cell_pts, D->d_cell_start, D->grid, pts, perm, qs, n, pc, max_sqdist, world, D->d_nn_idx, D->d_nn_d2, sel,
-        D->d_gstats + 4, D->d_fb_list, D->d_gstats + 2, D->timing ? D->d_cand : nullptr);
+        D->d_gstats + 4, D->d_fb_list, D->d_gstats + 2, D->timing ? D->d_cand : nullptr, ctl);
     // 8 queries per warp and iteration; at most one resident wave of 64-thread blocks
     uint32_t fb_blocks = (n + 15) / 16;
     const uint32_t wave = (uint32_t)D->sm_count * 8;
@@ -2313,7 +2341,7 @@ int run_knn(malio_handle* h, DeviceState* D, uint32_t n, const malio_scan_pt* pt
     if (D->tree_free) {   // device-resident map: no tree to walk, the open queries are settled on the cell list itself
       knn_ring_kernel<MODE><<<fb_blocks, KNN_THREADS, 0, st>>>(D->d_cell_pts, D->d_cell_start, D->grid, pts, perm, qs, n, pc, max_sqdist,
                                                              D->d_fb_list, D->d_gstats + 2, D->d_nn_idx, D->d_nn_d2, sel, D->d_gstats + 3,
-                                                             D->d_gstats + 7);
+                                                             D->d_gstats + 7, ctl);
       D->ctr.kernel_launches += 2;
       CUDA_TRY(cudaGetLastError());
       return MALIO_OK;
@@ -2321,10 +2349,10 @@ int run_knn(malio_handle* h, DeviceState* D, uint32_t n, const malio_scan_pt* pt
     if (int rc = need_boxes()) return rc;
     if (smem_stack)
       knn_list_kernel<MODE, true><<<fb_blocks, KNN_THREADS, 0, st>>>(D->d_nodes, D->n_nodes, pts, perm, qs, n, pc, max_sqdist,
-                                                                    D->d_fb_list, D->d_gstats + 2, D->d_nn_idx, D->d_nn_d2, sel, D->d_gstats + 3);
+                                                                    D->d_fb_list, D->d_gstats + 2, D->d_nn_idx, D->d_nn_d2, sel, D->d_gstats + 3, ctl);
     else
       knn_list_kernel<MODE, false><<<fb_blocks, KNN_THREADS, 0, st>>>(D->d_nodes, D->n_nodes, pts, perm, qs, n, pc, max_sqdist,
-                                                                     D->d_fb_list, D->d_gstats + 2, D->d_nn_idx, D->d_nn_d2, sel, D->d_gstats + 3);
+                                                                     D->d_fb_list, D->d_gstats + 2, D->d_nn_idx, D->d_nn_d2, sel, D->d_gstats + 3, ctl);
     D->ctr.kernel_launches += 2;
   } else {
     if (D->tree_free) { h->err = "device-resident map: the cell-list index is required (map extent too large for it?)"; return MALIO_ERR_STATE; }
@@ -2411,6 +2439,18 @@ int create(malio_handle* h) {
     if (const char* e = getenv("MALIO_KNN_CELL")) { D->env_knn_cell = (float)atof(e); D->env_knn_cell_set = true; }
     D->host_prof = getenv("MALIO_HOST_PROF") != nullptr;
   }
+  {   // iterated update on the device (malio_solve.cu)
+    CUDA_TRY(cudaMalloc((void**)&D->d_ctl, sizeof(ScanCtl)));
+    CUDA_TRY(cudaMemset(D->d_ctl, 0, sizeof(ScanCtl)));
+    CUDA_TRY(cudaHostAlloc((void**)&D->h_ctl, sizeof(ScanCtl), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc((void**)&D->h_upd, UPD_DOUBLES * sizeof(double), cudaHostAllocMapped));
+    std::memset(D->h_upd, 0, UPD_DOUBLES * sizeof(double));
+    CUDA_TRY(cudaHostGetDevicePointer((void**)&D->h_upd_dev, D->h_upd, 0));
+    CUDA_TRY(cudaEventCreate(&D->ev_seq[0])); CUDA_TRY(cudaEventCreate(&D->ev_seq[1]));
+    for (int k = 0; k < 3; ++k) for (int j = 0; j < MALIO_MAX_PASSES; ++j) CUDA_TRY(cudaEventCreate(&D->ev_pass[k][j]));
+    if (int rc = malio_solve::setup(h)) return rc;
+    if (const char* e = getenv("MALIO_DEVICE_SOLVE")) D->device_solve = atoi(e) != 0;
+  }
   D->h_gstats = reinterpret_cast<uint32_t*>(D->h_res + MALIO_RED_DOUBLES + 4);
   std::memset(D->h_gstats, 0, 8 * sizeof(uint32_t));
   CUDA_TRY(cudaFuncSetAttribute(reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2437,6 +2477,11 @@ void destroy(malio_handle* h) {
                   D->d_cell_start, D->d_cell_cnt, D->d_cell_of, D->d_ctot, D->d_cbase, D->d_cell_pts, D->d_fb_list, D->d_gstats, D->d_bar, D->d_cand};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (D->h_res) cudaFreeHost(D->h_res);
+  if (D->d_ctl) cudaFree(D->d_ctl);
+  if (D->h_ctl) cudaFreeHost(D->h_ctl);
+  if (D->h_upd) cudaFreeHost(D->h_upd);
+  for (auto& e : D->ev_seq) if (e) cudaEventDestroy(e);
+  for (auto& row : D->ev_pass) for (auto& e : row) if (e) cudaEventDestroy(e);
   for (auto& e : D->ev) if (e) cudaEventDestroy(e);
   if (D->stream2) { cudaStreamSynchronize(D->stream2); cudaStreamDestroy(D->stream2); }
   if (D->stream3) { cudaStreamSynchronize(D->stream3); cudaStreamDestroy(D->stream3); }
@@ -2992,6 +3037,157 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
   }
   if (st) *st = S;
   return MALIO_OK;
+}
+
+// ---- the whole iterated update as ONE enqueued sequence (malio_solve.cu has the per-pass algebra).
+// Returns MALIO_OK with *handled = 1 when the update was done here; *handled = 0 asks the caller to run its own loop
+// (configuration not eligible, or the degenerate n > N_eff branch was hit — the per-scan state has been re-armed then).
+int update_on_device(malio_handle* h, malio_state* x, double* P, int max_iter, malio_update_report* rep, int* handled) {
+  DeviceState* D = (DeviceState*)h->dev;
+  *handled = 0;
+  if (!D->device_solve || !D->fused || (D->comm && !D->p2p) || max_iter + 1 > MALIO_MAX_PASSES || max_iter < 1) return MALIO_OK;
+  if (h->mapst) { if (int rc = malio_map::commit(h)) return rc; }
+  if (!D->map_ready || !D->scan_ready) { h->err = "update before upload_map/upload_scan"; return MALIO_ERR_STATE; }
+  if (!D->grid_on || D->N == 0) return MALIO_OK;   // index-off mode and empty scans keep the host loop
+  CUDA_TRY(cudaSetDevice(D->device));
+  const malio_params& Pm = h->cfg.params;
+  const int L = Pm.n_lidar, n = 17 + 6 * L, c = 6 * (L + 1);
+  const uint32_t N = D->N;
+  cudaStream_t st_ = D->stream;
+  // ---- inputs of the control block
+  ScanCtl* hc = D->h_ctl;
+  hc->L = L; hc->n = n; hc->c = c; hc->max_iter = max_iter; hc->ext_en = Pm.extrinsic_est_en; hc->pad0 = 0;
+  hc->loc_thresh_max = Pm.localize_thresh_max; hc->loc_thresh_min = Pm.localize_thresh_min;
+  hc->loc_cov_max = Pm.localize_cov_max; hc->loc_cov_min = Pm.localize_cov_min;
+  hc->x_prop = *x;
+  std::memcpy(hc->P_prop, P, sizeof(double) * n * n);
+  for (int l = 0; l < MALIO_MAX_LIDAR; ++l) hc->tcomp[l] = D->tcomp[l];
+  for (int l = 0; l <= MALIO_MAX_LIDAR; ++l) hc->table_off[l] = D->table_off[l];
+  hc->scan_id = ++D->scan_id;
+  CUDA_TRY(cudaMemcpyAsync(D->d_ctl, hc, offsetof(ScanCtl, x), cudaMemcpyHostToDevice, st_));
+  if (D->timing) CUDA_TRY(cudaEventRecord(D->ev_seq[0], st_));
+  const uint32_t seq0 = D->seq + 1;
+  if (int rc = malio_solve::launch_init(h, st_, D->d_ctl, seq0, D->parity, D->d_bar)) return rc;
+  D->ctr.kernel_launches += 1;
+  // ---- state-independent preparation with the initial state: internal order of the scan, point covariance traces
+  malio_pass_state ps0;
+  std::memcpy(ps0.rot, x->rot, sizeof(ps0.rot)); std::memcpy(ps0.pos, x->pos, sizeof(ps0.pos)); std::memcpy(ps0.ext, x->ext, sizeof(ps0.ext));
+  const PassConst pc0 = make_pass_const(h, D, &ps0);
+  const ParamConst prm = make_param_const(Pm);
+  D->last_pc = pc0;
+  const malio_scan_pt* pts_k = h->cfg.sort_queries ? D->d_pts_sorted : D->d_pts;
+  bool sorted_now = false;
+  if (h->cfg.sort_queries && !D->perm_valid) {
+    if (int rc = sort_queries<0>(h, D, N, pc0)) return rc;
+    D->perm_valid = true;
+    sorted_now = true;
+  }
+  bool tau_async = false;
+  if (!D->tau_valid) {
+    CUDA_TRY(cudaEventRecord(D->ev_sorted, st_));
+    CUDA_TRY(cudaStreamWaitEvent(D->stream2, D->ev_sorted, 0));
+    tau_kernel<<<(N + PLANE_THREADS - 1) / PLANE_THREADS, PLANE_THREADS, 0, D->stream2>>>(pts_k, nullptr, N, pc0, D->d_table, D->d_tau2);
+    CUDA_TRY(cudaEventRecord(D->ev_tau, D->stream2));
+    D->tau_valid = true;
+    D->ctr.kernel_launches += 1;
+    tau_async = true;
+  }
+  // ---- the passes: k-NN (runs only where the control block says the search is repeated), pass kernel, solve kernel
+  const uint32_t n_tiles = (N + RED_THREADS - 1) / RED_THREADS;
+  const uint32_t wave = (uint32_t)D->pass_max_blocks < D->red_grid ? (uint32_t)D->pass_max_blocks : D->red_grid;
+  const uint32_t per_block = (n_tiles + wave - 1) / wave;
+  const uint32_t grid = (n_tiles + per_block - 1) / per_block;
+  PassArgs a{};
+  a.pts = pts_k; a.perm = nullptr; a.N = N; a.table = D->d_table; a.nodes = D->d_mpts; a.node_cov = D->d_cov;
+  a.nn_idx = D->d_nn_idx; a.sel = D->d_sel; a.world = D->d_world; a.plane = D->d_plane; a.ucov = D->d_ucov;
+  a.tau2 = D->d_tau2; a.pd2 = D->d_pd2; a.tau = D->d_tau; a.normal_y = D->d_normal_y; a.rows12 = D->d_rows12; a.lid8 = D->d_lid8;
+  a.gstats = D->d_gstats; a.bar = D->d_bar;
+  a.n_tiles = n_tiles; a.block_red = D->d_block_red; a.d_res = D->d_res; a.h_res = D->h_res_dev;
+  a.peer.rank = D->rank; a.peer.world = D->p2p ? D->world : 1;
+  for (int r = 0; r < MAIL_MAX_WORLD; ++r) a.peer.mail[r] = D->mail_peer[r];
+  a.ctl = D->d_ctl; a.mmkey_base = D->d_mmkey; a.cnt_base = D->d_counters + 4;
+  a.dbg = nullptr;
+  *reinterpret_cast<volatile uint32_t*>(D->h_res + MALIO_RED_DOUBLES + 9) = 0u;
+  PassConst pc_arg = pc0;
+  ParamConst prm_arg = prm;
+  void* kargs[] = {&a, &pc_arg, &prm_arg};
+  const void* kfn = per_block <= (uint32_t)PASS_FAST_TILES ? (const void*)pass_kernel<true> : (const void*)pass_kernel<false>;
+  volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(D->h_upd + UPD_DOUBLES - 1);
+  for (int k = 0; k <= max_iter; ++k) {
+    if (D->timing) CUDA_TRY(cudaEventRecord(D->ev_pass[0][k], st_));
+    if (int rc = run_knn<0>(h, D, N, pts_k, nullptr, pc0, Pm.knn_max_sqdist, D->d_ctl)) return rc;
+    if (D->timing) CUDA_TRY(cudaEventRecord(D->ev_pass[1][k], st_));
+    if (k == 0 && tau_async) CUDA_TRY(cudaStreamWaitEvent(st_, D->ev_tau, 0));
+    if (D->coop_launch) CUDA_TRY(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(RED_THREADS), kargs, RED_SMEM_DOUBLES * sizeof(double), st_));
+    else CUDA_TRY(cudaLaunchKernel(kfn, dim3(grid), dim3(RED_THREADS), kargs, RED_SMEM_DOUBLES * sizeof(double), st_));
+    if (D->timing) CUDA_TRY(cudaEventRecord(D->ev_pass[2][k], st_));
+    if (int rc = malio_solve::launch_solve(h, st_, D->d_ctl, D->d_res, D->d_bar, D->h_upd_dev, reinterpret_cast<uint32_t*>(D->h_upd_dev + UPD_DOUBLES - 1))) return rc;
+    D->ctr.kernel_launches += 2;
+  }
+  if (D->timing) CUDA_TRY(cudaEventRecord(D->ev_seq[1], st_));
+  // ---- one wait for the whole update
+  const auto t_wait = std::chrono::steady_clock::now();
+  for (uint64_t spins = 1; *flag != hc->scan_id; ++spins) {
+    __builtin_ia32_pause();
+    if ((spins & 0x3FFF) == 0) {
+      const cudaError_t q = cudaStreamQuery(st_);
+      if (q == cudaErrorNotReady) {
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t_wait).count() > 30.0) { h->err = "device-side update: no result after 30 s"; return MALIO_ERR_CUDA; }
+        continue;
+      }
+      if (q != cudaSuccess) { h->err = std::string("device-side update: ") + cudaGetErrorString(q); return MALIO_ERR_CUDA; }
+      if (*flag != hc->scan_id) { h->err = "device-side update finished without publishing its result"; return MALIO_ERR_CUDA; }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  CUDA_TRY(cudaStreamSynchronize(st_));   // the remaining (skipped) launches drain in a few microseconds; later calls may reuse buffers
+  if (const uint32_t fault = *reinterpret_cast<volatile uint32_t*>(D->h_res + MALIO_RED_DOUBLES + 9)) {
+    if (fault == 2u) { h->err = "pass_kernel: a grid barrier did not complete within 2 s (blocks not co-resident)"; return MALIO_ERR_CUDA; }
+    h->err = "pass_kernel: a peer GPU did not answer the in-kernel exchange within 2 s";
+    return MALIO_ERR_NCCL;
+  }
+  if (D->h_gstats[6] & FAULT_STACK_OVERFLOW) { h->err = "k-NN traversal stack overflow: the snapshot is deeper than the max_depth declared at upload"; return MALIO_ERR_TREE_TOO_DEEP; }
+  const double* up = D->h_upd;
+  const int32_t* r = reinterpret_cast<const int32_t*>(up + MALIO_MAX_DOF * MALIO_MAX_DOF + 64 + MALIO_MAX_DOF);
+  const int passes = r[0], searches = r[1], status = r[2], need_host = r[3];
+  D->seq = (uint32_t)r[6]; D->parity = r[7]; D->last_parity = 1 - r[7];
+  const uint32_t smask = (uint32_t)r[8];
+  D->bar_base[0] = D->bar_base[1] = D->bar_base[2] = 0;   // the solve kernel leaves the barrier counters at zero ...
+  CUDA_TRY(cudaMemsetAsync(D->d_bar, 0, 3 * sizeof(uint32_t), st_));   // ... except after the very last pass
+  D->pass_done = true; D->searched_once = true;
+  D->host_passes += passes;
+  if (D->grid_on) { D->ctr.knn_fallback_queries += (uint64_t)D->h_gstats[3] * searches; D->ctr.knn_ring2_queries += (uint64_t)D->h_gstats[5] * searches; }
+  float ms_total = 0.f;
+  if (D->timing) {
+    cudaEventElapsedTime(&ms_total, D->ev_seq[0], D->ev_seq[1]);
+    for (int k = 0; k < passes && k <= max_iter; ++k) {
+      float ms = 0.f;
+      if (smask & (1u << k)) { cudaEventElapsedTime(&ms, D->ev_pass[0][k], D->ev_pass[1][k]); D->ctr.knn_launches += 1; D->ctr.knn_queries += N; D->ctr.knn_ms += ms; D->ctr.pass_fit_launches += 1; }
+      cudaEventElapsedTime(&ms, D->ev_pass[1][k], D->ev_pass[2][k]);
+      D->ctr.pass_launches += 1; D->ctr.pass_points += N; D->ctr.pass_ms += ms;
+    }
+  }
+  D->ctr.d2h_bytes += UPD_DOUBLES * sizeof(double);
+  (void)sorted_now;
+  if (need_host) {   // degenerate branch: the dense rows are needed -> the caller's loop redoes this scan from its start
+    reset_scan_kernel<<<(D->capN + 255) / 256, 256, 0, st_>>>(D->capN, D->d_sel, D->d_normal_y, D->d_nn_idx, D->d_gstats);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st_));
+    D->pass_done = false; D->searched_once = false;   // sort order and point covariance traces stay valid
+    return MALIO_OK;
+  }
+  *handled = 1;
+  std::memcpy(P, up, sizeof(double) * n * n);
+  std::memcpy(x, up + MALIO_MAX_DOF * MALIO_MAX_DOF, sizeof(malio_state));
+  if (rep) {
+    malio_update_report rp{};
+    rp.passes = passes; rp.searches = searches; rp.converged_count = r[5]; rp.last_status = status == MALIO_ERR_NO_EFFECTIVE_POINTS ? status : MALIO_OK;
+    rp.n_eff_last = (uint32_t)r[4]; rp.ms_device_total = ms_total; rp.ms_host_solve = 0.f;
+    std::memcpy(rp.dx_last, up + MALIO_MAX_DOF * MALIO_MAX_DOF + 64, sizeof(double) * MALIO_MAX_DOF);
+    *rep = rp;
+  }
+  if (status == MALIO_ERR_INVALID_ARG) { h->err = "singular information matrix"; return MALIO_ERR_INVALID_ARG; }
+  return status == MALIO_ERR_NO_EFFECTIVE_POINTS ? MALIO_ERR_NO_EFFECTIVE_POINTS : MALIO_OK;
 }
 
 int download_rows(malio_handle* h, double* h_x, double* hvec, uint32_t cap, uint32_t* n_rows) {

@@ -33,6 +33,8 @@ constexpr int RED_TASKS = 9;              // upper-triangular 4x4 blocks of the 
 constexpr int RED_KS = 14;                // row-splits per task: 9 x 14 = 126 of the 128 threads work
 constexpr int RED_SMEM_DOUBLES = RED_THREADS * (RED_HS_STRIDE + RED_HX_STRIDE) + RED_TASKS * RED_KS * 16;   // staging + flush scratch
 constexpr int TABLE_DOUBLES = 52;         // malio_pose_entry
+constexpr int MALIO_MAX_PASSES = 12;      // max_iter + 1 passes the device-side update can enqueue
+constexpr int UPD_DOUBLES = MALIO_MAX_DOF * MALIO_MAX_DOF + 64 + MALIO_MAX_DOF + 8;   // result block of the device-side update (+ flag)
 
 struct PassConst {
   double rot[4], pos[3];
@@ -51,6 +53,33 @@ struct PassConst {
 struct ParamConst {
   float plane_th, knn_max_sqdist;
   double cov_threshold, point_cov_max, point_cov_min, plane_cov_max, plane_cov_min, range_min, range_max;
+};
+
+// Control block of one iterated update run entirely on the device (malio_solve.cu): the per-pass kernels are enqueued for all
+// max_iter + 1 passes up front and read from here whether they run, with which state, and whether the search is repeated; the
+// one-block solve kernel after every pass takes the IESKF step (esekfom.hpp:521-718) and rewrites it.
+struct ScanCtl {
+  // ---- written by the host before the sequence is enqueued
+  int32_t L, n, c, max_iter;
+  int32_t ext_en, pad0;
+  double loc_thresh_max, loc_thresh_min, loc_cov_max, loc_cov_min;   // localization weight (laserMapping.cpp:749-756)
+  malio_state x_prop;
+  double P_prop[MALIO_MAX_DOF * MALIO_MAX_DOF];
+  malio_rigid tcomp[MALIO_MAX_LIDAR];
+  uint32_t table_off[MALIO_MAX_LIDAR + 1];
+  uint32_t scan_id;                 // written to the host's done flag when the update has finished
+  // ---- evolving on the device
+  malio_state x;
+  PassConst pc;                     // pass constants of the NEXT pass
+  int32_t it, redo, active, t, parity, pad1;
+  uint32_t seq, pad2;               // sequence number of the next pass (peer mailboxes, host result flag)
+  double P_cur[MALIO_MAX_DOF * MALIO_MAX_DOF];   // P_ of the last valid pass (esekfom.hpp:530 + projections)
+  // ---- report
+  int32_t passes, searches, status, need_host;   // need_host: the degenerate n > N_eff branch was hit (host finishes the scan)
+  uint32_t n_eff_last, converged_count;
+  uint32_t searched_mask, pad3;     // bit k: pass k repeated the search
+  double dx_last[MALIO_MAX_DOF];
+  double P_out[MALIO_MAX_DOF * MALIO_MAX_DOF];
 };
 
 struct GridConst {
@@ -134,6 +163,11 @@ struct DeviceState {
   uint32_t* h_gstats = nullptr;            // pinned mirror (8 words, carved out of h_res)
   // fused pass (single cooperative launch per measurement pass)
   bool fused = true; int pass_max_blocks = 0; bool coop_launch = true;
+  // iterated update on the device (malio_solve.cu)
+  bool device_solve = true; ScanCtl* d_ctl = nullptr; ScanCtl* h_ctl = nullptr;   // h_ctl: pinned staging of the inputs
+  double* h_upd = nullptr; double* h_upd_dev = nullptr;   // mapped: P_out | state | dx_last | report ints | done flag (last 8 bytes)
+  uint32_t scan_id = 0;
+  cudaEvent_t ev_seq[2] = {nullptr, nullptr}; cudaEvent_t ev_pass[3][MALIO_MAX_PASSES] = {};
   bool tau_inline = false; int trace_passes = 0; float env_knn_cell = -1.f; bool env_knn_cell_set = false; bool host_prof = false;   // environment switches, read once in create()
   uint32_t* d_bar = nullptr; uint32_t bar_base[3] = {0, 0, 0}; uint32_t seq = 0;
   double* h_res_dev = nullptr;     // device-side address of the mapped host result buffer
