@@ -2465,6 +2465,9 @@ void destroy(malio_handle* h) {
   malio_pre::destroy(h);
   malio_map::destroy(h);
   if (D->d_ids) cudaFree(D->d_ids);
+  if (D->host_prof && D->solve_n)
+    fprintf(stderr, "[malio] device-side update: %.1f us per solve kernel (%llu timed), %.1f us per update (%llu timed)\n",
+            1e3 * D->solve_ms / D->solve_n, (unsigned long long)D->solve_n, 1e3 * D->upd_ms / (D->upd_n ? D->upd_n : 1), (unsigned long long)D->upd_n);
   if (D->host_prof && D->host_passes)
     fprintf(stderr, "[malio] passes %llu: host launch %.1f us/pass, host wait-for-device %.1f us/pass\n",
             (unsigned long long)D->host_passes, D->host_launch_us / D->host_passes, D->host_wait_us / D->host_passes);
@@ -3165,7 +3168,10 @@ int update_on_device(malio_handle* h, malio_state* x, double* P, int max_iter, m
       if (smask & (1u << k)) { cudaEventElapsedTime(&ms, D->ev_pass[0][k], D->ev_pass[1][k]); D->ctr.knn_launches += 1; D->ctr.knn_queries += N; D->ctr.knn_ms += ms; D->ctr.pass_fit_launches += 1; }
       cudaEventElapsedTime(&ms, D->ev_pass[1][k], D->ev_pass[2][k]);
       D->ctr.pass_launches += 1; D->ctr.pass_points += N; D->ctr.pass_ms += ms;
+      cudaEventElapsedTime(&ms, D->ev_pass[2][k], k < max_iter ? D->ev_pass[0][k + 1] : D->ev_seq[1]);
+      D->solve_ms += ms; D->solve_n += 1;
     }
+    D->upd_ms += ms_total; D->upd_n += 1;
   }
   D->ctr.d2h_bytes += UPD_DOUBLES * sizeof(double);
   (void)sorted_now;

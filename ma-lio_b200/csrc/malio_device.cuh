@@ -167,6 +167,7 @@ struct DeviceState {
   bool device_solve = true; ScanCtl* d_ctl = nullptr; ScanCtl* h_ctl = nullptr;   // h_ctl: pinned staging of the inputs
   double* h_upd = nullptr; double* h_upd_dev = nullptr;   // mapped: P_out | state | dx_last | report ints | done flag (last 8 bytes)
   uint32_t scan_id = 0;
+  double solve_ms = 0, upd_ms = 0; uint64_t solve_n = 0, upd_n = 0;   // MALIO_HOST_PROF=1 prints them at destroy
   cudaEvent_t ev_seq[2] = {nullptr, nullptr}; cudaEvent_t ev_pass[3][MALIO_MAX_PASSES] = {};
   bool tau_inline = false; int trace_passes = 0; float env_knn_cell = -1.f; bool env_knn_cell_set = false; bool host_prof = false;   // environment switches, read once in create()
   uint32_t* d_bar = nullptr; uint32_t bar_base[3] = {0, 0, 0}; uint32_t seq = 0;

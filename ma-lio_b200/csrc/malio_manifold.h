@@ -212,7 +212,8 @@ MALIO_HD inline void sym3_singular_values(const double S[6], double sv[3]) {
   double A[3][3] = {{S[0], S[1], S[2]}, {S[1], S[3], S[4]}, {S[2], S[4], S[5]}};
   for (int sweep = 0; sweep < 50; ++sweep) {
     const double off = std::fabs(A[0][1]) + std::fabs(A[0][2]) + std::fabs(A[1][2]);
-    if (off == 0.0) break;
+    // converged: the off-diagonal mass is below 1e-22 of the diagonal's (eigenvalue error ~ off^2 / gap: far below one ulp)
+    if (off <= 1e-22 * (std::fabs(A[0][0]) + std::fabs(A[1][1]) + std::fabs(A[2][2]))) break;
     for (int p = 0; p < 2; ++p)
       for (int q = p + 1; q < 3; ++q) {
         if (A[p][q] == 0.0) continue;

@@ -223,33 +223,7 @@ solve_kernel(ScanCtl* c, const double* __restrict__ d_res, uint32_t* bar, double
       LU[a * nc + b] = s + ((a == b) ? 1.0 : 0.0);
     }
     __syncthreads();
-    for (int k = 0; k < nc; ++k) {
-      if (tid == 0) {
-        int p = k;
-        double best = fabs(LU[k * nc + k]);
-        for (int i = k + 1; i < nc; ++i) if (fabs(LU[i * nc + k]) > best) { best = fabs(LU[i * nc + k]); p = i; }
-        if (best == 0.0) s_flag[1] = 1;
-        s_piv[k] = p;
-      }
-      __syncthreads();
-      const int p = s_piv[k];
-      if (p != k) {
-        for (int j = tid; j < nc; j += SV_T) { const double t_ = LU[k * nc + j]; LU[k * nc + j] = LU[p * nc + j]; LU[p * nc + j] = t_; }
-        __syncthreads();
-      }
-      const double inv = 1.0 / LU[k * nc + k];
-      __syncthreads();
-      for (int i = k + 1 + tid; i < nc; i += SV_T) LU[i * nc + k] = LU[i * nc + k] * inv;
-      __syncthreads();
-      const int m = nc - k - 1;
-      for (int e = tid; e < m * m; e += SV_T) {
-        const int i = k + 1 + e / m, j = k + 1 + e % m;
-        const double f = LU[i * nc + k];
-        if (f != 0.0) LU[i * nc + j] -= f * LU[k * nc + j];
-      }
-      __syncthreads();
-    }
-    // ---- S z = rhs for g and G dx_new: U^T w = rhs, L^T v = w, z = Pm^T v   (one thread: 2 x c^2 dependent FMAs)
+    // z1 = g, z2 = G dx_new (right-hand sides of S z = rhs)
     for (int k = tid; k < nc; k += SV_T) {
       z1[k] = g[k];
       double sdx = 0.0;
@@ -257,20 +231,49 @@ solve_kernel(ScanCtl* c, const double* __restrict__ d_res, uint32_t* bar, double
       z2[k] = sdx;
     }
     __syncthreads();
-    if (tid < 2) {
-      double* z = tid == 0 ? z1 : z2;
+    // LU of Mt with partial pivoting and the two transposed triangular solves, all inside warp 0: lane i owns row i (and
+    // entry i of both right-hand sides); same pivots and the same elimination arithmetic as malio_host.cpp, no block barriers
+    if (tid < 32) {
+      const int lane = tid;
+      for (int k = 0; k < nc; ++k) {
+        // pivot: largest |LU[i][k]|, i >= k, the FIRST one on ties (the host's strict '>')
+        double v = (lane >= k && lane < nc) ? fabs(LU[lane * nc + k]) : -1.0;
+        int who = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+          const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+          if (ov > v || (ov == v && ow < who)) { v = ov; who = ow; }
+        }
+        if (lane == 0) { s_piv[k] = who; if (v == 0.0) s_flag[1] = 1; }
+        if (who != k && lane < nc) { const double t_ = LU[k * nc + lane]; LU[k * nc + lane] = LU[who * nc + lane]; LU[who * nc + lane] = t_; }
+        __syncwarp();
+        const double inv = 1.0 / LU[k * nc + k];
+        if (lane > k && lane < nc) {
+          const double f = LU[lane * nc + k] * inv;
+          LU[lane * nc + k] = f;
+          if (f != 0.0)
+            for (int j = k + 1; j < nc; ++j) LU[lane * nc + j] -= f * LU[k * nc + j];
+        }
+        __syncwarp();
+      }
+      // S = Mt^T = U^T L^T Pm:  U^T w = rhs (forward), L^T v = w (backward, unit diagonal), z = Pm^T v
+      double s1 = lane < nc ? z1[lane] : 0.0, s2 = lane < nc ? z2[lane] : 0.0;
       for (int i = 0; i < nc; ++i) {
-        double s = z[i];
-        for (int k = 0; k < i; ++k) s -= LU[k * nc + i] * z[k];
-        z[i] = s * (1.0 / LU[i * nc + i]);
+        if (lane == i) { const double inv = 1.0 / LU[i * nc + i]; s1 = s1 * inv; s2 = s2 * inv; z1[i] = s1; z2[i] = s2; }
+        __syncwarp();
+        if (lane > i && lane < nc) { const double u = LU[i * nc + lane]; s1 -= u * z1[i]; s2 -= u * z2[i]; }
       }
+      __syncwarp();
       for (int i = nc - 1; i >= 0; --i) {
-        double s = z[i];
-        for (int k = i + 1; k < nc; ++k) s -= LU[k * nc + i] * z[k];
-        z[i] = s;
+        if (lane == i) { z1[i] = s1; z2[i] = s2; }
+        __syncwarp();
+        if (lane < i) { const double l_ = LU[i * nc + lane]; s1 -= l_ * z1[i]; s2 -= l_ * z2[i]; }
       }
-      for (int k = nc - 1; k >= 0; --k)
-        if (s_piv[k] != k) { const double t_ = z[k]; z[k] = z[s_piv[k]]; z[s_piv[k]] = t_; }
+      __syncwarp();
+      if (lane == 0)
+        for (int k = nc - 1; k >= 0; --k)
+          if (s_piv[k] != k) { double t_ = z1[k]; z1[k] = z1[s_piv[k]]; z1[s_piv[k]] = t_; t_ = z2[k]; z2[k] = z2[s_piv[k]]; z2[s_piv[k]] = t_; }
     }
     __syncthreads();
     for (int a = tid; a < n; a += SV_T) {
