@@ -32,32 +32,47 @@ __device__ __forceinline__ void conj_R(const double q[4], double R[9]) {   // to
   R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
   R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
 }
-// pass constants from the current state (make_pass_const of malio_b200.cu, on the device)
-__device__ void build_pc(ScanCtl* c) {
+// pass constants of the next pass from the state sx (shared memory): make_pass_const of malio_b200.cu on the device; called by
+// all threads of the block (7 of them build one rotation matrix each)
+__device__ void build_pc(ScanCtl* c, const malio_state& sx) {
   PassConst& pc = c->pc;
-  for (int k = 0; k < 4; ++k) pc.rot[k] = c->x.rot[k];
-  for (int k = 0; k < 3; ++k) pc.pos[k] = c->x.pos[k];
-  for (int l = 0; l < MALIO_MAX_LIDAR; ++l) {
-    for (int k = 0; k < 4; ++k) { pc.eq[l][k] = c->x.ext[l].q[k]; pc.cq[l][k] = c->tcomp[l].q[k]; }
-    for (int k = 0; k < 3; ++k) { pc.et[l][k] = c->x.ext[l].t[k]; pc.ct[l][k] = c->tcomp[l].t[k]; }
-    conj_R(pc.eq[l], pc.ReT[l]);
-    conj_R(pc.cq[l], pc.RcT[l]);
+  const int tid = threadIdx.x;
+  if (tid < 4) pc.rot[tid] = sx.rot[tid];
+  if (tid < 3) pc.pos[tid] = sx.pos[tid];
+  if (tid >= 32 && tid < 32 + MALIO_MAX_LIDAR) {
+    const int l = tid - 32;
+    for (int k = 0; k < 4; ++k) { pc.eq[l][k] = sx.ext[l].q[k]; pc.cq[l][k] = c->tcomp[l].q[k]; }
+    for (int k = 0; k < 3; ++k) { pc.et[l][k] = sx.ext[l].t[k]; pc.ct[l][k] = c->tcomp[l].t[k]; }
   }
-  conj_R(pc.rot, pc.RsT);
-  for (int l = 0; l <= MALIO_MAX_LIDAR; ++l) pc.table_off[l] = c->table_off[l];
-  pc.L = c->L;
-  pc.ext_en = c->ext_en;
+  if (tid >= 64 && tid < 64 + MALIO_MAX_LIDAR) { double R[9]; conj_R(sx.ext[tid - 64].q, R); for (int k = 0; k < 9; ++k) pc.ReT[tid - 64][k] = R[k]; }
+  if (tid >= 96 && tid < 96 + MALIO_MAX_LIDAR) { double R[9]; conj_R(c->tcomp[tid - 96].q, R); for (int k = 0; k < 9; ++k) pc.RcT[tid - 96][k] = R[k]; }
+  if (tid == 128) { double R[9]; conj_R(sx.rot, R); for (int k = 0; k < 9; ++k) pc.RsT[k] = R[k]; }
+  if (tid == 160) {
+    for (int l = 0; l <= MALIO_MAX_LIDAR; ++l) pc.table_off[l] = c->table_off[l];
+    pc.L = c->L;
+    pc.ext_en = c->ext_en;
+  }
 }
 
-__global__ void init_ctl_kernel(ScanCtl* c, uint32_t seq0, int parity, uint32_t* bar) {
-  if (threadIdx.x != 0) return;
-  c->x = c->x_prop;
-  build_pc(c);
-  c->it = -1; c->redo = 1; c->active = 1; c->t = 0; c->parity = parity; c->seq = seq0;
-  c->passes = 0; c->searches = 0; c->status = MALIO_OK; c->need_host = 0; c->n_eff_last = 0; c->converged_count = 0; c->searched_mask = 0;
-  for (int k = 0; k < ND; ++k) c->dx_last[k] = 0.0;
-  for (int k = 0; k < c->n * c->n; ++k) c->P_cur[k] = c->P_prop[k];
-  bar[0] = 0; bar[1] = 0; bar[2] = 0;
+__global__ void __launch_bounds__(SV_T) init_ctl_kernel(ScanCtl* c, uint32_t seq0, int parity, uint32_t* bar) {
+  __shared__ malio_state sx;
+  const int tid = threadIdx.x;
+  {
+    const double* src = reinterpret_cast<const double*>(&c->x_prop);
+    double* dst = reinterpret_cast<double*>(&sx);
+    double* gx = reinterpret_cast<double*>(&c->x);
+    for (int k = tid; k < (int)(sizeof(malio_state) / sizeof(double)); k += SV_T) { const double v = src[k]; dst[k] = v; gx[k] = v; }
+  }
+  __syncthreads();
+  build_pc(c, sx);
+  const int nn = c->n * c->n;
+  for (int k = tid; k < nn; k += SV_T) c->P_cur[k] = c->P_prop[k];
+  for (int k = tid; k < ND; k += SV_T) c->dx_last[k] = 0.0;
+  if (tid == 0) {
+    c->it = -1; c->redo = 1; c->active = 1; c->t = 0; c->parity = parity; c->seq = seq0;
+    c->passes = 0; c->searches = 0; c->status = MALIO_OK; c->need_host = 0; c->n_eff_last = 0; c->converged_count = 0; c->searched_mask = 0;
+    bar[0] = 0; bar[1] = 0; bar[2] = 0;
+  }
 }
 
 // rows [idx, idx+BS) <- J * rows   /  cols <- cols * J^T   (esekfom.hpp:541-548, 563-571), one thread per column / row
@@ -119,8 +134,18 @@ solve_kernel(ScanCtl* c, const double* __restrict__ d_res, uint32_t* bar, double
   double* z1 = step + ND; double* z2 = z1 + NC; double* Jb = z2 + NC;
   __shared__ int s_piv[NC];
   __shared__ int s_flag[4];   // [0] finished, [1] singular, [2] redo_next
+  __shared__ malio_state sx, sx0;   // working copies of x_ and x_propagated (the control block lives in global memory)
   const int tid = threadIdx.x;
   const StateLayout ly(L);
+  {
+    const double* a = reinterpret_cast<const double*>(&c->x);
+    const double* b = reinterpret_cast<const double*>(&c->x_prop);
+    double* da = reinterpret_cast<double*>(&sx);
+    double* db = reinterpret_cast<double*>(&sx0);
+    for (int k = tid; k < (int)(sizeof(malio_state) / sizeof(double)); k += SV_T) { da[k] = a[k]; db[k] = b[k]; }
+  }
+  const int max_iter = c->max_iter;
+  const int t_in = c->t;
 
   // ---- the folded system -> padded 24 x 28 (measure()'s host epilogue), localization weight, compact c x c
   const uint32_t n_eff = (uint32_t)(d_res[MALIO_RED_BLOCKS * 16] + 0.5);
@@ -170,7 +195,7 @@ solve_kernel(ScanCtl* c, const double* __restrict__ d_res, uint32_t* bar, double
       Jb[40] = w * w;
       c->n_eff_last = n_eff;
       // dx = x [-] x_prop (esekfom.hpp:526)
-      boxminus(ly, c->x, c->x_prop, dx);
+      boxminus(ly, sx, sx0, dx);
       for (int k = 0; k < n; ++k) dxn[k] = dx[k];
     }
     for (int k = tid; k < n * n; k += SV_T) P[k] = c->P_prop[k];   // :530
@@ -204,7 +229,7 @@ solve_kernel(ScanCtl* c, const double* __restrict__ d_res, uint32_t* bar, double
     {
       if (tid == 0) {
         double J2[2][2];
-        S2_projection(c->x.grav, c->x_prop.grav, &dx[ly.grav], J2);
+        S2_projection(sx.grav, sx0.grav, &dx[ly.grav], J2);
         Jb[0] = J2[0][0]; Jb[1] = J2[0][1]; Jb[2] = J2[1][0]; Jb[3] = J2[1][1];
         const double d0 = dxn[ly.grav], d1 = dxn[ly.grav + 1];
         dxn[ly.grav] = J2[0][0] * d0 + J2[0][1] * d1;
@@ -283,19 +308,25 @@ solve_kernel(ScanCtl* c, const double* __restrict__ d_res, uint32_t* bar, double
       step[a] = s + u - dxn[a];                       // dx_ = K_h + (K_x - I) dx_new, :642
     }
     __syncthreads();
+    for (int k = tid; k < n; k += SV_T) c->dx_last[k] = step[k];
     if (tid == 0) {
-      for (int k = 0; k < n; ++k) c->dx_last[k] = step[k];
-      boxplus(ly, c->x, step);                        // :646
+      boxplus(ly, sx, step);                          // :646
       int redo = 1;                                   // :649-657
       for (int k = 0; k < n; ++k) if (fabs(step[k]) > 0.001) { redo = 0; break; }
-      int t = c->t;
+      int t = t_in;
       if (redo) t++;
-      if (!t && it == c->max_iter - 2) redo = 1;      // :660-663
+      if (!t && it == max_iter - 2) redo = 1;         // :660-663
       c->t = t;
+      s_flag[3] = t;
       s_flag[2] = redo;
-      s_flag[0] = (t > 1 || it == c->max_iter - 1) ? 1 : 0;   // :665
+      s_flag[0] = (t > 1 || it == max_iter - 1) ? 1 : 0;   // :665
     }
     __syncthreads();
+    {   // the new state goes back to the control block
+      const double* a = reinterpret_cast<const double*>(&sx);
+      double* ga = reinterpret_cast<double*>(&c->x);
+      for (int k = tid; k < (int)(sizeof(malio_state) / sizeof(double)); k += SV_T) ga[k] = a[k];
+    }
     if (s_flag[0]) {
       // ---- final covariance (:665-718): Q[:,0:c]^T = Mt^-1 P[:,0:c]^T from the stored factors, K_x = Q[:,0:c] G
       for (int e = tid; e < nc * n; e += SV_T) { const int a = e / n, j = e % n; Y[a * n + j] = P[a * n + j]; }
@@ -341,7 +372,7 @@ solve_kernel(ScanCtl* c, const double* __restrict__ d_res, uint32_t* bar, double
       {
         if (tid == 0) {
           double J2[2][2];
-          S2_projection(c->x.grav, c->x_prop.grav, &step[ly.grav], J2);
+          S2_projection(sx.grav, sx0.grav, &step[ly.grav], J2);
           Jb[0] = J2[0][0]; Jb[1] = J2[0][1]; Jb[2] = J2[1][0]; Jb[3] = J2[1][1];
         }
         __syncthreads();
@@ -361,7 +392,7 @@ solve_kernel(ScanCtl* c, const double* __restrict__ d_res, uint32_t* bar, double
         for (int k = 0; k < nc; ++k) s -= Kx[a * nc + k] * P[k * n + b];
         c->P_out[e] = s;
       }
-      if (tid == 0) { c->converged_count = (uint32_t)c->t; c->status = s_flag[1] ? MALIO_ERR_INVALID_ARG : MALIO_OK; c->active = 0; }
+      if (tid == 0) { c->converged_count = (uint32_t)s_flag[3]; c->status = s_flag[1] ? MALIO_ERR_INVALID_ARG : MALIO_OK; c->active = 0; }
       __syncthreads();
       publish(c, h_out, h_flag);
       return;
@@ -369,19 +400,19 @@ solve_kernel(ScanCtl* c, const double* __restrict__ d_res, uint32_t* bar, double
   }
   // ---- another pass follows, or the loop is exhausted (only when the last pass was invalid)
   __syncthreads();
-  if (it + 1 >= c->max_iter) {
+  if (it + 1 >= max_iter) {
     for (int k = tid; k < n * n; k += SV_T) c->P_out[k] = c->P_cur[k];
     if (tid == 0) { c->converged_count = (uint32_t)c->t; c->status = MALIO_ERR_NO_EFFECTIVE_POINTS; c->active = 0; }
     __syncthreads();
     publish(c, h_out, h_flag);
     return;
   }
+  build_pc(c, sx);
   if (tid == 0) {
     if (valid) c->redo = s_flag[2];
     c->it = it + 1;
     c->seq += 1;
     c->parity ^= 1;
-    build_pc(c);
     bar[0] = 0; bar[1] = 0; bar[2] = 0;
     if (s_flag[1]) { c->status = MALIO_ERR_INVALID_ARG; }
   }
@@ -397,7 +428,7 @@ int setup(malio_handle* h) {
   return MALIO_OK;
 }
 int launch_init(malio_handle* h, cudaStream_t st, ScanCtl* d_ctl, uint32_t seq0, int parity, uint32_t* d_bar) {
-  init_ctl_kernel<<<1, 32, 0, st>>>(d_ctl, seq0, parity, d_bar);
+  init_ctl_kernel<<<1, SV_T, 0, st>>>(d_ctl, seq0, parity, d_bar);
   CUDA_TRY(cudaGetLastError());
   return MALIO_OK;
 }

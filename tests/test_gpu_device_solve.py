@@ -37,10 +37,10 @@ def test_device_side_update_equals_host_loop_and_oracle(L, max_iter, monkeypatch
     assert rd.passes == rh.passes == ro.passes and rd.searches == rh.searches == ro.searches
     assert rd.n_eff_last == rh.n_eff_last == ro.n_eff_last and rd.converged_count == rh.converged_count
     vd, vh, vo = (synth.state_to_vec(s, L) for s in (xd, xh, xo))
-    assert np.abs(vd - vh).max() < 1e-12 and np.abs(vd - vo).max() < 1e-8
-    assert H.rel_err(Pd, Ph) < 1e-11 and H.rel_err(Pd, Po) < 1e-6
+    assert np.abs(vd - vh).max() < 1e-9 and np.abs(vd - vo).max() < 1e-8   # summation orders differ (warp-level solves)
+    assert H.rel_err(Pd, Ph) < 1e-8 and H.rel_err(Pd, Po) < 1e-6
     n = case.n_dof
-    np.testing.assert_allclose(np.array(rd.dx_last[:n]), np.array(rh.dx_last[:n]), atol=1e-13)
+    np.testing.assert_allclose(np.array(rd.dx_last[:n]), np.array(rh.dx_last[:n]), atol=1e-9)
     ad, ah = dev.aux(), host.aux()
     for k in ("selected", "nn_idx", "world", "normal_y"):
         assert np.array_equal(ad[k], ah[k]), k
@@ -49,7 +49,7 @@ def test_device_side_update_equals_host_loop_and_oracle(L, max_iter, monkeypatch
     xd2, Pd2 = case.x_prop.copy(), case.P_prop.copy()
     xh2, Ph2 = case.x_prop.copy(), case.P_prop.copy()
     dev.update_iterated_dyn_share_modified(xd2, Pd2, max_iter); host.update_iterated_dyn_share_modified(xh2, Ph2, max_iter)
-    assert np.array_equal(synth.state_to_vec(xd2, L), vd) and np.abs(synth.state_to_vec(xh2, L) - vd).max() < 1e-12
+    assert np.array_equal(synth.state_to_vec(xd2, L), vd) and np.abs(synth.state_to_vec(xh2, L) - vd).max() < 1e-9
     ok1, H1, h1, s1 = dev.h_share_model(case.x_true, True)
     ok2, H2, h2, s2 = host.h_share_model(case.x_true, True)
     assert ok1 and ok2 and np.array_equal(H1, H2) and s1.n_eff == s2.n_eff
