@@ -164,7 +164,7 @@ struct DeviceState {
   // fused pass (single cooperative launch per measurement pass)
   bool fused = true; int pass_max_blocks = 0; bool coop_launch = true;
   // iterated update on the device (malio_solve.cu)
-  bool device_solve = true; ScanCtl* d_ctl = nullptr; ScanCtl* h_ctl = nullptr;   // h_ctl: pinned staging of the inputs
+  bool device_solve = false; ScanCtl* d_ctl = nullptr; ScanCtl* h_ctl = nullptr;   // h_ctl: pinned staging of the inputs
   double* h_upd = nullptr; double* h_upd_dev = nullptr;   // mapped: P_out | state | dx_last | report ints | done flag (last 8 bytes)
   uint32_t scan_id = 0;
   double solve_ms = 0, upd_ms = 0; uint64_t solve_n = 0, upd_n = 0;   // MALIO_HOST_PROF=1 prints them at destroy
