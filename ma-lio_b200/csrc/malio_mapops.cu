@@ -125,13 +125,19 @@ __global__ void kill_voxel_boxes_kernel(const float* __restrict__ boxes, uint32_
     }
   if (n) atomicAdd(killed, n);
 }
-__global__ void bbox_kernel(const float4* __restrict__ mpts, uint32_t n_slots, uint32_t* __restrict__ keys) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// bounding box + count of the live slots: grid-stride, warp shuffle + one shared-memory stage per block, ONE set of atomics
+// per block (a few hundred blocks: the atomics on the 8 result words stay uncontended)
+constexpr int BB_T = 256;
+__global__ void __launch_bounds__(BB_T) bbox_kernel(const float4* __restrict__ mpts, uint32_t n_slots, uint32_t* __restrict__ keys) {
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
   uint32_t live = 0;
-  if (i < n_slots) {
+  for (uint32_t i = blockIdx.x * BB_T + threadIdx.x; i < n_slots; i += gridDim.x * BB_T) {
     const float4 a = mpts[i];
-    if (!(__float_as_uint(a.w) & MALIO_LINK_POINT_DELETED)) { lo[0] = hi[0] = a.x; lo[1] = hi[1] = a.y; lo[2] = hi[2] = a.z; live = 1; }
+    if (!(__float_as_uint(a.w) & MALIO_LINK_POINT_DELETED)) {
+      lo[0] = fminf(lo[0], a.x); hi[0] = fmaxf(hi[0], a.x); lo[1] = fminf(lo[1], a.y); hi[1] = fmaxf(hi[1], a.y);
+      lo[2] = fminf(lo[2], a.z); hi[2] = fmaxf(hi[2], a.z);
+      live += 1;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -142,10 +148,23 @@ __global__ void bbox_kernel(const float4* __restrict__ mpts, uint32_t n_slots, u
     }
     live += __shfl_xor_sync(0xffffffffu, live, o);
   }
-  if ((threadIdx.x & 31) == 0 && live) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { atomicMin(keys + 2 * k, fkey(lo[k])); atomicMax(keys + 2 * k + 1, fkey(hi[k])); }
-    atomicAdd(keys + 7, live);
+  __shared__ float s_lo[BB_T / 32][3], s_hi[BB_T / 32][3];
+  __shared__ uint32_t s_live[BB_T / 32];
+  if ((threadIdx.x & 31) == 0) {
+    for (int k = 0; k < 3; ++k) { s_lo[threadIdx.x >> 5][k] = lo[k]; s_hi[threadIdx.x >> 5][k] = hi[k]; }
+    s_live[threadIdx.x >> 5] = live;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t tot = 0;
+    for (int w = 0; w < BB_T / 32; ++w) {
+      tot += s_live[w];
+      for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], s_lo[w][k]); hi[k] = fmaxf(hi[k], s_hi[w][k]); }
+    }
+    if (tot) {
+      for (int k = 0; k < 3; ++k) { atomicMin(keys + 2 * k, fkey(lo[k])); atomicMax(keys + 2 * k + 1, fkey(hi[k])); }
+      atomicAdd(keys + 7, tot);
+    }
   }
 }
 // stable compaction, three steps: live count per block of 1024 slots, exclusive scan of the block counts (one block),
@@ -273,7 +292,7 @@ int commit(malio_handle* h) {
   // ---- bounding box + live count
   const uint32_t init[8] = {0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u, 0u, 0u};
   CUDA_TRY(cudaMemcpyAsync(M->d_small, init, sizeof(init), cudaMemcpyHostToDevice, st));
-  if (n) bbox_kernel<<<(n + 255) / 256, 256, 0, st>>>(D->d_mpts, n, M->d_small);
+  if (n) bbox_kernel<<<(n + BB_T - 1) / BB_T < 592u ? (n + BB_T - 1) / BB_T : 592u, BB_T, 0, st>>>(D->d_mpts, n, M->d_small);
   CUDA_TRY(cudaMemcpyAsync(M->h_small, M->d_small, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   D->ctr.kernel_launches += 1;

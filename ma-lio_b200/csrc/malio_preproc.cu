@@ -372,12 +372,14 @@ __host__ __device__ inline float fkey_inv(uint32_t k) {
   memcpy(&f, &b, 4);
   return f;
 }
-__global__ void vg_bounds_kernel(const float* __restrict__ in, uint32_t n, uint32_t* __restrict__ keys) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) vg_bounds_kernel(const float* __restrict__ in, uint32_t n, uint32_t* __restrict__ keys) {
+  // getMinMax3D over the finite points: grid-stride, one set of atomics per block
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-  if (i < n) {
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
     const float x = in[5 * (size_t)i], y = in[5 * (size_t)i + 1], z = in[5 * (size_t)i + 2];
-    if (isfinite(x) && isfinite(y) && isfinite(z)) { lo[0] = hi[0] = x; lo[1] = hi[1] = y; lo[2] = hi[2] = z; }
+    if (isfinite(x) && isfinite(y) && isfinite(z)) {
+      lo[0] = fminf(lo[0], x); hi[0] = fmaxf(hi[0], x); lo[1] = fminf(lo[1], y); hi[1] = fmaxf(hi[1], y); lo[2] = fminf(lo[2], z); hi[2] = fmaxf(hi[2], z);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
@@ -386,9 +388,12 @@ __global__ void vg_bounds_kernel(const float* __restrict__ in, uint32_t n, uint3
       lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
       hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
     }
-  if ((threadIdx.x & 31) == 0 && lo[0] <= hi[0]) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { atomicMin(keys + k, fkey(lo[k])); atomicMax(keys + 3 + k, fkey(hi[k])); }
+  __shared__ float s_lo[8][3], s_hi[8][3];
+  if ((threadIdx.x & 31) == 0) for (int k = 0; k < 3; ++k) { s_lo[threadIdx.x >> 5][k] = lo[k]; s_hi[threadIdx.x >> 5][k] = hi[k]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < 8; ++w) for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], s_lo[w][k]); hi[k] = fmaxf(hi[k], s_hi[w][k]); }
+    if (lo[0] <= hi[0]) for (int k = 0; k < 3; ++k) { atomicMin(keys + k, fkey(lo[k])); atomicMax(keys + 3 + k, fkey(hi[k])); }
   }
 }
 struct VgConst { float il; int minb[3]; long long dx, dxy; };
@@ -641,7 +646,7 @@ int voxel_grid(malio_handle* h, int lidar, const float* in, uint32_t n, float le
   // ---- bounds (getMinMax3D), then the grid geometry on the host exactly as PCL derives it
   const uint32_t init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
   CUDA_TRY(cudaMemcpyAsync(S->d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
-  vg_bounds_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_in, n, S->d_bounds);
+  vg_bounds_kernel<<<(n + 255) / 256 < 296u ? (n + 255) / 256 : 296u, 256, 0, st>>>(d_in, n, S->d_bounds);
   CUDA_TRY(cudaMemcpyAsync(S->h_small, S->d_bounds, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   D->ctr.kernel_launches += 1;
