@@ -1724,7 +1724,7 @@ pass_kernel(PassArgs a_in, PassConst pc_in, ParamConst prm) {
     ef.do_tau = 0; ef.do_fit = a_in.ctl->redo;
     ef.mmkey = a_in.mmkey_base + 4 * par; ef.mmkey_next = a_in.mmkey_base + 4 * (1 - par);
     ef.cnt_cell = a_in.cnt_base + par; ef.cnt_next = a_in.cnt_base + (1 - par);
-    ef.bar_base[0] = ef.bar_base[1] = ef.bar_base[2] = 0u;   // the solve kernel zeroes the counters after every pass
+    ef.bar_base[0] = a_in.ctl->bar_base[0]; ef.bar_base[1] = a_in.ctl->bar_base[1]; ef.bar_base[2] = a_in.ctl->bar_base[2];
     ef.seq = a_in.ctl->seq;
   } else {
     ef.do_tau = a_in.do_tau; ef.do_fit = a_in.do_fit; ef.mmkey = a_in.mmkey; ef.mmkey_next = a_in.mmkey_next; ef.cnt_cell = a_in.cnt_cell;
@@ -2000,6 +2000,34 @@ pass_kernel(PassArgs a_in, PassConst pc_in, ParamConst prm) {
     }
   }
   pass_stamp(a, 5);
+}
+
+// Pipelined host loop: this one-block kernel sits in the stream in front of a pass that was enqueued before the host knew its
+// state.  It waits for the host's ticket in mapped memory, then copies the published pass constants and flags into the
+// control block the following (predicated) kernels read.  Gives up after ~5 s and marks the pass inactive.
+__global__ void fetch_ctl_kernel(ScanCtl* __restrict__ ctl, const PubCtl* __restrict__ pub, uint32_t ticket) {
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) {
+    unsigned long long t0 = 0;
+    int ok = 1;
+    for (uint32_t it = 0; ld_acquire_sys_u32(&pub->ticket) != ticket; ++it) {
+      if ((it & 0x3FFu) == 0x3FFu) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t0 == 0) t0 = t1;
+        else if (t1 - t0 > 5000000000ull) { ok = 0; break; }
+      }
+    }
+    s_ok = ok;
+  }
+  __syncthreads();
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&pub->pc);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&ctl->pc);
+  if (s_ok) for (int k = threadIdx.x; k < (int)(sizeof(PassConst) / 4); k += blockDim.x) dst[k] = src[k];
+  if (threadIdx.x == 0) {
+    ctl->redo = s_ok ? pub->redo : 0; ctl->active = s_ok ? pub->active : 0; ctl->parity = pub->parity; ctl->seq = pub->seq;
+    ctl->bar_base[0] = pub->bar_base[0]; ctl->bar_base[1] = pub->bar_base[1]; ctl->bar_base[2] = pub->bar_base[2];
+  }
 }
 
 // second stage: one warp per entry of the reduced system folds the per-block slots in a fixed order
@@ -2448,6 +2476,10 @@ int create(malio_handle* h) {
     CUDA_TRY(cudaHostGetDevicePointer((void**)&D->h_upd_dev, D->h_upd, 0));
     CUDA_TRY(cudaEventCreate(&D->ev_seq[0])); CUDA_TRY(cudaEventCreate(&D->ev_seq[1]));
     for (int k = 0; k < 3; ++k) for (int j = 0; j < MALIO_MAX_PASSES; ++j) CUDA_TRY(cudaEventCreate(&D->ev_pass[k][j]));
+    CUDA_TRY(cudaHostAlloc((void**)&D->h_pub, sizeof(PubCtl), cudaHostAllocMapped));
+    std::memset(D->h_pub, 0, sizeof(PubCtl));
+    CUDA_TRY(cudaHostGetDevicePointer((void**)&D->h_pub_dev, D->h_pub, 0));
+    if (const char* e = getenv("MALIO_PIPELINE")) D->pipeline = atoi(e) != 0;
     if (int rc = malio_solve::setup(h)) return rc;
     if (const char* e = getenv("MALIO_DEVICE_SOLVE")) D->device_solve = atoi(e) != 0;
   }
@@ -2459,9 +2491,27 @@ int create(malio_handle* h) {
   return MALIO_OK;
 }
 
+// publish a decision for the pass that was enqueued ahead of its state
+static void publish_pass(DeviceState* D, const PassConst* pc, int redo, int active, int parity, uint32_t seq, const uint32_t bar_base[3]) {
+  PubCtl* pub = D->h_pub;
+  if (pc) std::memcpy(&pub->pc, pc, sizeof(PassConst));
+  pub->redo = redo; pub->active = active; pub->parity = parity; pub->seq = seq;
+  for (int k = 0; k < 3; ++k) pub->bar_base[k] = bar_base[k];
+  std::atomic_thread_fence(std::memory_order_release);
+  *reinterpret_cast<volatile uint32_t*>(&pub->ticket) = D->pre_ticket;
+}
+int cancel_prelaunch(malio_handle* h) {
+  DeviceState* D = (DeviceState*)h->dev;
+  if (!D || !D->pre_armed) return MALIO_OK;
+  publish_pass(D, nullptr, 0, 0, D->parity, D->seq, D->bar_base);
+  D->pre_armed = false;
+  return MALIO_OK;
+}
+
 void destroy(malio_handle* h) {
   DeviceState* D = (DeviceState*)h->dev;
   if (!D) return;
+  cancel_prelaunch(h);
   malio_pre::destroy(h);
   malio_map::destroy(h);
   if (D->d_ids) cudaFree(D->d_ids);
@@ -2483,6 +2533,7 @@ void destroy(malio_handle* h) {
   if (D->d_ctl) cudaFree(D->d_ctl);
   if (D->h_ctl) cudaFreeHost(D->h_ctl);
   if (D->h_upd) cudaFreeHost(D->h_upd);
+  if (D->h_pub) cudaFreeHost(D->h_pub);
   for (auto& e : D->ev_seq) if (e) cudaEventDestroy(e);
   for (auto& row : D->ev_pass) for (auto& e : row) if (e) cudaEventDestroy(e);
   for (auto& e : D->ev) if (e) cudaEventDestroy(e);
@@ -2799,7 +2850,12 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
   // the per-pass kernels read the scan in position order: the sorted copy when the scan was sorted, else the upload itself
   const malio_scan_pt* pts_k = (h->cfg.sort_queries && N > 0) ? D->d_pts_sorted : D->d_pts;
   const uint32_t* perm_k = nullptr;
-  if (N > 0) {
+  // pipelined host loop: the kernels of THIS pass were enqueued while the previous pass ran and are waiting (fetch_ctl_kernel)
+  // for the state decided since; nothing is launched for it here, the decision is published below
+  const bool consume_pre = D->pre_armed;
+  if (consume_pre) {
+    if (redo_knn) { knn_now = true; D->searched_once = true; }
+  } else if (N > 0) {
     if (h->cfg.sort_queries) {
       if (!D->perm_valid) {
         if (int rc = sort_queries<0>(h, D, N, pc)) return rc;
@@ -2875,15 +2931,39 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
     ParamConst prm_arg = prm;
     void* kargs[] = {&a, &pc_arg, &prm_arg};
     const void* kfn = per_block <= (uint32_t)PASS_FAST_TILES ? (const void*)pass_kernel<true> : (const void*)pass_kernel<false>;
-    if (D->coop_launch) {
-      CUDA_TRY(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(RED_THREADS), kargs, RED_SMEM_DOUBLES * sizeof(double), st_));
+    auto launch_pass = [&]() -> int {
+      if (D->coop_launch) {
+        CUDA_TRY(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(RED_THREADS), kargs, RED_SMEM_DOUBLES * sizeof(double), st_));
+      } else {
+        // plain launch (MALIO_COOP_LAUNCH=0): the grid never exceeds the co-resident capacity, so the in-kernel barriers are
+        // safe as long as no OTHER grid-synchronising kernel competes for the same GPU at the same time (one handle in flight)
+        CUDA_TRY(cudaLaunchKernel(kfn, dim3(grid), dim3(RED_THREADS), kargs, RED_SMEM_DOUBLES * sizeof(double), st_));
+      }
+      D->ctr.kernel_launches += 1;
+      return MALIO_OK;
+    };
+    if (consume_pre) {
+      // the pass is already in the stream: hand it its state (a.seq / a.bar_base / parity were advanced above exactly as for a
+      // direct launch)
+      publish_pass(D, &pc, redo_knn ? 1 : 0, 1, D->parity, a.seq, a.bar_base);
+      D->pre_armed = false;
+      D->ctr.kernel_launches += 2;   // the fetch kernel and the pass kernel ran; the k-NN pair was counted by run_knn at enqueue time
     } else {
-      // plain launch (MALIO_COOP_LAUNCH=0): the grid never exceeds the co-resident capacity, so the in-kernel barriers are
-      // safe as long as no OTHER grid-synchronising kernel competes for the same GPU at the same time (one handle in flight)
-      CUDA_TRY(cudaLaunchKernel(kfn, dim3(grid), dim3(RED_THREADS), kargs, RED_SMEM_DOUBLES * sizeof(double), st_));
+      if (int rc = launch_pass()) return rc;
+    }
+    // enqueue the NEXT pass's kernels now, while this pass runs: they wait on the device for the decision the host takes after
+    // this pass's result (its own step), which hides the launch path of every pass but the first
+    if (h->want_prelaunch && D->pipeline && !D->timing && N > 0 && D->grid_on && a.dbg == nullptr) {
+      D->pre_ticket += 1;
+      fetch_ctl_kernel<<<1, 128, 0, st_>>>(D->d_ctl, D->h_pub_dev, D->pre_ticket);
+      if (int rc = run_knn<0>(h, D, N, pts_k, perm_k, pc, P.knn_max_sqdist, D->d_ctl)) return rc;
+      a.ctl = D->d_ctl; a.mmkey_base = D->d_mmkey; a.cnt_base = D->d_counters + 4;
+      if (int rc = launch_pass()) return rc;
+      a.ctl = nullptr;
+      D->ctr.kernel_launches -= 1;   // counted when (if) it is consumed
+      D->pre_armed = true;
     }
     D->tau_valid = D->tau_valid || N > 0;
-    D->ctr.kernel_launches += 1;
     if (D->timing) { CUDA_TRY(cudaEventRecord(D->ev[2], st_)); CUDA_TRY(cudaEventRecord(D->ev[3], st_)); CUDA_TRY(cudaEventRecord(D->ev[4], st_)); }
     D->last_parity = D->parity;
     D->parity = 1 - D->parity;

@@ -73,6 +73,7 @@ struct ScanCtl {
   PassConst pc;                     // pass constants of the NEXT pass
   int32_t it, redo, active, t, parity, pad1;
   uint32_t seq, pad2;               // sequence number of the next pass (peer mailboxes, host result flag)
+  uint32_t bar_base[4];             // values of the grid-barrier counters before the next pass (monotone counters)
   double P_cur[MALIO_MAX_DOF * MALIO_MAX_DOF];   // P_ of the last valid pass (esekfom.hpp:530 + projections)
   // ---- report
   int32_t passes, searches, status, need_host;   // need_host: the degenerate n > N_eff branch was hit (host finishes the scan)
@@ -80,6 +81,15 @@ struct ScanCtl {
   uint32_t searched_mask, pad3;     // bit k: pass k repeated the search
   double dx_last[MALIO_MAX_DOF];
   double P_out[MALIO_MAX_DOF * MALIO_MAX_DOF];
+};
+
+// What the HOST publishes for a pass whose kernels were enqueued before its state was known (pipelined host loop): lives in
+// mapped pinned memory; fetch_ctl_kernel waits for `ticket` and copies the rest into the device's ScanCtl.
+struct PubCtl {
+  PassConst pc;
+  int32_t redo, active, parity, pad;
+  uint32_t seq, bar_base[3];
+  uint32_t ticket, pad2[3];
 };
 
 struct GridConst {
@@ -167,6 +177,8 @@ struct DeviceState {
   bool device_solve = false; ScanCtl* d_ctl = nullptr; ScanCtl* h_ctl = nullptr;   // h_ctl: pinned staging of the inputs
   double* h_upd = nullptr; double* h_upd_dev = nullptr;   // mapped: P_out | state | dx_last | report ints | done flag (last 8 bytes)
   uint32_t scan_id = 0;
+  // pipelined host loop: the next pass's kernels are enqueued while the current pass runs and wait for the host's decision
+  bool pipeline = true; bool pre_armed = false; uint32_t pre_ticket = 0; PubCtl* h_pub = nullptr; PubCtl* h_pub_dev = nullptr;
   double solve_ms = 0, upd_ms = 0; uint64_t solve_n = 0, upd_n = 0;   // MALIO_HOST_PROF=1 prints them at destroy
   cudaEvent_t ev_seq[2] = {nullptr, nullptr}; cudaEvent_t ev_pass[3][MALIO_MAX_PASSES] = {};
   bool tau_inline = false; int trace_passes = 0; float env_knn_cell = -1.f; bool env_knn_cell_set = false; bool host_prof = false;   // environment switches, read once in create()

@@ -24,6 +24,7 @@ struct malio_handle {
   void* dev = nullptr;   // DeviceState*, owned by the CUDA TU
   void* pre = nullptr;   // PreState*, owned by malio_preproc.cu (undistortion / voxel grid buffers)
   void* mapst = nullptr; // MapOpsState*, owned by malio_mapops.cu (device-resident map replay)
+  int want_prelaunch = 0; // set by malio_ieskf_update around malio_dev::measure: another pass may follow this one
 };
 
 // CUDA TU entry points used by the C-ABI wrappers
@@ -44,6 +45,7 @@ int knn(malio_handle* h, const float* q, uint32_t nq, uint32_t* idx, float* d2, 
 int map_incremental(malio_handle* h, const malio_pass_state* s, double fs, int ekf_inited, uint8_t* cls, float* world);
 int rearm_scan(malio_handle* h);
 int reserve_scan(malio_handle* h, uint32_t n);
+int cancel_prelaunch(malio_handle* h);   // a pass enqueued ahead of its state is told not to run (no-op when none is pending)
 int update_on_device(malio_handle* h, malio_state* x, double* P, int max_iter, malio_update_report* rep, int* handled);
 int grow_slots(malio_handle* h, uint32_t n, uint32_t keep);
 int index_from_slots(malio_handle* h, uint32_t n_slots, const float box[6]);

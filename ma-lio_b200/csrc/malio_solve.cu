@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(SV_T) init_ctl_kernel(ScanCtl* c, uint32_t seq
     c->it = -1; c->redo = 1; c->active = 1; c->t = 0; c->parity = parity; c->seq = seq0;
     c->passes = 0; c->searches = 0; c->status = MALIO_OK; c->need_host = 0; c->n_eff_last = 0; c->converged_count = 0; c->searched_mask = 0;
     bar[0] = 0; bar[1] = 0; bar[2] = 0;
+    c->bar_base[0] = c->bar_base[1] = c->bar_base[2] = c->bar_base[3] = 0;
   }
 }
 
