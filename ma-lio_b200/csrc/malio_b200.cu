@@ -714,7 +714,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // One query per thread (3x3x3 cells).  Queries whose 5th neighbour is not proven inside the block are retried on the
 // 5x5x5 block by the whole warp (ring2_query_warp) before the kernel ends; tie hazards and out-of-grid queries go to the
 // traversal list.  (RING = 1 is the only instantiation; the constants keep the block geometry in one place.)
-template <int MODE, int RING>
+template <int MODE, int RING, bool CTL>
 __global__ void __launch_bounds__(GK_THREADS)
 knn_grid_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict__ cell_start, GridConst G,
                 const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm,
@@ -723,8 +723,8 @@ knn_grid_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict_
                 uint8_t* __restrict__ sel, uint32_t* __restrict__ r2_count, uint32_t* __restrict__ fb_list,
                 uint32_t* __restrict__ fb_count, unsigned long long* __restrict__ cand_total, const ScanCtl* __restrict__ ctl) {
   // device-side iterated update: this launch was enqueued before it was known whether the pass repeats the search
-  if (ctl && !(ctl->active && ctl->redo)) return;
-  const PassConst& pcr = ctl ? ctl->pc : pc;
+  if (CTL && !(ctl->active && ctl->redo)) return;
+  const PassConst& pcr = CTL ? ctl->pc : pc;
   constexpr int ROWS = RING == 1 ? GK_ROWS1 : GK_ROWS2;
   uint32_t n_cand = 0;   // candidates this thread scanned (statistics for the roofline; only summed when asked for)
   constexpr int HALF = RING == 1 ? 1 : 2;       // the block is (2*HALF+1)^3 cells
@@ -802,6 +802,109 @@ knn_grid_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict_
   // ---- 5x5x5 retry, one query at a time with the whole warp (rare: ~0.1 % of the queries on dense maps)
   unsigned r2mask = __ballot_sync(0xffffffffu, want_r2);
   if (r2mask && (threadIdx.x & 31u) == 0) atomicAdd(r2_count, (uint32_t)__popc(r2mask));   // statistics
+  while (r2mask) {
+    const int src = __ffs(r2mask) - 1;
+    r2mask &= r2mask - 1;
+    const float bx = __shfl_sync(0xffffffffu, qx, src), by = __shfl_sync(0xffffffffu, qy, src), bz = __shfl_sync(0xffffffffu, qz, src);
+    const uint32_t bp = __shfl_sync(0xffffffffu, p, src);
+    ring2_query_warp<MODE>(cell_pts, cell_start, G, bx, by, bz, bp, N, max_sqdist, nn_idx, nn_d2, sel, fb_list, fb_count);
+  }
+  if (cand_total) {
+    const uint32_t act = __activemask();
+    const uint32_t tot = __reduce_add_sync(act, n_cand);
+    if ((threadIdx.x & 31u) == (uint32_t)(__ffs(act) - 1)) atomicAdd(cand_total, (unsigned long long)tot);
+  }
+}
+
+// Direct-load variant of the 3x3x3 scan (no shared-memory staging): the nine cell ranges are fetched up front, the candidates are
+// read with independent 16-byte loads in batches of four straight into registers.  No dynamic shared memory, so occupancy is
+// bounded by registers only (many more warps per SM than the staged kernel's 10) and the latency of a batch is hidden by other
+// warps instead of by having all of a thread's candidates in flight at once.  Same arithmetic, same hand-over rules.
+constexpr int GD_THREADS = 128;
+template <int MODE, bool CTL>
+__global__ void __launch_bounds__(GD_THREADS)
+knn_direct_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict__ cell_start, GridConst G,
+                  const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm,
+                  const float* __restrict__ queries, uint32_t N, PassConst pc, float max_sqdist,
+                  float4* __restrict__ world, uint32_t* __restrict__ nn_idx, float* __restrict__ nn_d2,
+                  uint8_t* __restrict__ sel, uint32_t* __restrict__ r2_count, uint32_t* __restrict__ fb_list,
+                  uint32_t* __restrict__ fb_count, unsigned long long* __restrict__ cand_total, const ScanCtl* __restrict__ ctl) {
+  if (CTL && !(ctl->active && ctl->redo)) return;
+  const PassConst& pcr = CTL ? ctl->pc : pc;
+  uint32_t n_cand = 0;
+  const uint32_t p = blockIdx.x * GD_THREADS + threadIdx.x;
+  bool want_r2 = false;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (p < N) {
+    load_query<MODE>(pts, perm, queries, p, pcr, qx, qy, qz);
+    if (MODE == 0) world[p] = make_float4(qx, qy, qz, 0.f);
+    const float ux = (qx - G.ox) * G.inv_h, uy = (qy - G.oy) * G.inv_h, uz = (qz - G.oz) * G.inv_h;
+    const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
+    const bool in_grid = flx >= -1.f && fly >= -1.f && flz >= -1.f && flx <= (float)G.nx && fly <= (float)G.ny && flz <= (float)G.nz;
+    bool settled = false, hazard = false;
+    Top6 t;
+    t.reset();
+    if (in_grid) {
+      const int cx = (int)flx, cy = (int)fly, cz = (int)flz;
+      const float fx = ux - flx, fy = uy - fly, fz = uz - flz;
+      const float fmin = fminf(fminf(fminf(fx, 1.f - fx), fminf(fy, 1.f - fy)), fminf(fz, 1.f - fz));
+      uint32_t ra[9], rb[9];
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        const uint32_t row = grid_cell_index(G, cx, cy + (r % 3) - 1, cz + (r / 3) - 1);
+        ra[r] = __ldg(cell_start + row - 1);
+        rb[r] = __ldg(cell_start + row + 2);
+      }
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        uint32_t a = ra[r];
+        const uint32_t b = rb[r];
+        n_cand += b - a;
+        while (a < b) {
+          const uint32_t left = b - a;
+          // up to four independent loads in flight (indices past the run are clamped to its last entry and ignored below)
+          const float4 c0 = __ldg(cell_pts + a);
+          const float4 c1 = __ldg(cell_pts + (left > 1 ? a + 1 : a));
+          const float4 c2 = __ldg(cell_pts + (left > 2 ? a + 2 : a));
+          const float4 c3 = __ldg(cell_pts + (left > 3 ? a + 3 : a));
+          {
+            const float dist = (qx - c0.x) * (qx - c0.x) + (qy - c0.y) * (qy - c0.y) + (qz - c0.z) * (qz - c0.z);   // calc_dist
+            if (dist < t.d5) t.insert(dist, __float_as_uint(c0.w));
+          }
+          if (left > 1) {
+            const float dist = (qx - c1.x) * (qx - c1.x) + (qy - c1.y) * (qy - c1.y) + (qz - c1.z) * (qz - c1.z);
+            if (dist < t.d5) t.insert(dist, __float_as_uint(c1.w));
+          }
+          if (left > 2) {
+            const float dist = (qx - c2.x) * (qx - c2.x) + (qy - c2.y) * (qy - c2.y) + (qz - c2.z) * (qz - c2.z);
+            if (dist < t.d5) t.insert(dist, __float_as_uint(c2.w));
+          }
+          if (left > 3) {
+            const float dist = (qx - c3.x) * (qx - c3.x) + (qy - c3.y) * (qy - c3.y) + (qz - c3.z) * (qz - c3.z);
+            if (dist < t.d5) t.insert(dist, __float_as_uint(c3.w));
+          }
+          a += 4;
+        }
+      }
+      const float rg = (1.f + fmin - GRID_MARGIN) * G.h;
+      hazard = t.tie_hazard();
+      settled = (t.d4 < rg * rg) & !hazard;
+    }
+    if (settled) {
+      nn_idx[p] = t.i0;                  nn_d2[p] = t.d0;
+      nn_idx[(size_t)N + p] = t.i1;      nn_d2[(size_t)N + p] = t.d1;
+      nn_idx[(size_t)2 * N + p] = t.i2;  nn_d2[(size_t)2 * N + p] = t.d2;
+      nn_idx[(size_t)3 * N + p] = t.i3;  nn_d2[(size_t)3 * N + p] = t.d3;
+      nn_idx[(size_t)4 * N + p] = t.i4;  nn_d2[(size_t)4 * N + p] = t.d4;
+      if (MODE == 0) sel[p] = (t.d4 > max_sqdist) ? 0 : 1;
+    } else if (in_grid && !hazard) {
+      want_r2 = true;
+    } else {
+      fb_list[atomicAdd(fb_count, 1u)] = p;
+    }
+  }
+  unsigned r2mask = __ballot_sync(0xffffffffu, want_r2);
+  if (r2mask && (threadIdx.x & 31u) == 0) atomicAdd(r2_count, (uint32_t)__popc(r2mask));
   while (r2mask) {
     const int src = __ffs(r2mask) - 1;
     r2mask &= r2mask - 1;
@@ -1707,19 +1810,26 @@ __device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t target,
 // the accumulation (no global round trip, no staging pass); rows stay in their own positions and the workers pick the
 // rows of the LiDAR they are accumulating by a per-row tag, so no prefix sums or compaction barriers are needed.
 // !FAST: any number of tiles per block, rows go through global memory (reduce_block).
-constexpr int PASS_FAST_TILES = 2;
+#ifndef MALIO_PASS_TILES
+#define MALIO_PASS_TILES 2
+#endif
+#ifndef MALIO_PASS_MINB
+#define MALIO_PASS_MINB 4
+#endif
+constexpr int PASS_FAST_TILES = MALIO_PASS_TILES;   // tiles of 128 points a block keeps on chip (fast path)
+constexpr int PASS_MIN_BLOCKS = MALIO_PASS_MINB;    // co-resident blocks per SM the kernel is compiled for
 constexpr int PASS_ROW_STRIDE = 15;        // doubles per staged row: a*J12 (12) | 1/rho^ | z | rho^   (odd: conflict-free)
 constexpr int PASS_FAST_SMEM_DOUBLES = PASS_FAST_TILES * RED_THREADS * PASS_ROW_STRIDE + RED_TASKS * RED_KS * 16;
 static_assert(PASS_FAST_SMEM_DOUBLES <= RED_SMEM_DOUBLES, "the fast path must fit the generic path's shared memory");
-template <bool FAST>
-__global__ void __launch_bounds__(RED_THREADS, 4)
+template <bool FAST, bool CTL>
+__global__ void __launch_bounds__(RED_THREADS, FAST ? PASS_MIN_BLOCKS : 4)
 pass_kernel(PassArgs a_in, PassConst pc_in, ParamConst prm) {
-  if (a_in.ctl && !a_in.ctl->active) return;
+  if (CTL && !a_in.ctl->active) return;
   // the per-pass quantities: launch arguments, or (device-side update) the control block the solve kernel maintains
   struct Eff {
     int do_tau, do_fit; unsigned long long *mmkey, *mmkey_next; uint32_t *cnt_cell, *cnt_next; uint32_t bar_base[3]; uint32_t seq;
   } ef;
-  if (a_in.ctl) {
+  if (CTL) {
     const int par = a_in.ctl->parity;
     ef.do_tau = 0; ef.do_fit = a_in.ctl->redo;
     ef.mmkey = a_in.mmkey_base + 4 * par; ef.mmkey_next = a_in.mmkey_base + 4 * (1 - par);
@@ -1731,7 +1841,7 @@ pass_kernel(PassArgs a_in, PassConst pc_in, ParamConst prm) {
     ef.cnt_next = a_in.cnt_next; ef.bar_base[0] = a_in.bar_base[0]; ef.bar_base[1] = a_in.bar_base[1]; ef.bar_base[2] = a_in.bar_base[2];
     ef.seq = a_in.seq;
   }
-  const PassConst& pc = a_in.ctl ? a_in.ctl->pc : pc_in;
+  const PassConst& pc = CTL ? a_in.ctl->pc : pc_in;   // CTL == false: the launch arguments themselves (constant bank)
   const PassArgs& a = a_in;
   uint32_t t0, t1;
   block_tiles(a.n_tiles, t0, t1);
@@ -2359,9 +2469,23 @@ int run_knn(malio_handle* h, DeviceState* D, uint32_t n, const malio_scan_pt* pt
   if (D->grid_on) {
     // d_gstats: [2] traversal-list length, [4] ring-2 list length (both zeroed by the previous pass / the re-arm)
     constexpr size_t smem1 = (size_t)GK_CAP * GK_THREADS * sizeof(float4) + (size_t)GK_ROWS1 * GK_THREADS * sizeof(uint2);
-    knn_grid_kernel<MODE, 1><<<(n + GK_THREADS - 1) / GK_THREADS, GK_THREADS, smem1, st>>>(
-        D->d_cell_pts, D->d_cell_start, D->grid, pts, perm, qs, n, pc, max_sqdist, world, D->d_nn_idx, D->d_nn_d2, sel,
-        D->d_gstats + 4, D->d_fb_list, D->d_gstats + 2, D->timing ? D->d_cand : nullptr, ctl);
+    if (D->knn_direct) {
+      if (ctl)
+        knn_direct_kernel<MODE, true><<<(n + GD_THREADS - 1) / GD_THREADS, GD_THREADS, 0, st>>>(
+            D->d_cell_pts, D->d_cell_start, D->grid, pts, perm, qs, n, pc, max_sqdist, world, D->d_nn_idx, D->d_nn_d2, sel,
+            D->d_gstats + 4, D->d_fb_list, D->d_gstats + 2, D->timing ? D->d_cand : nullptr, ctl);
+      else
+        knn_direct_kernel<MODE, false><<<(n + GD_THREADS - 1) / GD_THREADS, GD_THREADS, 0, st>>>(
+            D->d_cell_pts, D->d_cell_start, D->grid, pts, perm, qs, n, pc, max_sqdist, world, D->d_nn_idx, D->d_nn_d2, sel,
+            D->d_gstats + 4, D->d_fb_list, D->d_gstats + 2, D->timing ? D->d_cand : nullptr, ctl);
+    } else if (ctl)
+      knn_grid_kernel<MODE, 1, true><<<(n + GK_THREADS - 1) / GK_THREADS, GK_THREADS, smem1, st>>>(
+          D->d_cell_pts, D->d_cell_start, D->grid, pts, perm, qs, n, pc, max_sqdist, world, D->d_nn_idx, D->d_nn_d2, sel,
+          D->d_gstats + 4, D->d_fb_list, D->d_gstats + 2, D->timing ? D->d_cand : nullptr, ctl);
+    else
+      knn_grid_kernel<MODE, 1, false><<<(n + GK_THREADS - 1) / GK_THREADS, GK_THREADS, smem1, st>>>(
+          D->d_cell_pts, D->d_cell_start, D->grid, pts, perm, qs, n, pc, max_sqdist, world, D->d_nn_idx, D->d_nn_d2, sel,
+          D->d_gstats + 4, D->d_fb_list, D->d_gstats + 2, D->timing ? D->d_cand : nullptr, ctl);
     // 8 queries per warp and iteration; at most one resident wave of 64-thread blocks
     uint32_t fb_blocks = (n + 15) / 16;
     const uint32_t wave = (uint32_t)D->sm_count * 8;
@@ -2441,7 +2565,7 @@ int create(malio_handle* h) {
   CUDA_TRY(cudaMalloc((void**)&D->d_btot, SCAN_BLOCKS * sizeof(uint32_t)));
   CUDA_TRY(cudaMemset(D->d_hist, 0, SORT_BINS * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc((void**)&D->d_rows, (size_t)ROWS_DOUBLES * (1 + MAIL_MAX_WORLD) * sizeof(double)));   // own rows | gathered rows of all ranks
-  D->red_grid = (uint32_t)D->sm_count * 4;   // 46 KB of shared memory per block: 4 blocks per SM are co-resident
+  D->red_grid = (uint32_t)D->sm_count * (PASS_MIN_BLOCKS > 4 ? PASS_MIN_BLOCKS : 4);   // slots for the per-block partial systems
   CUDA_TRY(cudaMalloc((void**)&D->d_block_red, (size_t)D->red_grid * MALIO_RED_DOUBLES * sizeof(double)));
   // pinned + mapped: [0, RED) result | +0..3 min/max keys | +4..7 k-NN list statistics | +8 pass sequence flag | +16.. rows
   CUDA_TRY(cudaHostAlloc((void**)&D->h_res, (MALIO_RED_DOUBLES + 16 + MALIO_MAX_DOF * 25) * sizeof(double), cudaHostAllocMapped));
@@ -2449,13 +2573,15 @@ int create(malio_handle* h) {
   CUDA_TRY(cudaHostGetDevicePointer((void**)&D->h_res_dev, D->h_res, 0));
   CUDA_TRY(cudaMalloc((void**)&D->d_bar, 4 * sizeof(uint32_t)));
   CUDA_TRY(cudaMemset(D->d_bar, 0, 4 * sizeof(uint32_t)));
-  CUDA_TRY(cudaFuncSetAttribute(pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RED_SMEM_DOUBLES * (int)sizeof(double)));
-  CUDA_TRY(cudaFuncSetAttribute(pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RED_SMEM_DOUBLES * (int)sizeof(double)));
+  CUDA_TRY(cudaFuncSetAttribute(pass_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RED_SMEM_DOUBLES * (int)sizeof(double)));
+  CUDA_TRY(cudaFuncSetAttribute(pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RED_SMEM_DOUBLES * (int)sizeof(double)));
+  CUDA_TRY(cudaFuncSetAttribute(pass_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RED_SMEM_DOUBLES * (int)sizeof(double)));
+  CUDA_TRY(cudaFuncSetAttribute(pass_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RED_SMEM_DOUBLES * (int)sizeof(double)));
   {
     int per_sm = 0, per_sm2 = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pass_kernel<true>, RED_THREADS, RED_SMEM_DOUBLES * sizeof(double)));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, pass_kernel<false>, RED_THREADS, RED_SMEM_DOUBLES * sizeof(double)));
-    if (per_sm2 < per_sm) per_sm = per_sm2;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pass_kernel<true, true>, RED_THREADS, PASS_FAST_SMEM_DOUBLES * sizeof(double)));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, pass_kernel<false, true>, RED_THREADS, RED_SMEM_DOUBLES * sizeof(double)));
+    D->pass_max_blocks_generic = per_sm2 * D->sm_count;
     int coop = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, D->device));
     D->pass_max_blocks = per_sm * D->sm_count;
@@ -2463,6 +2589,7 @@ int create(malio_handle* h) {
     if (const char* e = getenv("MALIO_FUSED_PASS")) D->fused = D->fused && atoi(e) != 0;
     if (const char* e = getenv("MALIO_COOP_LAUNCH")) D->coop_launch = atoi(e) != 0;
     D->tau_inline = getenv("MALIO_TAU_INLINE") != nullptr;
+    if (const char* e = getenv("MALIO_KNN_DIRECT")) D->knn_direct = atoi(e) != 0;
     if (const char* e = getenv("MALIO_PASS_TRACE")) D->trace_passes = atoi(e);
     if (const char* e = getenv("MALIO_KNN_CELL")) { D->env_knn_cell = (float)atof(e); D->env_knn_cell_set = true; }
     D->host_prof = getenv("MALIO_HOST_PROF") != nullptr;
@@ -2900,8 +3027,13 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
   uint32_t* cnt_next = D->d_counters + 4 + (1 - D->parity);
   const uint32_t n_tiles = (N + RED_THREADS - 1) / RED_THREADS;
   // one resident wave, every block the same number of tiles (+-1): no straggler blocks
-  const uint32_t wave = (D->fused && (!D->comm || D->p2p) && (uint32_t)D->pass_max_blocks < D->red_grid) ? (uint32_t)D->pass_max_blocks : D->red_grid;
-  const uint32_t per_block = n_tiles ? (n_tiles + wave - 1) / wave : 1;
+  const bool fused_now = D->fused && (!D->comm || D->p2p);
+  uint32_t wave = (fused_now && (uint32_t)D->pass_max_blocks < D->red_grid) ? (uint32_t)D->pass_max_blocks : D->red_grid;
+  uint32_t per_block = n_tiles ? (n_tiles + wave - 1) / wave : 1;
+  if (fused_now && per_block > (uint32_t)PASS_FAST_TILES) {   // rows through global memory: that variant's own co-residency limit
+    wave = (uint32_t)D->pass_max_blocks_generic < D->red_grid ? (uint32_t)D->pass_max_blocks_generic : D->red_grid;
+    per_block = (n_tiles + wave - 1) / wave;
+  }
   const uint32_t grid = n_tiles ? (n_tiles + per_block - 1) / per_block : 1;
   std::chrono::steady_clock::time_point hp1, hp2;
   if (D->fused && (!D->comm || D->p2p)) {
@@ -2930,14 +3062,17 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
     PassConst pc_arg = pc;
     ParamConst prm_arg = prm;
     void* kargs[] = {&a, &pc_arg, &prm_arg};
-    const void* kfn = per_block <= (uint32_t)PASS_FAST_TILES ? (const void*)pass_kernel<true> : (const void*)pass_kernel<false>;
+    const bool fast = per_block <= (uint32_t)PASS_FAST_TILES;
+    const size_t pass_smem = (fast ? PASS_FAST_SMEM_DOUBLES : RED_SMEM_DOUBLES) * sizeof(double);
     auto launch_pass = [&]() -> int {
+      const void* kfn = a.ctl ? (fast ? (const void*)pass_kernel<true, true> : (const void*)pass_kernel<false, true>)
+                              : (fast ? (const void*)pass_kernel<true, false> : (const void*)pass_kernel<false, false>);
       if (D->coop_launch) {
-        CUDA_TRY(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(RED_THREADS), kargs, RED_SMEM_DOUBLES * sizeof(double), st_));
+        CUDA_TRY(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(RED_THREADS), kargs, pass_smem, st_));
       } else {
         // plain launch (MALIO_COOP_LAUNCH=0): the grid never exceeds the co-resident capacity, so the in-kernel barriers are
         // safe as long as no OTHER grid-synchronising kernel competes for the same GPU at the same time (one handle in flight)
-        CUDA_TRY(cudaLaunchKernel(kfn, dim3(grid), dim3(RED_THREADS), kargs, RED_SMEM_DOUBLES * sizeof(double), st_));
+        CUDA_TRY(cudaLaunchKernel(kfn, dim3(grid), dim3(RED_THREADS), kargs, pass_smem, st_));
       }
       D->ctr.kernel_launches += 1;
       return MALIO_OK;
@@ -3177,9 +3312,14 @@ int update_on_device(malio_handle* h, malio_state* x, double* P, int max_iter, m
   }
   // ---- the passes: k-NN (runs only where the control block says the search is repeated), pass kernel, solve kernel
   const uint32_t n_tiles = (N + RED_THREADS - 1) / RED_THREADS;
-  const uint32_t wave = (uint32_t)D->pass_max_blocks < D->red_grid ? (uint32_t)D->pass_max_blocks : D->red_grid;
-  const uint32_t per_block = (n_tiles + wave - 1) / wave;
+  uint32_t wave = (uint32_t)D->pass_max_blocks < D->red_grid ? (uint32_t)D->pass_max_blocks : D->red_grid;
+  uint32_t per_block = (n_tiles + wave - 1) / wave;
+  if (per_block > (uint32_t)PASS_FAST_TILES) {
+    wave = (uint32_t)D->pass_max_blocks_generic < D->red_grid ? (uint32_t)D->pass_max_blocks_generic : D->red_grid;
+    per_block = (n_tiles + wave - 1) / wave;
+  }
   const uint32_t grid = (n_tiles + per_block - 1) / per_block;
+  const size_t pass_smem = (per_block <= (uint32_t)PASS_FAST_TILES ? PASS_FAST_SMEM_DOUBLES : RED_SMEM_DOUBLES) * sizeof(double);
   PassArgs a{};
   a.pts = pts_k; a.perm = nullptr; a.N = N; a.table = D->d_table; a.nodes = D->d_mpts; a.node_cov = D->d_cov;
   a.nn_idx = D->d_nn_idx; a.sel = D->d_sel; a.world = D->d_world; a.plane = D->d_plane; a.ucov = D->d_ucov;
@@ -3194,15 +3334,15 @@ int update_on_device(malio_handle* h, malio_state* x, double* P, int max_iter, m
   PassConst pc_arg = pc0;
   ParamConst prm_arg = prm;
   void* kargs[] = {&a, &pc_arg, &prm_arg};
-  const void* kfn = per_block <= (uint32_t)PASS_FAST_TILES ? (const void*)pass_kernel<true> : (const void*)pass_kernel<false>;
+  const void* kfn = per_block <= (uint32_t)PASS_FAST_TILES ? (const void*)pass_kernel<true, true> : (const void*)pass_kernel<false, true>;
   volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(D->h_upd + UPD_DOUBLES - 1);
   for (int k = 0; k <= max_iter; ++k) {
     if (D->timing) CUDA_TRY(cudaEventRecord(D->ev_pass[0][k], st_));
     if (int rc = run_knn<0>(h, D, N, pts_k, nullptr, pc0, Pm.knn_max_sqdist, D->d_ctl)) return rc;
     if (D->timing) CUDA_TRY(cudaEventRecord(D->ev_pass[1][k], st_));
     if (k == 0 && tau_async) CUDA_TRY(cudaStreamWaitEvent(st_, D->ev_tau, 0));
-    if (D->coop_launch) CUDA_TRY(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(RED_THREADS), kargs, RED_SMEM_DOUBLES * sizeof(double), st_));
-    else CUDA_TRY(cudaLaunchKernel(kfn, dim3(grid), dim3(RED_THREADS), kargs, RED_SMEM_DOUBLES * sizeof(double), st_));
+    if (D->coop_launch) CUDA_TRY(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(RED_THREADS), kargs, pass_smem, st_));
+    else CUDA_TRY(cudaLaunchKernel(kfn, dim3(grid), dim3(RED_THREADS), kargs, pass_smem, st_));
     if (D->timing) CUDA_TRY(cudaEventRecord(D->ev_pass[2][k], st_));
     if (int rc = malio_solve::launch_solve(h, st_, D->d_ctl, D->d_res, D->d_bar, D->h_upd_dev, reinterpret_cast<uint32_t*>(D->h_upd_dev + UPD_DOUBLES - 1))) return rc;
     D->ctr.kernel_launches += 2;

@@ -172,15 +172,17 @@ struct DeviceState {
   uint32_t* d_gstats = nullptr;           // [0] occupied cells, [1] live points, [2] fb count, [3] fb count of the last search, [4] ring-2 queries
   uint32_t* h_gstats = nullptr;            // pinned mirror (8 words, carved out of h_res)
   // fused pass (single cooperative launch per measurement pass)
-  bool fused = true; int pass_max_blocks = 0; bool coop_launch = true;
+  bool fused = true; int pass_max_blocks = 0, pass_max_blocks_generic = 0; bool coop_launch = true;
   // iterated update on the device (malio_solve.cu)
   bool device_solve = false; ScanCtl* d_ctl = nullptr; ScanCtl* h_ctl = nullptr;   // h_ctl: pinned staging of the inputs
   double* h_upd = nullptr; double* h_upd_dev = nullptr;   // mapped: P_out | state | dx_last | report ints | done flag (last 8 bytes)
   uint32_t scan_id = 0;
   // pipelined host loop: the next pass's kernels are enqueued while the current pass runs and wait for the host's decision
-  bool pipeline = true; bool pre_armed = false; uint32_t pre_ticket = 0; PubCtl* h_pub = nullptr; PubCtl* h_pub_dev = nullptr;
+  // (opt-in, MALIO_PIPELINE=1: measured break-even)
+  bool pipeline = false; bool pre_armed = false; uint32_t pre_ticket = 0; PubCtl* h_pub = nullptr; PubCtl* h_pub_dev = nullptr;
   double solve_ms = 0, upd_ms = 0; uint64_t solve_n = 0, upd_n = 0;   // MALIO_HOST_PROF=1 prints them at destroy
   cudaEvent_t ev_seq[2] = {nullptr, nullptr}; cudaEvent_t ev_pass[3][MALIO_MAX_PASSES] = {};
+  bool knn_direct = false;   // MALIO_KNN_DIRECT=1: 3x3x3 scan with direct register loads instead of the shared-memory staging
   bool tau_inline = false; int trace_passes = 0; float env_knn_cell = -1.f; bool env_knn_cell_set = false; bool host_prof = false;   // environment switches, read once in create()
   uint32_t* d_bar = nullptr; uint32_t bar_base[3] = {0, 0, 0}; uint32_t seq = 0;
   double* h_res_dev = nullptr;     // device-side address of the mapped host result buffer

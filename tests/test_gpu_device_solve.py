@@ -83,3 +83,38 @@ def test_degenerate_and_invalid_scans_through_the_device_path(monkeypatch):
     assert rd.passes == rh.passes == 4 and rd.last_status == rh.last_status == capi.ERR_NO_EFFECTIVE_POINTS
     assert np.array_equal(synth.state_to_vec(xd, 3), synth.state_to_vec(case.x_prop, 3)) and np.array_equal(Pd, Ph)
     dev.close(); host.close()
+
+
+@pytest.mark.parametrize("env", [{"MALIO_PIPELINE": "1"}, {"MALIO_KNN_DIRECT": "1"}, {"MALIO_PIPELINE": "1", "MALIO_KNN_DIRECT": "1"}])
+def test_optional_execution_variants_give_the_default_result(env, monkeypatch):
+    """Opt-in variants of HOW the same update is executed — the pipelined host loop (next pass enqueued ahead, waiting on the
+    device for the host's decision; only active with per-pass timing off) and the direct-load 3x3x3 k-NN scan — must give
+    the default path's result: neighbour lists and gates identical, state bit-identical."""
+    case = synth.make_case("variants", 30000, 300000, 3, 3, varied_map_cov=True)
+    snap = plugin.build_static_snapshot(case.map_xyz, case.map_normal_y)
+    ref = H.make_model(case, snap)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    var = H.make_model(case, snap)
+    for k in env:
+        monkeypatch.delenv(k)
+    ref.set_timing(False); var.set_timing(False)
+    for rnd in range(3):
+        xr, Pr = case.x_prop.copy(), case.P_prop.copy()
+        xv, Pv = case.x_prop.copy(), case.P_prop.copy()
+        ref.rearm_scan(); var.rearm_scan()
+        rr = ref.update_iterated_dyn_share_modified(xr, Pr, 3)
+        rv = var.update_iterated_dyn_share_modified(xv, Pv, 3)
+        assert rr.passes == rv.passes and rr.searches == rv.searches and rr.n_eff_last == rv.n_eff_last
+        assert np.array_equal(synth.state_to_vec(xr, 3), synth.state_to_vec(xv, 3)) and np.array_equal(Pr, Pv)
+        ar, av = ref.aux(), var.aux()
+        for k in ("selected", "nn_idx", "nn_sqdist", "world", "normal_y"):
+            assert np.array_equal(ar[k], av[k]), k
+    # a 1-iteration update (the pipelined loop cancels nothing / one pass) and a direct single pass afterwards
+    xr, Pr = case.x_prop.copy(), case.P_prop.copy(); xv, Pv = case.x_prop.copy(), case.P_prop.copy()
+    ref.rearm_scan(); var.rearm_scan()
+    ref.update_iterated_dyn_share_modified(xr, Pr, 1); var.update_iterated_dyn_share_modified(xv, Pv, 1)
+    assert np.array_equal(synth.state_to_vec(xr, 3), synth.state_to_vec(xv, 3))
+    ok1, H1, h1, s1 = ref.h_share_model(case.x_true, True); ok2, H2, h2, s2 = var.h_share_model(case.x_true, True)
+    assert ok1 and ok2 and np.array_equal(H1, H2)
+    ref.close(); var.close()
