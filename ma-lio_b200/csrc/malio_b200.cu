@@ -820,7 +820,14 @@ knn_grid_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict_
 // read with independent 16-byte loads in batches of four straight into registers.  No dynamic shared memory, so occupancy is
 // bounded by registers only (many more warps per SM than the staged kernel's 10) and the latency of a batch is hidden by other
 // warps instead of by having all of a thread's candidates in flight at once.  Same arithmetic, same hand-over rules.
-constexpr int GD_THREADS = 128;
+#ifndef MALIO_GD_THREADS
+#define MALIO_GD_THREADS 128
+#endif
+#ifndef MALIO_GD_BATCH
+#define MALIO_GD_BATCH 4
+#endif
+constexpr int GD_THREADS = MALIO_GD_THREADS;
+constexpr int GD_BATCH = MALIO_GD_BATCH;     // independent candidate loads in flight per thread
 template <int MODE, bool CTL>
 __global__ void __launch_bounds__(GD_THREADS)
 knn_direct_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict__ cell_start, GridConst G,
@@ -862,28 +869,18 @@ knn_direct_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restric
         n_cand += b - a;
         while (a < b) {
           const uint32_t left = b - a;
-          // up to four independent loads in flight (indices past the run are clamped to its last entry and ignored below)
-          const float4 c0 = __ldg(cell_pts + a);
-          const float4 c1 = __ldg(cell_pts + (left > 1 ? a + 1 : a));
-          const float4 c2 = __ldg(cell_pts + (left > 2 ? a + 2 : a));
-          const float4 c3 = __ldg(cell_pts + (left > 3 ? a + 3 : a));
-          {
-            const float dist = (qx - c0.x) * (qx - c0.x) + (qy - c0.y) * (qy - c0.y) + (qz - c0.z) * (qz - c0.z);   // calc_dist
-            if (dist < t.d5) t.insert(dist, __float_as_uint(c0.w));
+          // GD_BATCH independent loads in flight (indices past the run are clamped to its first entry and ignored below)
+          float4 c[GD_BATCH];
+#pragma unroll
+          for (int k = 0; k < GD_BATCH; ++k) c[k] = __ldg(cell_pts + (left > (uint32_t)k ? a + k : a));
+#pragma unroll
+          for (int k = 0; k < GD_BATCH; ++k) {
+            if (left > (uint32_t)k) {
+              const float dist = (qx - c[k].x) * (qx - c[k].x) + (qy - c[k].y) * (qy - c[k].y) + (qz - c[k].z) * (qz - c[k].z);   // calc_dist
+              if (dist < t.d5) t.insert(dist, __float_as_uint(c[k].w));
+            }
           }
-          if (left > 1) {
-            const float dist = (qx - c1.x) * (qx - c1.x) + (qy - c1.y) * (qy - c1.y) + (qz - c1.z) * (qz - c1.z);
-            if (dist < t.d5) t.insert(dist, __float_as_uint(c1.w));
-          }
-          if (left > 2) {
-            const float dist = (qx - c2.x) * (qx - c2.x) + (qy - c2.y) * (qy - c2.y) + (qz - c2.z) * (qz - c2.z);
-            if (dist < t.d5) t.insert(dist, __float_as_uint(c2.w));
-          }
-          if (left > 3) {
-            const float dist = (qx - c3.x) * (qx - c3.x) + (qy - c3.y) * (qy - c3.y) + (qz - c3.z) * (qz - c3.z);
-            if (dist < t.d5) t.insert(dist, __float_as_uint(c3.w));
-          }
-          a += 4;
+          a += GD_BATCH;
         }
       }
       const float rg = (1.f + fmin - GRID_MARGIN) * G.h;
@@ -2488,7 +2485,7 @@ int run_knn(malio_handle* h, DeviceState* D, uint32_t n, const malio_scan_pt* pt
           D->d_gstats + 4, D->d_fb_list, D->d_gstats + 2, D->timing ? D->d_cand : nullptr, ctl);
     // 8 queries per warp and iteration; at most one resident wave of 64-thread blocks
     uint32_t fb_blocks = (n + 15) / 16;
-    const uint32_t wave = (uint32_t)D->sm_count * 8;
+    const uint32_t wave = (uint32_t)D->sm_count * 2;   // the list is usually (near) empty: a small grid walks it by stride
     if (fb_blocks > wave) fb_blocks = wave;
     if (D->tree_free) {   // device-resident map: no tree to walk, the open queries are settled on the cell list itself
       knn_ring_kernel<MODE><<<fb_blocks, KNN_THREADS, 0, st>>>(D->d_cell_pts, D->d_cell_start, D->grid, pts, perm, qs, n, pc, max_sqdist,
