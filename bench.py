@@ -53,7 +53,7 @@ WORKLOADS = {
     "C5": "C5: k-NN microbench, 1M queries vs 10M-pt tree, k=5",
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (profiles/), C2 only
-NCU_DRAM_BYTES = {"knn": 8.23e6, "pass": None}
+NCU_DRAM_BYTES = {"knn": 8.24e6, "pass": 10.1e6, "knn_c5": 535.6e6}   # profiles/r02_knn_direct_c2_raw.csv, r02_kernels_raw.csv, r02_knn_direct_c5_raw.csv
 SYNC_THREADS = 16          # host threads of the per-scan voxel read-back (include/malio_mapsync.hpp)
 REF_CPU_BUDGET_S = 150.0   # bound of the CPU arms' total run time (both thread counts together)
 
@@ -369,8 +369,8 @@ def run_ours_c5(args, rank, world):
             "e2e": {"value": Q / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": (hi - lo) * 12, "d2h_bytes_per_step": (hi - lo) * 40,
                     "ms_per_step": e2e_s * 1e3, "what": "malio_knn: host queries -> sort -> search -> caller-order lists on the host"},
             "gpu_launches": int(c1.kernel_launches - c0.kernel_launches),
-            "roofline": {"bound": "hbm", "kernel": "knn_grid_kernel (+ knn_list_kernel)", "achieved": bytes_per_launch / dev_s / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": bytes_per_launch / dev_s / 1e9 / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": "knn_direct_kernel (+ knn_list_kernel)", "achieved": bytes_per_launch / dev_s / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": bytes_per_launch / dev_s / 1e9 / peak, "traffic": NCU_DRAM_BYTES["knn_c5"] if world == 1 else None,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "us_per_launch": dev_s * 1e6, "candidates_per_query": cand,
                          "fallback_queries_per_search": float(c1.knn_fallback_queries - c0.knn_fallback_queries) / steps,
                          "ring2_queries_per_search": float(c1.knn_ring2_queries - c0.knn_ring2_queries) / steps, "peak_source": peak_src,
@@ -669,7 +669,7 @@ def run_ours(args, rank, world):
         bytes_per_launch = q_per_launch * (16 + 9 * 8 + cbar * 16 + 40 + 16 + 1)
         t_launch = knn_ms * 1e-3 / knn_launches
         achieved = bytes_per_launch / t_launch / 1e9
-        roofs.append({"bound": "hbm", "kernel": "k-NN search: knn_grid_kernel (+ knn_list_kernel)",
+        roofs.append({"bound": "hbm", "kernel": "k-NN search: knn_direct_kernel (+ knn_list_kernel)",
                       "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                       "traffic": NCU_DRAM_BYTES["knn"] if (world == 1 and args.config == "C2") else None,
                       "algorithmic_bytes_per_launch": bytes_per_launch, "us_per_launch": t_launch * 1e6,
@@ -678,7 +678,8 @@ def run_ours(args, rank, world):
                       "ring2_queries_per_search": float(rc1.knn_ring2_queries - rc0.knn_ring2_queries) / knn_launches,
                       "peak_source": peak_src,
                       "note": "bytes = Q*(16 + 72 + C*16 + 57), C = candidates scanned per query (device counter); the cell-sorted point "
-                              "array and the scan are L2-resident at C2, so DRAM traffic is far below the algorithmic bytes"})
+                              "array and the scan are L2-resident at C2, so DRAM traffic is far below the algorithmic bytes; ncu: issue active 44 %, "
+                              "17 of 32 lanes, 0.59 waves (782 blocks): bound by divergence and latency at a grid that does not fill the machine"})
     if pass_launches:
         # per point and pass: in 16 (scan point) + 16 (plane) + 8 (plane cov) + 16 (traces) + 1 (selected);
         # out 16 (world) + 4 (residual) + 8 (trace) + 4 (normal_y) + 96 (Jacobian row kept for the degenerate branch) + 1 + 1;
