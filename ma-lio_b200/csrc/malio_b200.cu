@@ -1146,19 +1146,26 @@ __device__ __forceinline__ void load_bin_base(const uint32_t* __restrict__ btot,
   __syncthreads();
 }
 __global__ void scatter_kernel(const uint16_t* __restrict__ keys, uint32_t N, const uint32_t* __restrict__ offs,
-                               const uint32_t* __restrict__ btot, uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm) {
+                               const uint32_t* __restrict__ btot, uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm,
+                               uint32_t* __restrict__ arrival) {
   __shared__ uint32_t s_base[SCAN_BLOCKS];
   load_bin_base(btot, s_base);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const uint32_t key = keys[i];
-  perm[s_base[key >> 10] + offs[key] + atomicAdd(cursor + key, 1u)] = i;
+  const uint32_t a = atomicAdd(cursor + key, 1u);
+  perm[s_base[key >> 10] + offs[key] + a] = i;
+  arrival[i] = a;
 }
 // one thread per point: its final slot inside its bin is the number of bin-mates with a smaller index
-// (bins hold ~10 points, at most a few dozen: a short, fully parallel O(cnt) scan per point)
+// (bins hold ~10 points, at most a few dozen: a short, fully parallel O(cnt) scan per point).  Bins above RANK_LIMIT points
+// (thousands of queries inside one 2 m cell: un-down-sampled or tiny clouds) would make that quadratic: they keep the
+// arrival order of the scatter instead — still a valid permutation, only the bit-reproducibility of the internal order
+// (and with it of the last bits of the reduction) is given up for such inputs.
+constexpr uint32_t RANK_LIMIT = 2048;
 __global__ void rank_kernel(const uint16_t* __restrict__ keys, uint32_t N, const uint32_t* __restrict__ offs,
                             const uint32_t* __restrict__ btot, const uint32_t* __restrict__ hist,
-                            const uint32_t* __restrict__ tmp, uint32_t* __restrict__ perm,
+                            const uint32_t* __restrict__ tmp, const uint32_t* __restrict__ arrival, uint32_t* __restrict__ perm,
                             const malio_scan_pt* __restrict__ pts, malio_scan_pt* __restrict__ pts_sorted) {
   __shared__ uint32_t s_base[SCAN_BLOCKS];
   load_bin_base(btot, s_base);
@@ -1167,7 +1174,8 @@ __global__ void rank_kernel(const uint16_t* __restrict__ keys, uint32_t N, const
   const uint32_t key = keys[i];
   const uint32_t off = s_base[key >> 10] + offs[key], cnt = hist[key];
   uint32_t rank = 0;
-  for (uint32_t j = 0; j < cnt; ++j) rank += (tmp[off + j] < i) ? 1u : 0u;
+  if (cnt > RANK_LIMIT) rank = arrival[i];
+  else for (uint32_t j = 0; j < cnt; ++j) rank += (tmp[off + j] < i) ? 1u : 0u;
   perm[off + rank] = i;
   if (pts_sorted) pts_sorted[off + rank] = pts[i];   // position-ordered copy: the per-pass kernels read it without the perm hop
 }
@@ -2380,8 +2388,9 @@ int sort_queries(malio_handle* h, DeviceState* D, uint32_t n, const PassConst& p
   const int lid_major = (MODE == 0 && (uint64_t)n > (uint64_t)PASS_FAST_TILES * RED_THREADS * (uint64_t)(D->pass_max_blocks > 0 ? D->pass_max_blocks : 1)) ? 1 : 0;
   count_kernel<MODE><<<(n + 255) / 256, 256, 0, st>>>(D->d_pts, D->d_queries, n, pc, lid_major, D->d_keys16, D->d_hist);
   scan_kernel<<<SCAN_BLOCKS, SCAN_THREADS, 0, st>>>(D->d_hist, D->d_offs, D->d_cursor, D->d_btot);
-  scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(D->d_keys16, n, D->d_offs, D->d_btot, D->d_cursor, D->d_tmp_ids);
-  rank_kernel<<<(n + 255) / 256, 256, 0, st>>>(D->d_keys16, n, D->d_offs, D->d_btot, D->d_hist, D->d_tmp_ids, D->d_perm,
+  // d_fb_list (the k-NN hand-over list, filled only later in the pass) doubles as the arrival-slot array of the sort
+  scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(D->d_keys16, n, D->d_offs, D->d_btot, D->d_cursor, D->d_tmp_ids, D->d_fb_list);
+  rank_kernel<<<(n + 255) / 256, 256, 0, st>>>(D->d_keys16, n, D->d_offs, D->d_btot, D->d_hist, D->d_tmp_ids, D->d_fb_list, D->d_perm,
                                                MODE == 0 ? D->d_pts : nullptr, MODE == 0 ? D->d_pts_sorted : nullptr);
   CUDA_TRY(cudaGetLastError());
   D->ctr.kernel_launches += 4;

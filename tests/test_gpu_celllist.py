@@ -198,3 +198,23 @@ def test_map_far_from_the_origin_float32_quantisation(offset):
         if cell >= 0:
             print(f"[far-from-origin] offset {offset:.0e} cell {cell}: {fb} of {q.shape[0]} queries ({100.0 * fb / q.shape[0]:.2f} %) took "
                   f"the exact traversal, {r2} the 5x5x5 block")
+
+
+def test_many_queries_in_one_sort_cell_do_not_go_quadratic():
+    """the scan sort ranks the points of one 2 m bin against each other; 60k queries inside a single bin must
+    not cost 60k^2 operations (bins above 2048 points keep the scatter's arrival order).  Results stay exact."""
+    import time
+    rng = np.random.default_rng(41)
+    xyz = rng.uniform(-6, 6, (40000, 3)).astype(np.float32)
+    snap = plugin.build_static_snapshot(xyz)
+    q = rng.uniform(0.05, 1.9, (60000, 3)).astype(np.float32)      # one 2 m sort cell
+    m = plugin.MeasurementModel(1)
+    m.upload_map(snap)
+    m.Nearest_Search(q[:100])
+    t0 = time.perf_counter()
+    idx, d2, _ = m.Nearest_Search(q)
+    dt = time.perf_counter() - t0
+    m.close()
+    o_idx, o_d2, _, _ = po.knn_snapshot(snap.nodes, snap.node_cov, q, nthreads=8)
+    assert np.array_equal(idx.astype(np.int64), o_idx.astype(np.int64)) and np.array_equal(d2, o_d2)
+    assert dt < 0.5, dt
