@@ -17,18 +17,50 @@
 
 extern "C" {
 
-int malio_read_livox_bin(const char* path, malio_livox_pt* out, uint32_t cap, uint32_t* n_out, int eof_quirk) {
-  if (!path || !n_out) return MALIO_ERR_INVALID_ARG;
+}  // extern "C"
+
+namespace {
+// whole records of the file (a trailing partial record — what the player's failed last read leaves behind — is dropped, see eof_quirk).
+// count_only: the size comes from the file length, nothing is read.
+int slurp_records(const char* path, size_t rec_size, bool count_only, std::vector<unsigned char>& buf, uint32_t* n_rec) {
   FILE* f = std::fopen(path, "rb");
   if (!f) return MALIO_ERR_INVALID_ARG;
-  uint32_t n = 0;
-  unsigned char rec[17];   // x y z f32 | reflectivity u8 | tag u8 | line u8 | offset_time: sizeof(uint16_t) bytes (ROSThread.cpp:789)
   int rc = MALIO_OK;
-  for (;;) {
-    const size_t got = std::fread(rec, 1, sizeof(rec), f);
-    if (got != sizeof(rec)) break;   // a trailing partial record is what the player's failed reads leave zero: dropped here, see eof_quirk
-    if (out) {
-      if (n >= cap) { rc = MALIO_ERR_CAPACITY; break; }
+  if (std::fseek(f, 0, SEEK_END) != 0) rc = MALIO_ERR_INVALID_ARG;
+  const long sz = rc == MALIO_OK ? std::ftell(f) : -1;
+  if (sz < 0) rc = MALIO_ERR_INVALID_ARG;
+  if (rc == MALIO_OK) {
+    const size_t n = (size_t)sz / rec_size;
+    if (n > 0xFFFFFFF0u) rc = MALIO_ERR_CAPACITY;
+    else {
+      *n_rec = (uint32_t)n;
+      if (!count_only && n) {
+        buf.resize(n * rec_size);
+        std::rewind(f);
+        if (std::fread(buf.data(), 1, buf.size(), f) != buf.size()) rc = MALIO_ERR_INVALID_ARG;   // one read for the whole scan
+      }
+    }
+  }
+  std::fclose(f);
+  return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int malio_read_livox_bin(const char* path, malio_livox_pt* out, uint32_t cap, uint32_t* n_out, int eof_quirk) {
+  if (!path || !n_out) return MALIO_ERR_INVALID_ARG;
+  // x y z f32 | reflectivity u8 | tag u8 | line u8 | offset_time: sizeof(uint16_t) bytes (ROSThread.cpp:789)
+  constexpr size_t REC = 17;
+  std::vector<unsigned char> buf;
+  uint32_t n = 0;
+  if (int rc = slurp_records(path, REC, out == nullptr, buf, &n)) return rc;
+  int rc = MALIO_OK;
+  if (out) {
+    const uint32_t m = n < cap ? n : cap;
+    if (n > cap) rc = MALIO_ERR_CAPACITY;
+    for (uint32_t i = 0; i < m; ++i) {
+      const unsigned char* rec = buf.data() + (size_t)i * REC;
       malio_livox_pt p;
       std::memcpy(&p.x, rec, 12);
       p.reflectivity = rec[12]; p.tag = rec[13]; p.line = rec[14];
@@ -36,11 +68,10 @@ int malio_read_livox_bin(const char* path, malio_livox_pt* out, uint32_t cap, ui
       std::memcpy(&t16, rec + 15, 2);
       p.offset_time = t16;           // the upper half of CustomPoint::offset_time stays 0
       p.pad = 0;
-      out[n] = p;
+      out[i] = p;
     }
-    ++n;
+    if (rc != MALIO_OK) n = m;
   }
-  std::fclose(f);
   if (rc == MALIO_OK && eof_quirk) {
     if (out) {
       if (n >= cap) rc = MALIO_ERR_CAPACITY;
@@ -54,26 +85,25 @@ int malio_read_livox_bin(const char* path, malio_livox_pt* out, uint32_t cap, ui
 
 int malio_read_ouster_bin(const char* path, malio_ouster_pt* out, uint32_t cap, uint32_t* n_out, int eof_quirk) {
   if (!path || !n_out) return MALIO_ERR_INVALID_ARG;
-  FILE* f = std::fopen(path, "rb");
-  if (!f) return MALIO_ERR_INVALID_ARG;
+  constexpr size_t REC = 22;   // x y z intensity f32 | ring u16 | t u32 (ROSThread.cpp:960-965)
+  std::vector<unsigned char> buf;
   uint32_t n = 0;
-  unsigned char rec[22];   // x y z intensity f32 | ring u16 | t u32 (ROSThread.cpp:960-965)
+  if (int rc = slurp_records(path, REC, out == nullptr, buf, &n)) return rc;
   int rc = MALIO_OK;
-  for (;;) {
-    const size_t got = std::fread(rec, 1, sizeof(rec), f);
-    if (got != sizeof(rec)) break;
-    if (out) {
-      if (n >= cap) { rc = MALIO_ERR_CAPACITY; break; }
+  if (out) {
+    const uint32_t m = n < cap ? n : cap;
+    if (n > cap) rc = MALIO_ERR_CAPACITY;
+    for (uint32_t i = 0; i < m; ++i) {
+      const unsigned char* rec = buf.data() + (size_t)i * REC;
       malio_ouster_pt p;
       std::memcpy(&p.x, rec, 16);
       std::memcpy(&p.ring, rec + 16, 2);
       std::memcpy(&p.t, rec + 18, 4);
       p.pad = 0;
-      out[n] = p;
+      out[i] = p;
     }
-    ++n;
+    if (rc != MALIO_OK) n = m;
   }
-  std::fclose(f);
   if (rc == MALIO_OK && eof_quirk) {
     if (out) {
       if (n >= cap) rc = MALIO_ERR_CAPACITY;
