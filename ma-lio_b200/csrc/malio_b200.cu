@@ -916,6 +916,208 @@ knn_direct_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restric
   }
 }
 
+// Key scan: the 3x3x3 scan with ONE 32-bit key per kept candidate and G lanes per query (G = 2, 4; the template also covers 1, 8).
+//
+// (1) Keys.  The thread-per-query scans above spend most of their instructions on the sorted insertion of (distance, index)
+// pairs (5 compares + ~20 selects per candidate, executed by the whole warp whenever one lane inserts).  Here a candidate is
+// the key  (float bits of dist with the low 10 mantissa bits cleared) | row << 6 | offset-in-row : squared distances are
+// non-negative, so their bit patterns order like the numbers, the low bits make every key of a query unique, and the six
+// smallest keys are kept by a branch-free min/max chain (11 instructions).  The truncation keeps 13 mantissa bits; exactness
+// is restored afterwards: the five winners are re-read, their distances recomputed with calc_dist's expression and sorted
+// exactly.  Every candidate that was NOT kept has dist >= T5 := the truncated distance of the 6th key, so the five are the
+// true five nearest whenever T5 - e4 >= 1e-10 (e4 = their largest exact distance; 1e-10 = PointType_CMP's window).  Otherwise
+// (~0.06 % of the queries: 5th and 6th distance agree in 13 bits) the query is redone by the exact warp-cooperative 5x5x5
+// scan, as are the queries whose 5th neighbour is not proven inside the block; ties among the five go to the traversal list.
+// Rows longer than 64 candidates do not fit the 6-bit offset: such queries (maps far denser than the 2..9 points per cell
+// the index is tuned for) are handed to the list as well.  Results are identical to the scans above by construction.
+//
+// (2) Groups.  A 100k-query search is 0.59 waves of a thread-per-query kernel: it lasts as long as ONE warp's dependent chain
+// however few queries a GPU holds.  With G lanes per query the chain is G times shorter and there are G times more warps;
+// every lane keeps the six smallest keys of its share, six rounds of arg-min over the lane heads merge them (keys are unique,
+// so the owner of the minimum is unique).  The per-query preamble (state transform in double, cell coordinates, the nine row
+// ranges) is done once per query by the first 128/G threads of the block and handed over through shared memory.
+constexpr uint32_t KEY_LOW = 0x3FFu;                 // row (4 bits) << 6 | offset (6 bits)
+constexpr uint32_t KEY_ROW_MAX = 64;                 // candidates per row the offset field can number
+struct Keys6 {
+  uint32_t k0, k1, k2, k3, k4, k5;
+  __device__ __forceinline__ void reset() { k0 = k1 = k2 = k3 = k4 = k5 = 0xFFFFFFFFu; }
+  __device__ __forceinline__ void insert(uint32_t x) {
+    uint32_t m = max(k0, x); k0 = min(k0, x);
+    uint32_t t = max(k1, m); k1 = min(k1, m); m = t;
+    t = max(k2, m); k2 = min(k2, m); m = t;
+    t = max(k3, m); k3 = min(k3, m); m = t;
+    t = max(k4, m); k4 = min(k4, m); m = t;
+    k5 = min(k5, m);
+  }
+  __device__ __forceinline__ void pop() { k0 = k1; k1 = k2; k2 = k3; k3 = k4; k4 = k5; k5 = 0xFFFFFFFFu; }
+};
+template <int MODE, bool CTL, int G, bool PRE>
+__global__ void __launch_bounds__(GD_THREADS)
+knn_keys_kernel(const float4* __restrict__ cell_pts, const uint32_t* __restrict__ cell_start, GridConst Gc,
+                const malio_scan_pt* __restrict__ pts, const uint32_t* __restrict__ perm,
+                const float* __restrict__ queries, uint32_t N, PassConst pc, float max_sqdist,
+                float4* __restrict__ world, uint32_t* __restrict__ nn_idx, float* __restrict__ nn_d2,
+                uint8_t* __restrict__ sel, uint32_t* __restrict__ r2_count, uint32_t* __restrict__ fb_list,
+                uint32_t* __restrict__ fb_count, unsigned long long* __restrict__ cand_total, const ScanCtl* __restrict__ ctl) {
+  if (CTL && !(ctl->active && ctl->redo)) return;
+  const PassConst& pcr = CTL ? ctl->pc : pc;
+  constexpr int QPB = GD_THREADS / G;          // queries per block
+  constexpr int B = G == 1 ? 4 : 2;            // independent candidate loads in flight per lane
+  __shared__ float4 s_q[QPB];                  // x, y, z, containment radius^2 (-1: outside the grid, -2: row too long for the key)
+  __shared__ uint2 s_rng[9][QPB];              // first candidate, length of the nine x-rows
+  if (threadIdx.x < QPB) {
+    const uint32_t p = blockIdx.x * QPB + threadIdx.x;
+    uint32_t n_cand = 0;
+    float4 q = make_float4(0.f, 0.f, 0.f, -1.f);
+    uint2 rng[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) rng[r] = make_uint2(0u, 0u);
+    if (p < N) {
+      load_query<MODE>(pts, perm, queries, p, pcr, q.x, q.y, q.z);
+      if (MODE == 0) world[p] = make_float4(q.x, q.y, q.z, 0.f);
+      const float ux = (q.x - Gc.ox) * Gc.inv_h, uy = (q.y - Gc.oy) * Gc.inv_h, uz = (q.z - Gc.oz) * Gc.inv_h;
+      const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
+      const bool in_grid = flx >= -1.f && fly >= -1.f && flz >= -1.f && flx <= (float)Gc.nx && fly <= (float)Gc.ny && flz <= (float)Gc.nz;
+      if (in_grid) {
+        const int cx = (int)flx, cy = (int)fly, cz = (int)flz;
+        const float fx = ux - flx, fy = uy - fly, fz = uz - flz;
+        const float fmin = fminf(fminf(fminf(fx, 1.f - fx), fminf(fy, 1.f - fy)), fminf(fz, 1.f - fz));
+        const float rg = (1.f + fmin - GRID_MARGIN) * Gc.h;
+        q.w = rg * rg;
+        uint32_t longest = 0;
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+          const uint32_t row = grid_cell_index(Gc, cx, cy + (r % 3) - 1, cz + (r / 3) - 1);
+          const uint32_t a = __ldg(cell_start + row - 1), b = __ldg(cell_start + row + 2);
+          rng[r] = make_uint2(a, b - a);
+          n_cand += b - a;
+          longest = max(longest, b - a);
+        }
+        if (longest > KEY_ROW_MAX) {
+          q.w = -2.f;
+#pragma unroll
+          for (int r = 0; r < 9; ++r) rng[r].y = 0u;
+        }
+      }
+    }
+    s_q[threadIdx.x] = q;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) s_rng[r][threadIdx.x] = rng[r];
+    if (cand_total) {
+      const uint32_t act = __activemask();
+      const uint32_t tot = __reduce_add_sync(act, n_cand);
+      if ((threadIdx.x & 31u) == (uint32_t)(__ffs(act) - 1)) atomicAdd(cand_total, (unsigned long long)tot);
+    }
+  }
+  __syncthreads();
+  const uint32_t ql = threadIdx.x / G, sub = threadIdx.x % G;
+  const uint32_t p = blockIdx.x * QPB + ql;
+  const float4 q = s_q[ql];
+  Keys6 t;
+  t.reset();
+  if (PRE) {
+    // the first candidate of this lane in every row: nine independent loads in flight at once (with G >= 4 that is most of the
+    // block: rows hold ~4 candidates), instead of nine dependent load -> insert round trips
+    float4 c0[9];
+    uint32_t len[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const uint2 rg = s_rng[r][ql];
+      len[r] = rg.y;
+      c0[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (sub < rg.y) c0[r] = __ldg(cell_pts + rg.x + sub);
+    }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const float dist = (q.x - c0[r].x) * (q.x - c0[r].x) + (q.y - c0[r].y) * (q.y - c0[r].y) + (q.z - c0[r].z) * (q.z - c0[r].z);   // calc_dist
+      const uint32_t key = (__float_as_uint(dist) & ~KEY_LOW) | (uint32_t)(r << 6) | sub;
+      t.insert(sub < len[r] ? key : 0xFFFFFFFFu);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    const uint2 rg = s_rng[r][ql];
+    const float4* __restrict__ run = cell_pts + rg.x;
+    for (uint32_t off = sub + (PRE ? G : 0); off < rg.y; off += G * B) {
+      float4 c[B];
+      uint32_t o[B];
+#pragma unroll
+      for (int k = 0; k < B; ++k) {
+        o[k] = off + k * G;
+        c[k] = __ldg(run + (o[k] < rg.y ? o[k] : off));   // past the run: re-read the first one, its key is voided below
+      }
+#pragma unroll
+      for (int k = 0; k < B; ++k) {
+        const float dist = (q.x - c[k].x) * (q.x - c[k].x) + (q.y - c[k].y) * (q.y - c[k].y) + (q.z - c[k].z) * (q.z - c[k].z);   // calc_dist
+        const uint32_t key = (__float_as_uint(dist) & ~KEY_LOW) | (uint32_t)(r << 6) | o[k];
+        t.insert(o[k] < rg.y ? key : 0xFFFFFFFFu);
+      }
+    }
+  }
+  // ---- merge: six rounds of arg-min over the G lane heads (xor shuffles below G stay inside the aligned group)
+  uint32_t mk[6];
+  if (G == 1) {
+    mk[0] = t.k0; mk[1] = t.k1; mk[2] = t.k2; mk[3] = t.k3; mk[4] = t.k4; mk[5] = t.k5;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      uint32_t m = t.k0;
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+      mk[k] = m;
+      if (t.k0 == m) t.pop();       // keys are unique inside a query; several lanes popping the all-ones filler is harmless
+    }
+  }
+  // ---- exact distances of the five winners (calc_dist's expression), sorted exactly
+  float e[5];
+  uint32_t id[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    e[k] = INFINITY; id[k] = 0xFFFFFFFFu;
+    if (mk[k] != 0xFFFFFFFFu) {
+      const float4 c = __ldg(cell_pts + s_rng[(mk[k] >> 6) & 15u][ql].x + (mk[k] & 63u));
+      e[k] = (q.x - c.x) * (q.x - c.x) + (q.y - c.y) * (q.y - c.y) + (q.z - c.z) * (q.z - c.z);
+      id[k] = __float_as_uint(c.w);
+    }
+  }
+#define MALIO_CE(a, b)                                                               \
+  {                                                                                  \
+    const bool sw = e[a] > e[b];                                                     \
+    const float ea = sw ? e[b] : e[a], eb = sw ? e[a] : e[b];                        \
+    const uint32_t ia = sw ? id[b] : id[a], ib = sw ? id[a] : id[b];                 \
+    e[a] = ea; e[b] = eb; id[a] = ia; id[b] = ib;                                    \
+  }
+  MALIO_CE(0, 1) MALIO_CE(3, 4) MALIO_CE(2, 4) MALIO_CE(2, 3) MALIO_CE(1, 4) MALIO_CE(0, 3) MALIO_CE(0, 2) MALIO_CE(1, 3) MALIO_CE(1, 2)
+#undef MALIO_CE
+  const bool tie = (fabsf(e[1] - e[0]) < 1e-10f) | (fabsf(e[2] - e[1]) < 1e-10f) | (fabsf(e[3] - e[2]) < 1e-10f) | (fabsf(e[4] - e[3]) < 1e-10f);
+  const float t5 = mk[5] == 0xFFFFFFFFu ? INFINITY : __uint_as_float(mk[5] & ~KEY_LOW);
+  const bool set_exact = (t5 - e[4]) >= 1e-10f;         // every candidate outside the five is farther than e4 by the tie window
+  const bool in_grid = q.w >= 0.f;
+  const bool settled = in_grid & !tie & set_exact & (e[4] < q.w);
+  bool want_r2 = false;
+  if (p < N) {
+    if (settled) {
+#pragma unroll
+      for (int k = 0; k < MALIO_K; ++k)
+        if ((k % G) == (int)sub) { nn_idx[(size_t)k * N + p] = id[k]; nn_d2[(size_t)k * N + p] = e[k]; }
+      if (MODE == 0 && sub == 0) sel[p] = (e[4] > max_sqdist) ? 0 : 1;   // laserMapping.cpp:587 (five were found)
+    } else if (sub == 0) {
+      if (in_grid && !tie) want_r2 = true;        // not proven inside the 3x3x3 block, or the 13-bit keys could not separate 5th and 6th
+      else fb_list[atomicAdd(fb_count, 1u)] = p;  // outside the grid, over-long row, or a tie among the five
+    }
+  }
+  const uint32_t lane = threadIdx.x & 31u;
+  unsigned r2mask = __ballot_sync(0xffffffffu, want_r2);
+  if (r2mask && lane == 0) atomicAdd(r2_count, (uint32_t)__popc(r2mask));
+  while (r2mask) {
+    const int src = __ffs(r2mask) - 1;
+    r2mask &= r2mask - 1;
+    const float bx = __shfl_sync(0xffffffffu, q.x, src), by = __shfl_sync(0xffffffffu, q.y, src), bz = __shfl_sync(0xffffffffu, q.z, src);
+    const uint32_t bp = __shfl_sync(0xffffffffu, p, src);
+    ring2_query_warp<MODE>(cell_pts, cell_start, Gc, bx, by, bz, bp, N, max_sqdist, nn_idx, nn_d2, sel, fb_list, fb_count);
+  }
+}
+
 // ------------------------------------------------------------------ K1r: tree-free exact search (device-resident map mode)
 // When the map lives on the device as a point set kept in step with the host's ikd-Tree by deltas (malio_mapops.cu), there
 // is no flattened tree to walk.  The queries the 3x3x3 / 5x5x5 scans leave open — sparse neighbourhoods, queries outside the
@@ -2457,6 +2659,17 @@ int grid_build(malio_handle* h, DeviceState* D, const GridConst& G) {
   return MALIO_OK;
 }
 
+// lanes per query of the cell-list scan: small searches are latency-bound (one warp's chain), large ones issue-bound (the merge and
+// the replicated preamble are pure overhead there).  MALIO_KNN_GROUP=1|2|4 overrides (experiments).
+static int pick_group(uint32_t n, int sm_count) {
+  static const int forced = [] { const char* e = getenv("MALIO_KNN_GROUP"); return e ? atoi(e) : 0; }();
+  if (forced == 1 || forced == 2 || forced == 4) return forced;
+  const uint64_t per_sm = (uint64_t)n / (uint64_t)(sm_count > 0 ? sm_count : 1);
+  if (per_sm <= 256) return 4;        // <= ~38k queries on 148 SMs
+  if (per_sm <= 1280) return 2;       // <= ~190k
+  return 1;                           // knn_direct_kernel
+}
+
 // the k-NN of one search pass: cell-list fast path + exact ikd-Tree-order traversal for what it leaves, or the
 // traversal alone when the index is off
 template <int MODE>
@@ -2475,7 +2688,26 @@ int run_knn(malio_handle* h, DeviceState* D, uint32_t n, const malio_scan_pt* pt
   if (D->grid_on) {
     // d_gstats: [2] traversal-list length, [4] ring-2 list length (both zeroed by the previous pass / the re-arm)
     constexpr size_t smem1 = (size_t)GK_CAP * GK_THREADS * sizeof(float4) + (size_t)GK_ROWS1 * GK_THREADS * sizeof(uint2);
-    if (D->knn_direct) {
+    const int grp = (D->knn_direct && D->knn_keys) ? pick_group(n, D->sm_count) : 1;
+    if (grp > 1) {
+#define MALIO_LAUNCH_KEYS(GG, PP)                                                                                                \
+  do {                                                                                                                         \
+    const uint32_t qpb = GD_THREADS / GG;                                                                                      \
+    if (ctl)                                                                                                                   \
+      knn_keys_kernel<MODE, true, GG, PP><<<(n + qpb - 1) / qpb, GD_THREADS, 0, st>>>(                                         \
+          D->d_cell_pts, D->d_cell_start, D->grid, pts, perm, qs, n, pc, max_sqdist, world, D->d_nn_idx, D->d_nn_d2, sel,      \
+          D->d_gstats + 4, D->d_fb_list, D->d_gstats + 2, D->timing ? D->d_cand : nullptr, ctl);                               \
+    else                                                                                                                       \
+      knn_keys_kernel<MODE, false, GG, PP><<<(n + qpb - 1) / qpb, GD_THREADS, 0, st>>>(                                        \
+          D->d_cell_pts, D->d_cell_start, D->grid, pts, perm, qs, n, pc, max_sqdist, world, D->d_nn_idx, D->d_nn_d2, sel,      \
+          D->d_gstats + 4, D->d_fb_list, D->d_gstats + 2, D->timing ? D->d_cand : nullptr, ctl);                               \
+  } while (0)
+      // measured (ncu kernel time, C2 sub-sampled): 12.5k queries 31 -> 12 us with 4 lanes + row preload; 100k 29.5 -> 24 us with
+      // 2 lanes; from ~200k queries on (C4, C5) the thread-per-query kernel is as fast or faster and stays
+      if (grp == 2) MALIO_LAUNCH_KEYS(2, false);
+      else MALIO_LAUNCH_KEYS(4, true);
+#undef MALIO_LAUNCH_KEYS
+    } else if (D->knn_direct) {
       if (ctl)
         knn_direct_kernel<MODE, true><<<(n + GD_THREADS - 1) / GD_THREADS, GD_THREADS, 0, st>>>(
             D->d_cell_pts, D->d_cell_start, D->grid, pts, perm, qs, n, pc, max_sqdist, world, D->d_nn_idx, D->d_nn_d2, sel,
@@ -2596,6 +2828,7 @@ int create(malio_handle* h) {
     if (const char* e = getenv("MALIO_COOP_LAUNCH")) D->coop_launch = atoi(e) != 0;
     D->tau_inline = getenv("MALIO_TAU_INLINE") != nullptr;
     if (const char* e = getenv("MALIO_KNN_DIRECT")) D->knn_direct = atoi(e) != 0;
+    if (const char* e = getenv("MALIO_KNN_KEYS")) D->knn_keys = atoi(e) != 0;
     if (const char* e = getenv("MALIO_PASS_TRACE")) D->trace_passes = atoi(e);
     if (const char* e = getenv("MALIO_KNN_CELL")) { D->env_knn_cell = (float)atof(e); D->env_knn_cell_set = true; }
     D->host_prof = getenv("MALIO_HOST_PROF") != nullptr;

@@ -183,6 +183,7 @@ struct DeviceState {
   double solve_ms = 0, upd_ms = 0; uint64_t solve_n = 0, upd_n = 0;   // MALIO_HOST_PROF=1 prints them at destroy
   cudaEvent_t ev_seq[2] = {nullptr, nullptr}; cudaEvent_t ev_pass[3][MALIO_MAX_PASSES] = {};
   bool knn_direct = true;    // 3x3x3 scan with direct register loads (MALIO_KNN_DIRECT=0: the shared-memory-staged kernel)
+  bool knn_keys = true;      // ... with one 32-bit key per kept candidate and G lanes per query (MALIO_KNN_KEYS=0: knn_direct_kernel)
   bool tau_inline = false; int trace_passes = 0; float env_knn_cell = -1.f; bool env_knn_cell_set = false; bool host_prof = false;   // environment switches, read once in create()
   uint32_t* d_bar = nullptr; uint32_t bar_base[3] = {0, 0, 0}; uint32_t seq = 0;
   double* h_res_dev = nullptr;     // device-side address of the mapped host result buffer

@@ -218,3 +218,49 @@ def test_many_queries_in_one_sort_cell_do_not_go_quadratic():
     o_idx, o_d2, _, _ = po.knn_snapshot(snap.nodes, snap.node_cov, q, nthreads=8)
     assert np.array_equal(idx.astype(np.int64), o_idx.astype(np.int64)) and np.array_equal(d2, o_d2)
     assert dt < 0.5, dt
+
+
+@pytest.mark.parametrize("nq", [3000, 60000, 250000])
+def test_every_scan_variant_matches_the_oracle(nq):
+    """The 3x3x3 scan runs as 4 lanes per query with 32-bit keys (few queries), 2 lanes per query, or one thread per query
+    (knn_direct_kernel) depending on the number of queries: all three must give the oracle's lists bit for bit."""
+    rng = np.random.default_rng(100 + nq)
+    xyz = np.concatenate([rng.uniform(-40, 40, (150000, 2)), rng.normal(0, 0.15, (150000, 1))], axis=1).astype(np.float32)
+    snap = plugin.build_static_snapshot(xyz)
+    q = np.concatenate([rng.uniform(-41, 41, (nq, 2)), rng.normal(0, 0.3, (nq, 1))], axis=1).astype(np.float32)
+    idx, d2, fb, r2 = _search(snap, q, 0.0)
+    o_idx, o_d2, _, _ = po.knn_snapshot(snap.nodes, snap.node_cov, q, nthreads=8)
+    assert np.array_equal(idx.astype(np.int64), o_idx.astype(np.int64))
+    assert np.array_equal(d2, o_d2)
+    assert fb < nq // 20      # queries beyond the map edge walk the tree
+
+
+def test_key_scan_boundary_cases_and_overlong_rows():
+    """(a) 5th and 6th neighbour whose squared distances agree in the 13 mantissa bits the keys keep: the key scan cannot
+    separate them and must redo the query exactly; (b) rows of more than 64 candidates do not fit the key's offset field:
+    those queries are handed to the exact traversal.  Both must end with the oracle's lists."""
+    rng = np.random.default_rng(77)
+    nq = 1500
+    centres = (np.stack(np.meshgrid(np.arange(40), np.arange(40), indexing="ij"), -1).reshape(-1, 2)[:nq] * 3.0).astype(np.float64)
+    d2s = np.array([0.02, 0.05, 0.08, 0.11, 0.2500, 0.250004, 0.250008, 0.4, 0.5])
+    pts = []
+    for c in centres:
+        for d in d2s * rng.uniform(0.98, 1.02):
+            v = rng.normal(size=3); v /= np.linalg.norm(v)
+            pts.append(np.array([c[0], c[1], 0.0]) + v * np.sqrt(d))
+    xyz = np.array(pts, np.float32)
+    q = np.concatenate([centres, np.zeros((nq, 1))], axis=1).astype(np.float32)
+    snap = plugin.build_static_snapshot(xyz)
+    for cell in (0.0, 1.0, 1.5):
+        idx, d2, fb, r2 = _search(snap, q, cell)
+        o_idx, o_d2, _, _ = po.knn_snapshot(snap.nodes, snap.node_cov, q, nthreads=8)
+        assert np.array_equal(idx.astype(np.int64), o_idx.astype(np.int64)), cell
+        assert np.array_equal(d2, o_d2), cell
+    # (b) 30k points inside 3 x 3 x 1 m with 1.5 m cells: thousands of candidates per row
+    dense = rng.uniform([0, 0, 0], [3, 3, 1], (30000, 3)).astype(np.float32)
+    snap = plugin.build_static_snapshot(dense)
+    q = rng.uniform([0, 0, 0], [3, 3, 1], (2000, 3)).astype(np.float32)
+    idx, d2, fb, r2 = _search(snap, q, 1.5)
+    o_idx, o_d2, _, _ = po.knn_snapshot(snap.nodes, snap.node_cov, q, nthreads=8)
+    assert np.array_equal(idx.astype(np.int64), o_idx.astype(np.int64)) and np.array_equal(d2, o_d2)
+    assert fb == 2000
