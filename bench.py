@@ -517,12 +517,22 @@ def run_ours(args, rank, world):
         inc["rng"] = np.random.default_rng(99)
         inc["next_id"] = int(fid.max()) + 1
         K_DS, K_PLAIN = 2000, 500
-        t_sb, inc["boxes"] = pinned(np.zeros((K_DS, 6), np.float32)); keep.append(t_sb)
-        t_sc, inc["counts"] = pinned(np.zeros(K_DS, np.uint32)); keep.append(t_sc)
-        t_sx, inc["xyz"] = pinned(np.zeros((K_DS * 16, 3), np.float32)); keep.append(t_sx)
-        t_sn, inc["ny"] = pinned(np.zeros(K_DS * 16, np.float32)); keep.append(t_sn)
-        t_si, inc["ids"] = pinned(np.zeros(K_DS * 16, np.int32)); keep.append(t_si)
+        # one pinned record: header {n_boxes, n_points} | boxes | counts | xyz | normal_y | ids.  N > 1: rank 0 alone reads the deltas
+        # back from ITS host tree (one tree, one read-back, as an integration would) and the record is broadcast over NVLink
+        CAP_M = K_DS * 16
+        off_b = 16; off_c = off_b + K_DS * 24; off_x = off_c + K_DS * 4; off_n = off_x + CAP_M * 12; off_i = off_n + CAP_M * 4
+        pack_bytes = off_i + CAP_M * 4
+        t_pack = torch.zeros(pack_bytes, dtype=torch.uint8).pin_memory(); keep.append(t_pack)
+        h_pack = t_pack.numpy()
+        inc["hdr"] = h_pack[0:8].view(np.int32)
+        inc["boxes"] = h_pack[off_b:off_c].view(np.float32).reshape(K_DS, 6)
+        inc["counts"] = h_pack[off_c:off_x].view(np.uint32)
+        inc["xyz"] = h_pack[off_x:off_n].view(np.float32).reshape(CAP_M, 3)
+        inc["ny"] = h_pack[off_n:off_i].view(np.float32)
+        inc["ids"] = h_pack[off_i:pack_bytes].view(np.int32)
+        d_pack = torch.zeros(pack_bytes, dtype=torch.uint8, device="cuda") if world > 1 else None
         inc["sync_s"] = 0.0; inc["sync_pts"] = 0; inc["n"] = 0
+        inc["ny_plain"] = np.full(K_PLAIN, 0.001, np.float32)
 
         def prepare_scan_adds():
             # the reference's own map maintenance for one scan (laserMapping.cpp:443-444), NOT timed in either arm
@@ -537,18 +547,41 @@ def run_ours(args, rank, world):
                 tree.add_points(b, np.full(K_PLAIN, 0.001, np.float32), ib, downsample=False)
             inc["pending"] = (a, b, ib)
 
+        from concurrent.futures import ThreadPoolExecutor
+        inc["pool"] = ThreadPoolExecutor(max_workers=1)
+
         def step_e2e_incremental():
             a, b, ib = inc["pending"]
             t0 = time.perf_counter()
-            sync = tree.collect_sync(a, 0.5, out=dict(boxes=inc["boxes"], counts=inc["counts"], xyz=inc["xyz"], normal_y=inc["ny"], ids=inc["ids"]),
-                                     threads=SYNC_THREADS)
+            # the scan upload does not depend on the map deltas: a helper thread issues it (H2D + per-scan reset on the handle) while
+            # this thread reads the touched voxels back from the host tree (no handle involved); joined before the next handle call
+            up = inc["pool"].submit(mi.upload_scan, h_pts, case.table, case.table_off, case.temporal_comp)
+            if world == 1 or rank == 0:
+                sync = tree.collect_sync(a, 0.5, out=dict(boxes=inc["boxes"], counts=inc["counts"], xyz=inc["xyz"], normal_y=inc["ny"], ids=inc["ids"]),
+                                         threads=SYNC_THREADS)
+            if world > 1:
+                if rank == 0:
+                    inc["hdr"][0] = sync["boxes"].shape[0]; inc["hdr"][1] = sync["xyz"].shape[0]
+                    d_pack.copy_(t_pack, non_blocking=True)
+                dist.broadcast(d_pack, 0)
+                if rank != 0:
+                    t_pack.copy_(d_pack, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                nb_, m_ = int(inc["hdr"][0]), int(inc["hdr"][1])
+                sync = dict(boxes=inc["boxes"][:nb_], counts=inc["counts"][:nb_], xyz=inc["xyz"][:m_], normal_y=inc["ny"][:m_], ids=inc["ids"][:m_])
             inc["sync_s"] += time.perf_counter() - t0; inc["sync_pts"] += sync["xyz"].shape[0]; inc["n"] += 1
+            t0 = lap("i_collect_sync_host", t0)
+            up.result()
+            t0 = lap("i_upload_scan_join", t0)
             mi.map_sync_voxels(sync)
-            mi.map_add_points(b, np.full(b.shape[0], 0.001, np.float32), ib)
-            mi.upload_scan(h_pts, case.table, case.table_off, case.temporal_comp)
+            t0 = lap("i_map_sync_voxels", t0)
+            mi.map_add_points(b, inc["ny_plain"], ib)
+            t0 = lap("i_map_add_points", t0)
             x, P = case.x_prop.copy(), case.P_prop.copy()
             rep = mi.update_iterated_dyn_share_modified(x, P, case.max_iter)
+            t0 = lap("i_update_incl_map_commit", t0)
             mi.aux(out=aux_out)
+            lap("i_aux", t0)
             return rep, x
 
     def timed(fn, steps, warmup, before=None, ctr=None):
@@ -607,16 +640,26 @@ def run_ours(args, rank, world):
     if inc["model"] is not None:
         inc["sync_s"], inc["sync_pts"], inc["n"] = 0.0, 0, 0
         mi = inc["model"]
-        i_ms, i_reps, ic0, ic1, i_out, _ = timed(step_e2e_incremental, e_steps, min(args.warmup, 3), before=prepare_scan_adds, ctr=mi)
+        for _ in range(max(1, min(args.warmup, 3))):   # warm-up, untimed
+            prepare_scan_adds(); step_e2e_incremental(); flush.fill_(1)
+        inc["sync_s"], inc["sync_pts"], inc["n"] = 0.0, 0, 0
+        stages.clear()
+        i_ms, i_reps, ic0, ic1, i_out, _ = timed(step_e2e_incremental, e_steps, 0, before=prepare_scan_adds, ctr=mi)
+        i_stage_ms = {k[2:]: 1e3 * v / e_steps for k, v in stages.items() if k.startswith("i_")}
         i_live, i_slots = mi.map_info()
         i_obj = {"value": e_steps / (i_ms * 1e-3), "unit": UNIT, "ms_per_step": i_ms / e_steps, "steps": e_steps,
                  "h2d_bytes_per_step": int(ic1.h2d_bytes - ic0.h2d_bytes) // e_steps, "d2h_bytes_per_step": int(ic1.d2h_bytes - ic0.d2h_bytes) // e_steps,
-                 "map_sync_host_ms": 1e3 * inc["sync_s"] / max(inc["n"], 1), "map_sync_host_threads": SYNC_THREADS, "synced_points_per_step": inc["sync_pts"] / max(inc["n"], 1),
+                 "map_sync_host_ms": 1e3 * inc["sync_s"] / max(inc["n"], 1), "map_sync_host_threads": SYNC_THREADS,
+                 "map_sync_mode": "local read-back" if world == 1 else "rank 0 reads back from its host tree, one NCCL broadcast of the record (time included)",
+                 "synced_points_per_step": inc["sync_pts"] / max(inc["n"], 1),
+                 "host_wall_ms_per_stage": i_stage_ms,
                  "new_points_per_step": 2500, "map_live_points": i_live, "map_slots": i_slots,
                  "knn_tie_queries": int(ic1.knn_tie_queries - ic0.knn_tie_queries), "passes_per_scan": sum(r.passes for r in i_reps) / e_steps,
                  "what": "map kept on the device by deltas: Box_Search read-back of the voxels the scan's 2000 down-sampled adds touch (host, in the "
-                         "bracket) + upload of those points and boxes + 500 plain appends + device kill/append + cell-index rebuild + upload_scan "
-                         "+ IESKF update + download of normal_y/selected; the tree's own Add_Points runs outside the bracket (untimed in both arms)"}
+                         "bracket; the scan upload runs beside it on a helper thread) + upload of those points and boxes + 500 plain appends + device "
+                         "kill/append + cell-index rebuild + IESKF update + download of normal_y/selected; the tree's own Add_Points runs outside "
+                         "the bracket (untimed in both arms)"}
+        inc["pool"].shutdown()
         mi.close()
     step_e2e_snapshot_only(); stages.clear()
     s_ms, _, _, _, _, _ = timed(step_e2e_snapshot_only, e_steps, 0)
