@@ -718,7 +718,10 @@ def run_ours(args, rank, world):
         bytes_per_launch = q_per_launch * (16 + 9 * 8 + cbar * 16 + 40 + 16 + 1)
         t_launch = knn_ms * 1e-3 / knn_launches
         achieved = bytes_per_launch / t_launch / 1e9
-        roofs.append({"bound": "hbm", "kernel": "k-NN search: knn_direct_kernel (+ knn_list_kernel)",
+        n_q = case.pts.shape[0] // max(world, 1)
+        knn_name = ("knn_keys_kernel, 4 lanes per query" if n_q <= 256 * 148 else
+                    "knn_keys_kernel, 2 lanes per query" if n_q <= 1280 * 148 else "knn_direct_kernel, thread per query")
+        roofs.append({"bound": "hbm", "kernel": f"k-NN search: {knn_name} (+ knn_list_kernel)",
                       "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                       "traffic": NCU_DRAM_BYTES["knn"] if (world == 1 and args.config == "C2") else None,
                       "algorithmic_bytes_per_launch": bytes_per_launch, "us_per_launch": t_launch * 1e6,
