@@ -27,8 +27,10 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
-#include <unordered_set>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace malio {
 
@@ -58,11 +60,14 @@ inline void voxel_box_of(float x, float y, float z, float ds, float box[6]) {
 // Nearest_Search (laserMapping.cpp:559-563).  Callers that prefer not to rely on that keep threads = 1.
 template <class Tree, class BoxT, class PointVector, class IdFn>
 void collect_voxel_sync(Tree& tree, const PointVector& added, float downsample_size, VoxelSync& out, IdFn id_of, int threads = 1) {
-  out = VoxelSync{};
-  struct Key { int32_t a, b, c; bool operator==(const Key& o) const { return a == o.a && b == o.b && c == o.c; } };
-  struct KeyHash { size_t operator()(const Key& k) const { return (size_t)k.a * 73856093u ^ (size_t)k.b * 19349663u ^ (size_t)k.c * 83492791u; } };
-  std::unordered_set<Key, KeyHash> seen;
-  seen.reserve(added.size() * 2 + 16);
+  out.boxes.clear(); out.counts.clear(); out.xyz.clear(); out.normal_y.clear(); out.ids.clear(); out.outside_own_box = 0;
+  // ---- distinct voxels, in order of first appearance: open-addressing table over the packed voxel coordinates
+  size_t cap = 64;
+  while (cap < added.size() * 2 + 16) cap <<= 1;
+  struct Key { int32_t a, b, c; };
+  std::vector<Key> slot_key(cap);
+  std::vector<uint8_t> slot_used(cap, 0);
+  out.boxes.reserve(added.size() * 6);
   for (size_t i = 0; i < added.size(); ++i) {
     float box[6];
     voxel_box_of(added[i].x, added[i].y, added[i].z, downsample_size, box);
@@ -70,29 +75,55 @@ void collect_voxel_sync(Tree& tree, const PointVector& added, float downsample_s
       out.outside_own_box++;
     const Key k{(int32_t)std::floor(added[i].x / downsample_size), (int32_t)std::floor(added[i].y / downsample_size),
                 (int32_t)std::floor(added[i].z / downsample_size)};
-    if (!seen.insert(k).second) continue;
+    size_t s = ((size_t)(uint32_t)k.a * 73856093u ^ (size_t)(uint32_t)k.b * 19349663u ^ (size_t)(uint32_t)k.c * 83492791u) & (cap - 1);
+    bool dup = false;
+    while (slot_used[s]) {
+      if (slot_key[s].a == k.a && slot_key[s].b == k.b && slot_key[s].c == k.c) { dup = true; break; }
+      s = (s + 1) & (cap - 1);
+    }
+    if (dup) continue;
+    slot_used[s] = 1; slot_key[s] = k;
     out.boxes.insert(out.boxes.end(), box, box + 6);
   }
   const int64_t nb = (int64_t)(out.boxes.size() / 6);
   out.counts.assign((size_t)nb, 0u);
-  std::vector<PointVector> found((size_t)nb);
   if (threads < 1) threads = 1;
-#pragma omp parallel for num_threads(threads) schedule(dynamic, 16) if (threads > 1)
-  for (int64_t k = 0; k < nb; ++k) {
-    BoxT b;
-    for (int a = 0; a < 3; ++a) { b.vertex_min[a] = out.boxes[6 * (size_t)k + a]; b.vertex_max[a] = out.boxes[6 * (size_t)k + 3 + a]; }
-    tree.Box_Search(b, found[(size_t)k]);
-    out.counts[(size_t)k] = (uint32_t)found[(size_t)k].size();
+  if ((int64_t)threads > nb) threads = nb > 0 ? (int)nb : 1;
+  // ---- one Box_Search per voxel; thread t owns the contiguous box range [nb t / T, nb (t+1) / T) and appends to buffers of its
+  // own, so that concatenating the buffers in thread order is box order (deterministic whatever the thread count)
+  struct Local { std::vector<float> xyz, ny; std::vector<int32_t> ids; };
+  std::vector<Local> loc((size_t)threads);
+#pragma omp parallel num_threads(threads) if (threads > 1)
+  {
+#ifdef _OPENMP
+    const int t = omp_get_thread_num(), T = omp_get_num_threads();
+#else
+    const int t = 0, T = 1;
+#endif
+    Local& L = loc[(size_t)t];
+    PointVector found;
+    const int64_t k0 = nb * t / T, k1 = nb * (t + 1) / T;
+    L.xyz.reserve((size_t)(k1 - k0) * 6); L.ny.reserve((size_t)(k1 - k0) * 2); L.ids.reserve((size_t)(k1 - k0) * 2);
+    for (int64_t k = k0; k < k1; ++k) {
+      BoxT b;
+      for (int a = 0; a < 3; ++a) { b.vertex_min[a] = out.boxes[6 * (size_t)k + a]; b.vertex_max[a] = out.boxes[6 * (size_t)k + 3 + a]; }
+      tree.Box_Search(b, found);
+      out.counts[(size_t)k] = (uint32_t)found.size();
+      for (const auto& p : found) {
+        L.xyz.push_back(p.x); L.xyz.push_back(p.y); L.xyz.push_back(p.z);
+        L.ny.push_back(p.normal_y);
+        L.ids.push_back(id_of(p));
+      }
+    }
   }
   size_t total = 0;
-  for (int64_t k = 0; k < nb; ++k) total += out.counts[(size_t)k];
+  for (const Local& L : loc) total += L.ny.size();
   out.xyz.reserve(total * 3); out.normal_y.reserve(total); out.ids.reserve(total);
-  for (int64_t k = 0; k < nb; ++k)
-    for (const auto& p : found[(size_t)k]) {
-      out.xyz.push_back(p.x); out.xyz.push_back(p.y); out.xyz.push_back(p.z);
-      out.normal_y.push_back(p.normal_y);
-      out.ids.push_back(id_of(p));
-    }
+  for (const Local& L : loc) {
+    out.xyz.insert(out.xyz.end(), L.xyz.begin(), L.xyz.end());
+    out.normal_y.insert(out.normal_y.end(), L.ny.begin(), L.ny.end());
+    out.ids.insert(out.ids.end(), L.ids.begin(), L.ids.end());
+  }
 }
 
 }  // namespace malio
