@@ -573,7 +573,7 @@ def run_ours(args, rank, world):
             t0 = lap("i_collect_sync_host", t0)
             up.result()
             t0 = lap("i_upload_scan_join", t0)
-            mi.map_sync_voxels(sync)
+            mi.map_sync_voxels(sync, want_count=False)
             t0 = lap("i_map_sync_voxels", t0)
             mi.map_add_points(b, inc["ny_plain"], ib)
             t0 = lap("i_map_add_points", t0)

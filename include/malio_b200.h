@@ -351,7 +351,9 @@ int malio_preprocess_ouster(const malio_ouster_pt* pts, uint32_t n, int point_fi
  * neighbour list and every distance is the reference's, except for exact distance ties, which the reference breaks by
  * traversal order — those queries are counted (malio_counters.knn_tie_queries) and broken by slot index.
  * nn_idx of malio_download_aux / malio_knn are SLOT indices in this mode; malio_map_download gives slot -> id.
- * A later malio_upload_map* call switches the handle back to snapshot mode. */
+ * A later malio_upload_map* call switches the handle back to snapshot mode.
+ * Host arrays are consumed when a call returns.  Per-scan-sized batches (<= 65536 points, <= 16384 boxes) pass through a pinned
+ * bounce buffer and the call returns WITHOUT waiting for the device; n_deleted (may be NULL) costs a device round trip when asked. */
 int malio_map_build(malio_handle* h, const float* xyz, const float* normal_y, const int32_t* ids /* may be NULL: 0..n-1 */, uint32_t n);
 int malio_map_add_points(malio_handle* h, const float* xyz, const float* normal_y, const int32_t* ids /* may be NULL */, uint32_t n);
 int malio_map_delete_boxes(malio_handle* h, const float* boxes /* nb x {min3, max3} */, uint32_t nb, uint32_t* n_deleted);

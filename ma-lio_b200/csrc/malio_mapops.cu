@@ -36,7 +36,13 @@ struct MapOps {
   uint32_t* h_small = nullptr;   // pinned mirror
   uint32_t *d_blk = nullptr, *d_blkoff = nullptr; uint32_t cap_blk = 0;   // compaction: live count / offset per 1024-slot block
   float4* d_mpts2 = nullptr; float* d_cov2 = nullptr; int32_t* d_ids2 = nullptr; uint32_t cap2 = 0;   // compaction targets
+  // small batches (the per-scan deltas) go through a pinned bounce buffer: one host memcpy, one H2D, and the call returns
+  // without waiting for the device — the caller's arrays are consumed, the bounce buffer is protected by ev_bounce
+  float* h_bounce[2] = {nullptr, nullptr}; cudaEvent_t ev_bounce[2] = {nullptr, nullptr}; bool bounce_busy[2] = {false, false}; int bounce_next = 0;
+  float* h_bounce_box = nullptr; cudaEvent_t ev_bounce_box = nullptr; bool bounce_box_busy = false;   // same for the voxel boxes
 };
+constexpr uint32_t BOUNCE_POINTS = 65536;      // 5 floats per point: 1.3 MB of pinned memory
+constexpr uint32_t BOUNCE_BOXES = 16384;       // 6 floats per box
 
 int state(malio_handle* h, MapOps*& M) {
   M = (MapOps*)h->mapst;
@@ -239,15 +245,38 @@ __global__ void gather_live_kernel(const float4* __restrict__ mpts, const float*
 
 // host arrays -> staging buffer on the device: xyz | normal_y | ids
 int stage(malio_handle* h, DeviceState* D, MapOps* M, const float* xyz, const float* ny, const int32_t* ids, uint32_t n, const float** d_xyz,
-          const float** d_ny, const int32_t** d_ids) {
+          const float** d_ny, const int32_t** d_ids, bool* synced_needed) {
   if (n > M->cap_stage) { if (int rc = grow(h, M->d_stage, (size_t)(n + n / 4 + 1024) * 5)) return rc; M->cap_stage = n + n / 4 + 1024; }
   float* base = M->d_stage;
-  CUDA_TRY(cudaMemcpyAsync(base, xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, D->stream));
-  CUDA_TRY(cudaMemcpyAsync(base + 3 * (size_t)M->cap_stage, ny, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, D->stream));
-  if (ids) CUDA_TRY(cudaMemcpyAsync(base + 4 * (size_t)M->cap_stage, ids, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, D->stream));
   *d_xyz = base; *d_ny = base + 3 * (size_t)M->cap_stage;
   *d_ids = ids ? reinterpret_cast<const int32_t*>(base + 4 * (size_t)M->cap_stage) : nullptr;
   D->ctr.h2d_bytes += (uint64_t)n * (16 + (ids ? 4 : 0));
+  *synced_needed = true;
+  if (n <= BOUNCE_POINTS) {
+    // two bounce slots used in turn: the sync-voxel points and the plain appends of one scan do not wait for each other
+    const int bs = M->bounce_next;
+    M->bounce_next ^= 1;
+    if (!M->h_bounce[bs]) {
+      CUDA_TRY(cudaHostAlloc((void**)&M->h_bounce[bs], (size_t)BOUNCE_POINTS * 5 * sizeof(float), cudaHostAllocDefault));
+      CUDA_TRY(cudaEventCreateWithFlags(&M->ev_bounce[bs], cudaEventDisableTiming));
+    }
+    if (M->bounce_busy[bs]) { CUDA_TRY(cudaEventSynchronize(M->ev_bounce[bs])); M->bounce_busy[bs] = false; }   // its previous batch has left it
+    float* hb = M->h_bounce[bs];
+    // packed xyz | normal_y | ids, then three device-side destinations out of one pinned source (no host wait)
+    std::memcpy(hb, xyz, (size_t)n * 12);
+    std::memcpy(hb + 3 * (size_t)n, ny, (size_t)n * 4);
+    if (ids) std::memcpy(hb + 4 * (size_t)n, ids, (size_t)n * 4);
+    CUDA_TRY(cudaMemcpyAsync(base, hb, (size_t)n * 12, cudaMemcpyHostToDevice, D->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + 3 * (size_t)M->cap_stage, hb + 3 * (size_t)n, (size_t)n * 4, cudaMemcpyHostToDevice, D->stream));
+    if (ids) CUDA_TRY(cudaMemcpyAsync(base + 4 * (size_t)M->cap_stage, hb + 4 * (size_t)n, (size_t)n * 4, cudaMemcpyHostToDevice, D->stream));
+    CUDA_TRY(cudaEventRecord(M->ev_bounce[bs], D->stream));
+    M->bounce_busy[bs] = true;
+    *synced_needed = false;
+    return MALIO_OK;
+  }
+  CUDA_TRY(cudaMemcpyAsync(base, xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, D->stream));
+  CUDA_TRY(cudaMemcpyAsync(base + 3 * (size_t)M->cap_stage, ny, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, D->stream));
+  if (ids) CUDA_TRY(cudaMemcpyAsync(base + 4 * (size_t)M->cap_stage, ids, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, D->stream));
   return MALIO_OK;
 }
 int append(malio_handle* h, DeviceState* D, MapOps* M, const float* xyz, const float* ny, const int32_t* ids, uint32_t n) {
@@ -256,10 +285,13 @@ int append(malio_handle* h, DeviceState* D, MapOps* M, const float* xyz, const f
   if (int rc = malio_dev::grow_slots(h, M->n_slots + n, M->n_slots)) return rc;
   const float *d_xyz, *d_ny;
   const int32_t* d_ids;
-  if (int rc = stage(h, D, M, xyz, ny, ids, n, &d_xyz, &d_ny, &d_ids)) return rc;
+  bool need_sync = true;
+  if (int rc = stage(h, D, M, xyz, ny, ids, n, &d_xyz, &d_ny, &d_ids, &need_sync)) return rc;
   append_kernel<<<(n + 255) / 256, 256, 0, D->stream>>>(d_xyz, d_ny, d_ids, n, M->n_slots, (int32_t)M->n_slots, D->d_mpts, D->d_cov, D->d_ids);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaStreamSynchronize(D->stream));   // the staging buffer is reused by the next call; host arrays are consumed
+  // large batches are copied straight from the caller's arrays: wait until they are consumed.  (The device staging buffer itself is
+  // reused in stream order.)
+  if (need_sync) CUDA_TRY(cudaStreamSynchronize(D->stream));
   D->ctr.kernel_launches += 1;
   M->n_slots += n;
   M->dirty = true;
@@ -277,6 +309,9 @@ void destroy(malio_handle* h) {
   void* p[] = {M->d_stage, M->d_boxes, M->d_small, M->d_blk, M->d_blkoff, M->d_mpts2, M->d_cov2, M->d_ids2};
   for (void* q : p) if (q) cudaFree(q);
   if (M->h_small) cudaFreeHost(M->h_small);
+  for (int k = 0; k < 2; ++k) { if (M->h_bounce[k]) cudaFreeHost(M->h_bounce[k]); if (M->ev_bounce[k]) cudaEventDestroy(M->ev_bounce[k]); }
+  if (M->h_bounce_box) cudaFreeHost(M->h_bounce_box);
+  if (M->ev_bounce_box) cudaEventDestroy(M->ev_bounce_box);
   delete M;
   h->mapst = nullptr;
 }
@@ -389,13 +424,31 @@ int sync_voxels(malio_handle* h, const float* boxes, uint32_t nb, const float* x
   uint32_t killed = 0;
   if (nb && D->grid_on) {
     if (nb > M->cap_boxes) { if (int rc = grow(h, M->d_boxes, (size_t)(nb + nb / 4 + 1024) * 6)) return rc; M->cap_boxes = nb + nb / 4 + 1024; }
-    CUDA_TRY(cudaMemcpyAsync(M->d_boxes, boxes, (size_t)nb * 6 * sizeof(float), cudaMemcpyHostToDevice, D->stream));
+    const bool via_bounce = !n_deleted && nb <= BOUNCE_BOXES;
+    if (via_bounce) {
+      if (!M->h_bounce_box) {
+        CUDA_TRY(cudaHostAlloc((void**)&M->h_bounce_box, (size_t)BOUNCE_BOXES * 6 * sizeof(float), cudaHostAllocDefault));
+        CUDA_TRY(cudaEventCreateWithFlags(&M->ev_bounce_box, cudaEventDisableTiming));
+      }
+      if (M->bounce_box_busy) { CUDA_TRY(cudaEventSynchronize(M->ev_bounce_box)); M->bounce_box_busy = false; }
+      std::memcpy(M->h_bounce_box, boxes, (size_t)nb * 6 * sizeof(float));
+      CUDA_TRY(cudaMemcpyAsync(M->d_boxes, M->h_bounce_box, (size_t)nb * 6 * sizeof(float), cudaMemcpyHostToDevice, D->stream));
+      CUDA_TRY(cudaEventRecord(M->ev_bounce_box, D->stream));
+      M->bounce_box_busy = true;
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(M->d_boxes, boxes, (size_t)nb * 6 * sizeof(float), cudaMemcpyHostToDevice, D->stream));
+    }
     CUDA_TRY(cudaMemsetAsync(M->d_small + 6, 0, sizeof(uint32_t), D->stream));
     kill_voxel_boxes_kernel<<<(nb + 127) / 128, 128, 0, D->stream>>>(M->d_boxes, nb, D->grid, D->d_cell_start, D->d_cell_pts, D->d_mpts, M->d_small + 6);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(M->h_small + 6, M->d_small + 6, sizeof(uint32_t), cudaMemcpyDeviceToHost, D->stream));
-    CUDA_TRY(cudaStreamSynchronize(D->stream));
-    killed = M->h_small[6];
+    if (n_deleted) {   // the count is only fetched (and waited for) when the caller asks for it
+      CUDA_TRY(cudaMemcpyAsync(M->h_small + 6, M->d_small + 6, sizeof(uint32_t), cudaMemcpyDeviceToHost, D->stream));
+      CUDA_TRY(cudaStreamSynchronize(D->stream));
+      killed = M->h_small[6];
+    } else {
+      if (!via_bounce) CUDA_TRY(cudaStreamSynchronize(D->stream));   // boxes were copied straight from the caller's array
+      killed = 1;      // unknown: treat the index as stale
+    }
     D->ctr.kernel_launches += 1;
     D->ctr.h2d_bytes += (uint64_t)nb * 24;
   }

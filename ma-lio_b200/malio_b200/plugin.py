@@ -195,16 +195,18 @@ class MeasurementModel:
         self._check(self.lib.malio_map_delete_boxes(self._h, capi.ptr(b), b.shape[0], C.byref(n)))
         return int(n.value)
 
-    def map_sync_voxels(self, sync: dict) -> int:
+    def map_sync_voxels(self, sync: dict, want_count: bool = True) -> int:
         """After the host tree's Add_Points(points, true): replace the content of every touched voxel box by what
-        malio::collect_voxel_sync read back from the tree (dict with boxes, xyz, normal_y, ids)."""
+        malio::collect_voxel_sync read back from the tree (dict with boxes, xyz, normal_y, ids).  want_count=False passes
+        n_deleted = NULL: the call then returns without waiting for the device (-1 is returned)."""
         b = self._f32(sync["boxes"], 6); xyz = self._f32(sync["xyz"], 3); ny = self._f32(sync["normal_y"])
         i = None if sync.get("ids") is None else np.ascontiguousarray(sync["ids"], np.int32)
         n = C.c_uint32(0)
         self._check(self.lib.malio_map_sync_voxels(self._h, capi.ptr(b) if b.shape[0] else None, b.shape[0],
                                                    capi.ptr(xyz) if xyz.shape[0] else None, capi.ptr(ny) if xyz.shape[0] else None,
-                                                   capi.ptr(i) if (i is not None and xyz.shape[0]) else None, xyz.shape[0], C.byref(n)))
-        return int(n.value)
+                                                   capi.ptr(i) if (i is not None and xyz.shape[0]) else None, xyz.shape[0],
+                                                   C.byref(n) if want_count else None))
+        return int(n.value) if want_count else -1
 
     def map_commit(self):
         self._check(self.lib.malio_map_commit(self._h))
