@@ -99,37 +99,47 @@ __global__ void kill_big_boxes_kernel(float4* __restrict__ mpts, uint32_t n_slot
   const uint32_t bal = __ballot_sync(0xffffffffu, hit);
   if ((threadIdx.x & 31) == 0 && bal) atomicAdd(killed, (uint32_t)__popc(bal));
 }
-// sync_voxels: many small boxes -> one thread per box walks the cells the box overlaps (the index holds every live point
-// that existed at the last commit) and kills what lies inside (Search_by_range's test, ikd_Tree.cpp:1270)
-__global__ void kill_voxel_boxes_kernel(const float* __restrict__ boxes, uint32_t nb, GridConst G, const uint32_t* __restrict__ cell_start,
-                                        const float4* __restrict__ cell_pts, float4* __restrict__ mpts, uint32_t* __restrict__ killed) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nb) return;
+// sync_voxels: many small boxes -> one WARP per box; the lanes take the x-rows of cells the box overlaps (the index holds every
+// live point that existed at the last commit) and kill what lies inside (Search_by_range's test, ikd_Tree.cpp:1270).  A thread
+// per box was 95 us for 2000 boxes (16 blocks of dependent cell_start -> point -> slot loads); boxes are disjoint voxels, so a
+// slot is written by one lane only.
+constexpr int KV_T = 128;
+__global__ void __launch_bounds__(KV_T) kill_voxel_boxes_kernel(const float* __restrict__ boxes, uint32_t nb, GridConst G,
+                                                                const uint32_t* __restrict__ cell_start, const float4* __restrict__ cell_pts,
+                                                                float4* __restrict__ mpts, uint32_t* __restrict__ killed) {
+  const uint32_t k = (blockIdx.x * KV_T + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  if (k >= nb) return;                         // warp-uniform
   const float* b = boxes + 6 * (size_t)k;
+  const float b0 = b[0], b1 = b[1], b2 = b[2], b3 = b[3], b4 = b[4], b5 = b[5];
   // one cell of slack on both sides covers the float rounding of the cell arithmetic; the exact test below decides
   int c0[3], c1[3];
   const float o[3] = {G.ox, G.oy, G.oz};
   const int nn[3] = {G.nx, G.ny, G.nz};
+  const float bl[3] = {b0, b1, b2}, bh[3] = {b3, b4, b5};
+#pragma unroll
   for (int a = 0; a < 3; ++a) {
-    const float lo = floorf((b[a] - o[a]) * G.inv_h) - 1.f, hi = floorf((b[3 + a] - o[a]) * G.inv_h) + 1.f;
+    const float lo = floorf((bl[a] - o[a]) * G.inv_h) - 1.f, hi = floorf((bh[a] - o[a]) * G.inv_h) + 1.f;
     c0[a] = (int)fminf(fmaxf(lo, 0.f), (float)(nn[a] - 1));
     c1[a] = (int)fminf(fmaxf(hi, 0.f), (float)(nn[a] - 1));
     if (hi < 0.f || lo > (float)(nn[a] - 1)) return;   // the box lies outside the grid: nothing indexed there
   }
+  const int ny = c1[1] - c0[1] + 1, nz = c1[2] - c0[2] + 1;
   uint32_t n = 0;
-  for (int z = c0[2]; z <= c1[2]; ++z)
-    for (int y = c0[1]; y <= c1[1]; ++y) {
-      const uint32_t rs = cell_start[grid_cell_index(G, c0[0], y, z)], re = cell_start[grid_cell_index(G, c1[0], y, z) + 1];
-      for (uint32_t j = rs; j < re; ++j) {
-        const float4 c = cell_pts[j];
-        if (b[0] <= c.x && b[3] > c.x && b[1] <= c.y && b[4] > c.y && b[2] <= c.z && b[5] > c.z) {
-          const uint32_t slot = __float_as_uint(c.w);
-          const uint32_t w = __float_as_uint(mpts[slot].w);
-          if (!(w & MALIO_LINK_POINT_DELETED)) { mpts[slot].w = __uint_as_float(w | MALIO_LINK_POINT_DELETED); ++n; }
-        }
+  for (int row = (int)lane; row < ny * nz; row += 32) {
+    const int y = c0[1] + row % ny, z = c0[2] + row / ny;
+    const uint32_t rs = cell_start[grid_cell_index(G, c0[0], y, z)], re = cell_start[grid_cell_index(G, c1[0], y, z) + 1];
+    for (uint32_t j = rs; j < re; ++j) {
+      const float4 c = cell_pts[j];
+      if (b0 <= c.x && b3 > c.x && b1 <= c.y && b4 > c.y && b2 <= c.z && b5 > c.z) {
+        const uint32_t slot = __float_as_uint(c.w);
+        const uint32_t w = __float_as_uint(mpts[slot].w);
+        if (!(w & MALIO_LINK_POINT_DELETED)) { mpts[slot].w = __uint_as_float(w | MALIO_LINK_POINT_DELETED); ++n; }
       }
     }
-  if (n) atomicAdd(killed, n);
+  }
+#pragma unroll
+  for (int o2 = 16; o2 > 0; o2 >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o2);
+  if (lane == 0 && n) atomicAdd(killed, n);
 }
 // bounding box + count of the live slots: grid-stride, warp shuffle + one shared-memory stage per block, ONE set of atomics
 // per block (a few hundred blocks: the atomics on the 8 result words stay uncontended)
@@ -439,7 +449,7 @@ int sync_voxels(malio_handle* h, const float* boxes, uint32_t nb, const float* x
       CUDA_TRY(cudaMemcpyAsync(M->d_boxes, boxes, (size_t)nb * 6 * sizeof(float), cudaMemcpyHostToDevice, D->stream));
     }
     CUDA_TRY(cudaMemsetAsync(M->d_small + 6, 0, sizeof(uint32_t), D->stream));
-    kill_voxel_boxes_kernel<<<(nb + 127) / 128, 128, 0, D->stream>>>(M->d_boxes, nb, D->grid, D->d_cell_start, D->d_cell_pts, D->d_mpts, M->d_small + 6);
+    kill_voxel_boxes_kernel<<<(nb + KV_T / 32 - 1) / (KV_T / 32), KV_T, 0, D->stream>>>(M->d_boxes, nb, D->grid, D->d_cell_start, D->d_cell_pts, D->d_mpts, M->d_small + 6);
     CUDA_TRY(cudaGetLastError());
     if (n_deleted) {   // the count is only fetched (and waited for) when the caller asks for it
       CUDA_TRY(cudaMemcpyAsync(M->h_small + 6, M->d_small + 6, sizeof(uint32_t), cudaMemcpyDeviceToHost, D->stream));
