@@ -789,6 +789,13 @@ def run_ours(args, rank, world):
         line["e2e"] = dict(full, mode="full snapshot per scan")
     if parity_n is not None:
         line["parity_n"] = parity_n
+    if world > 1:
+        xp = int(c1.exchange_passes - c0.exchange_passes)
+        line["exchange_wait_us_per_pass"] = {
+            "min_exchange": 1e3 * float(c1.exchange_min_wait_ms - c0.exchange_min_wait_ms) / max(xp, 1),
+            "sum_exchange": 1e3 * float(c1.exchange_sum_wait_ms - c0.exchange_sum_wait_ms) / max(xp, 1), "passes": xp,
+            "what": "rank 0, %globaltimer inside pass_kernel: push of this GPU's keys / system to every peer + wait for all of theirs; the "
+                    "MIN exchange is where a rank waits for the slowest rank to have launched its pass (host launch skew)"}
     print(json.dumps(line))
     model.close()
     if tree is not None:

@@ -383,6 +383,11 @@ typedef struct malio_counters {
                                      1e-10 window, broken by slot index instead of the reference's traversal order (exempted ties) */
   uint64_t map_slots, map_live;   /* device-resident map: slots in use / live points after the last commit */
   uint64_t map_compactions;
+  /* multi-GPU, in-kernel exchange: device time (globaltimer) block 0 spent pushing its min/max keys to the peers and waiting for
+   * all of theirs (this includes waiting for the slowest rank to LAUNCH its pass), the same for the system sum, and the number
+   * of passes that exchanged */
+  double exchange_min_wait_ms, exchange_sum_wait_ms;
+  uint64_t exchange_passes;
 } malio_counters;
 int malio_get_counters(malio_handle* h, malio_counters* out);
 

@@ -1980,6 +1980,7 @@ struct PassArgs {
   // device-side iterated update: non-null -> run / repeat-the-plane-fit / parity / sequence number come from the control block
   const ScanCtl* ctl; unsigned long long* mmkey_base; uint32_t* cnt_base;
   unsigned long long* dbg; // optional [grid][8] %globaltimer stamps at the phase boundaries (MALIO_PASS_TRACE=1)
+  unsigned long long* xwait;   // multi-GPU: [0] ns spent in the MIN exchange (push + wait for every peer), [1] same for the SUM exchange, [2] passes
 };
 __device__ __forceinline__ void pass_stamp(const PassArgs& a, int k) {
   if (a.dbg && threadIdx.x == 0) {
@@ -2112,6 +2113,8 @@ pass_kernel(PassArgs a_in, PassConst pc_in, ParamConst prm) {
       const int lane = threadIdx.x, me = a.peer.rank, W = a.peer.world;
       if (lane == 0) while ((int32_t)(ld_acquire_u32(a.bar + 0) - (ef.bar_base[0] + gridDim.x)) < 0) { }
       __syncwarp();
+      unsigned long long xw0 = 0;
+      if (lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(xw0));
       unsigned long long k[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) k[c] = __ldcg(ef.mmkey + c);
@@ -2138,6 +2141,10 @@ pass_kernel(PassArgs a_in, PassConst pc_in, ParamConst prm) {
       }
       const bool all_ok = __all_sync(0xffffffffu, ok);
       if (lane == 0) {
+        unsigned long long xw1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(xw1));
+        a.xwait[0] += xw1 - xw0;      // only this thread of this GPU ever writes these words
+        a.xwait[2] += 1;
 #pragma unroll
         for (int c = 0; c < 4; ++c) ef.mmkey[c] = k[c];
         if (!all_ok) *reinterpret_cast<volatile uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 9) = 1u;   // peer timeout
@@ -2287,6 +2294,8 @@ pass_kernel(PassArgs a_in, PassConst pc_in, ParamConst prm) {
         // cross-GPU SUM: this GPU's folded system goes into slot [me] of every mailbox (its own included), then the
         // slots of all ranks are added in rank order — the same order on every GPU, so all ranks hold identical bits
         const int me = a.peer.rank, W = a.peer.world;
+        unsigned long long xs0 = 0;
+        if (lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(xs0));
         for (int r = 0; r < W; ++r) {
           volatile double* dst = reinterpret_cast<volatile double*>(mail_sum_slot(a.peer.mail[r], ef.seq, me));
           for (uint32_t e = lane; e < MALIO_RED_DOUBLES; e += 32) dst[e] = __ldcg(a.d_res + e);
@@ -2299,6 +2308,11 @@ pass_kernel(PassArgs a_in, PassConst pc_in, ParamConst prm) {
           ok = wait_seq_sys(reinterpret_cast<const uint32_t*>(mail_sum_slot(a.peer.mail[me], ef.seq, (int)lane) + MAIL_SUM_SEQ_OFF), ef.seq);
         }
         if (!__all_sync(0xffffffffu, ok) && lane == 0) *reinterpret_cast<volatile uint32_t*>(a.h_res + MALIO_RED_DOUBLES + 9) = 1u;
+        if (lane == 0) {
+          unsigned long long xs1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(xs1));
+          a.xwait[1] += xs1 - xs0;    // the last-folding warp of the grid: one writer per pass
+        }
         for (uint32_t e = lane; e < MALIO_RED_DOUBLES; e += 32) {
           double sum = 0.0;
           for (int r = 0; r < W; ++r) sum += reinterpret_cast<const volatile double*>(mail_sum_slot(a.peer.mail[me], ef.seq, r))[e];
@@ -2793,8 +2807,8 @@ int create(malio_handle* h) {
     CUDA_TRY(cudaMemcpy(D->d_mmkey, init, sizeof(init), cudaMemcpyHostToDevice));
   }
   CUDA_TRY(cudaMalloc((void**)&D->d_res, MALIO_RED_DOUBLES * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void**)&D->d_cand, sizeof(unsigned long long)));
-  CUDA_TRY(cudaMemset(D->d_cand, 0, sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc((void**)&D->d_cand, 4 * sizeof(unsigned long long)));   // [0] candidates, [1..3] multi-GPU exchange waits (ns, ns, passes)
+  CUDA_TRY(cudaMemset(D->d_cand, 0, 4 * sizeof(unsigned long long)));
   CUDA_TRY(cudaMalloc((void**)&D->d_gstats, 8 * sizeof(uint32_t)));
   CUDA_TRY(cudaMemset(D->d_gstats, 0, 8 * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc((void**)&D->d_hist, SORT_BINS * sizeof(uint32_t)));
@@ -3188,9 +3202,12 @@ int set_timing(malio_handle* h, int enable) {
 int get_counters(malio_handle* h, malio_counters* out) {
   DeviceState* D = (DeviceState*)h->dev;
   CUDA_TRY(cudaSetDevice(D->device));
-  unsigned long long c = 0;
-  CUDA_TRY(cudaMemcpy(&c, D->d_cand, sizeof(c), cudaMemcpyDeviceToHost));
-  D->ctr.knn_candidates = c;
+  unsigned long long c[4] = {0, 0, 0, 0};
+  CUDA_TRY(cudaMemcpy(c, D->d_cand, sizeof(c), cudaMemcpyDeviceToHost));
+  D->ctr.knn_candidates = c[0];
+  D->ctr.exchange_min_wait_ms = (double)c[1] * 1e-6;
+  D->ctr.exchange_sum_wait_ms = (double)c[2] * 1e-6;
+  D->ctr.exchange_passes = c[3];
   D->ctr.knn_tie_queries = D->h_gstats[7];
   *out = D->ctr;
   return MALIO_OK;
@@ -3294,6 +3311,8 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
     for (int r = 0; r < MAIL_MAX_WORLD; ++r) a.peer.mail[r] = D->mail_peer[r];
     *reinterpret_cast<volatile uint32_t*>(D->h_res + MALIO_RED_DOUBLES + 9) = 0u;
     a.dbg = nullptr;
+  a.xwait = D->d_cand + 1;
+    a.xwait = D->d_cand + 1;
     if (D->trace_passes > 0) {
       if (!D->d_dbg) { CUDA_TRY(cudaMalloc((void**)&D->d_dbg, (size_t)4096 * 8 * sizeof(unsigned long long))); D->trace_left = D->trace_passes; }
       if (D->trace_left > 0 && grid <= 4096) a.dbg = D->d_dbg;

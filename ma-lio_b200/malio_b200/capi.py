@@ -98,7 +98,8 @@ class Counters(C.Structure):
                 ("knn_fallback_queries", C.c_uint64), ("knn_ring2_queries", C.c_uint64),
                 ("knn_candidates", C.c_uint64), ("pass_launches", C.c_uint64), ("pass_points", C.c_uint64),
                 ("pass_fit_launches", C.c_uint64), ("pass_ms", C.c_double), ("knn_tie_queries", C.c_uint64),
-                ("map_slots", C.c_uint64), ("map_live", C.c_uint64), ("map_compactions", C.c_uint64)]
+                ("map_slots", C.c_uint64), ("map_live", C.c_uint64), ("map_compactions", C.c_uint64),
+                ("exchange_min_wait_ms", C.c_double), ("exchange_sum_wait_ms", C.c_double), ("exchange_passes", C.c_uint64)]
 
 
 class UpdateReport(C.Structure):
