@@ -2296,9 +2296,17 @@ pass_kernel(PassArgs a_in, PassConst pc_in, ParamConst prm) {
         const int me = a.peer.rank, W = a.peer.world;
         unsigned long long xs0 = 0;
         if (lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(xs0));
-        for (int r = 0; r < W; ++r) {
-          volatile double* dst = reinterpret_cast<volatile double*>(mail_sum_slot(a.peer.mail[r], ef.seq, me));
-          for (uint32_t e = lane; e < MALIO_RED_DOUBLES; e += 32) dst[e] = __ldcg(a.d_res + e);
+        // payload with ordinary (weak) stores: they pipeline over NVLink; the system-scope fence + the release flag below publish
+        // them.  (volatile = strong system-scope stores cost ~0.5 us EACH here: 17 us per pass at N = 2, ~60 us at N = 8.)
+        {
+          double v[(MALIO_RED_DOUBLES + 31) / 32];
+#pragma unroll
+          for (uint32_t j = 0; j < (MALIO_RED_DOUBLES + 31) / 32; ++j) { const uint32_t e = lane + 32 * j; v[j] = e < MALIO_RED_DOUBLES ? __ldcg(a.d_res + e) : 0.0; }
+          for (int r = 0; r < W; ++r) {
+            double* dst = reinterpret_cast<double*>(mail_sum_slot(a.peer.mail[r], ef.seq, me));
+#pragma unroll
+            for (uint32_t j = 0; j < (MALIO_RED_DOUBLES + 31) / 32; ++j) { const uint32_t e = lane + 32 * j; if (e < MALIO_RED_DOUBLES) dst[e] = v[j]; }
+          }
         }
         __threadfence_system();
         __syncwarp();
@@ -2313,9 +2321,10 @@ pass_kernel(PassArgs a_in, PassConst pc_in, ParamConst prm) {
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(xs1));
           a.xwait[1] += xs1 - xs0;    // the last-folding warp of the grid: one writer per pass
         }
+        __syncwarp();     // every lane's peer has published (acquire loads above); L2 is the coherence point for the peers' writes
         for (uint32_t e = lane; e < MALIO_RED_DOUBLES; e += 32) {
           double sum = 0.0;
-          for (int r = 0; r < W; ++r) sum += reinterpret_cast<const volatile double*>(mail_sum_slot(a.peer.mail[me], ef.seq, r))[e];
+          for (int r = 0; r < W; ++r) sum += __ldcg(reinterpret_cast<const double*>(mail_sum_slot(a.peer.mail[me], ef.seq, r)) + e);
           a.d_res[e] = sum;
           a.h_res[e] = sum;
         }
