@@ -56,7 +56,7 @@ WORKLOADS = {
     "C5": "C5: k-NN microbench, 1M queries vs 10M-pt tree, k=5",
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (profiles/), C2 only
-NCU_DRAM_BYTES = {"knn": 8.24e6, "pass": 10.1e6, "knn_c5": 535.6e6}   # profiles/r02_knn_direct_c2_raw.csv, r02_kernels_raw.csv, r02_knn_direct_c5_raw.csv
+NCU_DRAM_BYTES = {"knn": 8.26e6, "pass": 10.1e6, "knn_c5": 535.6e6}   # profiles/r02_keys_pass_raw.csv (knn_keys_kernel, pass_kernel), r02_knn_direct_c5_raw.csv
 SYNC_THREADS = 16          # host threads of the per-scan voxel read-back (include/malio_mapsync.hpp)
 REF_CPU_BUDGET_S = 150.0   # bound of the CPU arms' total run time (both thread counts together)
 
