@@ -3320,7 +3320,6 @@ int measure(malio_handle* h, const malio_pass_state* s, int redo_knn, double* Ht
     for (int r = 0; r < MAIL_MAX_WORLD; ++r) a.peer.mail[r] = D->mail_peer[r];
     *reinterpret_cast<volatile uint32_t*>(D->h_res + MALIO_RED_DOUBLES + 9) = 0u;
     a.dbg = nullptr;
-  a.xwait = D->d_cand + 1;
     a.xwait = D->d_cand + 1;
     if (D->trace_passes > 0) {
       if (!D->d_dbg) { CUDA_TRY(cudaMalloc((void**)&D->d_dbg, (size_t)4096 * 8 * sizeof(unsigned long long))); D->trace_left = D->trace_passes; }
@@ -3597,6 +3596,7 @@ int update_on_device(malio_handle* h, malio_state* x, double* P, int max_iter, m
   for (int r = 0; r < MAIL_MAX_WORLD; ++r) a.peer.mail[r] = D->mail_peer[r];
   a.ctl = D->d_ctl; a.mmkey_base = D->d_mmkey; a.cnt_base = D->d_counters + 4;
   a.dbg = nullptr;
+  a.xwait = D->d_cand + 1;
   *reinterpret_cast<volatile uint32_t*>(D->h_res + MALIO_RED_DOUBLES + 9) = 0u;
   PassConst pc_arg = pc0;
   ParamConst prm_arg = prm;
