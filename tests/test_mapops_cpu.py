@@ -64,3 +64,40 @@ def test_delta_protocol_keeps_a_flat_mirror_equal_to_the_real_tree(threads):
         assert same_set(tree, mir.live_points())
     assert synced_pts < 50 * 400 * 3      # the deltas stay proportional to the changed points
     tree.close()
+
+
+@pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref (the real ikd_Tree.cpp) was not built")
+def test_collect_voxel_sync_edge_cases_and_thread_independence():
+    """malio::collect_voxel_sync: nothing added -> empty record; many new points in ONE voxel -> one box; more threads than voxels;
+    the record (boxes in order of first appearance, points in box order) does not depend on the thread count; a voxel the tree
+    holds nothing in comes back with count 0 (its box still travels: the device must empty it)."""
+    rng = np.random.default_rng(5)
+    M = 5000
+    xyz = rng.uniform(-10, 10, (M, 3)).astype(np.float32)
+    tree = po.RefTree(box_length=0.5)
+    tree.build(xyz, np.full(M, 0.001, np.float32), np.arange(M, dtype=np.int32))
+    s = tree.collect_sync(np.zeros((0, 3), np.float32), 0.5, threads=4)
+    assert s["boxes"].shape[0] == 0 and s["xyz"].shape[0] == 0
+    one = (np.array([[1.1, 2.1, 3.1]], np.float32) + rng.uniform(0, 0.3, (40, 3)).astype(np.float32))
+    tree.add_points(one, np.full(40, 0.001, np.float32), np.arange(M, M + 40, dtype=np.int32), downsample=True)
+    s = tree.collect_sync(one, 0.5, threads=8)       # 8 threads, 1 voxel
+    assert s["boxes"].shape[0] == 1 and s["counts"][0] == s["xyz"].shape[0] >= 1
+    assert np.allclose(s["boxes"][0], [1.0, 2.0, 3.0, 1.5, 2.5, 3.5])
+    inside = (s["xyz"] >= s["boxes"][0, :3]).all() and (s["xyz"] < s["boxes"][0, 3:]).all()
+    assert inside
+    # a box far outside the map: no live point, count 0, the box is still reported
+    far = np.array([[500.2, 500.2, 500.2]], np.float32)
+    s = tree.collect_sync(far, 0.5, threads=2)
+    assert s["boxes"].shape[0] == 1 and s["counts"][0] == 0 and s["xyz"].shape[0] == 0
+    # thread independence on a batch with repeats
+    a = (xyz[rng.integers(0, M, 600)] + rng.normal(0, 0.3, (600, 3))).astype(np.float32)
+    a[100:200] = a[0:100]
+    tree.add_points(a, np.full(600, 0.001, np.float32), np.arange(M + 40, M + 640, dtype=np.int32), downsample=True)
+    ref = tree.collect_sync(a, 0.5, threads=1)
+    assert ref["boxes"].shape[0] < 600                      # repeats collapse
+    for th in (2, 3, 8, 64):
+        s = tree.collect_sync(a, 0.5, threads=th)
+        for k in ("boxes", "counts", "xyz", "normal_y", "ids"):
+            assert np.array_equal(s[k], ref[k]), (th, k)
+    assert int(ref["counts"].sum()) == ref["xyz"].shape[0]
+    tree.close()

@@ -155,3 +155,33 @@ def test_city_bin_readers_and_preprocess_handlers(tmp_path):
             assert np.array_equal(g["xyz"], r[:, :3]) and np.array_equal(g["curvature"], r[:, 3]) and np.array_equal(gi, ri)
     with pytest.raises(capi.MalioError):
         dataset.read_livox_bin(str(tmp_path / "missing.bin"))
+
+
+def test_city_bin_reader_edge_cases(tmp_path):
+    """Empty file, a file shorter than one record, capacity below the record count, NULL arguments."""
+    import ctypes as C
+    import np_dataset as nd
+    from malio_b200 import dataset
+    empty = tmp_path / "empty.bin"; empty.write_bytes(b"")
+    short = tmp_path / "short.bin"; short.write_bytes(b"\x00" * 10)
+    for f in (empty, short):
+        assert dataset.read_ouster_bin(str(f), True).shape[0] == 1       # only the player's extra default record
+        assert dataset.read_ouster_bin(str(f), False).shape[0] == 0
+        assert dataset.read_livox_bin(str(f), False).shape[0] == 0
+    rec = np.zeros(10, nd.OUSTER_REC); rec["x"] = np.arange(10)
+    f = tmp_path / "ten.bin"; f.write_bytes(rec.tobytes())
+    lib = capi.load()
+    n = C.c_uint32(0)
+    out = np.zeros(4, capi.OUSTER_PT)
+    assert lib.malio_read_ouster_bin(str(f).encode(), capi.ptr(out), 4, C.byref(n), 0) == capi.ERR_CAPACITY
+    assert n.value == 4 and np.array_equal(out["xyz"][:, 0], np.arange(4, dtype=np.float32))    # what fitted was delivered
+    out = np.zeros(10, capi.OUSTER_PT)
+    assert lib.malio_read_ouster_bin(str(f).encode(), capi.ptr(out), 10, C.byref(n), 1) == capi.ERR_CAPACITY   # no room for the extra record
+    assert lib.malio_read_ouster_bin(str(f).encode(), capi.ptr(out), 10, C.byref(n), 0) == capi.OK and n.value == 10
+    assert lib.malio_read_ouster_bin(None, capi.ptr(out), 10, C.byref(n), 0) == capi.ERR_INVALID_ARG
+    assert lib.malio_read_ouster_bin(str(f).encode(), capi.ptr(out), 10, None, 0) == capi.ERR_INVALID_ARG
+    # handlers: nothing in, nothing out; an invalid decimation is rejected
+    g, gi = dataset.preprocess_ouster(np.zeros(0, capi.OUSTER_PT))
+    assert g.shape[0] == 0 and gi.shape[0] == 0
+    m = C.c_uint32(0)
+    assert lib.malio_preprocess_ouster(capi.ptr(out), 10, 0, C.c_double(0.5), C.c_float(1e-3), None, None, 0, C.byref(m)) == capi.ERR_INVALID_ARG
