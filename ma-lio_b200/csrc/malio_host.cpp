@@ -124,6 +124,7 @@ extern "C" {
 const char* malio_version(void) { return "malio_b200 0.1 (sm_100a)"; }
 
 void malio_default_params(malio_params* p, int n_lidar) {
+  if (!p) return;
   std::memset(p, 0, sizeof(*p));
   p->n_lidar = n_lidar;
   p->extrinsic_est_en = 1;          // config/City.yaml:23
@@ -160,7 +161,7 @@ void malio_destroy(malio_handle* h) {
   malio_dev::destroy(h);
   delete h;
 }
-int malio_get_nccl_unique_id(uint8_t id[MALIO_NCCL_UNIQUE_ID_BYTES]) { return malio_dev::get_unique_id(id); }
+int malio_get_nccl_unique_id(uint8_t id[MALIO_NCCL_UNIQUE_ID_BYTES]) { return id ? malio_dev::get_unique_id(id) : MALIO_ERR_INVALID_ARG; }
 int malio_comm_init(malio_handle* h, const uint8_t id[MALIO_NCCL_UNIQUE_ID_BYTES], int rank, int world) {
   if (!h || !id || world < 1 || rank < 0 || rank >= world) return MALIO_ERR_INVALID_ARG;
   return malio_dev::comm_init(h, id, rank, world);
@@ -329,6 +330,7 @@ inline void compound_cov(const M6& c1p, const M6& c2, double* out) {
 }  // namespace
 
 void malio_pose_initial(malio_pose* pose, const double t[3], const double q[4], const double cov[36]) {
+  if (!pose || !t || !q || !cov) return;   // void like the reference's helper: a NULL argument leaves everything untouched
   for (int k = 0; k < 3; ++k) pose->t[k] = t[k];
   for (int k = 0; k < 4; ++k) pose->q[k] = q[k];
   set_T(pose);
@@ -336,6 +338,7 @@ void malio_pose_initial(malio_pose* pose, const double t[3], const double q[4], 
 }
 void malio_compound_pose_with_cov(const malio_pose* pose_1, const double* cov_1, const malio_pose* pose_2, const double* cov_2,
                                   malio_pose* pose_cp, double* cov_cp) {
+  if (!pose_1 || !cov_1 || !pose_2 || !cov_2 || !pose_cp || !cov_cp) return;
   // field order of associate_uct.hpp:93-100 — pose_cp may be pose_2
   double q[4], t[3];
   q_mul_h(pose_1->q, pose_2->q, q);
@@ -353,6 +356,7 @@ void malio_compound_pose_with_cov(const malio_pose* pose_1, const double* cov_1,
 }
 void malio_compound_inv_pose_with_cov(const malio_pose* pose_1, const double* cov_1, const malio_pose* pose_2, const double* cov_2,
                                       malio_pose* pose_cp, double* cov_cp) {
+  if (!pose_1 || !cov_1 || !pose_2 || !cov_2 || !pose_cp || !cov_cp) return;
   const double qc[4] = {pose_1->q[0], -pose_1->q[1], -pose_1->q[2], -pose_1->q[3]};
   double q[4], d[3], t[3];
   q_mul_h(qc, pose_2->q, q);

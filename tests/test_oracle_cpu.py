@@ -537,3 +537,22 @@ def test_reference_arm_does_not_map_the_cuda_library_and_reports_the_split():
     assert r["mapped"] == 0
     assert r["best"]["steps"] == 2 and set(r["best"]["split_ms_per_pass"]) == {"K_nearest_search", "B_h_share_model_rest", "A_ieskf_rest"}
     assert r["n_runs"] >= 1
+
+
+def test_every_entry_point_survives_null_arguments():
+    """C-ABI robustness without a GPU: every exported function called with NULL for every pointer and 0 for every scalar must
+    return (an error code where it has one) instead of dereferencing — run in a subprocess, a missing check is a SIGSEGV."""
+    import subprocess
+    import sys
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "ma-lio_b200"))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "null_handle_probe.py")], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout[-400:], r.stderr[-400:])
+    lines = [l.split() for l in r.stdout.strip().splitlines()]
+    assert lines[-1] == ["DONE"]
+    rc = {l[0]: l[1] for l in lines[:-1] if len(l) == 2}
+    assert len(rc) >= 38
+    for name, code in rc.items():
+        takes_handle = name not in ("malio_default_params", "malio_build_static_snapshot", "malio_bspline_get_pose", "malio_pose_initial",
+                                    "malio_compound_pose_with_cov", "malio_compound_inv_pose_with_cov", "malio_destroy", "malio_last_error")
+        if takes_handle:
+            assert code not in ("0", "ptr"), (name, code)      # an error code, never success
