@@ -267,7 +267,7 @@ def run_reference(args, rank):
         "cpu_baseline": cpu_baseline_obj(best, runs, f"{best['steps']} full {args.config} scans per thread count (steps bounded by a "
                                                          f"{REF_CPU_BUDGET_S:.0f} s CPU budget)"),
         "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "clocks": None, "roofline": None,      # CPU arm: no GPU clocks, no kernel roofline
     }
     print(json.dumps(line))
 
