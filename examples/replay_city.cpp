@@ -14,6 +14,8 @@
 // There is no IMU stream in this example: the spline's control points are a constant pose (no motion inside the scan) and the
 // uncertainty lists hold two entries of a small constant covariance, so the numbers it prints are those of a static sensor.
 // The point is the call sequence and that it compiles and links against the header, the library and the reference's tree.
+// Status: compiled, linked and its --host-only part run in the CPU container; the device part was written after the round's GPU
+// budget was spent and has NOT been executed on a B200 yet (every call it makes is covered by tests/ through the ctypes mirror).
 //
 // Build (tests/test_examples_cpu.py does this when /root/reference is present; running it needs a B200):
 //   g++ -O2 -std=c++14 -fopenmp -pthread -w -Ioracle/pcl_shim -I/root/reference/MA_LIO/include/ikd-Tree -Iinclude \
