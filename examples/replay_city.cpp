@@ -187,12 +187,12 @@ int main(int argc, char** argv) {
   {
     std::mt19937 gen(1);
     std::uniform_real_distribution<float> u(-1.f, 1.f);
-    for (int i = 0; i < 200000; ++i) {       // a ground plane and a wall on the 0.5 m lattice, like a down-sampled first scan
+    for (int i = 0; i < 200000; ++i) {       // a ground plane and a wall, the surfaces the synthetic scans see
       PointType p;
       const bool wall = (i % 3) == 0;
-      p.x = wall ? 12.f : 0.5f * std::floor(60.f * u(gen));
-      p.y = 0.5f * std::floor(60.f * u(gen));
-      p.z = wall ? 0.5f * std::floor(10.f * (u(gen) + 1.f)) : -1.5f;
+      p.x = wall ? 12.f + 0.01f * u(gen) : 30.f * u(gen);
+      p.y = 30.f * u(gen);
+      p.z = wall ? 5.f * (u(gen) + 1.f) : -1.5f + 0.01f * u(gen);
       p.normal_y = 0.001f;
       map_pts.push_back(p);
     }
