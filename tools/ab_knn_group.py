@@ -32,14 +32,16 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
             ts.append(st.ms_knn * 1e3)
         out.append(f"C4/300000: {np.median(ts[3:]):.1f}")
         m.close()
-    print("keys", os.environ.get("MALIO_KNN_KEYS", "1"), "group", os.environ.get("MALIO_KNN_GROUP", "auto"), "pre", os.environ.get("MALIO_KNN_PRE", "1"), "knn us:", "  ".join(out), flush=True)
+    print("keys", os.environ.get("MALIO_KNN_KEYS", "1"), "group", os.environ.get("MALIO_KNN_GROUP", "auto"), "knn us:", "  ".join(out), flush=True)
 else:
-    for g, pre in (("old", "1"), ("1", "0"), ("1", "1"), ("2", "0"), ("2", "1"), ("4", "0"), ("4", "1"), ("8", "1"), ("auto", "1")):
+    # "old" = knn_direct_kernel; 2 / 4 = the key scan with that many lanes per query (4 lanes also preload the rows' first candidates).
+    # The sweep of profiles/r02_knn_variants_sweep.log also varied the preload and tried 1 and 8 lanes: those instantiations were
+    # removed from the library afterwards (MALIO_KNN_GROUP accepts 1, 2, 4).
+    for g in ("old", "2", "4", "auto"):
         env = dict(os.environ)
         env.pop("MALIO_KNN_GROUP", None)
-        env["MALIO_KNN_PRE"] = pre
         if g == "old":
-            env["MALIO_KNN_KEYS"] = "0"      # knn_direct_kernel (thread per query, sorted (distance, index) insertion)
+            env["MALIO_KNN_KEYS"] = "0"
         elif g != "auto":
             env["MALIO_KNN_GROUP"] = g
         subprocess.run([sys.executable, os.path.abspath(__file__), "child", "c4"], env=env, check=False)
